@@ -1,0 +1,217 @@
+/*
+ * mld_c_api.h -- C ABI of libmld_cuda.so, the B200 (sm_100a) implementation of the
+ * monolidar_fusion depth-estimation hot path.
+ *
+ * This is the drop-in boundary: the reference's C++ class Mono_Lidar::DepthEstimator
+ * (monolidar_fusion/include/monolidar_fusion/DepthEstimator.h:39-359) keeps its public
+ * signature and forwards to these entry points (see shim/ and INTEGRATION.md). Plain C
+ * types only; no torch / Eigen / PCL types cross this boundary. There is no CPU fallback:
+ * every compute entry point returns MLD_ERR_CUDA when no usable device is present.
+ *
+ * Conventions
+ *   - every function returns 0 (MLD_OK) or a negative mld_error; mld_last_error() gives text.
+ *   - "host" pointers are ordinary (ideally pinned) host memory, "device" pointers are CUDA
+ *     device memory on the handle's device.
+ *   - points: x,y,z as the first three floats of each element, stride_bytes apart
+ *     (16 for float4, 32 for pcl::PointXYZI).
+ *   - features: 2 x F column-major doubles (u0,v0,u1,v1,...) == Eigen::Matrix2Xd::data().
+ *   - status codes are Mono_Lidar::DepthResultType (eDepthResultType.h:9-31).
+ */
+#ifndef MLD_C_API_H
+#define MLD_C_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum mld_error {
+    MLD_OK = 0,
+    MLD_ERR_INVALID_ARG = -1,
+    MLD_ERR_NOT_CONFIGURED = -2,   /* reference: throw "Call 'InitConfig' before calling 'Initialize'." (DepthEstimator.cpp:38) */
+    MLD_ERR_NOT_INITIALIZED = -3,  /* reference: throw "call of 'setInputCloud' without 'initialize'" (:227) */
+    MLD_ERR_NO_CLOUD = -4,         /* reference: throw "call of 'CalculateDepth' without 'SetInputCloud'" (:439) */
+    MLD_ERR_BAD_SEARCH_MODE = -5,  /* reference: throw "neighbor_search_mode has the invalid value" (:57) */
+    MLD_ERR_REGION_GROWING = -6,   /* reference: runtime_error "Region growing not supported!" (:608) */
+    MLD_ERR_PCL_INVALID = -7,      /* reference: GroundPlane::ExceptionPclInvalid, cloud < 3 points (RansacPlane.cpp:44-50) */
+    MLD_ERR_NO_ROAD_ESTIMATOR = -8,/* reference: throw "No road depth estimator selected." (:94) */
+    MLD_ERR_CAPACITY = -9,         /* search window larger than the kernels' neighbour capacity */
+    MLD_ERR_CUDA = -10,            /* CUDA runtime error or no device */
+    MLD_ERR_NO_MODEL = -11,        /* RANSAC found no model */
+    MLD_ERR_IO = -12               /* settings file cannot be read (reference: throw "Cant find settings file") */
+} mld_error;
+
+/* Mono_Lidar::DepthEstimatorParameters (DepthEstimatorParameters.h:12-172): same field names,
+ * bools as int32 (the reference's loader reads them as (int), DepthEstimatorParameters.cpp:27 ff.).
+ * Only the fields the hot path reads are present. */
+typedef struct mld_params {
+    int32_t neighbor_search_mode;
+    int32_t pixelarea_search_witdh;
+    int32_t pixelarea_search_height;
+    int32_t radiusSearch_count_min;
+
+    int32_t do_use_histogram_segmentation;
+    int32_t histogram_segmentation_min_pointcount;
+    double histogram_segmentation_bin_witdh;
+
+    int32_t do_use_depth_segmentation;
+
+    int32_t treshold_depth_enabled;
+    int32_t treshold_depth_mode;
+    int32_t treshold_depth_max;
+    int32_t treshold_depth_min;
+
+    int32_t treshold_depth_local_enabled;
+    int32_t treshold_depth_local_mode;
+    int32_t treshold_depth_local_valuetype;
+    double treshold_depth_local_value;
+
+    int32_t do_use_PCA;
+    int32_t pca_debug;
+    double pca_treshold_3_abs_min;
+    double pca_treshold_3_2_rel_max;
+    double pca_treshold_2_1_rel_min;
+
+    int32_t do_use_ransac_plane;
+    int32_t ransac_plane_max_iterations;
+    double ransac_plane_distance_treshold;
+    double ransac_plane_min_z;
+    double ransac_plane_max_z;
+    int32_t ransac_plane_use_refinement;
+    int32_t ransac_plane_use_camx_treshold;
+    double ransac_plane_refinement_treshold;
+    double ransac_plane_treshold_camx;
+    double ransac_plane_point_distance_treshold;
+    double ransac_plane_probability;
+
+    int32_t plane_estimator_use_triangle_maximation;
+    int32_t plane_estimator_use_leastsquares;
+    int32_t plane_estimator_use_mestimator;
+    int32_t do_use_cut_behind_camera;
+    double plane_estimator_z_x_min_relation;
+
+    int32_t do_use_triangle_size_maximation;
+    int32_t do_check_triangleplanar_condition;
+    double triangleplanar_crossnorm_treshold;
+    double viewray_plane_orthoganality_treshold;
+    int32_t set_all_depths_to_zero;
+    int32_t reserved0;
+} mld_params;
+
+/* Host view of Mono_Lidar::GroundPlane (RansacPlane.h:38-126): getModelCoeffs(), getInlinersIndex()
+ * / CheckPointInPlane(), isSegmented(). Coefficients are in the LIDAR frame. The library never
+ * frees inlier_idx: on output (mld_set_cloud with RANSAC, mld_estimate_ground_plane) the caller
+ * provides inlier_idx with room for inlier_capacity entries. */
+typedef struct mld_plane {
+    float coeffs[4];
+    int32_t* inlier_idx;
+    int64_t n_inliers;
+    int64_t inlier_capacity;
+    int32_t segmented;
+    int32_t reserved0;
+} mld_plane;
+
+typedef struct mld_handle mld_handle;
+
+/* ---- configuration (DepthEstimator::InitConfig, DepthEstimator.cpp:129-154) ---- */
+int mld_sizeof_params(void);
+void mld_default_params(mld_params* p);                       /* C++ member defaults */
+int mld_params_from_yaml(const char* path, mld_params* p);    /* DepthEstimatorParameters::fromFile (DepthEstimatorParameters.cpp:16-114):
+                                                                 flat "key: value # comment" OpenCV-YAML; absent keys read as 0 */
+const char* mld_status_name(int status);                      /* DepthResultTypeMap (DepthEstimator.h:45-60) */
+const char* mld_last_error(const mld_handle* h);              /* h may be NULL: error of the last failed mld_create on this thread */
+
+int mld_create(const mld_params* p, int device, mld_handle** out);   /* device < 0: current device */
+int mld_destroy(mld_handle* h);
+
+/* ---- DepthEstimator::Initialize (DepthEstimator.cpp:35-127) ----
+ * camera = CameraPinhole(W,H,f,cx,cy) (camera_pinhole.h:21-26); T = row-major 3x4 [R|t] of
+ * transform_lidar_to_cam (Eigen::Affine3d::matrix().topRows<3>()). */
+int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, const double* T_lidar_to_cam);
+
+/* ---- DepthEstimator::setInputCloud (DepthEstimator.cpp:220-312) ----
+ * Host points in, one H2D copy, projection + pixel map on the device. When do_use_ransac_plane is
+ * set and inout_plane is non-NULL with segmented == 0, the ground plane is fitted on the device
+ * (RansacPlane::CalculateInliersPlane) with ransac_seed and written back to *inout_plane. */
+int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, mld_plane* inout_plane,
+                  uint64_t ransac_seed);
+
+/* ---- DepthEstimator::CalculateDepth (DepthEstimator.cpp:429-488) on the current cloud ----
+ * plane == NULL is the reference's ransacPlane == nullptr (road path skipped). */
+int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* depth_host, int32_t* status_host,
+                        const mld_plane* plane);
+
+/* ---- RansacPlane::CalculateInliersPlane (RansacPlane.cpp:41-140), stand-alone ---- */
+int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, uint64_t seed,
+                              mld_plane* out_plane, int32_t* iterations_out);
+
+/* ---- batched, device-resident sequence (the benchmark path; frames are independent) ----
+ * d_points: nframes clouds, frame_pitch_points elements apart, n_points valid in each.
+ * d_uv: nframes x (2 x F) doubles; d_depth: nframes x F; d_status: nframes x F.
+ * road: 0 = plane nullptr for every frame; 1 = fit a RANSAC ground plane per frame on the device
+ * (seed + frame index) and run the road path with it.
+ * d_plane_coeffs_out (nullable): nframes x 4 floats, the fitted coefficients.
+ * Work is enqueued on `stream` (a cudaStream_t, may be 0); the call does not synchronise. */
+int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
+                              int stride_bytes, const double* d_uv, int F, double* d_depth, int32_t* d_status,
+                              int64_t nframes, int road, uint64_t seed, float* d_plane_coeffs_out, void* stream);
+
+/* ---- batched, host-resident sequence: same as above with pinned (or pageable) host buffers;
+ * H2D / kernels / D2H are pipelined over internal streams; returns after the results are in host
+ * memory. plane_coeffs_out_host nullable. */
+int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_points, int64_t frame_pitch_points,
+                            int stride_bytes, const double* uv_host, int F, double* depth_host, int32_t* status_host,
+                            int64_t nframes, int road, uint64_t seed, float* plane_coeffs_out_host);
+
+/* number of kernels this handle has launched since creation (for bench.py's gpu_launches) */
+int64_t mld_kernel_launch_count(const mld_handle* h);
+/* largest neighbour count per feature the kernels were built for */
+int mld_neighbor_capacity(void);
+
+/* ---- debug / parity views of the current cloud (NeighborFinderPixel::_img_points_lidar etc.) ---- */
+/* H x W row-major (offset x + y*W), RAW point index of the first point (in cloud order) that
+ * projects into the pixel with z > 0, -1 = empty (NeighborFinderPixel.cpp:40-55). */
+int mld_get_pixel_map(mld_handle* h, int32_t* out_host);
+/* neighbours of one feature in the reference's scan order (rows outer, columns inner), RAW indices;
+ * *k_out = number found (may exceed cap; only cap are written) (NeighborFinderPixel.cpp:60-95). */
+int mld_get_neighbors(mld_handle* h, double u, double v, double scale_w, double scale_h, int32_t* out_raw, int cap,
+                      int* k_out);
+/* visible flags per raw point (Transform_Cloud_LidarToCamera's cull, DepthEstimator.cpp:184-207):
+ * out_visible_host[n] bytes; *n_visible_out = count. */
+int mld_get_visible(mld_handle* h, uint8_t* out_visible_host, int64_t* n_visible_out);
+/* camera-frame coordinates of raw point i (3 doubles each), _points_cs_camera */
+int mld_get_points_camera(mld_handle* h, double* out_host);
+
+/* ---- synthetic KITTI-shaped input (bench / tests; deterministic, host and device agree bit for bit) ---- */
+typedef struct mld_synth_config {
+    int32_t rings;            /* 64 (HDL-64) or 128 */
+    int32_t azimuth_steps;    /* 1875 -> 120000 points */
+    float elev_top_deg;       /* +2.0 */
+    float elev_bottom_deg;    /* -24.8 */
+    float sensor_height;      /* 1.73 m above ground */
+    float max_range;          /* 120 m */
+    float range_noise_sigma;  /* 0.02 m */
+    float dropout_prob;       /* 0.02 -> NaN points */
+    int32_t n_boxes;          /* <= 64 obstacles per frame */
+    int32_t image_width, image_height;
+    float band_top_frac;      /* features: fraction of image height where the lidar band starts */
+    float band_feature_frac;  /* fraction of features placed inside the band (0.7) */
+    int32_t reserved0;
+} mld_synth_config;
+
+void mld_synth_default_config(mld_synth_config* c, int dense);   /* dense=0: KITTI shape, 1: 128-beam shape */
+int64_t mld_synth_points_per_frame(const mld_synth_config* c);
+/* host generators (no GPU needed): points as float4 (x,y,z,intensity), features as 2 x F doubles */
+int mld_synth_points_host(const mld_synth_config* c, uint64_t seed, int64_t frame, float* out_xyzi);
+int mld_synth_features_host(const mld_synth_config* c, uint64_t seed, int64_t frame, int F, double* out_uv);
+/* device generators: frames [frame0, frame0 + nframes) written frame_pitch_points apart */
+int mld_synth_points_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,
+                            int64_t frame_pitch_points, float* d_out_xyzi, void* stream);
+int mld_synth_features_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,
+                              int F, double* d_out_uv, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

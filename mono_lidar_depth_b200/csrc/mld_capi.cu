@@ -1,0 +1,835 @@
+// mld_capi.cu -- the C ABI of libmld_cuda.so (include/mld_c_api.h): handle, parameter loading,
+// device buffers, stream pipelines and kernel launches. No arithmetic of the hot path lives here and
+// there is no CPU fallback: without a CUDA device every compute entry point fails with MLD_ERR_CUDA.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <fstream>
+#include <map>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "mld_c_api.h"
+#include "mld_common.cuh"
+#include "mld_kernels.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int MLD_PIPE_SLOTS = 3;
+
+// everything one in-flight chunk of frames needs on the device
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    void* d_pts = nullptr;      size_t pts_bytes = 0;
+    double* d_uv = nullptr;     size_t uv_bytes = 0;
+    double* d_depth = nullptr;  size_t depth_bytes = 0;
+    int* d_status = nullptr;    size_t status_bytes = 0;
+    unsigned int* d_maps = nullptr; size_t maps_bytes = 0;
+    unsigned int* d_bits = nullptr; size_t bits_bytes = 0;
+    float* d_coeffs = nullptr;  size_t coeffs_bytes = 0;
+    void* d_scratch = nullptr;  size_t scratch_bytes = 0;
+    int* d_small = nullptr;     size_t small_bytes = 0;  // n_inliers | iterations | rc, per frame
+};
+
+template <typename T>
+cudaError_t ensure(T*& p, size_t& cap, size_t need) {
+    if (need <= cap && p != nullptr) return cudaSuccess;
+    if (p) {
+        cudaError_t e = cudaFree(p);
+        if (e != cudaSuccess) return e;
+        p = nullptr;
+        cap = 0;
+    }
+    size_t alloc = need + need / 4 + 256;
+    void* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, alloc);
+    if (e != cudaSuccess) return e;
+    p = static_cast<T*>(q);
+    cap = alloc;
+    return cudaSuccess;
+}
+
+}  // namespace
+
+struct mld_handle {
+    mld_params params;
+    DevParams dp;
+    int device = 0;
+    bool initialized = false;
+    bool have_cloud = false;
+    int kcap = 0;
+    int chunk_frames = 16;
+    long long cur_n = 0;
+    int cur_stride_f = 4;
+    Slot slots[MLD_PIPE_SLOTS];
+    int* d_dbg = nullptr;           // neighbour debug buffer
+    float* d_synth_tables = nullptr;
+    mld_synth_config synth_cfg_cached;
+    bool synth_tables_valid = false;
+    long long launches = 0;
+    std::string error;
+};
+
+namespace {
+
+int fail(mld_handle* h, int code, const std::string& msg) {
+    if (h) h->error = msg;
+    else g_create_error = msg;
+    return code;
+}
+int fail_cuda(mld_handle* h, cudaError_t e, const char* where) {
+    return fail(h, MLD_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+#define CK(call)                                               \
+    do {                                                       \
+        cudaError_t e__ = (call);                              \
+        if (e__ != cudaSuccess) return fail_cuda(h, e__, #call); \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
+RansacConfig ransac_config(const mld_params& p) {
+    RansacConfig c;
+    c.distance_treshold = p.ransac_plane_distance_treshold;
+    c.refinement_treshold = p.ransac_plane_refinement_treshold;
+    c.probability = p.ransac_plane_probability;
+    c.min_z = p.ransac_plane_min_z;
+    c.max_z = p.ransac_plane_max_z;
+    c.max_iterations = p.ransac_plane_max_iterations;
+    c.use_refinement = p.ransac_plane_use_refinement;
+    c.cos_eps = cos(M_PI / 18.);
+    c.log_probability = log(1.0 - p.ransac_plane_probability);
+    return c;
+}
+
+// largest number of pixels NeighborFinderPixel::getNeighbors can scan for half sizes (hx, hy)
+int max_window_area(double hx, double hy, int W, int H) {
+    double cx = floor(2.0 * hx) + 2.0, cy = floor(2.0 * hy) + 2.0;
+    if (cx > W) cx = W;
+    if (cy > H) cy = H;
+    if (cx < 0) cx = 0;
+    if (cy < 0) cy = 0;
+    double a = cx * cy;
+    return a > 1e9 ? 1000000000 : (int)a;
+}
+
+int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, int F, int frames, bool own_io, bool road) {
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    if (own_io) {
+        CK(ensure(s.d_pts, s.pts_bytes, (size_t)frames * (size_t)n_points * (size_t)stride_bytes));
+        CK(ensure(s.d_uv, s.uv_bytes, (size_t)frames * (size_t)F * 2 * sizeof(double)));
+        CK(ensure(s.d_depth, s.depth_bytes, (size_t)frames * (size_t)F * sizeof(double)));
+        CK(ensure(s.d_status, s.status_bytes, (size_t)frames * (size_t)F * sizeof(int)));
+    }
+    CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int)));
+    if (road) {
+        const size_t words = (size_t)((n_points + 31) / 32);
+        CK(ensure(s.d_bits, s.bits_bytes, (size_t)frames * words * sizeof(unsigned int)));
+        CK(ensure(s.d_coeffs, s.coeffs_bytes, (size_t)frames * 4 * sizeof(float)));
+        CK(ensure(s.d_scratch, s.scratch_bytes, mld_ransac_scratch_bytes(n_points, frames)));
+        CK(ensure(s.d_small, s.small_bytes, (size_t)frames * 3 * sizeof(int)));
+    }
+    return MLD_OK;
+}
+
+// one chunk of frames on one stream: clear maps, K1, [K4], K2
+int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, long long n_points, long long pitch_pts,
+                  int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
+                  long long frame0, float* d_coeffs_out) {
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    CK(cudaMemsetAsync(s.d_maps, 0xFF, (size_t)frames * WH * sizeof(unsigned int), st));
+    CK(mld_launch_project_scatter(h->dp, d_pts, stride_f, n_points, pitch_pts, s.d_maps, frames, st));
+    if (n_points > 0) h->launches++;
+    const float* coeffs = nullptr;
+    const unsigned int* bits = nullptr;
+    const long long words = (n_points + 31) / 32;
+    if (road && h->dp.road_mode != ROAD_NONE) {
+        float* cdst = d_coeffs_out ? d_coeffs_out : s.d_coeffs;
+        int nl = 0;
+        CK(mld_launch_ransac(ransac_config(h->params), d_pts, stride_f, n_points, pitch_pts, frames, seed, frame0, s.d_scratch,
+                             cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, st, &nl));
+        h->launches += nl;
+        coeffs = cdst;
+        bits = s.d_bits;
+    }
+    CK(mld_launch_feature_depth(h->dp, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs, bits,
+                                words, frames, st));
+    if (F > 0) h->launches++;
+    return MLD_OK;
+}
+
+// ---- flat OpenCV-YAML reader (cv::FileStorage subset used by DepthEstimatorParameters::fromFile) ----
+bool parse_yaml(const char* path, std::map<std::string, std::string>& kv) {
+    std::ifstream in(path);
+    if (!in.is_open()) return false;
+    std::string line;
+    while (std::getline(in, line)) {
+        size_t hash = line.find('#');
+        if (hash != std::string::npos) line = line.substr(0, hash);
+        if (line.empty() || line[0] == '%') continue;
+        size_t colon = line.find(':');
+        if (colon == std::string::npos) continue;
+        auto trim = [](std::string s) {
+            size_t a = s.find_first_not_of(" \t\r\n\"'"), b = s.find_last_not_of(" \t\r\n\"'");
+            return a == std::string::npos ? std::string() : s.substr(a, b - a + 1);
+        };
+        std::string k = trim(line.substr(0, colon)), v = trim(line.substr(colon + 1));
+        if (!k.empty()) kv[k] = v;
+    }
+    return true;
+}
+// cv::FileNode -> double: absent 0, int node -> (double)i, real node -> f
+double yaml_double(const std::map<std::string, std::string>& kv, const char* key) {
+    auto it = kv.find(key);
+    if (it == kv.end() || it->second.empty()) return 0.0;
+    char* end = nullptr;
+    double d = strtod(it->second.c_str(), &end);
+    return end == it->second.c_str() ? 0.0 : d;
+}
+// cv::FileNode -> int: absent 0, int node -> i, real node -> cvRound(f) (round half to even)
+int yaml_int(const std::map<std::string, std::string>& kv, const char* key) {
+    auto it = kv.find(key);
+    if (it == kv.end() || it->second.empty()) return 0;
+    const std::string& s = it->second;
+    char* end = nullptr;
+    long li = strtol(s.c_str(), &end, 0);
+    if (end != s.c_str() && *end == '\0') return (int)li;
+    double d = strtod(s.c_str(), &end);
+    if (end == s.c_str()) return 0x7fffffff;
+    return (int)nearbyint(d);
+}
+
+}  // namespace
+
+extern "C" {
+
+int mld_sizeof_params(void) { return (int)sizeof(mld_params); }
+
+void mld_default_params(mld_params* p) {
+    memset(p, 0, sizeof(*p));
+    // DepthEstimatorParameters.h:12-172 member initialisers
+    p->neighbor_search_mode = 0;
+    p->pixelarea_search_witdh = 12;
+    p->pixelarea_search_height = 15;
+    p->radiusSearch_count_min = 3;
+    p->do_use_histogram_segmentation = 1;
+    p->histogram_segmentation_bin_witdh = 0.5;
+    p->histogram_segmentation_min_pointcount = 3;
+    p->do_use_depth_segmentation = 0;
+    p->treshold_depth_enabled = 1;
+    p->treshold_depth_mode = 0;
+    p->treshold_depth_max = 100;
+    p->treshold_depth_min = 0;
+    p->treshold_depth_local_enabled = 1;
+    p->treshold_depth_local_mode = 0;
+    p->treshold_depth_local_valuetype = 1;
+    p->treshold_depth_local_value = 0.5;
+    p->do_use_PCA = 0;
+    p->pca_debug = 0;
+    p->pca_treshold_3_abs_min = 0.005;
+    p->pca_treshold_3_2_rel_max = 15;
+    p->pca_treshold_2_1_rel_min = 0.5;
+    p->do_use_ransac_plane = 1;
+    p->ransac_plane_distance_treshold = 0.2;
+    p->ransac_plane_min_z = -10000;
+    p->ransac_plane_max_z = 10000;
+    p->ransac_plane_max_iterations = 10000;
+    p->ransac_plane_use_refinement = 1;
+    p->ransac_plane_refinement_treshold = 10.2;
+    p->ransac_plane_use_camx_treshold = 0;
+    p->ransac_plane_treshold_camx = 2.0;
+    p->ransac_plane_point_distance_treshold = 0.2;
+    p->ransac_plane_probability = 0.999;
+    p->plane_estimator_use_triangle_maximation = 0;
+    p->plane_estimator_z_x_min_relation = 0;
+    p->plane_estimator_use_leastsquares = 0;
+    p->plane_estimator_use_mestimator = 1;
+    p->do_use_cut_behind_camera = 1;
+    p->do_use_triangle_size_maximation = 1;
+    p->do_check_triangleplanar_condition = 1;
+    p->triangleplanar_crossnorm_treshold = 0.1;
+    p->viewray_plane_orthoganality_treshold = 1.0;  // the header's `{01}` is an octal literal
+    p->set_all_depths_to_zero = 0;
+}
+
+int mld_params_from_yaml(const char* path, mld_params* p) {
+    std::map<std::string, std::string> kv;
+    if (!path || !p) return fail(nullptr, MLD_ERR_INVALID_ARG, "mld_params_from_yaml: null argument");
+    if (!parse_yaml(path, kv)) return fail(nullptr, MLD_ERR_IO, std::string("Cant find settings file: ") + path);
+    memset(p, 0, sizeof(*p));
+    // every read below mirrors one line of DepthEstimatorParameters::fromFile; bools are read through (int)
+    p->neighbor_search_mode = yaml_int(kv, "neighbor_search_mode");
+    p->pixelarea_search_witdh = yaml_int(kv, "pixelarea_search_witdh");
+    p->pixelarea_search_height = yaml_int(kv, "pixelarea_search_height");
+    p->radiusSearch_count_min = yaml_int(kv, "radiusSearch_count_min");
+    p->do_use_histogram_segmentation = yaml_int(kv, "do_use_histogram_segmentation") != 0;
+    p->histogram_segmentation_bin_witdh = yaml_double(kv, "histogram_segmentation_bin_witdh");
+    p->histogram_segmentation_min_pointcount = yaml_int(kv, "histogram_segmentation_min_pointcount");
+    p->do_use_depth_segmentation = yaml_int(kv, "do_use_depth_segmentation") != 0;
+    p->treshold_depth_enabled = yaml_int(kv, "treshold_depth_enabled") != 0;
+    p->treshold_depth_mode = yaml_int(kv, "treshold_depth_mode");
+    p->treshold_depth_max = yaml_int(kv, "treshold_depth_max");
+    p->treshold_depth_min = yaml_int(kv, "treshold_depth_min");
+    p->treshold_depth_local_enabled = yaml_int(kv, "treshold_depth_local_enabled") != 0;
+    p->treshold_depth_local_mode = yaml_int(kv, "treshold_depth_local_mode");
+    p->treshold_depth_local_valuetype = yaml_int(kv, "treshold_depth_local_valuetype");
+    p->treshold_depth_local_value = yaml_double(kv, "treshold_depth_local_value");
+    p->do_use_PCA = yaml_double(kv, "do_use_PCA") != 0.0;  // read through (double) upstream (:76)
+    p->pca_debug = yaml_int(kv, "pca_debug") != 0;
+    p->pca_treshold_3_abs_min = yaml_double(kv, "pca_treshold_3_abs_min");
+    p->pca_treshold_3_2_rel_max = yaml_double(kv, "pca_treshold_3_2_rel_max");
+    p->pca_treshold_2_1_rel_min = yaml_double(kv, "pca_treshold_2_1_rel_min");
+    p->do_use_ransac_plane = yaml_int(kv, "do_use_ransac_plane") != 0;
+    p->ransac_plane_distance_treshold = yaml_double(kv, "ransac_plane_distance_treshold");
+    p->ransac_plane_min_z = yaml_double(kv, "ransac_plane_min_z");
+    p->ransac_plane_max_z = yaml_double(kv, "ransac_plane_max_z");
+    p->ransac_plane_max_iterations = yaml_int(kv, "ransac_plane_max_iterations");
+    p->ransac_plane_use_refinement = yaml_int(kv, "ransac_plane_use_refinement") != 0;
+    p->ransac_plane_refinement_treshold = yaml_double(kv, "ransac_plane_refinement_treshold");
+    p->ransac_plane_use_camx_treshold = yaml_int(kv, "ransac_plane_use_camx_treshold") != 0;
+    p->ransac_plane_treshold_camx = yaml_double(kv, "ransac_plane_treshold_camx");
+    p->ransac_plane_point_distance_treshold = yaml_double(kv, "ransac_plane_point_distance_treshold");
+    p->ransac_plane_probability = yaml_double(kv, "ransac_plane_probability");
+    p->plane_estimator_use_triangle_maximation = yaml_int(kv, "plane_estimator_use_triangle_maximation") != 0;
+    p->plane_estimator_z_x_min_relation = yaml_double(kv, "plane_estimator_z_x_min_relation");
+    p->plane_estimator_use_leastsquares = yaml_int(kv, "plane_estimator_use_leastsquares") != 0;
+    p->plane_estimator_use_mestimator = yaml_int(kv, "plane_estimator_use_mestimator") != 0;
+    p->do_use_cut_behind_camera = yaml_int(kv, "do_use_cut_behind_camera") != 0;
+    p->do_use_triangle_size_maximation = yaml_int(kv, "do_use_triangle_size_maximation") != 0;
+    p->do_check_triangleplanar_condition = yaml_int(kv, "do_check_triangleplanar_condition") != 0;
+    p->triangleplanar_crossnorm_treshold = yaml_double(kv, "triangleplanar_crossnorm_treshold");
+    p->viewray_plane_orthoganality_treshold = yaml_double(kv, "viewray_plane_orthoganality_treshold");
+    p->set_all_depths_to_zero = yaml_int(kv, "set_all_depths_to_zero") != 0;
+    return MLD_OK;
+}
+
+const char* mld_status_name(int status) {
+    switch (status) {
+        case 0: return "Unspecified";
+        case 1: return "Success";
+        case 2: return "RadiusSearchInsufficientPoints";
+        case 3: return "HistogramNoLocalMax";
+        case 4: return "TresholdDepthGlobalGreaterMax";
+        case 5: return "TresholdDepthGlobalSmallerMin";
+        case 6: return "TresholdDepthLocalGreaterMax";
+        case 7: return "TresholdDepthLocalSmallerMin";
+        case 8: return "TriangleNotPlanar";
+        case 9: return "TriangleNotPlanarInsufficientPoints";
+        case 10: return "CornerBehindCamera";
+        case 11: return "PlaneViewrayNotOrthogonal";
+        case 12: return "PcaIsPoint";
+        case 13: return "PcaIsLine";
+        case 14: return "PcaIsCubic";
+        case 15: return "InsufficientRoadPoints";
+        case 16: return "SuccessRoad";
+        case 17: return "RegionGrowingNearestSeedNotAvailable";
+        case 18: return "RegionGrowingSeedsOutOfRange";
+        case 19: return "RegionGrowingInsufficientPoints";
+        case 20: return "SuccessRegionGrowing";
+        default: return "unknown";
+    }
+}
+
+const char* mld_last_error(const mld_handle* h) { return h ? h->error.c_str() : g_create_error.c_str(); }
+
+int mld_create(const mld_params* p, int device, mld_handle** out) {
+    if (!p || !out) return fail(nullptr, MLD_ERR_INVALID_ARG, "mld_create: null argument");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(nullptr, MLD_ERR_CUDA,
+                    std::string("mld_create: no CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "count 0") +
+                        "); this library has no CPU fallback");
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaGetDevice");
+    }
+    if (device >= count) return fail(nullptr, MLD_ERR_INVALID_ARG, "mld_create: device index out of range");
+    if (p->treshold_depth_enabled && (p->treshold_depth_mode < 0 || p->treshold_depth_mode > 1))
+        return fail(nullptr, MLD_ERR_INVALID_ARG, "Undefined treshold depth mode in config");
+    if (p->treshold_depth_local_enabled && (p->treshold_depth_local_mode < 0 || p->treshold_depth_local_mode > 1))
+        return fail(nullptr, MLD_ERR_INVALID_ARG, "Undefined treshold depth mode in config (local)");
+    if (p->treshold_depth_local_enabled && (p->treshold_depth_local_valuetype < 0 || p->treshold_depth_local_valuetype > 1))
+        return fail(nullptr, MLD_ERR_INVALID_ARG, "Undefined treshold tolerance mode for tresholdDepthLocal");
+    if (p->do_use_histogram_segmentation && !(p->histogram_segmentation_bin_witdh > 1e-6))
+        return fail(nullptr, MLD_ERR_INVALID_ARG, "histogram_segmentation_bin_witdh must be > 1e-6");
+    mld_handle* h = new mld_handle();
+    h->params = *p;
+    h->device = device;
+    const char* env = getenv("MLD_CHUNK_FRAMES");
+    if (env && atoi(env) > 0) h->chunk_frames = atoi(env);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        delete h;
+        return fail(nullptr, MLD_ERR_CUDA, "mld_create: cudaSetDevice failed");
+    }
+    for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
+        e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            mld_destroy(h);
+            return fail_cuda(nullptr, e, "stream/event creation");
+        }
+    }
+    *out = h;
+    return MLD_OK;
+}
+
+int mld_destroy(mld_handle* h) {
+    if (!h) return MLD_OK;
+    DeviceGuard g(h->device);
+    for (auto& s : h->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(h->d_dbg);
+    cudaFree(h->d_synth_tables);
+    delete h;
+    return MLD_OK;
+}
+
+int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, const double* T) {
+    if (!h) return fail(nullptr, MLD_ERR_NOT_CONFIGURED, "Call 'InitConfig' before calling 'Initialize'.");
+    if (!T || W <= 0 || H <= 0) return fail(h, MLD_ERR_INVALID_ARG, "mld_initialize: bad camera or transform");
+    const mld_params& p = h->params;
+    if (p.neighbor_search_mode != 0)
+        return fail(h, MLD_ERR_BAD_SEARCH_MODE, "neighbor_search_mode has the invalid value: " + std::to_string(p.neighbor_search_mode));
+    DevParams& d = h->dp;
+    memset(&d, 0, sizeof(d));
+    d.W = W; d.H = H; d.f = f; d.cx = cx; d.cy = cy;
+    for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++) d.R[r * 3 + c] = T[r * 4 + c];
+        d.t[r] = T[r * 4 + 3];
+    }
+    // Eigen::Affine3d::inverse(): linear part by cofactors, translation = (-linear^-1) * t
+    mld_inverse3_host(d.R, d.Ri);
+    for (int r = 0; r < 3; r++)
+        d.ti[r] = ((-d.Ri[r * 3 + 0]) * d.t[0] + (-d.Ri[r * 3 + 1]) * d.t[1]) + (-d.Ri[r * 3 + 2]) * d.t[2];
+    const double K[9] = {f, 0, cx, 0, f, cy, 0, 0, 1};
+    mld_inverse3_host(K, d.Kinv);
+    // NeighborFinderPixel::getNeighbors: half = size * 0.5 * (double)(float)scale
+    d.hx1 = static_cast<double>(p.pixelarea_search_witdh) * 0.5 * static_cast<double>(1.0f);
+    d.hy1 = static_cast<double>(p.pixelarea_search_height) * 0.5 * static_cast<double>(1.0f);
+    d.hx2 = static_cast<double>(p.pixelarea_search_witdh) * 0.5 * static_cast<double>(2.0f);
+    d.hy2 = static_cast<double>(p.pixelarea_search_height) * 0.5 * static_cast<double>(1.5f);
+    d.count_min = p.radiusSearch_count_min;
+    d.use_hist = p.do_use_histogram_segmentation != 0;
+    d.hist_min = p.histogram_segmentation_min_pointcount;
+    d.bin_w = p.histogram_segmentation_bin_witdh;
+    d.use_tri_max = p.do_use_triangle_size_maximation != 0;
+    d.check_planar = p.do_check_triangleplanar_condition != 0;
+    d.crossnorm_thr = p.triangleplanar_crossnorm_treshold;
+    d.ortho_thr = p.viewray_plane_orthoganality_treshold;
+    d.use_pca = p.do_use_PCA != 0;
+    d.pca_3_abs_min = p.pca_treshold_3_abs_min;
+    d.pca_3_2_rel_max = p.pca_treshold_3_2_rel_max;
+    d.pca_2_1_rel_min = p.pca_treshold_2_1_rel_min;
+    d.glob_en = p.treshold_depth_enabled != 0;
+    d.glob_mode = p.treshold_depth_mode;
+    d.glob_min = (double)p.treshold_depth_min;
+    d.glob_max = (double)p.treshold_depth_max;
+    d.loc_en = p.treshold_depth_local_enabled != 0;
+    d.loc_mode = p.treshold_depth_local_mode;
+    d.loc_type = p.treshold_depth_local_valuetype;
+    d.loc_val = p.treshold_depth_local_value;
+    d.cut_behind = p.do_use_cut_behind_camera != 0;
+    d.road_mode = ROAD_NONE;
+    if (p.do_use_ransac_plane) {  // estimator priority, DepthEstimator.cpp:84-94
+        if (p.plane_estimator_use_triangle_maximation) d.road_mode = ROAD_TRIANGLE;
+        else if (p.plane_estimator_use_leastsquares) d.road_mode = ROAD_LEASTSQUARES;
+        else if (p.plane_estimator_use_mestimator) d.road_mode = ROAD_MESTIMATOR;
+        else return fail(h, MLD_ERR_NO_ROAD_ESTIMATOR, "No road depth estimator selected.");
+    }
+    d.road_dist_thr = p.ransac_plane_point_distance_treshold;
+    d.zx_min_rel = p.plane_estimator_z_x_min_relation;
+    d.set_all_zero = p.set_all_depths_to_zero != 0;
+
+    int area = max_window_area(d.hx1, d.hy1, W, H);
+    if (d.road_mode != ROAD_NONE) area = std::max(area, max_window_area(d.hx2, d.hy2, W, H));
+    h->kcap = mld_feature_capacity_for(area);
+    if (h->kcap < 0)
+        return fail(h, MLD_ERR_CAPACITY, "search window of " + std::to_string(area) + " pixels exceeds the neighbour capacity " +
+                                             std::to_string(mld_neighbor_capacity()));
+    DeviceGuard g(h->device);
+    CK(mld_configure_feature_depth(h->kcap));
+    h->initialized = true;
+    h->have_cloud = false;
+    return MLD_OK;
+}
+
+int mld_neighbor_capacity(void) { return 1024; }
+int64_t mld_kernel_launch_count(const mld_handle* h) { return h ? h->launches : 0; }
+
+static int check_stride(mld_handle* h, int stride_bytes) {
+    if (stride_bytes < 16 || stride_bytes % 16 != 0)
+        return fail(h, MLD_ERR_INVALID_ARG, "point stride must be a positive multiple of 16 bytes (float4 / pcl::PointXYZI)");
+    return MLD_OK;
+}
+
+static void bits_to_plane(const std::vector<unsigned int>& bits, long long n, mld_plane* pl) {
+    int64_t cnt = 0;
+    for (long long i = 0; i < n; i++)
+        if ((bits[(size_t)(i >> 5)] >> (i & 31)) & 1u) {
+            if (pl->inlier_idx && cnt < pl->inlier_capacity) pl->inlier_idx[cnt] = (int32_t)i;
+            cnt++;
+        }
+    pl->n_inliers = cnt;
+}
+
+static int run_ransac_single(mld_handle* h, Slot& s, long long n, int stride_f, uint64_t seed, mld_plane* pl, int32_t* iters) {
+    const long long words = (n + 31) / 32;
+    int rc = slot_reserve(h, s, n, stride_f * 4, 0, 1, false, true);
+    if (rc) return rc;
+    int nl = 0;
+    CK(mld_launch_ransac(ransac_config(h->params), reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, 1, seed, 0, s.d_scratch,
+                         s.d_coeffs, s.d_bits, words, s.d_small, s.d_small + 1, s.d_small + 2, s.stream, &nl));
+    h->launches += nl;
+    std::vector<unsigned int> bits((size_t)words);
+    int small[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(pl->coeffs, s.d_coeffs, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(bits.data(), s.d_bits, (size_t)words * sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(small, s.d_small, 3 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (iters) *iters = small[1];
+    if (small[2] == MLD_ERR_PCL_INVALID) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    if (small[2] != 0) return fail(h, MLD_ERR_NO_MODEL, "RANSAC found no plane model");
+    bits_to_plane(bits, n, pl);
+    pl->segmented = 1;
+    return MLD_OK;
+}
+
+int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, mld_plane* inout_plane, uint64_t ransac_seed) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
+    if (n < 0 || (n > 0 && !points_host)) return fail(h, MLD_ERR_INVALID_ARG, "mld_set_cloud: bad cloud");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    const bool want_ransac = h->params.do_use_ransac_plane && inout_plane && !inout_plane->segmented;
+    // the reference throws ExceptionPclInvalid before doing anything else with the plane (RansacPlane.cpp:44-50)
+    if (want_ransac && n < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, 0, 1, true, false);
+    if (rc) return rc;
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemsetAsync(s.d_maps, 0xFF, WH * sizeof(unsigned int), s.stream));
+    CK(mld_launch_project_scatter(h->dp, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps, 1, s.stream));
+    if (n > 0) h->launches++;
+    h->cur_n = n;
+    h->cur_stride_f = stride_bytes / 4;
+    h->have_cloud = true;
+    if (want_ransac) {
+        rc = run_ransac_single(h, s, n, stride_bytes / 4, ransac_seed, inout_plane, nullptr);
+        if (rc) return rc;
+    }
+    CK(cudaStreamSynchronize(s.stream));
+    return MLD_OK;
+}
+
+int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, uint64_t seed,
+                              mld_plane* out_plane, int32_t* iterations_out) {
+    if (!h || !out_plane) return MLD_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && !points_host)) return fail(h, MLD_ERR_INVALID_ARG, "mld_estimate_ground_plane: bad cloud");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (n < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[1];  // does not disturb the current cloud of slot 0
+    CK(ensure(s.d_pts, s.pts_bytes, (size_t)n * (size_t)stride_bytes));
+    CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    return run_ransac_single(h, s, n, stride_bytes / 4, seed, out_plane, iterations_out);
+}
+
+int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* depth_host, int32_t* status_host,
+                        const mld_plane* plane) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "call of 'CalculateDepth' without 'SetInputCloud'");
+    if (F < 0 || (F > 0 && (!uv_host || !depth_host || !status_host))) return fail(h, MLD_ERR_INVALID_ARG, "mld_calculate_depth: bad buffers");
+    if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
+        return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
+    if (F == 0) return MLD_OK;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    CK(ensure(s.d_uv, s.uv_bytes, (size_t)F * 2 * sizeof(double)));
+    CK(ensure(s.d_depth, s.depth_bytes, (size_t)F * sizeof(double)));
+    CK(ensure(s.d_status, s.status_bytes, (size_t)F * sizeof(int)));
+    const long long n = h->cur_n;
+    const long long words = (n + 31) / 32;
+    const float* coeffs = nullptr;
+    const unsigned int* bits = nullptr;
+    std::vector<unsigned int> hb;
+    if (plane && h->dp.road_mode != ROAD_NONE) {
+        CK(ensure(s.d_bits, s.bits_bytes, (size_t)std::max<long long>(words, 1) * sizeof(unsigned int)));
+        CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
+        hb.assign((size_t)std::max<long long>(words, 1), 0u);
+        for (int64_t i = 0; i < plane->n_inliers; i++) {
+            int32_t r = plane->inlier_idx[i];
+            if (r >= 0 && r < n) hb[(size_t)(r >> 5)] |= 1u << (r & 31);
+        }
+        CK(cudaMemcpyAsync(s.d_bits, hb.data(), hb.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_coeffs, plane->coeffs, 4 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        coeffs = s.d_coeffs;
+        bits = s.d_bits;
+    }
+    CK(cudaMemcpyAsync(s.d_uv, uv_host, (size_t)F * 2 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    CK(mld_launch_feature_depth(h->dp, h->kcap, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, n, s.d_maps, s.d_uv, F,
+                                s.d_depth, s.d_status, coeffs, bits, words, 1, s.stream));
+    h->launches++;
+    CK(cudaMemcpyAsync(depth_host, s.d_depth, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(status_host, s.d_status, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return MLD_OK;
+}
+
+int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                              const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
+                              uint64_t seed, float* d_plane_coeffs_out, void* stream) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (nframes < 0 || n_points < 0 || frame_pitch_points < n_points || F < 0)
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device: bad sizes");
+    if (nframes > 0 && ((n_points > 0 && !d_points) || (F > 0 && (!d_uv || !d_depth || !d_status))))
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device: null buffer");
+    if ((reinterpret_cast<uintptr_t>(d_points) & 15u) != 0)
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device: points must be 16-byte aligned");
+    if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
+        return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
+    if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    DeviceGuard g(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    Slot& s = h->slots[0];
+    const int chunk = h->chunk_frames;
+    const bool use_road = road && h->dp.road_mode != ROAD_NONE;
+    rc = slot_reserve(h, s, std::max<int64_t>(n_points, 1), stride_bytes, F, chunk, false, use_road);
+    if (rc) return rc;
+    const int stride_f = stride_bytes / 4;
+    const float* pts = reinterpret_cast<const float*>(d_points);
+    for (int64_t f0 = 0; f0 < nframes; f0 += chunk) {
+        int c = (int)std::min<int64_t>(chunk, nframes - f0);
+        rc = enqueue_chunk(h, s, st, pts + f0 * frame_pitch_points * stride_f, n_points, frame_pitch_points, stride_f,
+                           d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F, d_status + f0 * (int64_t)F, c, use_road, seed,
+                           f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr);
+        if (rc) return rc;
+    }
+    h->have_cloud = false;  // slot 0's map now belongs to the batch
+    return MLD_OK;
+}
+
+int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                            const double* uv_host, int F, double* depth_host, int32_t* status_host, int64_t nframes, int road,
+                            uint64_t seed, float* plane_coeffs_out_host) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (nframes < 0 || n_points < 0 || frame_pitch_points < n_points || F < 0)
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_host: bad sizes");
+    if (nframes > 0 && ((n_points > 0 && !points_host) || (F > 0 && (!uv_host || !depth_host || !status_host))))
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_host: null buffer");
+    if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
+        return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
+    if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    DeviceGuard g(h->device);
+    const int chunk = h->chunk_frames;
+    const bool use_road = road && h->dp.road_mode != ROAD_NONE;
+    const int stride_f = stride_bytes / 4;
+    const size_t frame_bytes = (size_t)n_points * (size_t)stride_bytes;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(points_host);
+    for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
+        rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_bytes, std::max(F, 1), chunk, true, use_road);
+        if (rc) return rc;
+    }
+    int64_t ci = 0;
+    for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
+        Slot& s = h->slots[ci % MLD_PIPE_SLOTS];
+        int c = (int)std::min<int64_t>(chunk, nframes - f0);
+        // stream order makes the slot's buffers safe to reuse: the previous chunk on this stream is complete
+        // (its D2H copies included) before these copies start
+        if (n_points > 0)
+            CK(cudaMemcpy2DAsync(s.d_pts, frame_bytes, src + (size_t)f0 * (size_t)frame_pitch_points * (size_t)stride_bytes,
+                                 (size_t)frame_pitch_points * (size_t)stride_bytes, frame_bytes, (size_t)c, cudaMemcpyHostToDevice,
+                                 s.stream));
+        if (F > 0)
+            CK(cudaMemcpyAsync(s.d_uv, uv_host + f0 * (int64_t)F * 2, (size_t)c * (size_t)F * 2 * sizeof(double),
+                               cudaMemcpyHostToDevice, s.stream));
+        rc = enqueue_chunk(h, s, s.stream, reinterpret_cast<const float*>(s.d_pts), n_points, n_points, stride_f, s.d_uv, F, s.d_depth,
+                           s.d_status, c, use_road, seed, f0, nullptr);
+        if (rc) return rc;
+        if (F > 0) {
+            CK(cudaMemcpyAsync(depth_host + f0 * (int64_t)F, s.d_depth, (size_t)c * (size_t)F * sizeof(double), cudaMemcpyDeviceToHost,
+                               s.stream));
+            CK(cudaMemcpyAsync(status_host + f0 * (int64_t)F, s.d_status, (size_t)c * (size_t)F * sizeof(int), cudaMemcpyDeviceToHost,
+                               s.stream));
+        }
+        if (use_road && plane_coeffs_out_host)
+            CK(cudaMemcpyAsync(plane_coeffs_out_host + f0 * 4, s.d_coeffs, (size_t)c * 4 * sizeof(float), cudaMemcpyDeviceToHost,
+                               s.stream));
+    }
+    for (int i = 0; i < MLD_PIPE_SLOTS; i++) CK(cudaStreamSynchronize(h->slots[i].stream));
+    h->have_cloud = false;
+    return MLD_OK;
+}
+
+// ---- debug / parity views ----
+int mld_get_pixel_map(mld_handle* h, int32_t* out_host) {
+    if (!h || !out_host) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    CK(cudaMemcpyAsync(out_host, s.d_maps, (size_t)h->dp.W * (size_t)h->dp.H * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    return MLD_OK;
+}
+
+int mld_get_neighbors(mld_handle* h, double u, double v, double scale_w, double scale_h, int32_t* out_raw, int cap, int* k_out) {
+    if (!h || !k_out || cap < 0) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    if (!h->d_dbg) CK(cudaMalloc(&h->d_dbg, (size_t)(mld_neighbor_capacity() + 1) * sizeof(int)));
+    int dcap = std::min(cap, mld_neighbor_capacity());
+    double hx = static_cast<double>(h->params.pixelarea_search_witdh) * 0.5 * static_cast<double>((float)scale_w);
+    double hy = static_cast<double>(h->params.pixelarea_search_height) * 0.5 * static_cast<double>((float)scale_h);
+    CK(mld_launch_neighbors_debug(h->dp, s.d_maps, u, v, hx, hy, h->d_dbg + 1, dcap, h->d_dbg, s.stream));
+    h->launches++;
+    int k = 0;
+    CK(cudaMemcpyAsync(&k, h->d_dbg, sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    int ncopy = std::min(k, dcap);
+    if (ncopy > 0 && out_raw) CK(cudaMemcpy(out_raw, h->d_dbg + 1, (size_t)ncopy * sizeof(int), cudaMemcpyDeviceToHost));
+    *k_out = k;
+    return MLD_OK;
+}
+
+static int debug_views(mld_handle* h, uint8_t* vis_host, int64_t* n_vis, double* cam_host) {
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    const long long n = h->cur_n;
+    if (n == 0) {
+        if (n_vis) *n_vis = 0;
+        return MLD_OK;
+    }
+    unsigned char* d_vis = nullptr;
+    double* d_cam = nullptr;
+    if (vis_host) CK(cudaMalloc(&d_vis, (size_t)n));
+    if (cam_host) CK(cudaMalloc(&d_cam, (size_t)n * 3 * sizeof(double)));
+    cudaError_t e = mld_launch_visible_debug(h->dp, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, n, d_vis, d_cam, s.stream);
+    h->launches++;
+    if (e == cudaSuccess && vis_host) e = cudaMemcpyAsync(vis_host, d_vis, (size_t)n, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess && cam_host) e = cudaMemcpyAsync(cam_host, d_cam, (size_t)n * 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_vis);
+    cudaFree(d_cam);
+    if (e != cudaSuccess) return fail_cuda(h, e, "debug_views");
+    if (vis_host && n_vis) {
+        int64_t c = 0;
+        for (long long i = 0; i < n; i++) c += vis_host[i] ? 1 : 0;
+        *n_vis = c;
+    }
+    return MLD_OK;
+}
+
+int mld_get_visible(mld_handle* h, uint8_t* out_visible_host, int64_t* n_visible_out) {
+    if (!h || !out_visible_host) return MLD_ERR_INVALID_ARG;
+    return debug_views(h, out_visible_host, n_visible_out, nullptr);
+}
+int mld_get_points_camera(mld_handle* h, double* out_host) {
+    if (!h || !out_host) return MLD_ERR_INVALID_ARG;
+    return debug_views(h, nullptr, nullptr, out_host);
+}
+
+// ---- synthetic input ----
+void mld_synth_default_config(mld_synth_config* c, int dense) {
+    memset(c, 0, sizeof(*c));
+    c->rings = dense ? 128 : 64;
+    c->azimuth_steps = dense ? 2032 : 1875;
+    c->elev_top_deg = 2.0f;
+    c->elev_bottom_deg = -24.8f;
+    c->sensor_height = 1.73f;
+    c->max_range = 120.0f;
+    c->range_noise_sigma = 0.02f;
+    c->dropout_prob = 0.02f;
+    c->n_boxes = 40;
+    c->image_width = dense ? 2048 : 1241;
+    c->image_height = dense ? 1024 : 376;
+    c->band_top_frac = 0.4f;
+    c->band_feature_frac = 0.7f;
+}
+int64_t mld_synth_points_per_frame(const mld_synth_config* c) { return (int64_t)c->rings * c->azimuth_steps; }
+
+static bool synth_cfg_ok(const mld_synth_config* c) {
+    return c && c->rings > 0 && c->azimuth_steps >= 6 && c->n_boxes >= 0 && c->n_boxes <= 64 && c->image_width > 0 && c->image_height > 1;
+}
+
+int mld_synth_points_host(const mld_synth_config* c, uint64_t seed, int64_t frame, float* out_xyzi) {
+    if (!synth_cfg_ok(c) || !out_xyzi) return MLD_ERR_INVALID_ARG;
+    std::vector<float> tables((size_t)(2 * c->rings + 2 * c->azimuth_steps));
+    mld_synth_build_tables(*c, tables.data());
+    mld_synth_points_host_impl(*c, seed, frame, tables.data(), out_xyzi);
+    return MLD_OK;
+}
+int mld_synth_features_host(const mld_synth_config* c, uint64_t seed, int64_t frame, int F, double* out_uv) {
+    if (!synth_cfg_ok(c) || !out_uv || F < 0) return MLD_ERR_INVALID_ARG;
+    mld_synth_features_host_impl(*c, seed, frame, F, out_uv);
+    return MLD_OK;
+}
+
+int mld_synth_points_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,
+                            int64_t frame_pitch_points, float* d_out_xyzi, void* stream) {
+    if (!h || !synth_cfg_ok(c) || !d_out_xyzi) return MLD_ERR_INVALID_ARG;
+    if (frame_pitch_points < mld_synth_points_per_frame(c)) return fail(h, MLD_ERR_INVALID_ARG, "frame pitch smaller than the cloud");
+    DeviceGuard g(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    const size_t tn = (size_t)(2 * c->rings + 2 * c->azimuth_steps);
+    if (!h->synth_tables_valid || memcmp(&h->synth_cfg_cached, c, sizeof(*c)) != 0) {
+        std::vector<float> tables(tn);
+        mld_synth_build_tables(*c, tables.data());
+        CK(cudaStreamSynchronize(st));
+        if (h->d_synth_tables) CK(cudaFree(h->d_synth_tables));
+        h->d_synth_tables = nullptr;
+        CK(cudaMalloc(&h->d_synth_tables, tn * sizeof(float)));
+        CK(cudaMemcpy(h->d_synth_tables, tables.data(), tn * sizeof(float), cudaMemcpyHostToDevice));
+        h->synth_cfg_cached = *c;
+        h->synth_tables_valid = true;
+    }
+    CK(mld_launch_synth_points(*c, seed, frame0, nframes, frame_pitch_points, h->d_synth_tables, d_out_xyzi, st));
+    return MLD_OK;
+}
+
+int mld_synth_features_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes, int F,
+                              double* d_out_uv, void* stream) {
+    if (!h || !synth_cfg_ok(c) || !d_out_uv || F < 0) return MLD_ERR_INVALID_ARG;
+    DeviceGuard g(h->device);
+    CK(mld_launch_synth_features(*c, seed, frame0, nframes, F, d_out_uv, reinterpret_cast<cudaStream_t>(stream)));
+    return MLD_OK;
+}
+
+}  // extern "C"

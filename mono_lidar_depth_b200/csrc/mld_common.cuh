@@ -1,0 +1,201 @@
+// mld_common.cuh -- shared device/host definitions for libmld_cuda.so (sm_100a).
+//
+// All hot-path arithmetic is IEEE double (the reference works on Eigen::Matrix3Xd / Vector3d,
+// monolidar_fusion/src/DepthEstimator.cpp:169) and every translation unit is compiled with
+// -fmad=false so that no multiply-add is contracted: the (int) casts, bin indices and threshold
+// compares then see exactly the values a plain SSE2 build of the reference computes.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mld_c_api.h"
+
+#define MLD_FULL_MASK 0xffffffffu
+#define MLD_EMPTY 0xffffffffu  // pixel-map cell without a point; reads as int32 -1 (POINT_NOT_DEFINED)
+
+// Mono_Lidar::DepthResultType, monolidar_fusion/include/monolidar_fusion/eDepthResultType.h:9-31
+enum MldStatus : int {
+    ST_Unspecified = 0,
+    ST_Success = 1,
+    ST_RadiusSearchInsufficientPoints = 2,
+    ST_HistogramNoLocalMax = 3,
+    ST_TresholdDepthGlobalGreaterMax = 4,
+    ST_TresholdDepthGlobalSmallerMin = 5,
+    ST_TresholdDepthLocalGreaterMax = 6,
+    ST_TresholdDepthLocalSmallerMin = 7,
+    ST_TriangleNotPlanar = 8,
+    ST_TriangleNotPlanarInsufficientPoints = 9,
+    ST_CornerBehindCamera = 10,
+    ST_PlaneViewrayNotOrthogonal = 11,
+    ST_PcaIsPoint = 12,
+    ST_PcaIsLine = 13,
+    ST_PcaIsCubic = 14,
+    ST_InsufficientRoadPoints = 15,
+    ST_SuccessRoad = 16
+};
+
+enum MldRoadMode : int { ROAD_NONE = 0, ROAD_TRIANGLE = 1, ROAD_LEASTSQUARES = 2, ROAD_MESTIMATOR = 3 };
+
+// Constant block handed to every kernel by value (DepthEstimator::Initialize's module selection,
+// monolidar_fusion/src/DepthEstimator.cpp:35-127, flattened into flags).
+struct DevParams {
+    int W, H;
+    double f, cx, cy;
+    double R[9], t[3];    // transform_lidar_to_cam
+    double Ri[9], ti[3];  // transform_cam_to_lidar (Affine3d::inverse(), :44)
+    double Kinv[9];       // makeIntrinsics().inverse() (camera_pinhole.h:65)
+    double hx1, hy1;      // half window, scale (1,1)      (NeighborFinderPixel.cpp:67-68)
+    double hx2, hy2;      // half window, scale (2.0,1.5)  (DepthEstimator.cpp:585)
+    int count_min;        // radiusSearch_count_min
+    int use_hist;
+    int hist_min;
+    double bin_w;
+    int use_tri_max;      // do_use_triangle_size_maximation
+    int check_planar;     // do_check_triangleplanar_condition
+    double crossnorm_thr;
+    double ortho_thr;     // > 0 selects LinePlaneIntersectionOrthogonalTreshold (:77-81)
+    int use_pca;
+    double pca_3_abs_min, pca_3_2_rel_max, pca_2_1_rel_min;
+    int glob_en, glob_mode;
+    double glob_min, glob_max;
+    int loc_en, loc_mode, loc_type;
+    double loc_val;
+    int cut_behind;
+    int road_mode;        // MldRoadMode; ROAD_NONE when do_use_ransac_plane == 0
+    double road_dist_thr; // ransac_plane_point_distance_treshold
+    double zx_min_rel;    // plane_estimator_z_x_min_relation
+    int set_all_zero;
+};
+
+struct D3 {
+    double x, y, z;
+};
+
+__host__ __device__ __forceinline__ D3 d3(double x, double y, double z) { return D3{x, y, z}; }
+__host__ __device__ __forceinline__ D3 operator-(const D3& a, const D3& b) { return D3{a.x - b.x, a.y - b.y, a.z - b.z}; }
+__host__ __device__ __forceinline__ D3 operator+(const D3& a, const D3& b) { return D3{a.x + b.x, a.y + b.y, a.z + b.z}; }
+__host__ __device__ __forceinline__ D3 operator*(const D3& a, double s) { return D3{a.x * s, a.y * s, a.z * s}; }
+__host__ __device__ __forceinline__ D3 operator/(const D3& a, double s) { return D3{a.x / s, a.y / s, a.z / s}; }
+// 3-term reductions left to right, like Eigen's unrolled redux on Vector3d
+__host__ __device__ __forceinline__ double dot3(const D3& a, const D3& b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__host__ __device__ __forceinline__ double sqnorm3(const D3& a) { return dot3(a, a); }
+__host__ __device__ __forceinline__ double norm3(const D3& a) { return sqrt(sqnorm3(a)); }
+__host__ __device__ __forceinline__ D3 cross3(const D3& a, const D3& b) {
+    return D3{a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+// Eigen 3.3 normalized(): untouched when the squared norm is not > 0
+__host__ __device__ __forceinline__ D3 normalized3(const D3& a) {
+    double z = sqnorm3(a);
+    if (z > 0) return a / sqrt(z);
+    return a;
+}
+
+// lidar -> camera, "((r0*x + r1*y) + r2*z) + t" with explicitly rounded operations
+// (Eigen: res = t; res += R * p, monolidar_fusion/src/DepthEstimator.cpp:173)
+__device__ __forceinline__ D3 lidar_to_cam(const DevParams& P, float x, float y, float z) {
+    double dx = (double)x, dy = (double)y, dz = (double)z;
+    D3 r;
+    r.x = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[0], dx), __dmul_rn(P.R[1], dy)), __dmul_rn(P.R[2], dz)), P.t[0]);
+    r.y = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[3], dx), __dmul_rn(P.R[4], dy)), __dmul_rn(P.R[5], dz)), P.t[1]);
+    r.z = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(P.R[6], dx), __dmul_rn(P.R[7], dy)), __dmul_rn(P.R[8], dz)), P.t[2]);
+    return r;
+}
+
+// streaming 16-byte load that does not pollute L1 (points are read once per kernel)
+__device__ __forceinline__ float4 ld_stream_f4(const float* p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+
+__device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(MLD_FULL_MASK, v, m); }
+
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += shfl_xor_d(v, m);
+    return v;
+}
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        double o = shfl_xor_d(v, m);
+        v = (o > v) ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ double warp_min_d(double v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        double o = shfl_xor_d(v, m);
+        v = (o < v) ? o : v;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_min_i(int v) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v = min(v, __shfl_xor_sync(MLD_FULL_MASK, v, m));
+    return v;
+}
+
+// counter-based RNG (splitmix64 finaliser) shared by the RANSAC kernels and the synthetic generator
+__host__ __device__ __forceinline__ uint64_t mld_mix64(uint64_t z) {
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__host__ __device__ __forceinline__ uint64_t mld_hash3(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
+    return mld_mix64(mld_mix64(mld_mix64(mld_mix64(seed) ^ a) ^ b) ^ c);
+}
+
+// Jacobi eigen-decomposition of a symmetric 3x3 held in registers. a = (a00,a01,a02,a11,a12,a22).
+// Eigenvalues are returned unsorted in w with eigenvector columns v[c] (each a D3).
+#define MLD_JACOBI_ROT(app, aqq, apq, arp, arq, vp, vq)                                   \
+    if ((apq) != 0.0) {                                                                  \
+        double theta = ((aqq) - (app)) / (2.0 * (apq));                                   \
+        double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
+        if (!isfinite(theta)) tt = 0.0;                                                   \
+        double cc = 1.0 / sqrt(tt * tt + 1.0), ss = tt * cc;                              \
+        double napp = (app) - tt * (apq), naqq = (aqq) + tt * (apq);                      \
+        double nrp = cc * (arp) - ss * (arq), nrq = ss * (arp) + cc * (arq);              \
+        (app) = napp; (aqq) = naqq; (apq) = 0.0; (arp) = nrp; (arq) = nrq;                \
+        D3 nvp = (vp) * cc - (vq) * ss, nvq = (vp) * ss + (vq) * cc;                      \
+        (vp) = nvp; (vq) = nvq;                                                           \
+    }
+
+__host__ __device__ inline void eig3_sym_regs(double a00, double a01, double a02, double a11, double a12, double a22,
+                                              double w[3], D3 v[3]) {
+    // v[c] is eigenvector c (columns of the rotation product)
+    D3 v0 = D3{1, 0, 0}, v1 = D3{0, 1, 0}, v2 = D3{0, 0, 1};
+    // store eigenvector *columns* as (row0,row1,row2) triples: updating columns p,q of V
+    for (int sweep = 0; sweep < 16; sweep++) {
+        double off = a01 * a01 + a02 * a02 + a12 * a12;
+        double diag = a00 * a00 + a11 * a11 + a22 * a22;
+        if (!(off > 1e-32 * diag) || !(off > 0)) break;
+        // (p,q) = (0,1): r = 2 -> a02 (arp), a12 (arq)
+        MLD_JACOBI_ROT(a00, a11, a01, a02, a12, v0, v1)
+        // (p,q) = (0,2): r = 1 -> a01 (arp), a12 (arq)
+        MLD_JACOBI_ROT(a00, a22, a02, a01, a12, v0, v2)
+        // (p,q) = (1,2): r = 0 -> a01 (arp), a02 (arq)
+        MLD_JACOBI_ROT(a11, a22, a12, a01, a02, v1, v2)
+    }
+    w[0] = a00; w[1] = a11; w[2] = a22;
+    v[0] = v0; v[1] = v1; v[2] = v2;
+}
+
+// cofactor inverse of a row-major 3x3, the way Eigen evaluates Matrix3d::inverse()
+// (result(i,j) = cofactor(j,i) * (1/det)); host only, used once per Initialize.
+inline void mld_inverse3_host(const double* m, double* out) {
+    auto cof = [&](int i, int j) {
+        int i1 = (i + 1) % 3, i2 = (i + 2) % 3, j1 = (j + 1) % 3, j2 = (j + 2) % 3;
+        return m[i1 * 3 + j1] * m[i2 * 3 + j2] - m[i1 * 3 + j2] * m[i2 * 3 + j1];
+    };
+    double c0 = cof(0, 0), c1 = cof(1, 0), c2 = cof(2, 0);
+    double det = (c0 * m[0] + c1 * m[3]) + c2 * m[6];
+    double invdet = 1.0 / det;
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) out[i * 3 + j] = cof(j, i) * invdet;
+}

@@ -1,0 +1,698 @@
+// mld_feature.cu -- K2/K3: per-feature depth estimation, one warp per feature.
+//
+// Replaces (reference, /root/reference/monolidar_fusion/src unless noted):
+//   DepthEstimator::CalculateDepth (batch loop + per-feature driver)   DepthEstimator.cpp:429-600
+//   DepthEstimator::CalculateNeighbors                                 DepthEstimator.cpp:636-684
+//   NeighborFinderPixel::getNeighbors                                  NeighborFinderPixel.cpp:60-95
+//   NeighborFinderBase::getNeighbors                                   NeighborFinderBase.cpp:15-27
+//   PointHistogram::FilterPointsMinDistBlob / Histogram::AddElement    HistogramPointDepth.cpp:15-123, Histogram.cpp:19-33
+//   PlaneEstimationCalcMaxSpanningTriangle::CalculatePlaneCorners      PlaneEstimationCalcMaxSpanningTriangle.cpp:37-145
+//   PlaneEstimationCheckPlanar::CheckPlanar                            PlaneEstimationCheckPlanar.cpp:18-44
+//   CameraPinhole::getViewingRays                                      include/monolidar_fusion/camera_pinhole.h:52-69
+//   LinePlaneIntersection{Base,Normal,OrthogonalTreshold}              LinePlaneIntersection*.cpp
+//   TresholdDepthGlobal::CheckInDepth / TresholdDepthLocal::CheckInBounds
+//   Mono_LidarPipeline::PCA                                            PCA.cpp:11-62
+//   DepthEstimator::CalculateDepthSegmentationPlane                    DepthEstimator.cpp:782-900
+//   RoadDepthEstimator{MEstimator,LeastSquares,MaxSpanningTriangle}    RoadDepthEstimator*.cpp
+//   PlaneEstimationMEstimator::EstimatePlane                           PlaneEstimationMEstimator.cpp:18-55
+//
+// Mapping. A warp owns one feature. Lanes stride the search window in the reference's row-major
+// scan order; ballot + popc compaction keeps that order (it decides ties in the farthest-pair
+// search). Neighbour points are re-derived from the float cloud in FP64 (bit-identical to K1) and
+// parked in a per-warp shared-memory slab; the histogram is evaluated with ballots over bin ids
+// (only the first run of occupied bins can decide the reference's sequential scan), the
+// farthest-pair / third-corner searches are lane-parallel arg-max reductions with the reference's
+// first-wins tie-break, and the scalar geometry is evaluated redundantly by all lanes so every
+// branch is warp-uniform.
+//
+// HBM traffic per feature: 16 B read (u,v), 12 B written (depth f64 + status i32). Window reads
+// (<= 4*70 B) and the neighbour gather hit L2 (K1 just streamed the same frame).
+#include "mld_common.cuh"
+#include "mld_kernels.h"
+
+namespace {
+
+
+struct WarpSlab {
+    double* x;
+    double* y;
+    double* z;
+    int* raw;  // raw point index in the normal path; reused for bin ids by the histogram
+};
+
+__device__ __forceinline__ unsigned lanemask_lt() {
+    unsigned m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---- A5: window scan + gather --------------------------------------------------------------
+// Returns the neighbour count k; slab[0..k) holds the camera-frame points in scan order.
+template <int KCAP>
+__device__ int gather_window(const DevParams& P, const unsigned int* __restrict__ map, const float* __restrict__ pts,
+                             int stride_f, double u, double v, double hx, double hy, int lane, const WarpSlab& s) {
+    // NaN / out-of-int-range features are undefined behaviour in the reference ((int) casts of the
+    // window edges); they are defined here as "empty window".
+    if (!(fabs(u) < 1e9) || !(fabs(v) < 1e9)) return 0;
+    double leftEdgeX = fmax(u - hx, 0.);
+    double rightEdgeX = fmin(u + hx, (double)(P.W - 1));
+    double topEdgeY = fmax(v - hy, 0.);
+    double bottomEdgeY = fmin(v + hy, (double)(P.H - 1));
+    int x0 = (int)leftEdgeX, x1 = (int)rightEdgeX, y0 = (int)topEdgeY, y1 = (int)bottomEdgeY;
+    int wc = x1 - x0 + 1, wr = y1 - y0 + 1;
+    if (wc <= 0 || wr <= 0) return 0;
+    int area = wc * wr;
+    int k = 0;
+    const unsigned lt = lanemask_lt();
+    for (int base = 0; base < area; base += 32) {
+        int idx = base + lane;
+        unsigned int cell = MLD_EMPTY;
+        if (idx < area) {
+            int ry = idx / wc;
+            int rx = idx - ry * wc;
+            cell = __ldg(&map[(long long)(y0 + ry) * P.W + (x0 + rx)]);
+        }
+        unsigned m = __ballot_sync(MLD_FULL_MASK, cell != MLD_EMPTY);
+        if (cell != MLD_EMPTY) {
+            int pos = k + __popc(m & lt);
+            if (pos < KCAP) s.raw[pos] = (int)cell;
+        }
+        k += __popc(m);
+    }
+    if (k > KCAP) k = KCAP;  // cannot happen: mld_create rejects windows with area > KCAP
+    __syncwarp();
+    for (int i = lane; i < k; i += 32) {
+        const float* p = pts + (long long)s.raw[i] * stride_f;
+        float4 q = __ldg(reinterpret_cast<const float4*>(p));
+        D3 c = lidar_to_cam(P, q.x, q.y, q.z);
+        s.x[i] = c.x;
+        s.y[i] = c.y;
+        s.z[i] = c.z;
+    }
+    __syncwarp();
+    return k;
+}
+
+// in-place, order-preserving compaction of slab entries with keep flag; flags are evaluated by
+// `pred(i)` for i in [0,n). Chunks of 32 are read before they are overwritten.
+template <typename Pred>
+__device__ int compact_slab(int n, int lane, const WarpSlab& s, bool with_raw, Pred pred) {
+    int out = 0;
+    const unsigned lt = lanemask_lt();
+    for (int base = 0; base < n; base += 32) {
+        int i = base + lane;
+        bool keep = false;
+        double x = 0, y = 0, z = 0;
+        int r = 0;
+        if (i < n) {
+            x = s.x[i]; y = s.y[i]; z = s.z[i];
+            if (with_raw) r = s.raw[i];
+            keep = pred(i, x, y, z, r);
+        }
+        unsigned m = __ballot_sync(MLD_FULL_MASK, keep);
+        __syncwarp();
+        if (keep) {
+            int pos = out + __popc(m & lt);
+            s.x[pos] = x; s.y[pos] = y; s.z[pos] = z;
+            if (with_raw) s.raw[pos] = r;
+        }
+        out += __popc(m);
+        __syncwarp();
+    }
+    return out;
+}
+
+// ---- A6: histogram foreground segmentation ---------------------------------------------------
+// Returns the segmented count (slab compacted in place) or -1 for "no local maximum".
+__device__ int histogram_segment(const DevParams& P, int k, int lane, const WarpSlab& s) {
+    // depth = min(z, 999.) (DepthEstimator.cpp:741-744); maxDist = running (int)ceil(depth) maximum
+    // (HistogramPointDepth.cpp:36-41) == (int)ceil(max depth) for positive depths, else 0.
+    double dmax = -1.0;
+    for (int i = lane; i < k; i += 32) {
+        double d = fmin(s.z[i], 999.);
+        dmax = (d > dmax) ? d : dmax;
+    }
+    dmax = warp_max_d(dmax);
+    int maxDist = 0;
+    if (dmax > 0.0) maxDist = (int)ceil(dmax);
+    int binCount = (int)((maxDist) / P.bin_w + 1);  // :43
+    if (binCount <= 1) return -1;                  // :53
+    // bin ids (Histogram.cpp:29-30) parked in s.raw (the normal path does not need raw ids any more)
+    int bmin = 0x7fffffff;
+    for (int i = lane; i < k; i += 32) {
+        double value = fmin(fmin(s.z[i], 999.), 1e10);
+        int b = (int)fmin(fabs(value / P.bin_w), (double)binCount - 1.);
+        s.raw[i] = b;
+        bmin = min(bmin, b);
+    }
+    bmin = warp_min_i(bmin);
+    __syncwarp();
+    if (k == 0) bmin = binCount;  // no occupied bin at all
+    // sequential first-local-maximum scan (:66-85). Bins before the first occupied one hold 0
+    // elements and can only register a "maximum" when the minimum count is <= 0.
+    int binMaxId = -1, binMaxVal = -1, binValue = 0;
+    if (bmin > 0 && 0 >= P.hist_min) {
+        binMaxVal = 0;
+        binMaxId = 0;
+    }
+    bool fail = false;
+    for (int b = bmin; b < binCount; b++) {
+        int lastBinValue = binValue;
+        int cnt = 0;
+        for (int base = 0; base < k; base += 32) {
+            int i = base + lane;
+            bool hit = (i < k) && (s.raw[i] == b);
+            cnt += __popc(__ballot_sync(MLD_FULL_MASK, hit));
+        }
+        binValue = cnt;
+        if ((binValue > binMaxVal) && (binValue >= P.hist_min)) {
+            binMaxVal = binValue;
+            binMaxId = b;
+        } else if (binValue < binMaxVal)
+            break;
+        if ((lastBinValue > 0) && (binValue == 0)) {
+            fail = true;
+            break;
+        }
+        // an empty bin that neither broke nor failed can only be followed by more empty bins
+        if (binValue == 0) break;
+    }
+    if (fail || binMaxId < 0) return -1;
+    double lowerBorder = binMaxId * P.bin_w - 0.0 * P.bin_w;   // :99
+    double higherBorder = (binMaxId)*P.bin_w + 1.0 * P.bin_w;  // :100
+    __syncwarp();
+    return compact_slab(k, lane, s, false, [&](int, double, double, double z, int) {
+        double d = fmin(z, 999.);
+        return (d >= lowerBorder) && (d < higherBorder);  // :116
+    });
+}
+
+// ---- A7: max spanning triangle -----------------------------------------------------------------
+__device__ __forceinline__ D3 slab_pt(const WarpSlab& s, int i) { return D3{s.x[i], s.y[i], s.z[i]}; }
+
+// linear pair index p (lexicographic over i<j) -> (i,j)
+__device__ __forceinline__ void pair_from_index(int p, int n, int& i, int& j) {
+    float fn = (float)(2 * n - 1);
+    int ii = (int)((fn - sqrtf(fn * fn - 8.0f * (float)p)) * 0.5f);
+    if (ii < 0) ii = 0;
+    if (ii > n - 2) ii = n - 2;
+    // row start S(i) = i*(2n-i-1)/2
+    while (ii > 0 && (ii * (2 * n - ii - 1)) / 2 > p) ii--;
+    while (ii < n - 2 && ((ii + 1) * (2 * n - ii - 2)) / 2 <= p) ii++;
+    i = ii;
+    j = p - (ii * (2 * n - ii - 1)) / 2 + ii + 1;
+}
+
+// returns false for the reference's `return false` sites; corners by slab index
+__device__ bool max_spanning_triangle(int n, int lane, const WarpSlab& s, int& ci, int& cj, int& ck) {
+    if (n < 3) return false;  // :44
+    // farthest pair, strict '>' in lexicographic order == first maximum (:52-62)
+    const int npairs = n * (n - 1) / 2;
+    double best = -1.0;
+    int bestp = 0x7fffffff;
+    for (int p = lane; p < npairs; p += 32) {
+        int i, j;
+        pair_from_index(p, n, i, j);
+        double dist = sqnorm3(slab_pt(s, i) - slab_pt(s, j));
+        if (dist > best) {
+            best = dist;
+            bestp = p;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        double ob = shfl_xor_d(best, m);
+        int op = __shfl_xor_sync(MLD_FULL_MASK, bestp, m);
+        if (ob > best || (ob == best && op < bestp)) {
+            best = ob;
+            bestp = op;
+        }
+    }
+    if (best <= 0.0) return false;  // maxdist <= _distTreshold (== 0, bool ctor) (:65)
+    int mi, mj;
+    pair_from_index(bestp, n, mi, mj);
+    // third corner: k in [0, n-2] (the last point is never eligible, :71), first maximum of d1+d2
+    D3 pi = slab_pt(s, mi), pj = slab_pt(s, mj);
+    double best2 = -1.0;
+    int bestk = 0x7fffffff;
+    for (int k = lane; k < n - 1; k += 32) {
+        if (k == mi || k == mj) continue;
+        D3 pk = slab_pt(s, k);
+        double dist1 = sqnorm3(pk - pi);
+        if (dist1 <= 0.0) continue;
+        double dist2 = sqnorm3(pk - pj);
+        if (dist2 <= 0.0) continue;
+        double dist = dist1 + dist2;
+        if (dist > best2) {
+            best2 = dist;
+            bestk = k;
+        }
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        double ob = shfl_xor_d(best2, m);
+        int ok = __shfl_xor_sync(MLD_FULL_MASK, bestk, m);
+        if (ob > best2 || (ob == best2 && ok < bestk)) {
+            best2 = ob;
+            bestk = ok;
+        }
+    }
+    if (bestk == 0x7fffffff) return false;  // maxDist_k == -1 (:93)
+    ci = mi;
+    cj = mj;
+    ck = bestk;
+    return true;
+}
+
+// ---- scalar geometry (identical on every lane) -------------------------------------------------
+struct Plane {
+    D3 n;
+    double off;
+};
+
+// A8 PlaneEstimationCheckPlanar::CheckPlanar
+__device__ bool check_planar(const D3& c1, const D3& c2, const D3& c3, double treshold) {
+    D3 e1 = normalized3(c2 - c1), e2 = normalized3(c3 - c1), e3 = normalized3(c3 - c2);
+    double l12 = norm3(cross3(e1, e2)), l13 = norm3(cross3(e1, e3)), l23 = norm3(cross3(e2, e3));
+    return (l12 >= treshold) && (l13 >= treshold) && (l23 >= treshold);
+}
+
+// Eigen::Hyperplane<double,3>::Through(p0,p1,p2)
+__device__ Plane plane_through(const D3& p0, const D3& p1, const D3& p2) {
+    D3 v0 = p2 - p0, v1 = p1 - p0;
+    D3 n = cross3(v0, v1);
+    double nn = norm3(n);
+    if (nn <= norm3(v0) * norm3(v1) * 2.220446049250313e-16) {
+        // degenerate: null direction of [v0; v1] (Eigen: 2x3 JacobiSVD, column 2 of V)
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs(v0.x * v0.x + v1.x * v1.x, v0.x * v0.y + v1.x * v1.y, v0.x * v0.z + v1.x * v1.z,
+                      v0.y * v0.y + v1.y * v1.y, v0.y * v0.z + v1.y * v1.z, v0.z * v0.z + v1.z * v1.z, w, ev);
+        int b = 0;
+        if (w[1] < w[b]) b = 1;
+        if (w[2] < w[b]) b = 2;
+        n = (b == 0) ? ev[0] : (b == 1 ? ev[1] : ev[2]);
+    } else {
+        n = n / nn;
+    }
+    return Plane{n, -dot3(p0, n)};
+}
+
+// A10 LinePlaneIntersection{Normal,OrthogonalTreshold}::GetIntersection
+__device__ bool line_plane(const Plane& pl, const D3& n0, const D3& n1, double ortho_treshold, double& depth) {
+    D3 dir = normalized3(n1 - n0);  // ParametrizedLine::Through
+    if (ortho_treshold > 0) {
+        D3 lineNormal = normalized3(n1);
+        D3 planeNormal = normalized3(pl.n);
+        if (!(fabs(dot3(planeNormal, lineNormal)) >= ortho_treshold)) return false;
+    }
+    double t = -(pl.off + dot3(pl.n, n0)) / dot3(pl.n, dir);
+    D3 pt = n0 + dir * t;
+    depth = pt.z;
+    return true;
+}
+
+// A9 CameraPinhole::getViewingRays (+ the caller's z flip, DepthEstimator.cpp:938-939)
+__device__ D3 viewing_ray(const DevParams& P, double u, double v) {
+    D3 d = D3{(P.Kinv[0] * u + P.Kinv[1] * v) + P.Kinv[2] * 1.0, (P.Kinv[3] * u + P.Kinv[4] * v) + P.Kinv[5] * 1.0,
+              (P.Kinv[6] * u + P.Kinv[7] * v) + P.Kinv[8] * 1.0};
+    d = normalized3(d);
+    if (d.z < 0) d = d * -1.0;
+    return d;
+}
+
+// A11 thresholds; returns 0 or the failing status, may clamp depth in Adjust mode
+__device__ int apply_tresholds(const DevParams& P, double& depth, double minZ, double maxZ) {
+    if (P.glob_en) {  // TresholdDepthGlobal::CheckInDepth
+        if (depth < P.glob_min) {
+            if (P.glob_mode == 0) return ST_TresholdDepthGlobalSmallerMin;
+            depth = P.glob_min;
+        } else if (depth > P.glob_max) {
+            if (P.glob_mode == 0) return ST_TresholdDepthGlobalGreaterMax;
+            depth = P.glob_max;
+        }
+    }
+    if (P.loc_en) {  // TresholdDepthLocal::CheckInBounds
+        double depthInterval = maxZ - minZ;
+        double lo, hi;
+        if (P.loc_type == 1) {
+            double r = depthInterval * P.loc_val;
+            lo = minZ - r;
+            hi = maxZ + r;
+        } else {
+            lo = minZ - P.loc_val;
+            hi = maxZ + P.loc_val;
+        }
+        if (depth < lo) {
+            if (P.loc_mode == 0) return ST_TresholdDepthLocalSmallerMin;
+            depth = lo;
+        } else if (depth > hi) {
+            if (P.loc_mode == 0) return ST_TresholdDepthLocalGreaterMax;
+            depth = hi;
+        }
+    }
+    return 0;
+}
+
+__device__ void slab_z_range(int n, int lane, const WarpSlab& s, double& minZ, double& maxZ) {
+    double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
+    for (int i = lane; i < n; i += 32) {
+        double z = s.z[i];
+        if (z < lo) lo = z;
+        if (z > hi) hi = z;
+    }
+    minZ = warp_min_d(lo);
+    maxZ = warp_max_d(hi);
+}
+
+// weighted centroid + scatter of slab[0..n); w_i = 1/|prior.n . p + prior.off| or 1
+__device__ void slab_weighted_scatter(int n, int lane, const WarpSlab& s, bool weighted, const Plane& prior, D3& center,
+                                      double c[6]) {
+    double sw = 0, sx = 0, sy = 0, sz = 0;
+    for (int i = lane; i < n; i += 32) {
+        D3 p = slab_pt(s, i);
+        double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
+        sw += w;
+        sx += w * p.x;
+        sy += w * p.y;
+        sz += w * p.z;
+    }
+    sw = warp_sum_d(sw);
+    sx = warp_sum_d(sx);
+    sy = warp_sum_d(sy);
+    sz = warp_sum_d(sz);
+    center = D3{sx / sw, sy / sw, sz / sw};
+    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
+    for (int i = lane; i < n; i += 32) {
+        D3 p = slab_pt(s, i);
+        double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
+        D3 d = p - center;
+        a00 += w * d.x * d.x; a01 += w * d.x * d.y; a02 += w * d.x * d.z;
+        a11 += w * d.y * d.y; a12 += w * d.y * d.z; a22 += w * d.z * d.z;
+    }
+    c[0] = warp_sum_d(a00); c[1] = warp_sum_d(a01); c[2] = warp_sum_d(a02);
+    c[3] = warp_sum_d(a11); c[4] = warp_sum_d(a12); c[5] = warp_sum_d(a22);
+}
+
+// ---- A12: CalculateDepthSegmented ----------------------------------------------------------------
+__device__ int depth_segmented(const DevParams& P, double u, double v, int n, int lane, const WarpSlab& s, double& depth_out) {
+    depth_out = -1;
+    D3 c1{}, c2{}, c3{};
+    if (!P.use_pca && P.use_tri_max) {
+        int i, j, k;
+        if (!max_spanning_triangle(n, lane, s, i, j, k)) return ST_TriangleNotPlanarInsufficientPoints;
+        c1 = slab_pt(s, i); c2 = slab_pt(s, j); c3 = slab_pt(s, k);
+    } else {
+        if (n < 3) return ST_HistogramNoLocalMax;  // DepthEstimator.cpp:920-921
+        c1 = slab_pt(s, 0); c2 = slab_pt(s, 1); c3 = slab_pt(s, 2);
+    }
+    if (!P.use_pca && P.check_planar)
+        if (!check_planar(c1, c2, c3, P.crossnorm_thr)) return ST_TriangleNotPlanar;
+
+    D3 support = D3{0, 0, 0};
+    D3 dir = viewing_ray(P, u, v);
+    double depth;
+    if (P.use_pca) {
+        // Mono_LidarPipeline::PCA (PCA.cpp:42-62): mean, un-normalised scatter, ascending eigenvalues
+        D3 mean;
+        double c[6];
+        Plane none{};
+        slab_weighted_scatter(n, lane, s, false, none, mean, c);
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs(c[0], c[1], c[2], c[3], c[4], c[5], w, ev);
+        // sort ascending
+        int i0 = 0, i1 = 1, i2 = 2, tmp;
+        if (w[i1] < w[i0]) { tmp = i0; i0 = i1; i1 = tmp; }
+        if (w[i2] < w[i1]) { tmp = i1; i1 = i2; i2 = tmp; }
+        if (w[i1] < w[i0]) { tmp = i0; i0 = i1; i1 = tmp; }
+        double ev1 = w[i0], ev2 = w[i1], ev3 = w[i2];
+        float planarity = (float)((ev2 - ev1) / ev3);  // PCA.cpp:27-28
+        float linearity = (float)((ev3 - ev2) / ev3);
+        if (planarity < P.pca_2_1_rel_min) return ST_PcaIsCubic;
+        if (linearity > P.pca_3_2_rel_max) return ST_PcaIsLine;
+        if (ev3 < P.pca_3_abs_min) return ST_PcaIsPoint;
+        D3 e0 = (i0 == 0) ? ev[0] : (i0 == 1 ? ev[1] : ev[2]);
+        D3 normal = e0 / norm3(e0);
+        Plane pl{normal, -dot3(normal, mean)};
+        if (!line_plane(pl, support, dir, P.ortho_thr, depth)) return ST_PlaneViewrayNotOrthogonal;
+    } else {
+        Plane pl = plane_through(c1, c2, c3);
+        if (!line_plane(pl, support, dir, P.ortho_thr, depth)) return ST_PlaneViewrayNotOrthogonal;
+    }
+    double minZ, maxZ;
+    slab_z_range(n, lane, s, minZ, maxZ);
+    int r = apply_tresholds(P, depth, minZ, maxZ);
+    if (r) return r;
+    if (depth < 0 && P.cut_behind) return ST_CornerBehindCamera;
+    depth_out = depth;
+    return ST_Success;
+}
+
+// ---- road path: R2 + R3/R4/R5 -------------------------------------------------------------------
+__device__ int road_depth(const DevParams& P, double u, double v, int k2, int lane, const WarpSlab& s, const float* coeffs,
+                          const unsigned int* __restrict__ inlier_bits, int old_status, double& depth_out) {
+    depth_out = -1;
+    const float a = coeffs[0], b = coeffs[1], c = coeffs[2], d = coeffs[3];
+    // R2 gate: any neighbour farther than the threshold from the plane rejects the feature
+    // (DepthEstimator.cpp:803-815). pcl::pointToPlaneDistance on a PointXYZ evaluates in float.
+    bool far = false;
+    for (int i = lane; i < k2; i += 32) {
+        D3 p = slab_pt(s, i);
+        double lx = ((P.Ri[0] * p.x + P.Ri[1] * p.y) + P.Ri[2] * p.z) + P.ti[0];
+        double ly = ((P.Ri[3] * p.x + P.Ri[4] * p.y) + P.Ri[5] * p.z) + P.ti[1];
+        double lz = ((P.Ri[6] * p.x + P.Ri[7] * p.y) + P.Ri[8] * p.z) + P.ti[2];
+        float fx = (float)lx, fy = (float)ly, fz = (float)lz;
+        float sd = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, fx), __fmul_rn(b, fy)), __fmul_rn(c, fz)), d);
+        double distance = fabs((double)sd);
+        if (distance > P.road_dist_thr) far = true;
+    }
+    if (__any_sync(MLD_FULL_MASK, far)) return old_status;
+    // keep the plane inliers (GroundPlane::CheckPointInPlane on the raw index, :817)
+    int n = compact_slab(k2, lane, s, true, [&](int, double, double, double, int raw) {
+        return ((inlier_bits[raw >> 5] >> (raw & 31)) & 1u) != 0;
+    });
+    if (n < 3) return old_status;  // :827-829
+
+    Plane pl;
+    if (P.road_mode == ROAD_TRIANGLE) {
+        int i, j, k;
+        if (!max_spanning_triangle(n, lane, s, i, j, k)) return ST_RadiusSearchInsufficientPoints;
+        // LinePlaneIntersectionCeckXZTreshold::Check
+        double loX = 1.7976931348623157e308, hiX = -1.7976931348623157e308, loZ = loX, hiZ = hiX;
+        for (int q = lane; q < n; q += 32) {
+            double x = s.x[q], z = s.z[q];
+            if (x < loX) loX = x;
+            if (x > hiX) hiX = x;
+            if (z < loZ) loZ = z;
+            if (z > hiZ) hiZ = z;
+        }
+        loX = warp_min_d(loX); hiX = warp_max_d(hiX); loZ = warp_min_d(loZ); hiZ = warp_max_d(hiZ);
+        double relation = (hiZ - loZ) / (hiX - loX);
+        if (!(relation >= P.zx_min_rel)) return ST_InsufficientRoadPoints;
+        pl = plane_through(slab_pt(s, i), slab_pt(s, j), slab_pt(s, k));
+    } else {
+        // PlaneEstimationMEstimator::EstimatePlane; prior = Hyperplane(normalized(a,b,c), d) in the
+        // lidar frame applied to camera-frame points, as the reference does (DepthEstimator.cpp:286-292).
+        // The last left-singular vector of [sqrt(w_i)(p_i - c)] is the eigenvector of the smallest
+        // eigenvalue of sum w_i (p_i-c)(p_i-c)^T, solved in registers.
+        Plane prior{normalized3(D3{(double)a, (double)b, (double)c}), (double)d};
+        D3 center;
+        double cv[6];
+        slab_weighted_scatter(n, lane, s, P.road_mode == ROAD_MESTIMATOR, prior, center, cv);
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], w, ev);
+        int bi = 0;
+        if (w[1] < w[bi]) bi = 1;
+        if (w[2] < w[bi]) bi = 2;
+        D3 nrm = normalized3((bi == 0) ? ev[0] : (bi == 1 ? ev[1] : ev[2]));
+        pl = Plane{nrm, -dot3(nrm, center)};
+    }
+    // ray with swapped arguments (origin = direction, RoadDepthEstimatorMEstimator.cpp:52-53), no orthogonality gate
+    D3 support = D3{0, 0, 0};
+    D3 dir = viewing_ray(P, u, v);
+    double depth;
+    line_plane(pl, dir, support, 0.0, depth);
+    double minZ, maxZ;
+    slab_z_range(n, lane, s, minZ, maxZ);
+    int r = apply_tresholds(P, depth, minZ, maxZ);
+    if (r) return r;
+    depth_out = depth;
+    return ST_SuccessRoad;
+}
+
+// ---- per-feature driver (DepthEstimator.cpp:491-600) --------------------------------------------
+template <int KCAP>
+__device__ void feature_depth(const DevParams& P, const unsigned int* __restrict__ map, const float* __restrict__ pts,
+                              int stride_f, double u, double v, const float* plane_coeffs,
+                              const unsigned int* __restrict__ inlier_bits, int lane, const WarpSlab& s, int& status_out,
+                              double& depth_out) {
+    depth_out = -1;
+    int k = gather_window<KCAP>(P, map, pts, stride_f, u, v, P.hx1, P.hy1, lane, s);
+    if ((unsigned)k < (unsigned)P.count_min) {  // neighbors.size() < (uint)radiusSearch_count_min (:680)
+        status_out = ST_RadiusSearchInsufficientPoints;
+        return;
+    }
+    int status = ST_Unspecified;
+    int n = k;
+    if (P.use_hist) {
+        n = histogram_segment(P, k, lane, s);
+        if (n < 0) status = ST_HistogramNoLocalMax;
+    }
+    if (status != ST_HistogramNoLocalMax) {
+        double depth;
+        status = depth_segmented(P, u, v, n, lane, s, depth);
+        if (status == ST_Success) {
+            status_out = status;
+            depth_out = depth;
+            return;
+        }
+    }
+    if (plane_coeffs != nullptr && P.road_mode != ROAD_NONE) {
+        __syncwarp();
+        int k2 = gather_window<KCAP>(P, map, pts, stride_f, u, v, P.hx2, P.hy2, lane, s);
+        if ((unsigned)k2 < (unsigned)P.count_min) {
+            status_out = ST_RadiusSearchInsufficientPoints;
+            return;
+        }
+        double depth;
+        status = road_depth(P, u, v, k2, lane, s, plane_coeffs, inlier_bits, status, depth);
+        depth_out = depth;
+    }
+    status_out = status;
+}
+
+template <int KCAP, int K2_WARPS>
+__global__ void __launch_bounds__(K2_WARPS * 32)
+feature_depth_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                     const unsigned int* __restrict__ maps, const double* __restrict__ uv, int F,
+                     double* __restrict__ depth, int* __restrict__ status, const float* __restrict__ plane_coeffs,
+                     const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long frame = blockIdx.y;
+    const int fi = blockIdx.x * K2_WARPS + warp;
+    if (fi >= F) return;
+
+    double* sx = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 3 * KCAP;
+    WarpSlab s{sx, sx + KCAP, sx + 2 * KCAP,
+               reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)K2_WARPS * 3 * KCAP) + (size_t)warp * KCAP};
+
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const long long o = frame * (long long)F + fi;
+    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
+        if (lane == 0) {
+            status[o] = 1;
+            depth[o] = -1;
+        }
+        return;
+    }
+    double u = uv[o * 2], v = uv[o * 2 + 1];
+    const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
+    const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
+    int st;
+    double dp;
+    feature_depth<KCAP>(P, map, fp, stride_f, u, v, pc, bits, lane, s, st, dp);
+    if (lane == 0) {
+        status[o] = st;
+        depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
+    }
+}
+
+// debug: neighbour list of one feature in scan order (raw indices)
+__global__ void neighbors_debug_kernel(DevParams P, const unsigned int* __restrict__ map, double u, double v, double hx,
+                                       double hy, int* __restrict__ out, int cap, int* __restrict__ k_out) {
+    const int lane = threadIdx.x;
+    if (!(fabs(u) < 1e9) || !(fabs(v) < 1e9)) {
+        if (lane == 0) *k_out = 0;
+        return;
+    }
+    int x0 = (int)fmax(u - hx, 0.), x1 = (int)fmin(u + hx, (double)(P.W - 1));
+    int y0 = (int)fmax(v - hy, 0.), y1 = (int)fmin(v + hy, (double)(P.H - 1));
+    int wc = x1 - x0 + 1, wr = y1 - y0 + 1;
+    int k = 0;
+    if (wc > 0 && wr > 0) {
+        int area = wc * wr;
+        const unsigned lt = lanemask_lt();
+        for (int base = 0; base < area; base += 32) {
+            int idx = base + lane;
+            unsigned int cell = MLD_EMPTY;
+            if (idx < area) {
+                int ry = idx / wc, rx = idx - (idx / wc) * wc;
+                cell = map[(long long)(y0 + ry) * P.W + (x0 + rx)];
+            }
+            unsigned m = __ballot_sync(MLD_FULL_MASK, cell != MLD_EMPTY);
+            if (cell != MLD_EMPTY) {
+                int pos = k + __popc(m & lt);
+                if (pos < cap) out[pos] = (int)cell;
+            }
+            k += __popc(m);
+        }
+    }
+    if (lane == 0) *k_out = k;
+}
+
+template <int KCAP, int K2_WARPS>
+cudaError_t launch_feature(const DevParams& P, const float* d_pts, int stride_f, long long pitch_pts,
+                           const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
+                           const float* d_plane_coeffs, const unsigned int* d_inlier_bits, long long words_per_frame,
+                           int nframes, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)K2_WARPS * KCAP * (3 * sizeof(double) + sizeof(int));
+    dim3 grid((unsigned)((F + K2_WARPS - 1) / K2_WARPS), (unsigned)nframes);
+    feature_depth_kernel<KCAP, K2_WARPS><<<grid, K2_WARPS * 32, smem, stream>>>(
+        P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs, d_inlier_bits, words_per_frame);
+    return cudaGetLastError();
+}
+
+template <int KCAP, int K2_WARPS>
+cudaError_t configure_feature() {
+    constexpr size_t smem = (size_t)K2_WARPS * KCAP * (3 * sizeof(double) + sizeof(int));
+    return cudaFuncSetAttribute(feature_depth_kernel<KCAP, K2_WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+
+}  // namespace
+
+int mld_feature_capacity_for(int max_area) {
+    if (max_area <= 96) return 96;
+    if (max_area <= 256) return 256;
+    if (max_area <= 1024) return 1024;
+    return -1;
+}
+
+cudaError_t mld_launch_feature_depth(const DevParams& P, int kcap, const float* d_pts, int stride_f, long long pitch_pts,
+                                     const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
+                                     const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, cudaStream_t stream) {
+    if (F <= 0 || nframes <= 0) return cudaSuccess;
+    switch (kcap) {
+        case 96:
+            return launch_feature<96, 8>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                      d_inlier_bits, words_per_frame, nframes, stream);
+        case 256:
+            return launch_feature<256, 8>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                       d_inlier_bits, words_per_frame, nframes, stream);
+        case 1024:
+            return launch_feature<1024, 4>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                        d_inlier_bits, words_per_frame, nframes, stream);
+        default:
+            return cudaErrorInvalidValue;
+    }
+}
+
+// opt in to the dynamic shared memory the chosen variant needs (once per device, at mld_create)
+cudaError_t mld_configure_feature_depth(int kcap) {
+    switch (kcap) {
+        case 96: return configure_feature<96, 8>();
+        case 256: return configure_feature<256, 8>();
+        case 1024: return configure_feature<1024, 4>();
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t mld_launch_neighbors_debug(const DevParams& P, const unsigned int* d_map, double u, double v, double hx, double hy,
+                                       int* d_out, int cap, int* d_k, cudaStream_t stream) {
+    neighbors_debug_kernel<<<1, 32, 0, stream>>>(P, d_map, u, v, hx, hy, d_out, cap, d_k);
+    return cudaGetLastError();
+}

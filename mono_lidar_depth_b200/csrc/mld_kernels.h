@@ -1,0 +1,56 @@
+// mld_kernels.h -- host-callable launchers of the sm_100a kernels (internal to libmld_cuda.so).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mld_c_api.h"
+
+struct DevParams;
+
+// K1 (mld_project.cu)
+cudaError_t mld_launch_project_scatter(const DevParams& P, const float* d_pts, int stride_f, long long n,
+                                       long long pitch_pts, unsigned int* d_maps, int nframes, cudaStream_t stream);
+cudaError_t mld_launch_visible_debug(const DevParams& P, const float* d_pts, int stride_f, long long n,
+                                     unsigned char* d_visible, double* d_cam, cudaStream_t stream);
+
+// K2/K3 (mld_feature.cu)
+int mld_feature_capacity_for(int max_area);
+cudaError_t mld_configure_feature_depth(int kcap);
+cudaError_t mld_launch_feature_depth(const DevParams& P, int kcap, const float* d_pts, int stride_f, long long pitch_pts,
+                                     const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
+                                     const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, cudaStream_t stream);
+cudaError_t mld_launch_neighbors_debug(const DevParams& P, const unsigned int* d_map, double u, double v, double hx, double hy,
+                                       int* d_out, int cap, int* d_k, cudaStream_t stream);
+
+// K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
+struct RansacConfig {
+    double distance_treshold;     // ransac_plane_distance_treshold
+    double refinement_treshold;   // ransac_plane_refinement_treshold
+    double probability;           // ransac_plane_probability
+    double min_z, max_z;          // ransac_plane_min_z / max_z (PassThrough when min_z > -1001)
+    int max_iterations;           // ransac_plane_max_iterations
+    int use_refinement;           // ransac_plane_use_refinement
+    double cos_eps;               // cos(M_PI / 18.): SampleConsensusModelPerpendicularPlane eps angle (RansacPlane.cpp:99)
+    double log_probability;       // log(1 - probability)
+};
+constexpr int MLD_RANSAC_SAMPLE = 6000;  // _numberRandomSamplePoints, RansacPlane.cpp:32
+
+// Scratch per frame (device): see mld_ransac.cu. Sizes in bytes for nframes.
+size_t mld_ransac_scratch_bytes(long long n_points, int nframes);
+// Fits one plane per frame. Outputs per frame: coeffs[4] (float), inlier bitmask over raw indices
+// (words_per_frame uint32), n_inliers, iterations, rc (0 ok, MLD_ERR_PCL_INVALID, MLD_ERR_NO_MODEL).
+cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int stride_f, long long n_points,
+                              long long pitch_pts, int nframes, uint64_t seed, long long frame0, void* d_scratch,
+                              float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame, int* d_n_inliers,
+                              int* d_iterations, int* d_rc, cudaStream_t stream, int* launches);
+// synthetic data (mld_synth.cu)
+cudaError_t mld_launch_synth_points(const mld_synth_config& c, uint64_t seed, long long frame0, long long nframes,
+                                    long long pitch_pts, const float* d_tables, float* d_out, cudaStream_t stream);
+cudaError_t mld_launch_synth_features(const mld_synth_config& c, uint64_t seed, long long frame0, long long nframes, int F,
+                                      double* d_out, cudaStream_t stream);
+// host side of the same generator
+void mld_synth_build_tables(const mld_synth_config& c, float* tables /* 2*rings + 2*azimuth_steps */);
+void mld_synth_points_host_impl(const mld_synth_config& c, uint64_t seed, long long frame, const float* tables, float* out);
+void mld_synth_features_host_impl(const mld_synth_config& c, uint64_t seed, long long frame, int F, double* out);

@@ -1,0 +1,307 @@
+"""Host-side mirror of the reference's operator interface, Mono_Lidar::DepthEstimator
+(monolidar_fusion/include/monolidar_fusion/DepthEstimator.h:39-359), on top of the C ABI.
+
+Same method names, argument meaning and error behaviour as the C++ class:
+    InitConfig -> Initialize -> setInputCloud -> CalculateDepth
+All arithmetic runs in libmld_cuda.so on the GPU; this file only moves buffers and mirrors the
+reference's exceptions. Python has no reference arguments, so the in/out ``GroundPlane::Ptr&`` of
+setInputCloud / CalculateDepth is returned instead.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _capi
+from .params import DepthEstimatorParameters
+
+
+class ExceptionPclInvalid(Exception):
+    """GroundPlane::ExceptionPclInvalid (RansacPlane.h:46-50)."""
+
+    def __str__(self):
+        return "In GroundPlane: Input pointcloud is invalid"
+
+
+class CameraPinhole:
+    """CameraPinhole(width, height, focal_length, principal_point_x, principal_point_y) (camera_pinhole.h:21-26)."""
+
+    def __init__(self, width: int, height: int, focal_length: float, principal_point_x: float, principal_point_y: float):
+        self.width_, self.height_ = int(width), int(height)
+        self.focal_length_ = float(focal_length)
+        self.principal_point_x_, self.principal_point_y_ = float(principal_point_x), float(principal_point_y)
+
+    def getImageSize(self) -> Tuple[int, int]:
+        return self.width_, self.height_
+
+
+class GroundPlane:
+    """Mono_Lidar::GroundPlane (RansacPlane.h:38-126): model coefficients in the lidar frame, inlier
+    indices into the raw cloud, isSegmented(). Construct it empty (to be fitted by RANSAC on the GPU)
+    or with externally computed coefficients/inliers (e.g. a SemanticPlane computed by the caller)."""
+
+    def __init__(self, coeffs=None, inliers=None):
+        self._coeffs = np.zeros(4, np.float32) if coeffs is None else np.asarray(coeffs, np.float32).reshape(4).copy()
+        self._inliers = np.zeros(0, np.int32) if inliers is None else np.ascontiguousarray(inliers, np.int32)
+        self.is_segmented_ = coeffs is not None
+
+    def isSegmented(self) -> bool:
+        return bool(self.is_segmented_)
+
+    def getModelCoeffs(self) -> np.ndarray:
+        return self._coeffs
+
+    def getInlinersIndex(self) -> np.ndarray:
+        return self._inliers
+
+    def CheckPointInPlane(self, index: int) -> bool:
+        i = int(np.searchsorted(self._inliers, index))
+        return i < len(self._inliers) and int(self._inliers[i]) == int(index)
+
+    def _as_c(self, capacity: int = 0) -> _capi.MldPlane:
+        pl = _capi.MldPlane()
+        if capacity > len(self._inliers):
+            buf = np.zeros(capacity, np.int32)
+            buf[: len(self._inliers)] = self._inliers
+            self._inliers_buf = buf
+        else:
+            self._inliers_buf = self._inliers
+        for i in range(4):
+            pl.coeffs[i] = float(self._coeffs[i])
+        pl.inlier_idx = self._inliers_buf.ctypes.data_as(C.POINTER(C.c_int32)) if len(self._inliers_buf) else None
+        pl.n_inliers = len(self._inliers)
+        pl.inlier_capacity = len(self._inliers_buf)
+        pl.segmented = 1 if self.is_segmented_ else 0
+        return pl
+
+    def _from_c(self, pl: _capi.MldPlane) -> None:
+        self._coeffs = np.array([pl.coeffs[i] for i in range(4)], np.float32)
+        self._inliers = self._inliers_buf[: min(pl.n_inliers, len(self._inliers_buf))].copy()
+        self.is_segmented_ = bool(pl.segmented)
+
+
+class RansacPlane(GroundPlane):
+    """Mono_Lidar::RansacPlane (RansacPlane.h:132-164); the fit itself runs on the GPU."""
+
+    def __init__(self, parameters: Optional[DepthEstimatorParameters] = None, seed: int = 0):
+        super().__init__()
+        self.parameters = parameters
+        self.seed = int(seed)
+        self.iterations = 0
+
+
+def _cloud_buffer(cloud) -> Tuple[np.ndarray, int, int]:
+    """Accepts (n,4) float32 [x,y,z,i] (float4) or (n,8) float32 (pcl::PointXYZI's 32-byte layout)."""
+    a = np.ascontiguousarray(cloud, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (4, 8):
+        raise ValueError("cloud must be (n,4) or (n,8) float32")
+    return a, a.shape[0], a.shape[1] * 4
+
+
+class DepthEstimator:
+    def __init__(self, device: int = -1):
+        self._lib = _capi.load()
+        self._h = C.c_void_p()
+        self._device = device
+        self._parameters: Optional[DepthEstimatorParameters] = None
+        self._camera: Optional[CameraPinhole] = None
+        self._transform = None
+        self._isInitializedConfig = False
+        self._isInitialized = False
+        self._isInitializedPointCloud = False
+        self.ransac_seed = 0
+
+    # -- lifetime ---------------------------------------------------------------------------
+    def close(self):
+        if self._h:
+            self._lib.mld_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc == _capi.MLD_OK:
+            return
+        msg = self._lib.mld_last_error(self._h)
+        msg = msg.decode("utf-8", "replace") if msg else ""
+        if rc == _capi.MLD_ERR_PCL_INVALID:
+            raise ExceptionPclInvalid()
+        raise _capi.MldError(rc, msg)
+
+    # -- DepthEstimator::InitConfig (DepthEstimator.cpp:129-154) ---------------------------------
+    def InitConfig(self, parameters=None, printparams: bool = False) -> bool:
+        if isinstance(parameters, (str, bytes)) or hasattr(parameters, "__fspath__"):
+            p = DepthEstimatorParameters()
+            p.fromFile(parameters)
+            parameters = p
+        elif parameters is None:
+            parameters = DepthEstimatorParameters()
+        self._parameters = parameters
+        if printparams:
+            parameters.print()
+        self.close()
+        rc = self._lib.mld_create(C.byref(parameters.c_struct), self._device, C.byref(self._h))
+        if rc != _capi.MLD_OK:
+            _capi.check(rc, None)
+        self._isInitializedConfig = True
+        self._isInitialized = False
+        self._isInitializedPointCloud = False
+        return True
+
+    # -- DepthEstimator::Initialize (DepthEstimator.cpp:35-127) ----------------------------------
+    def Initialize(self, camera: CameraPinhole, transform_lidar_to_cam) -> bool:
+        if not self._isInitializedConfig:
+            raise RuntimeError("Call 'InitConfig' before calling 'Initialize'.")
+        T = np.ascontiguousarray(np.asarray(transform_lidar_to_cam, np.float64)[:3, :4])
+        if T.shape != (3, 4):
+            raise ValueError("transform_lidar_to_cam must be 4x4 or 3x4")
+        self._camera, self._transform = camera, T.copy()
+        W, H = camera.getImageSize()
+        self._check(self._lib.mld_initialize(self._h, W, H, camera.focal_length_, camera.principal_point_x_,
+                                             camera.principal_point_y_, T.ctypes.data_as(C.POINTER(C.c_double))))
+        self._isInitialized = True
+        return True
+
+    def getParameters(self):
+        return self._parameters
+
+    def getCamera(self):
+        return self._camera
+
+    def getTransformLidarToCam(self):
+        return self._transform
+
+    # -- DepthEstimator::setInputCloud (DepthEstimator.cpp:220-312) -----------------------------
+    def setInputCloud(self, cloud, groundPlane: Optional[GroundPlane] = None) -> Optional[GroundPlane]:
+        if not self._isInitialized:
+            raise RuntimeError("call of 'setInputCloud' without 'initialize'")
+        a, n, stride = _cloud_buffer(cloud)
+        self._n = n
+        pl_c = None
+        if self._parameters.do_use_ransac_plane:
+            if groundPlane is None:  # DepthEstimator.cpp:275-278
+                groundPlane = RansacPlane(self._parameters, self.ransac_seed)
+            if not groundPlane.isSegmented():
+                pl_c = groundPlane._as_c(capacity=max(n, 1))
+        seed = getattr(groundPlane, "seed", self.ransac_seed) if groundPlane is not None else 0
+        self._check(self._lib.mld_set_cloud(self._h, a.ctypes.data if n else None, n, stride,
+                                            C.byref(pl_c) if pl_c is not None else None, seed))
+        if pl_c is not None:
+            groundPlane._from_c(pl_c)
+        self._isInitializedPointCloud = True
+        return groundPlane
+
+    # -- DepthEstimator::CalculateDepth (DepthEstimator.cpp:404-488) -----------------------------
+    def CalculateDepth(self, *args):
+        """CalculateDepth(points_image_cs, ransacPlane=None) -> (depths, resultType)
+        CalculateDepth(pointCloud, points_image_cs, ransacPlane=None) -> (depths, resultType, ransacPlane)
+
+        points_image_cs: 2xF (reference layout) or Fx2 array of pixel coordinates."""
+        if len(args) >= 2 and np.ndim(args[0]) == 2 and np.ndim(args[1]) == 2:
+            cloud, feats = args[0], args[1]
+            plane = args[2] if len(args) > 2 else None
+            plane = self.setInputCloud(cloud, plane)
+            d, s = self._calculate(feats, plane)
+            return d, s, plane
+        feats = args[0]
+        plane = args[1] if len(args) > 1 else None
+        return self._calculate(feats, plane)
+
+    def _calculate(self, feats, plane):
+        if not self._isInitializedPointCloud:
+            raise RuntimeError("call of 'CalculateDepth' without 'SetInputCloud'")
+        f = np.asarray(feats, np.float64)
+        if f.ndim != 2 or 2 not in f.shape:
+            raise ValueError("features must be 2xF or Fx2")
+        if f.shape[0] == 2 and f.shape[1] != 2:
+            f = f.T  # Eigen::Matrix2Xd is column-major: memory order u0,v0,u1,v1,... == (F,2) C-order
+        f = np.ascontiguousarray(f)
+        F = f.shape[0]
+        depths = np.empty(F, np.float64)
+        status = np.empty(F, np.int32)
+        pl_c = plane._as_c() if plane is not None else None
+        self._check(self._lib.mld_calculate_depth(self._h, f.ctypes.data, F, depths.ctypes.data, status.ctypes.data,
+                                                  C.byref(pl_c) if pl_c is not None else None))
+        return depths, status
+
+    # -- stand-alone RansacPlane::CalculateInliersPlane -------------------------------------------
+    def estimateGroundPlane(self, cloud, seed: int = 0) -> RansacPlane:
+        a, n, stride = _cloud_buffer(cloud)
+        plane = RansacPlane(self._parameters, seed)
+        pl_c = plane._as_c(capacity=max(n, 1))
+        it = C.c_int32(0)
+        self._check(self._lib.mld_estimate_ground_plane(self._h, a.ctypes.data if n else None, n, stride, seed, C.byref(pl_c), C.byref(it)))
+        plane._from_c(pl_c)
+        plane.iterations = it.value
+        return plane
+
+    # -- debug views (DepthEstimator.h:116-164) ------------------------------------------------
+    def getPixelMap(self) -> np.ndarray:
+        W, H = self._camera.getImageSize()
+        out = np.empty((H, W), np.int32)
+        self._check(self._lib.mld_get_pixel_map(self._h, out.ctypes.data))
+        return out
+
+    def getNeighbors(self, u: float, v: float, scale_w: float = 1.0, scale_h: float = 1.0) -> np.ndarray:
+        cap = self._lib.mld_neighbor_capacity()
+        out = np.empty(cap, np.int32)
+        k = C.c_int(0)
+        self._check(self._lib.mld_get_neighbors(self._h, u, v, scale_w, scale_h, out.ctypes.data, cap, C.byref(k)))
+        return out[: min(k.value, cap)].copy()
+
+    def getVisible(self) -> np.ndarray:
+        out = np.zeros(max(self._n, 1), np.uint8)
+        nv = C.c_int64(0)
+        self._check(self._lib.mld_get_visible(self._h, out.ctypes.data, C.byref(nv)))
+        return out[: self._n].astype(bool)
+
+    def getPointsCloudCameraCs(self) -> np.ndarray:
+        out = np.zeros((max(self._n, 1), 3), np.float64)
+        self._check(self._lib.mld_get_points_camera(self._h, out.ctypes.data))
+        return out[: self._n]
+
+    def getPointsCloudImageCs(self) -> np.ndarray:
+        """_points_cs_image_visible as (nvis, 2): projection of the visible points, cloud order."""
+        cam = self.getPointsCloudCameraCs()
+        vis = self.getVisible()
+        c = cam[vis]
+        f, cx, cy = self._camera.focal_length_, self._camera.principal_point_x_, self._camera.principal_point_y_
+        with np.errstate(all="ignore"):
+            u = ((f * c[:, 0] + 0.0 * c[:, 1]) + cx * c[:, 2]) / c[:, 2]
+            v = ((0.0 * c[:, 0] + f * c[:, 1]) + cy * c[:, 2]) / c[:, 2]
+        return np.stack([u, v], 1)
+
+    # -- batched sequences (frames are independent; see bench.py) ---------------------------------
+    def processFramesDevice(self, d_points: int, n_points: int, frame_pitch_points: int, stride_bytes: int, d_uv: int, F: int,
+                            d_depth: int, d_status: int, nframes: int, road: bool = False, seed: int = 0,
+                            d_plane_coeffs_out: int = 0, stream: int = 0) -> None:
+        """Raw device pointers (e.g. torch ``tensor.data_ptr()``); enqueues on ``stream`` without synchronising."""
+        self._check(self._lib.mld_process_frames_device(self._h, d_points, n_points, frame_pitch_points, stride_bytes, d_uv, F,
+                                                        d_depth, d_status, nframes, int(road), seed,
+                                                        d_plane_coeffs_out or None, stream or None))
+
+    def processFramesHost(self, points: np.ndarray, uv: np.ndarray, depth: np.ndarray, status: np.ndarray, road: bool = False,
+                          seed: int = 0, plane_coeffs_out: Optional[np.ndarray] = None) -> None:
+        """points (nframes, n, 4|8) float32, uv (nframes, F, 2) float64 -> depth (nframes, F) f64, status (nframes, F) i32."""
+        nframes, n, k = points.shape
+        F = uv.shape[1]
+        self.processFramesHostPtr(points.ctypes.data, n, n, k * 4, uv.ctypes.data, F, depth.ctypes.data, status.ctypes.data,
+                                  nframes, road, seed, plane_coeffs_out.ctypes.data if plane_coeffs_out is not None else 0)
+
+    def processFramesHostPtr(self, points: int, n_points: int, frame_pitch_points: int, stride_bytes: int, uv: int, F: int,
+                             depth: int, status: int, nframes: int, road: bool = False, seed: int = 0, plane_coeffs_out: int = 0):
+        self._check(self._lib.mld_process_frames_host(self._h, points, n_points, frame_pitch_points, stride_bytes, uv, F, depth,
+                                                      status, nframes, int(road), seed, plane_coeffs_out or None))
+
+    def kernelLaunchCount(self) -> int:
+        return int(self._lib.mld_kernel_launch_count(self._h))
+
+    @property
+    def handle(self):
+        return self._h
