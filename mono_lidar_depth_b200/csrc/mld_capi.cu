@@ -76,7 +76,14 @@ struct mld_handle {
     bool synth_tables_valid = false;
     long long launches = 0;
     std::string error;
+    // profiling (mld_profile_enable): events around each kernel class of a chunk
+    bool prof_on = false;
+    std::vector<cudaEvent_t> prof_events;  // 5 per sampled chunk
+    std::vector<int> prof_frames;          // frames of each sampled chunk
+    std::vector<int> prof_ransac_launches;
+    size_t prof_used = 0;                  // sampled chunks
 };
+constexpr size_t MLD_PROF_MAX_CHUNKS = 2048;
 
 namespace {
 
@@ -157,9 +164,27 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
                   int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
                   long long frame0, float* d_coeffs_out) {
     const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    cudaEvent_t* ev = nullptr;
+    if (h->prof_on && h->prof_used < MLD_PROF_MAX_CHUNKS) {
+        if (h->prof_events.size() < (h->prof_used + 1) * 5) {
+            for (int q = 0; q < 5; q++) {
+                cudaEvent_t e;
+                CK(cudaEventCreate(&e));
+                h->prof_events.push_back(e);
+            }
+            h->prof_frames.push_back(0);
+            h->prof_ransac_launches.push_back(0);
+        }
+        ev = &h->prof_events[h->prof_used * 5];
+        h->prof_frames[h->prof_used] = frames;
+        h->prof_ransac_launches[h->prof_used] = 0;
+    }
+    if (ev) CK(cudaEventRecord(ev[0], st));
     CK(cudaMemsetAsync(s.d_maps, 0xFF, (size_t)frames * WH * sizeof(unsigned int), st));
+    if (ev) CK(cudaEventRecord(ev[1], st));
     CK(mld_launch_project_scatter(h->dp, d_pts, stride_f, n_points, pitch_pts, s.d_maps, frames, st));
     if (n_points > 0) h->launches++;
+    if (ev) CK(cudaEventRecord(ev[2], st));
     const float* coeffs = nullptr;
     const unsigned int* bits = nullptr;
     const long long words = (n_points + 31) / 32;
@@ -169,12 +194,18 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         CK(mld_launch_ransac(ransac_config(h->params), d_pts, stride_f, n_points, pitch_pts, frames, seed, frame0, s.d_scratch,
                              cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, st, &nl));
         h->launches += nl;
+        if (ev) h->prof_ransac_launches[h->prof_used] = nl;
         coeffs = cdst;
         bits = s.d_bits;
     }
+    if (ev) CK(cudaEventRecord(ev[3], st));
     CK(mld_launch_feature_depth(h->dp, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs, bits,
                                 words, frames, st));
     if (F > 0) h->launches++;
+    if (ev) {
+        CK(cudaEventRecord(ev[4], st));
+        h->prof_used++;
+    }
     return MLD_OK;
 }
 
@@ -408,6 +439,7 @@ int mld_destroy(mld_handle* h) {
     }
     cudaFree(h->d_dbg);
     cudaFree(h->d_synth_tables);
+    for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     delete h;
     return MLD_OK;
 }
@@ -482,6 +514,40 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
 }
 
 int mld_neighbor_capacity(void) { return 1024; }
+int mld_chunk_frames(const mld_handle* h) { return h ? h->chunk_frames : 0; }
+
+int mld_profile_enable(mld_handle* h, int on) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    h->prof_on = on != 0;
+    return MLD_OK;
+}
+
+int mld_profile_read(mld_handle* h, double* ms4, int64_t* launches4, int64_t* frames_sampled) {
+    if (!h || !ms4 || !launches4) return MLD_ERR_INVALID_ARG;
+    DeviceGuard g(h->device);
+    for (int q = 0; q < 4; q++) {
+        ms4[q] = 0.0;
+        launches4[q] = 0;
+    }
+    int64_t frames = 0;
+    for (size_t c = 0; c < h->prof_used; c++) {
+        cudaEvent_t* ev = &h->prof_events[c * 5];
+        CK(cudaEventSynchronize(ev[4]));
+        for (int q = 0; q < 4; q++) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, ev[q], ev[q + 1]));
+            ms4[q] += (double)ms;
+        }
+        launches4[0] += 1;
+        launches4[1] += 1;
+        launches4[2] += h->prof_ransac_launches[c];
+        launches4[3] += 1;
+        frames += h->prof_frames[c];
+    }
+    if (frames_sampled) *frames_sampled = frames;
+    h->prof_used = 0;
+    return MLD_OK;
+}
 int64_t mld_kernel_launch_count(const mld_handle* h) { return h ? h->launches : 0; }
 
 static int check_stride(mld_handle* h, int stride_bytes) {

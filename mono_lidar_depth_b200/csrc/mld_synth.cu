@@ -54,7 +54,7 @@ __host__ __device__ inline SynthBox synth_box(const mld_synth_config& c, uint64_
     } else {
         az = (int)(h1 % (uint64_t)c.azimuth_steps);
     }
-    float r = 4.0f + 76.0f * u01(h2) * u01b(h2);  // denser near the sensor
+    float r = 8.0f + 72.0f * u01(h2) * u01b(h2);  // denser near the sensor, never on top of it
     float cx = r * cos_az[az], cy = r * sin_az[az];
     float hx = 0.5f + 2.5f * u01(h3), hy = 0.5f + 2.5f * u01(h4), hh = 0.5f + 3.5f * u01(h5);
     SynthBox bx;

@@ -299,6 +299,21 @@ class DepthEstimator:
         self._check(self._lib.mld_process_frames_host(self._h, points, n_points, frame_pitch_points, stride_bytes, uv, F, depth,
                                                       status, nframes, int(road), seed, plane_coeffs_out or None))
 
+    def profileEnable(self, on: bool = True) -> None:
+        self._check(self._lib.mld_profile_enable(self._h, int(on)))
+
+    def profileRead(self):
+        """{class: (total ms, launches)} for clear / project_scatter / ransac / feature_depth, frames sampled."""
+        ms = (C.c_double * 4)()
+        ln = (C.c_int64 * 4)()
+        fr = C.c_int64(0)
+        self._check(self._lib.mld_profile_read(self._h, ms, ln, C.byref(fr)))
+        names = ("map_clear", "project_scatter", "ransac", "feature_depth")
+        return {n: (ms[i], ln[i]) for i, n in enumerate(names)}, fr.value
+
+    def chunkFrames(self) -> int:
+        return int(self._lib.mld_chunk_frames(self._h))
+
     def kernelLaunchCount(self) -> int:
         return int(self._lib.mld_kernel_launch_count(self._h))
 

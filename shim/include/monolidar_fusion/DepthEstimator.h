@@ -1,0 +1,82 @@
+// Mono_Lidar::DepthEstimator -- source-compatible host shim over the C ABI (include/mld_c_api.h).
+//
+// Public interface = the reference's (monolidar_fusion/include/monolidar_fusion/DepthEstimator.h:73-222):
+// InitConfig (file or struct), Initialize, setInputCloud, the five CalculateDepth overloads and the
+// getters tracklets_depth uses (tracklets_depth/src/tracklet_depth_module.cpp:80,115,401,413). The shim
+// holds no arithmetic: every method moves buffers and calls libmld_cuda.so. Errors are rethrown with
+// the reference's exception types (const char*, std::string, std::runtime_error,
+// GroundPlane::ExceptionPclInvalid).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <utility>
+
+#include <Eigen/Eigen>
+#include <Eigen/Geometry>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+
+#include "DepthEstimatorParameters.h"
+#include "RansacPlane.h"
+#include "camera_pinhole.h"
+#include "eDepthResultType.h"
+
+namespace Mono_Lidar {
+
+class DepthEstimator {
+public:
+    EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+    using Point = pcl::PointXYZI;
+    using Cloud = pcl::PointCloud<Point>;
+    using UniquePtr = std::unique_ptr<DepthEstimator>;
+    using SharedPtr = std::shared_ptr<DepthEstimator>;
+
+    std::map<DepthResultType, std::string> DepthResultTypeMap;
+
+    DepthEstimator();
+    ~DepthEstimator();
+    DepthEstimator(const DepthEstimator&) = delete;
+    DepthEstimator& operator=(const DepthEstimator&) = delete;
+
+    bool Initialize(const std::shared_ptr<CameraPinhole>& camera, const Eigen::Affine3d& transform_lidar_to_cam);
+    bool InitConfig(const std::string& filePath, const bool printparams = true);
+    bool InitConfig(std::shared_ptr<DepthEstimatorParameters> parameters = nullptr, const bool printparams = false);
+
+    void setInputCloud(const Cloud::ConstPtr& pointCloud, GroundPlane::Ptr& ransacPlane);
+
+    std::shared_ptr<DepthEstimatorParameters> getParameters() { return _parameters; }
+    std::shared_ptr<CameraPinhole> getCamera() { return _camera; }
+    Eigen::Affine3d getTransformLidarToCam() { return _transform_lidar_to_cam; }
+
+    void CalculateDepth(const Cloud::ConstPtr& pointCloud, const Eigen::Matrix2Xd& points_image_cs, Eigen::VectorXd& points_depths,
+                        GroundPlane::Ptr& ransacPlane);
+    void CalculateDepth(const Cloud::ConstPtr& pointCloud, const Eigen::Matrix2Xd& points_image_cs, Eigen::VectorXd& points_depths,
+                        Eigen::VectorXi& resultType, GroundPlane::Ptr& ransacPlane);
+    void CalculateDepth(const Eigen::Matrix2Xd& points_image_cs, Eigen::VectorXd& points_depths, const GroundPlane::Ptr& ransacPlane);
+    void CalculateDepth(const Eigen::Matrix2Xd& points_image_cs, Eigen::VectorXd& points_depths, Eigen::VectorXi& resultType,
+                        const GroundPlane::Ptr& ransacPlane);
+    std::pair<DepthResultType, double> CalculateDepth(const Eigen::Vector2d& point_image_cs, const GroundPlane::Ptr& ransacPlane);
+
+    // debug views served from device buffers on demand
+    void getPointsCloudImageCs(Eigen::Matrix2Xd& visiblePointsImageCs);
+    void getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs);
+
+    void setRansacSeed(unsigned long long seed) { _ransacSeed = seed; }
+
+private:
+    [[noreturn]] void rethrow(int rc);
+
+    std::shared_ptr<DepthEstimatorParameters> _parameters;
+    std::shared_ptr<CameraPinhole> _camera;
+    Eigen::Affine3d _transform_lidar_to_cam;
+    mld_handle* _handle{nullptr};
+    bool _isInitializedConfig{false};
+    bool _isInitialized{false};
+    bool _isInitializedPointCloud{false};
+    long long _pointCount{0};
+    unsigned long long _ransacSeed{0};
+};
+
+}  // namespace Mono_Lidar

@@ -1,0 +1,270 @@
+// Host shim: the reference's Mono_Lidar::DepthEstimator / RansacPlane member functions implemented
+// as buffer plumbing over the C ABI. Reference behaviour mirrored per method:
+//   Initialize     monolidar_fusion/src/DepthEstimator.cpp:35-127
+//   InitConfig     :129-154
+//   setInputCloud  :220-312
+//   CalculateDepth :404-488 (+ the single-point overload :491-600)
+//   RansacPlane::CalculateInliersPlane  monolidar_fusion/src/RansacPlane.cpp:41-140
+#include "monolidar_fusion/DepthEstimator.h"
+
+#include <cstring>
+#include <iostream>
+#include <stdexcept>
+#include <vector>
+
+namespace Mono_Lidar {
+
+namespace {
+
+// host view of a GroundPlane for the C ABI; keeps the index buffer alive for the call
+struct PlaneView {
+    mld_plane c;
+    std::vector<int32_t> idx;
+};
+
+void fill_plane(PlaneView& v, Eigen::Vector4f& coeffs, const std::vector<int>& inliers, bool segmented, int64_t capacity) {
+    std::memset(&v.c, 0, sizeof(v.c));
+    for (int i = 0; i < 4; i++) v.c.coeffs[i] = coeffs[i];
+    v.idx.assign(inliers.begin(), inliers.end());
+    if ((int64_t)v.idx.size() < capacity) v.idx.resize((size_t)capacity);
+    v.c.inlier_idx = v.idx.empty() ? nullptr : v.idx.data();
+    v.c.n_inliers = (int64_t)inliers.size();
+    v.c.inlier_capacity = (int64_t)v.idx.size();
+    v.c.segmented = segmented ? 1 : 0;
+}
+
+}  // namespace
+
+void DepthEstimatorParameters::print() {
+    std::cout << "DepthEstimator parameters: " << std::endl << std::endl;
+    std::cout << "pixelarea_search_witdh: " << pixelarea_search_witdh << std::endl;
+    std::cout << "pixelarea_search_height: " << pixelarea_search_height << std::endl;
+    std::cout << "radiusSearch_count_min: " << radiusSearch_count_min << std::endl;
+    std::cout << "do_use_histogram_segmentation: " << do_use_histogram_segmentation << std::endl;
+    std::cout << "histogram_segmentation_bin_witdh: " << histogram_segmentation_bin_witdh << std::endl;
+    std::cout << "histogram_segmentation_min_pointcount: " << histogram_segmentation_min_pointcount << std::endl;
+    std::cout << "do_use_ransac_plane: " << do_use_ransac_plane << std::endl;
+    std::cout << "viewray_plane_orthoganality_treshold: " << viewray_plane_orthoganality_treshold << std::endl;
+}
+
+// ---------------------------------------------------------------------------------------------
+RansacPlane::RansacPlane() {
+    params_.ransac_plane_distance_treshold = 0;
+    params_.ransac_plane_max_iterations = 0;
+    params_.ransac_plane_probability = 0.999;
+    params_.ransac_plane_refinement_treshold = 10000;
+    params_.ransac_plane_use_refinement = 0;
+}
+
+RansacPlane::RansacPlane(const std::shared_ptr<DepthEstimatorParameters>& parameters) : params_(*parameters) {}
+
+RansacPlane::~RansacPlane() { mld_destroy(handle_); }
+
+void RansacPlane::CalculateInliersPlane(const Cloud::ConstPtr& pointCloud) { CalculateInliersPlane(pointCloud, -1000, 1000); }
+
+void RansacPlane::CalculateInliersPlane(const Cloud::ConstPtr& pointCloud, double min_z, double max_z) {
+    if (pointCloud->points.size() < 3) throw ExceptionPclInvalid();
+    if (!handle_) {
+        if (mld_create(&params_, -1, &handle_) != MLD_OK) throw std::runtime_error(mld_last_error(nullptr));
+    }
+    // min_z / max_z are call arguments in the reference (RansacPlane.cpp:41); forward them through the parameter block
+    DepthEstimatorParameters p = params_;
+    p.ransac_plane_min_z = min_z;
+    p.ransac_plane_max_z = max_z;
+    if (p.ransac_plane_min_z != params_.ransac_plane_min_z || p.ransac_plane_max_z != params_.ransac_plane_max_z) {
+        mld_destroy(handle_);
+        handle_ = nullptr;
+        params_ = p;
+        if (mld_create(&params_, -1, &handle_) != MLD_OK) throw std::runtime_error(mld_last_error(nullptr));
+    }
+    PlaneView v;
+    std::vector<int> none;
+    fill_plane(v, _modelCoeffs, none, false, (int64_t)pointCloud->points.size());
+    int rc = mld_estimate_ground_plane(handle_, pointCloud->points.data(), (int64_t)pointCloud->points.size(), (int)sizeof(Point), seed_,
+                                       &v.c, nullptr);
+    if (rc == MLD_ERR_PCL_INVALID) throw ExceptionPclInvalid();
+    if (rc != MLD_OK) throw std::runtime_error(mld_last_error(handle_));
+    for (int i = 0; i < 4; i++) _modelCoeffs[i] = v.c.coeffs[i];
+    _inliersIndex.assign(v.idx.begin(), v.idx.begin() + v.c.n_inliers);
+    _pointIsInPlane.clear();
+    for (const auto& index : _inliersIndex) _pointIsInPlane.insert(std::pair<int, bool>(index, true));
+    is_segmented_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------
+DepthEstimator::DepthEstimator() {
+    for (int s = 1; s <= 15; s++) DepthResultTypeMap[(DepthResultType)s] = mld_status_name(s);
+}
+
+DepthEstimator::~DepthEstimator() { mld_destroy(_handle); }
+
+void DepthEstimator::rethrow(int rc) {
+    const char* msg = mld_last_error(_handle);
+    switch (rc) {
+        case MLD_ERR_PCL_INVALID: throw GroundPlane::ExceptionPclInvalid();
+        case MLD_ERR_REGION_GROWING: throw std::runtime_error("DepthEstimator: Region growing not supported!");
+        case MLD_ERR_BAD_SEARCH_MODE: throw std::string(msg);
+        case MLD_ERR_NOT_CONFIGURED: throw "Call 'InitConfig' before calling 'Initialize'.";
+        case MLD_ERR_NOT_INITIALIZED: throw "call of 'setInputCloud' without 'initialize'";
+        case MLD_ERR_NO_CLOUD: throw "call of 'CalculateDepth' without 'SetInputCloud'";
+        case MLD_ERR_NO_ROAD_ESTIMATOR: throw "No road depth estimator selected.";
+        default: throw std::runtime_error(std::string("mld: ") + msg);
+    }
+}
+
+bool DepthEstimator::InitConfig(const std::string& filePath, const bool printparams) {
+    auto p = std::make_shared<DepthEstimatorParameters>();
+    p->fromFile(filePath);
+    return InitConfig(p, printparams);
+}
+
+bool DepthEstimator::InitConfig(std::shared_ptr<DepthEstimatorParameters> parameters, const bool printparams) {
+    _parameters = parameters ? parameters : std::make_shared<DepthEstimatorParameters>();
+    if (printparams) _parameters->print();
+    mld_destroy(_handle);
+    _handle = nullptr;
+    int rc = mld_create(_parameters.get(), -1, &_handle);
+    if (rc != MLD_OK) throw std::runtime_error(std::string("mld: ") + mld_last_error(nullptr));
+    _isInitializedConfig = true;
+    _isInitialized = false;
+    _isInitializedPointCloud = false;
+    return true;
+}
+
+bool DepthEstimator::Initialize(const std::shared_ptr<CameraPinhole>& camera, const Eigen::Affine3d& transform_lidar_to_cam) {
+    if (!_isInitializedConfig) throw "Call 'InitConfig' before calling 'Initialize'.";
+    _camera = camera;
+    _transform_lidar_to_cam = transform_lidar_to_cam;
+    int W, H;
+    _camera->getImageSize(W, H);
+    double T[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[r * 4 + c] = transform_lidar_to_cam.matrix()(r, c);
+    int rc = mld_initialize(_handle, W, H, camera->focalLength(), camera->principalPointX(), camera->principalPointY(), T);
+    if (rc != MLD_OK) rethrow(rc);
+    _isInitialized = true;
+    return true;
+}
+
+void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Ptr& groundPlane) {
+    if (!_isInitialized) throw "call of 'setInputCloud' without 'initialize'";
+    const int64_t n = (int64_t)cloud->points.size();
+    int rc;
+    if (_parameters->do_use_ransac_plane) {
+        if (groundPlane == nullptr) groundPlane = std::make_shared<RansacPlane>(_parameters);  // DepthEstimator.cpp:275-278
+        if (!groundPlane->isSegmented()) {
+            if (dynamic_cast<RansacPlane*>(groundPlane.get()) != nullptr) {
+                // the RANSAC fit shares the H2D copy of the cloud with the projection
+                if (n < 3) throw GroundPlane::ExceptionPclInvalid();
+                PlaneView v;
+                std::vector<int> none;
+                fill_plane(v, groundPlane->_modelCoeffs, none, false, n);
+                rc = mld_set_cloud(_handle, cloud->points.data(), n, (int)sizeof(Point), &v.c, _ransacSeed);
+                if (rc != MLD_OK) rethrow(rc);
+                for (int i = 0; i < 4; i++) groundPlane->_modelCoeffs[i] = v.c.coeffs[i];
+                groundPlane->_inliersIndex.assign(v.idx.begin(), v.idx.begin() + v.c.n_inliers);
+                groundPlane->_pointIsInPlane.clear();
+                for (const auto& index : groundPlane->_inliersIndex) groundPlane->_pointIsInPlane.insert(std::pair<int, bool>(index, true));
+                groundPlane->is_segmented_ = true;
+                _pointCount = n;
+                _isInitializedPointCloud = true;
+                return;
+            }
+            // any other GroundPlane (e.g. the reference's SemanticPlane) segments itself on the host
+            groundPlane->CalculateInliersPlane(cloud, _parameters->ransac_plane_min_z, _parameters->ransac_plane_max_z);
+        }
+    }
+    rc = mld_set_cloud(_handle, cloud->points.data(), n, (int)sizeof(Point), nullptr, 0);
+    if (rc != MLD_OK) rethrow(rc);
+    _pointCount = n;
+    _isInitializedPointCloud = true;
+}
+
+void DepthEstimator::CalculateDepth(const Cloud::ConstPtr& pointCloud, const Eigen::Matrix2Xd& points_image_cs,
+                                    Eigen::VectorXd& points_depths, GroundPlane::Ptr& ransacPlane) {
+    setInputCloud(pointCloud, ransacPlane);
+    CalculateDepth(points_image_cs, points_depths, ransacPlane);
+}
+
+void DepthEstimator::CalculateDepth(const Cloud::ConstPtr& pointCloud, const Eigen::Matrix2Xd& points_image_cs,
+                                    Eigen::VectorXd& points_depths, Eigen::VectorXi& resultType, GroundPlane::Ptr& ransacPlane) {
+    setInputCloud(pointCloud, ransacPlane);
+    CalculateDepth(points_image_cs, points_depths, resultType, ransacPlane);
+}
+
+void DepthEstimator::CalculateDepth(const Eigen::Matrix2Xd& featurePoints_image_cs, Eigen::VectorXd& points_depths,
+                                    const GroundPlane::Ptr& ransacPlane) {
+    Eigen::VectorXi depthTypes(featurePoints_image_cs.cols());
+    CalculateDepth(featurePoints_image_cs, points_depths, depthTypes, ransacPlane);
+}
+
+void DepthEstimator::CalculateDepth(const Eigen::Matrix2Xd& featurePoints_image_cs, Eigen::VectorXd& points_depths,
+                                    Eigen::VectorXi& resultType, const GroundPlane::Ptr& ransacPlane) {
+    if (!_isInitializedPointCloud) throw "call of 'CalculateDepth' without 'SetInputCloud'";
+    int imgPointCount = featurePoints_image_cs.cols();
+    points_depths.resize(imgPointCount);
+    resultType.resize(imgPointCount);
+    static_assert(sizeof(int) == sizeof(int32_t), "Eigen::VectorXi holds 32-bit ints");
+    PlaneView v;
+    const mld_plane* pl = nullptr;
+    if (ransacPlane != nullptr) {
+        fill_plane(v, ransacPlane->getModelCoeffs(), ransacPlane->getInlinersIndex(), ransacPlane->isSegmented(), 0);
+        pl = &v.c;
+    }
+    int rc = mld_calculate_depth(_handle, featurePoints_image_cs.data(), imgPointCount, points_depths.data(),
+                                 reinterpret_cast<int32_t*>(resultType.data()), pl);
+    if (rc != MLD_OK) rethrow(rc);
+}
+
+std::pair<DepthResultType, double> DepthEstimator::CalculateDepth(const Eigen::Vector2d& featurePoint_image_cs,
+                                                                  const GroundPlane::Ptr& ransacPlane) {
+    Eigen::Matrix2Xd f(2, 1);
+    f(0, 0) = featurePoint_image_cs[0];
+    f(1, 0) = featurePoint_image_cs[1];
+    Eigen::VectorXd d;
+    Eigen::VectorXi t;
+    CalculateDepth(f, d, t, ransacPlane);
+    return std::pair<DepthResultType, double>((DepthResultType)t(0), d(0));
+}
+
+void DepthEstimator::getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs) {
+    std::vector<double> cam((size_t)std::max<long long>(_pointCount, 1) * 3);
+    int rc = mld_get_points_camera(_handle, cam.data());
+    if (rc != MLD_OK) rethrow(rc);
+    pointCloud_cam_cs->clear();
+    for (long long i = 0; i < _pointCount; i++) {
+        pcl::PointXYZI point;
+        point.x = (float)cam[(size_t)i * 3];
+        point.y = (float)cam[(size_t)i * 3 + 1];
+        point.z = (float)cam[(size_t)i * 3 + 2];
+        point.intensity = 1;
+        pointCloud_cam_cs->points.push_back(point);
+    }
+    pointCloud_cam_cs->width = (uint32_t)pointCloud_cam_cs->points.size();
+    pointCloud_cam_cs->height = 1;
+    pointCloud_cam_cs->is_dense = false;
+}
+
+void DepthEstimator::getPointsCloudImageCs(Eigen::Matrix2Xd& visiblePointsImageCs) {
+    // _points_cs_image_visible: the visible points' image coordinates in cloud order; flags and
+    // camera-frame coordinates come from the device, the per-point division is the debug view's only host work
+    std::vector<uint8_t> vis((size_t)std::max<long long>(_pointCount, 1));
+    std::vector<double> cam((size_t)std::max<long long>(_pointCount, 1) * 3);
+    int64_t nvis = 0;
+    int rc = mld_get_visible(_handle, vis.data(), &nvis);
+    if (rc != MLD_OK) rethrow(rc);
+    rc = mld_get_points_camera(_handle, cam.data());
+    if (rc != MLD_OK) rethrow(rc);
+    visiblePointsImageCs.resize(2, (int)nvis);
+    const double f = _camera->focalLength(), cx = _camera->principalPointX(), cy = _camera->principalPointY();
+    int k = 0;
+    for (long long i = 0; i < _pointCount; i++) {
+        if (!vis[(size_t)i]) continue;
+        const double X = cam[(size_t)i * 3], Y = cam[(size_t)i * 3 + 1], Z = cam[(size_t)i * 3 + 2];
+        visiblePointsImageCs(0, k) = ((f * X + 0.0 * Y) + cx * Z) / Z;
+        visiblePointsImageCs(1, k) = ((0.0 * X + f * Y) + cy * Z) / Z;
+        k++;
+    }
+}
+
+}  // namespace Mono_Lidar

@@ -1,0 +1,93 @@
+"""Shared helpers of the GPU parity tests: run the same inputs through the CUDA path (via the
+reference-shaped DepthEstimator mirror -> C ABI) and through the CPU oracle, and compare.
+
+Parity contract (BASELINE.json north_star): pixel indices, neighbour lists and status codes
+bit-exact; depths within 1e-4 relative."""
+import ctypes as C
+
+import numpy as np
+
+import oracle_lib as O
+from mono_lidar_depth_b200 import CameraPinhole, DepthEstimator, DepthEstimatorParameters, GroundPlane
+from mono_lidar_depth_b200._capi import MldParams
+
+DEPTH_RTOL = 1e-4
+
+
+def params_from_c(c: MldParams) -> DepthEstimatorParameters:
+    p = DepthEstimatorParameters()
+    C.memmove(C.byref(p.c_struct), C.byref(c), C.sizeof(MldParams))
+    return p
+
+
+def make_pair(c_params: MldParams, cam: CameraPinhole, T):
+    """(GPU estimator, oracle) configured identically."""
+    est = DepthEstimator()
+    est.InitConfig(params_from_c(c_params))
+    est.Initialize(cam, T)
+    orc = O.Oracle(c_params)
+    W, H = cam.getImageSize()
+    orc.initialize(W, H, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, T)
+    return est, orc
+
+
+def assert_depth_status_equal(d_gpu, s_gpu, d_ref, s_ref, what=""):
+    s_gpu = np.asarray(s_gpu)
+    s_ref = np.asarray(s_ref)
+    bad = np.nonzero(s_gpu != s_ref)[0]
+    assert len(bad) == 0, f"{what}: {len(bad)} status mismatches, first {bad[:5]} gpu {s_gpu[bad[:5]]} ref {s_ref[bad[:5]]}"
+    both_nan = np.isnan(d_gpu) & np.isnan(d_ref)
+    ok = both_nan | (np.abs(d_gpu - d_ref) <= DEPTH_RTOL * np.abs(d_ref))
+    bad = np.nonzero(~ok)[0]
+    assert len(bad) == 0, f"{what}: {len(bad)} depth mismatches, first {bad[:5]} gpu {d_gpu[bad[:5]]} ref {d_ref[bad[:5]]}"
+
+
+def compare_frame(est, orc, cloud, uv, plane=None, what="", check_map=True, neighbor_samples=64):
+    """plane: None or (coeffs[4], inlier raw indices)."""
+    gp = GroundPlane(plane[0], plane[1]) if plane is not None else None
+    est.setInputCloud(cloud, gp)
+    orc.set_cloud(cloud)
+    if check_map:
+        m_gpu = est.getPixelMap()
+        m_ref = orc.pixel_map_raw()
+        assert np.array_equal(m_gpu, m_ref), f"{what}: pixel map differs in {(m_gpu != m_ref).sum()} cells"
+    step = max(1, len(uv) // max(neighbor_samples, 1))
+    for u, v in uv[::step][:neighbor_samples]:
+        for sw, sh in ((1.0, 1.0), (2.0, 1.5)):
+            a = est.getNeighbors(float(u), float(v), sw, sh)
+            b = orc.neighbors(float(u), float(v), sw, sh)
+            assert np.array_equal(a, b), f"{what}: neighbours of ({u},{v}) scale ({sw},{sh}): {a} vs {b}"
+    d_gpu, s_gpu = est.CalculateDepth(uv, gp)
+    d_ref, s_ref = orc.calculate_depth(uv, plane)
+    assert_depth_status_equal(d_gpu, s_gpu, d_ref, s_ref, what)
+    return d_gpu, s_gpu
+
+
+def random_scene_cloud(rng, n, W, H, f, cx, cy, T, zmin=2.0, zmax=60.0, dense_patches=12):
+    """A cloud that fills the image densely enough to exercise every branch: random points plus a few
+    locally planar patches (several points per search window), expressed in the lidar frame."""
+    Tm = np.vstack([np.asarray(T, np.float64)[:3], [0, 0, 0, 1]])
+    Ti = np.linalg.inv(Tm)
+    pts = []
+    # planar patches: plane z = z0 + a*(x) + b*(y) in camera frame sampled on a pixel grid
+    for _ in range(dense_patches):
+        u0, v0 = rng.uniform(0, W - 40), rng.uniform(0, H - 30)
+        z0 = rng.uniform(zmin, zmax)
+        a, b = rng.uniform(-0.5, 0.5, 2)
+        us, vs = np.meshgrid(u0 + np.arange(0, 40, rng.choice([1.3, 2.1, 3.7])), v0 + np.arange(0, 30, rng.choice([1.7, 2.9, 4.3])))
+        us, vs = us.ravel(), vs.ravel()
+        xn, yn = (us - cx) / f, (vs - cy) / f
+        z = z0 / np.maximum(1e-3, (1 - a * xn - b * yn))
+        z = z + rng.normal(0, 0.01, z.shape)
+        pts.append(np.stack([xn * z, yn * z, z], 1))
+    m = n - sum(len(p) for p in pts)
+    if m > 0:
+        us, vs = rng.uniform(-20, W + 20, m), rng.uniform(-20, H + 20, m)
+        z = rng.uniform(-5.0, zmax, m)  # some behind the camera
+        pts.append(np.stack([(us - cx) / f * z, (vs - cy) / f * z, z], 1))
+    cam = np.concatenate(pts, 0)
+    rng.shuffle(cam)
+    lid = (Ti[:3, :3] @ cam.T).T + Ti[:3, 3]
+    out = np.zeros((len(lid), 4), np.float32)
+    out[:, :3] = lid.astype(np.float32)
+    return out

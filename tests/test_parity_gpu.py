@@ -1,0 +1,326 @@
+"""GPU parity: CUDA path (through the C ABI) against the CPU oracle on identical inputs."""
+import collections
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity_util as PU
+from mono_lidar_depth_b200 import CameraPinhole, DepthEstimator, DepthEstimatorParameters, ExceptionPclInvalid, GroundPlane, MldError, synth
+
+pytestmark = pytest.mark.gpu
+
+KT = synth.KITTI_T_LIDAR_TO_CAM
+
+
+def kitti_pair(c_params):
+    return PU.make_pair(c_params, synth.kitti_camera(), KT)
+
+
+def test_kitti_shape_frames_non_road():
+    """config[1] shape: HDL-64 ~120k points, 1241x376, 2000 integer features, yaml parameters, plane nullptr."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    hist = collections.Counter()
+    for frame in range(4):
+        cloud = synth.points_host(cfg, 11, frame)
+        uv = synth.features_host(cfg, 11, frame, 2000)
+        d, s = PU.compare_frame(est, orc, cloud, uv, what=f"frame {frame}")
+        hist.update(s.tolist())
+    assert hist[1] > 0 and hist[2] > 0 and hist[3] > 0  # the mix exercises success and failures
+
+
+def test_visible_and_camera_points_views():
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cloud = synth.points_host(synth.default_config(), 3, 0)
+    est.setInputCloud(cloud)
+    orc.set_cloud(cloud)
+    vis = est.getVisible()
+    assert np.array_equal(np.nonzero(vis)[0].astype(np.int32), orc.point_index())
+    cam_gpu = est.getPointsCloudCameraCs()
+    cam_ref = orc.points_camera()
+    assert np.array_equal(np.isnan(cam_gpu), np.isnan(cam_ref))
+    assert np.array_equal(cam_gpu[~np.isnan(cam_gpu)], cam_ref[~np.isnan(cam_ref)])  # bit-exact FP64 transform
+    img = est.getPointsCloudImageCs()
+    assert np.array_equal(img, orc.image_points_visible())
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_dense_random_scenes_all_branches(seed):
+    """Dense clouds with fractional feature coordinates: many neighbours per window, histogram blobs,
+    planarity / orthogonality / threshold failures."""
+    rng = np.random.RandomState(seed)
+    W, H, f, cx, cy = 320, 240, 300.0, 160.3, 119.6
+    cam = CameraPinhole(W, H, f, cx, cy)
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = PU.make_pair(p, cam, KT)
+    cloud = PU.random_scene_cloud(rng, 14000, W, H, f, cx, cy, KT, dense_patches=60)
+    uv = np.stack([rng.uniform(-10, W + 10, 3000), rng.uniform(-10, H + 10, 3000)], 1)
+    d, s = PU.compare_frame(est, orc, cloud, uv, what=f"dense {seed}")
+    hist = collections.Counter(s.tolist())
+    assert hist[1] > 50
+    assert len(hist) >= 5, hist
+
+
+@pytest.mark.parametrize(
+    "variant",
+    ["defaults", "no_hist", "no_trimax", "no_planar_check", "no_ortho", "adjust_mode", "absolute_local", "no_thresholds", "count_min3",
+     "pca", "big_window", "hist_min0", "no_cut_behind", "cut_behind_only"],
+)
+def test_parameter_variants(variant):
+    rng = np.random.RandomState(42)
+    W, H, f, cx, cy = 256, 192, 250.0, 128.0, 96.0
+    cam = CameraPinhole(W, H, f, cx, cy)
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    if variant == "defaults":
+        p = O.default_params()
+        p.do_use_ransac_plane = 0
+        p.viewray_plane_orthoganality_treshold = 0.05
+    elif variant == "no_hist":
+        p.do_use_histogram_segmentation = 0
+    elif variant == "no_trimax":
+        p.do_use_triangle_size_maximation = 0
+    elif variant == "no_planar_check":
+        p.do_check_triangleplanar_condition = 0
+    elif variant == "no_ortho":
+        p.viewray_plane_orthoganality_treshold = 0.0
+    elif variant == "adjust_mode":
+        p.treshold_depth_mode = 1
+        p.treshold_depth_local_mode = 1
+        p.treshold_depth_max = 20
+        p.treshold_depth_min = 5
+    elif variant == "absolute_local":
+        p.treshold_depth_local_valuetype = 0
+        p.treshold_depth_local_value = 0.05
+    elif variant == "no_thresholds":
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+    elif variant == "count_min3":
+        p.radiusSearch_count_min = 3
+    elif variant == "pca":
+        p.do_use_PCA = 1
+        p.pca_treshold_2_1_rel_min = 0.5
+    elif variant == "big_window":
+        p.pixelarea_search_witdh = 14
+        p.pixelarea_search_height = 17
+    elif variant == "hist_min0":
+        p.histogram_segmentation_min_pointcount = 0
+    elif variant == "no_cut_behind":
+        p.do_use_cut_behind_camera = 0
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+    elif variant == "cut_behind_only":
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+        p.do_check_triangleplanar_condition = 0
+        p.viewray_plane_orthoganality_treshold = 0.0
+    est, orc = PU.make_pair(p, cam, KT)
+    cloud = PU.random_scene_cloud(rng, 10000, W, H, f, cx, cy, KT, dense_patches=45)
+    uv = np.stack([rng.uniform(0, W, 2000), rng.uniform(0, H, 2000)], 1)
+    if variant == "pca":
+        # eigenvalue ratios are compared in float against thresholds (PCA.cpp:27-37): the warp-parallel
+        # scatter sums differ from the oracle's sequential sums in the last ulp, which can flip a
+        # status only when a ratio sits on a threshold; allow a handful of such flips.
+        est.setInputCloud(cloud)
+        orc.set_cloud(cloud)
+        d_gpu, s_gpu = est.CalculateDepth(uv)
+        d_ref, s_ref = orc.calculate_depth(uv)
+        same = s_gpu == s_ref
+        assert same.mean() > 0.999
+        PU.assert_depth_status_equal(d_gpu[same], s_gpu[same], d_ref[same], s_ref[same], "pca")
+    else:
+        PU.compare_frame(est, orc, cloud, uv, what=variant)
+
+
+@pytest.mark.parametrize("mode", ["mestimator", "leastsquares", "triangle"])
+def test_road_path_with_injected_plane(mode):
+    """Road features with the same plane + inlier set injected into both sides."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 1
+    p.plane_estimator_use_mestimator = 1 if mode == "mestimator" else 0
+    p.plane_estimator_use_leastsquares = 1 if mode == "leastsquares" else 0
+    p.plane_estimator_use_triangle_maximation = 1 if mode == "triangle" else 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    cloud = synth.points_host(cfg, 5, 1)
+    rng = np.random.RandomState(1)
+    # plane: the synthetic ground z = -1.73 in the lidar frame; inliers: every finite point near it
+    coeffs = np.array([0.0, 0.0, 1.0, 1.73], np.float32)
+    dist = np.abs(cloud[:, 2] + 1.73)
+    inl = np.nonzero(np.isfinite(dist) & (dist < 0.1))[0].astype(np.int32)
+    # features mostly in the lower image half, on the road
+    uv = np.stack([rng.randint(0, 1241, 3000), rng.randint(180, 376, 3000)], 1).astype(np.float64)
+    d, s = PU.compare_frame(est, orc, cloud, uv, plane=(coeffs, inl), what=mode)
+    hist = collections.Counter(s.tolist())
+    assert hist[16] > 100, hist  # SuccessRoad is exercised
+
+
+def test_road_path_sparse_inliers_and_far_gate():
+    p = O.yaml_params()
+    est, orc = kitti_pair(p)
+    cloud = synth.points_host(synth.default_config(), 6, 2)
+    coeffs = np.array([0.01, -0.02, 0.999, 1.70], np.float32)
+    fin = np.nonzero(np.isfinite(cloud[:, 2]))[0]
+    inl = fin[::7].astype(np.int32)
+    uv = synth.features_host(synth.default_config(), 6, 2, 2000)
+    PU.compare_frame(est, orc, cloud, uv, plane=(coeffs, inl), what="sparse inliers")
+
+
+def test_edge_cases_empty_nan_offimage():
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    # empty cloud
+    empty = np.zeros((0, 4), np.float32)
+    uv = np.array([[10.0, 10.0], [600.0, 200.0]])
+    est.setInputCloud(empty)
+    d, s = est.CalculateDepth(uv)
+    assert list(s) == [2, 2] and list(d) == [-1, -1]
+    # all-NaN cloud, off-image / NaN / huge features, zero features
+    cloud = np.full((1000, 4), np.nan, np.float32)
+    feats = np.array([[-50.0, -50.0], [5000.0, 100.0], [np.nan, 3.0], [1e12, 5.0], [0.0, 0.0], [1240.9, 375.9]])
+    PU.compare_frame(est, orc, cloud, feats, what="nan cloud", neighbor_samples=6)
+    d, s = est.CalculateDepth(np.zeros((0, 2)))
+    assert len(d) == 0 and len(s) == 0
+    # a real frame with the same odd features (window truncation at the borders, (-1,0) -> row 0)
+    cloud = synth.points_host(synth.default_config(), 9, 0)
+    feats = np.array([[-2.5, 200.0], [1243.0, 300.0], [620.0, -4.2], [620.0, 379.9], [0.0, 375.0], [1240.0, 170.0], [300.3, 250.7]])
+    PU.compare_frame(est, orc, cloud, feats, what="border features", neighbor_samples=7)
+
+
+def test_error_behaviour_mirrors_reference():
+    est = DepthEstimator()
+    with pytest.raises(RuntimeError, match="InitConfig"):
+        est.Initialize(synth.kitti_camera(), KT)
+    p = DepthEstimatorParameters.reference_yaml(0)
+    est.InitConfig(p)
+    with pytest.raises(RuntimeError, match="without 'initialize'"):
+        est.setInputCloud(np.zeros((3, 4), np.float32))
+    est.Initialize(synth.kitti_camera(), KT)
+    with pytest.raises(RuntimeError, match="without 'SetInputCloud'"):
+        est.CalculateDepth(np.zeros((1, 2)))
+    q = DepthEstimatorParameters.reference_yaml(0)
+    q.neighbor_search_mode = 2
+    e2 = DepthEstimator()
+    e2.InitConfig(q)
+    with pytest.raises(MldError, match="neighbor_search_mode has the invalid value"):
+        e2.Initialize(synth.kitti_camera(), KT)
+    r = DepthEstimatorParameters.reference_yaml(0)
+    r.do_use_depth_segmentation = 1  # shipped yaml value: region growing throws (DepthEstimator.cpp:608)
+    e3 = DepthEstimator()
+    e3.InitConfig(r)
+    e3.Initialize(synth.kitti_camera(), KT)
+    e3.setInputCloud(np.zeros((3, 4), np.float32))
+    with pytest.raises(MldError, match="Region growing not supported"):
+        e3.CalculateDepth(np.zeros((1, 2)))
+    s = DepthEstimatorParameters.reference_yaml(1)
+    e4 = DepthEstimator()
+    e4.InitConfig(s)
+    e4.Initialize(synth.kitti_camera(), KT)
+    with pytest.raises(ExceptionPclInvalid):
+        e4.setInputCloud(np.zeros((2, 4), np.float32))  # < 3 points with RANSAC requested (RansacPlane.cpp:44-50)
+
+
+def test_set_all_depths_to_zero():
+    p = O.yaml_params()
+    p.set_all_depths_to_zero = 1
+    est, orc = kitti_pair(p)
+    cloud = synth.points_host(synth.default_config(), 1, 0)
+    uv = synth.features_host(synth.default_config(), 1, 0, 100)
+    est.setInputCloud(cloud, GroundPlane([0, 0, 1, 1.7], np.zeros(0, np.int32)))
+    d, s = est.CalculateDepth(uv)
+    assert np.all(s == 1) and np.all(d == -1)
+
+
+def test_pointxyzi_stride_32():
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    c4 = synth.points_host(cfg, 2, 0)
+    c8 = np.zeros((len(c4), 8), np.float32)  # pcl::PointXYZI: xyz_ at 0..11, intensity at byte 16
+    c8[:, :3] = c4[:, :3]
+    c8[:, 4] = c4[:, 3]
+    uv = synth.features_host(cfg, 2, 0, 500)
+    est.setInputCloud(c8)
+    d8, s8 = est.CalculateDepth(uv)
+    est.setInputCloud(c4)
+    d4, s4 = est.CalculateDepth(uv)
+    assert np.array_equal(s8, s4) and np.array_equal(d8, d4)
+
+
+def test_dense_128_beam_shape():
+    """config[3] shape: 128 x 2032 points, 2048x1024 image, 20000 features."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    cam = synth.dense_camera()
+    est, orc = PU.make_pair(p, cam, KT)
+    cfg = synth.default_config(dense=True)
+    cloud = synth.points_host(cfg, 4, 0)
+    assert len(cloud) == 260096
+    uv = synth.features_host(cfg, 4, 0, 20000)
+    PU.compare_frame(est, orc, cloud, uv, what="dense 128")
+
+
+def test_synth_host_equals_device():
+    import torch
+
+    est = DepthEstimator()
+    est.InitConfig(DepthEstimatorParameters.reference_yaml(0))
+    for dense in (False, True):
+        cfg = synth.default_config(dense)
+        n = synth.points_per_frame(cfg)
+        F = 777
+        pts = torch.empty((3, n, 4), dtype=torch.float32, device="cuda")
+        uv = torch.empty((3, F, 2), dtype=torch.float64, device="cuda")
+        synth.points_device(est, cfg, 99, 5, 3, pts.data_ptr())
+        synth.features_device(est, cfg, 99, 5, 3, F, uv.data_ptr())
+        torch.cuda.synchronize()
+        for i in range(3):
+            h = synth.points_host(cfg, 99, 5 + i)
+            assert np.array_equal(h.view(np.uint32), pts[i].cpu().numpy().view(np.uint32)), f"dense={dense} frame {i}"
+            assert np.array_equal(synth.features_host(cfg, 99, 5 + i, F), uv[i].cpu().numpy())
+
+
+def test_batched_device_and_host_paths_match_per_frame():
+    """mld_process_frames_device / _host over a sequence == per-frame setInputCloud + CalculateDepth == oracle."""
+    import torch
+
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    n = synth.points_per_frame(cfg)
+    F, nframes = 2000, 37  # not a multiple of the chunk size
+    pts = torch.empty((nframes, n, 4), dtype=torch.float32, device="cuda")
+    uv = torch.empty((nframes, F, 2), dtype=torch.float64, device="cuda")
+    depth = torch.empty((nframes, F), dtype=torch.float64, device="cuda")
+    status = torch.empty((nframes, F), dtype=torch.int32, device="cuda")
+    synth.points_device(est, cfg, 21, 0, nframes, pts.data_ptr())
+    synth.features_device(est, cfg, 21, 0, nframes, F, uv.data_ptr())
+    torch.cuda.synchronize()
+    est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes,
+                            stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    d_dev, s_dev = depth.cpu().numpy(), status.cpu().numpy()
+    # host pipeline
+    pts_h, uv_h = pts.cpu().numpy(), uv.cpu().numpy()
+    d_host = np.empty((nframes, F), np.float64)
+    s_host = np.empty((nframes, F), np.int32)
+    est.processFramesHost(pts_h, uv_h, d_host, s_host)
+    assert np.array_equal(s_dev, s_host) and np.array_equal(d_dev, d_host)
+    for i in (0, 15, 16, 36):
+        orc.set_cloud(pts_h[i])
+        d_ref, s_ref = orc.calculate_depth(uv_h[i])
+        PU.assert_depth_status_equal(d_dev[i], s_dev[i], d_ref, s_ref, f"batched frame {i}")
+        est.setInputCloud(pts_h[i])
+        d1, s1 = est.CalculateDepth(uv_h[i])
+        assert np.array_equal(s1, s_dev[i]) and np.array_equal(d1, d_dev[i])
+    assert est.kernelLaunchCount() > 0
