@@ -1,7 +1,7 @@
 """ctypes binding of libmld_cuda.so (include/mld_c_api.h).
 
 The library is the product: if it is missing, or if no CUDA device is usable, every entry point
-raises -- there is no CPU fallback and nothing here ever imports oracle/.
+raises -- there is no CPU fallback and nothing here ever touches the CPU parity checker.
 """
 from __future__ import annotations
 

@@ -37,11 +37,15 @@ struct Slot {
     float* d_coeffs = nullptr;  size_t coeffs_bytes = 0;
     void* d_scratch = nullptr;  size_t scratch_bytes = 0;
     int* d_small = nullptr;     size_t small_bytes = 0;  // n_inliers | iterations | rc, per frame
+    int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
+    unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
+    MapCode mc = {0u, 0u};      // encoding of the maps currently held by this slot
 };
 
 template <typename T>
-cudaError_t ensure(T*& p, size_t& cap, size_t need) {
+cudaError_t ensure(T*& p, size_t& cap, size_t need, bool* changed = nullptr) {
     if (need <= cap && p != nullptr) return cudaSuccess;
+    if (changed) *changed = true;
     if (p) {
         cudaError_t e = cudaFree(p);
         if (e != cudaSuccess) return e;
@@ -66,7 +70,10 @@ struct mld_handle {
     bool initialized = false;
     bool have_cloud = false;
     int kcap = 0;
-    int chunk_frames = 16;
+    int chunk_frames = 64;
+    int feature_mode = 1;  // 1: thread per feature + warp-per-feature overflow pass; 0: warp per feature only
+    int overflow_blocks = 296;
+    bool use_tagged_maps = true;
     long long cur_n = 0;
     int cur_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
@@ -148,7 +155,10 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
         CK(ensure(s.d_depth, s.depth_bytes, (size_t)frames * (size_t)F * sizeof(double)));
         CK(ensure(s.d_status, s.status_bytes, (size_t)frames * (size_t)F * sizeof(int)));
     }
-    CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int)));
+    bool maps_changed = false;
+    CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int), &maps_changed));
+    if (maps_changed) s.epoch = 0;  // fresh memory holds no valid tags
+    CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)frames * (size_t)std::max(F, 1) + 1) * sizeof(int)));
     if (road) {
         const size_t words = (size_t)((n_points + 31) / 32);
         CK(ensure(s.d_bits, s.bits_bytes, (size_t)frames * words * sizeof(unsigned int)));
@@ -159,11 +169,52 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
     return MLD_OK;
 }
 
-// one chunk of frames on one stream: clear maps, K1, [K4], K2
+// Prepare the slot's maps for `frames` new frames: tagged mode bumps the epoch (and clears only when the
+// 14-bit epoch space is exhausted or the memory is fresh), plain mode clears every time.
+int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStream_t st, MapCode& mc) {
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    const bool tagged = h->use_tagged_maps && n_points <= (long long)(MLD_TAG_IDX_MASK + 1u);
+    if (!tagged) {
+        CK(cudaMemsetAsync(s.d_maps, 0xFF, (size_t)frames * WH * sizeof(unsigned int), st));
+        s.epoch = 0;
+        mc = MapCode{0u, 0u};
+    } else {
+        if (s.epoch == 0 || s.epoch >= MLD_TAG_MAX_EPOCH) {
+            // whole buffer: frames beyond this chunk may hold stale tags from a previous epoch cycle
+            CK(cudaMemsetAsync(s.d_maps, 0xFF, s.maps_bytes, st));
+            s.epoch = 0;
+        }
+        s.epoch++;
+        mc = MapCode{1u, MLD_TAG_MAX_EPOCH - s.epoch};
+    }
+    s.mc = mc;
+    return MLD_OK;
+}
+
+// K2: thread-per-feature kernel + warp-per-feature pass over its overflow list, or warp-per-feature only
+int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, const float* d_pts, int stride_f, long long pitch_pts,
+                    const double* d_uv, int F, double* d_depth, int* d_status, const float* coeffs, const unsigned int* bits,
+                    long long words, int frames) {
+    if (F <= 0 || frames <= 0) return MLD_OK;
+    if (h->feature_mode == 1) {
+        CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
+        CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs, bits,
+                                           words, frames, s.d_ovf + 1, s.d_ovf, st));
+        CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
+                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, h->overflow_blocks, st));
+        h->launches += 2;
+    } else {
+        CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
+                                    bits, words, frames, nullptr, nullptr, 0, st));
+        h->launches++;
+    }
+    return MLD_OK;
+}
+
+// one chunk of frames on one stream: [clear maps], K1, [K4], K2
 int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, long long n_points, long long pitch_pts,
                   int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
                   long long frame0, float* d_coeffs_out) {
-    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
     cudaEvent_t* ev = nullptr;
     if (h->prof_on && h->prof_used < MLD_PROF_MAX_CHUNKS) {
         if (h->prof_events.size() < (h->prof_used + 1) * 5) {
@@ -180,9 +231,11 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         h->prof_ransac_launches[h->prof_used] = 0;
     }
     if (ev) CK(cudaEventRecord(ev[0], st));
-    CK(cudaMemsetAsync(s.d_maps, 0xFF, (size_t)frames * WH * sizeof(unsigned int), st));
+    MapCode mc;
+    int rcm = begin_maps(h, s, frames, n_points, st, mc);
+    if (rcm) return rcm;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(mld_launch_project_scatter(h->dp, d_pts, stride_f, n_points, pitch_pts, s.d_maps, frames, st));
+    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, frames, st));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
     const float* coeffs = nullptr;
@@ -199,9 +252,8 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         bits = s.d_bits;
     }
     if (ev) CK(cudaEventRecord(ev[3], st));
-    CK(mld_launch_feature_depth(h->dp, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs, bits,
-                                words, frames, st));
-    if (F > 0) h->launches++;
+    int rcf = launch_features(h, s, mc, st, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames);
+    if (rcf) return rcf;
     if (ev) {
         CK(cudaEventRecord(ev[4], st));
         h->prof_used++;
@@ -410,6 +462,10 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     h->device = device;
     const char* env = getenv("MLD_CHUNK_FRAMES");
     if (env && atoi(env) > 0) h->chunk_frames = atoi(env);
+    env = getenv("MLD_FEATURE_MODE");  // "warp": warp-per-feature kernel only (A/B measurements)
+    if (env && strcmp(env, "warp") == 0) h->feature_mode = 0;
+    env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
+    if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
     DeviceGuard g(device);
     if (!g.ok) {
         delete h;
@@ -433,7 +489,7 @@ int mld_destroy(mld_handle* h) {
     for (auto& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
-        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -506,8 +562,12 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     if (h->kcap < 0)
         return fail(h, MLD_ERR_CAPACITY, "search window of " + std::to_string(area) + " pixels exceeds the neighbour capacity " +
                                              std::to_string(mld_neighbor_capacity()));
+    mld_setup_prefilter(d);
     DeviceGuard g(h->device);
     CK(mld_configure_feature_depth(h->kcap));
+    int sms = 148;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->overflow_blocks = 2 * sms;
+    for (auto& sl : h->slots) sl.epoch = 0;  // image size may have changed
     h->initialized = true;
     h->have_cloud = false;
     return MLD_OK;
@@ -601,10 +661,11 @@ int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_
     if (want_ransac && n < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, 0, 1, true, false);
     if (rc) return rc;
-    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
     if (n > 0) CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
-    CK(cudaMemsetAsync(s.d_maps, 0xFF, WH * sizeof(unsigned int), s.stream));
-    CK(mld_launch_project_scatter(h->dp, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps, 1, s.stream));
+    MapCode mc;
+    rc = begin_maps(h, s, 1, n, s.stream, mc);
+    if (rc) return rc;
+    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps, 1, s.stream));
     if (n > 0) h->launches++;
     h->cur_n = n;
     h->cur_stride_f = stride_bytes / 4;
@@ -649,6 +710,7 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
     const float* coeffs = nullptr;
     const unsigned int* bits = nullptr;
     std::vector<unsigned int> hb;
+    int rc = MLD_OK;
     if (plane && h->dp.road_mode != ROAD_NONE) {
         CK(ensure(s.d_bits, s.bits_bytes, (size_t)std::max<long long>(words, 1) * sizeof(unsigned int)));
         CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
@@ -663,9 +725,10 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
         bits = s.d_bits;
     }
     CK(cudaMemcpyAsync(s.d_uv, uv_host, (size_t)F * 2 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    CK(mld_launch_feature_depth(h->dp, h->kcap, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, n, s.d_maps, s.d_uv, F,
-                                s.d_depth, s.d_status, coeffs, bits, words, 1, s.stream));
-    h->launches++;
+    CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)F + 1) * sizeof(int)));
+    rc = launch_features(h, s, s.mc, s.stream, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, n, s.d_uv, F, s.d_depth,
+                         s.d_status, coeffs, bits, words, 1);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(depth_host, s.d_depth, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpyAsync(status_host, s.d_status, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
@@ -769,8 +832,13 @@ int mld_get_pixel_map(mld_handle* h, int32_t* out_host) {
     if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
     DeviceGuard g(h->device);
     Slot& s = h->slots[0];
-    CK(cudaMemcpyAsync(out_host, s.d_maps, (size_t)h->dp.W * (size_t)h->dp.H * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    CK(cudaMemcpyAsync(out_host, s.d_maps, WH * sizeof(int32_t), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaStreamSynchronize(s.stream));
+    for (size_t i = 0; i < WH; i++) {  // decode the epoch-tagged cells into raw indices / -1
+        unsigned int cell = (unsigned int)out_host[i];
+        out_host[i] = map_cell_valid(s.mc, cell) ? (int32_t)map_cell_index(s.mc, cell) : -1;
+    }
     return MLD_OK;
 }
 
@@ -783,7 +851,7 @@ int mld_get_neighbors(mld_handle* h, double u, double v, double scale_w, double 
     int dcap = std::min(cap, mld_neighbor_capacity());
     double hx = static_cast<double>(h->params.pixelarea_search_witdh) * 0.5 * static_cast<double>((float)scale_w);
     double hy = static_cast<double>(h->params.pixelarea_search_height) * 0.5 * static_cast<double>((float)scale_h);
-    CK(mld_launch_neighbors_debug(h->dp, s.d_maps, u, v, hx, hy, h->d_dbg + 1, dcap, h->d_dbg, s.stream));
+    CK(mld_launch_neighbors_debug(h->dp, s.mc, s.d_maps, u, v, hx, hy, h->d_dbg + 1, dcap, h->d_dbg, s.stream));
     h->launches++;
     int k = 0;
     CK(cudaMemcpyAsync(&k, h->d_dbg, sizeof(int), cudaMemcpyDeviceToHost, s.stream));

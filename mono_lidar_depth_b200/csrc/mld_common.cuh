@@ -66,7 +66,30 @@ struct DevParams {
     double road_dist_thr; // ransac_plane_point_distance_treshold
     double zx_min_rel;    // plane_estimator_z_x_min_relation
     int set_all_zero;
+    // FP32 pre-filter of K1 (see mld_project.cu): five linear forms g.(x,y,z)+h in the lidar point --
+    // z_cam, f*X+cx*Z, f*X+(cx-W)*Z, f*Y+cy*Z, f*Y+(cy-H)*Z -- with a rigorous float error bound
+    // G*(|x|+|y|+|z|)+H each. A point is dropped without any FP64 work only when one of the exact
+    // visibility tests is violated by more than that bound.
+    float pf_g[5][3], pf_h[5], pf_G[5], pf_H[5];
 };
+
+// pixel-map cell encoding. Tagged mode (clouds of <= 2^18 points): key = (tag << 18) | raw index
+// with tag = 0x3FFF - epoch; a newer epoch has a smaller tag, so atomicMin lets it overwrite every
+// stale cell and the 4*W*H-byte clear per frame disappears (one clear per 16383 uses of a map slot).
+// Plain mode (bigger clouds): key = raw index, map cleared to 0xFFFFFFFF before every use.
+#define MLD_TAG_SHIFT 18
+#define MLD_TAG_IDX_MASK 0x3FFFFu
+#define MLD_TAG_MAX_EPOCH 16383u
+struct MapCode {
+    unsigned int tagged;  // 0 plain, 1 tagged
+    unsigned int tag;     // current tag (tagged mode)
+};
+__host__ __device__ __forceinline__ bool map_cell_valid(const MapCode& mc, unsigned int cell) {
+    return mc.tagged ? ((cell >> MLD_TAG_SHIFT) == mc.tag) : (cell != MLD_EMPTY);
+}
+__host__ __device__ __forceinline__ unsigned int map_cell_index(const MapCode& mc, unsigned int cell) {
+    return mc.tagged ? (cell & MLD_TAG_IDX_MASK) : cell;
+}
 
 struct D3 {
     double x, y, z;

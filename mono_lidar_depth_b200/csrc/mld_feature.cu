@@ -28,6 +28,7 @@
 // HBM traffic per feature: 16 B read (u,v), 12 B written (depth f64 + status i32). Window reads
 // (<= 4*70 B) and the neighbour gather hit L2 (K1 just streamed the same frame).
 #include "mld_common.cuh"
+#include "mld_geometry.cuh"
 #include "mld_kernels.h"
 
 namespace {
@@ -49,7 +50,7 @@ __device__ __forceinline__ unsigned lanemask_lt() {
 // ---- A5: window scan + gather --------------------------------------------------------------
 // Returns the neighbour count k; slab[0..k) holds the camera-frame points in scan order.
 template <int KCAP>
-__device__ int gather_window(const DevParams& P, const unsigned int* __restrict__ map, const float* __restrict__ pts,
+__device__ int gather_window(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map, const float* __restrict__ pts,
                              int stride_f, double u, double v, double hx, double hy, int lane, const WarpSlab& s) {
     // NaN / out-of-int-range features are undefined behaviour in the reference ((int) casts of the
     // window edges); they are defined here as "empty window".
@@ -72,10 +73,11 @@ __device__ int gather_window(const DevParams& P, const unsigned int* __restrict_
             int rx = idx - ry * wc;
             cell = __ldg(&map[(long long)(y0 + ry) * P.W + (x0 + rx)]);
         }
-        unsigned m = __ballot_sync(MLD_FULL_MASK, cell != MLD_EMPTY);
-        if (cell != MLD_EMPTY) {
+        const bool hit = (idx < area) && map_cell_valid(mc, cell);
+        unsigned m = __ballot_sync(MLD_FULL_MASK, hit);
+        if (hit) {
             int pos = k + __popc(m & lt);
-            if (pos < KCAP) s.raw[pos] = (int)cell;
+            if (pos < KCAP) s.raw[pos] = (int)map_cell_index(mc, cell);
         }
         k += __popc(m);
     }
@@ -264,96 +266,6 @@ __device__ bool max_spanning_triangle(int n, int lane, const WarpSlab& s, int& c
     return true;
 }
 
-// ---- scalar geometry (identical on every lane) -------------------------------------------------
-struct Plane {
-    D3 n;
-    double off;
-};
-
-// A8 PlaneEstimationCheckPlanar::CheckPlanar
-__device__ bool check_planar(const D3& c1, const D3& c2, const D3& c3, double treshold) {
-    D3 e1 = normalized3(c2 - c1), e2 = normalized3(c3 - c1), e3 = normalized3(c3 - c2);
-    double l12 = norm3(cross3(e1, e2)), l13 = norm3(cross3(e1, e3)), l23 = norm3(cross3(e2, e3));
-    return (l12 >= treshold) && (l13 >= treshold) && (l23 >= treshold);
-}
-
-// Eigen::Hyperplane<double,3>::Through(p0,p1,p2)
-__device__ Plane plane_through(const D3& p0, const D3& p1, const D3& p2) {
-    D3 v0 = p2 - p0, v1 = p1 - p0;
-    D3 n = cross3(v0, v1);
-    double nn = norm3(n);
-    if (nn <= norm3(v0) * norm3(v1) * 2.220446049250313e-16) {
-        // degenerate: null direction of [v0; v1] (Eigen: 2x3 JacobiSVD, column 2 of V)
-        double w[3];
-        D3 ev[3];
-        eig3_sym_regs(v0.x * v0.x + v1.x * v1.x, v0.x * v0.y + v1.x * v1.y, v0.x * v0.z + v1.x * v1.z,
-                      v0.y * v0.y + v1.y * v1.y, v0.y * v0.z + v1.y * v1.z, v0.z * v0.z + v1.z * v1.z, w, ev);
-        int b = 0;
-        if (w[1] < w[b]) b = 1;
-        if (w[2] < w[b]) b = 2;
-        n = (b == 0) ? ev[0] : (b == 1 ? ev[1] : ev[2]);
-    } else {
-        n = n / nn;
-    }
-    return Plane{n, -dot3(p0, n)};
-}
-
-// A10 LinePlaneIntersection{Normal,OrthogonalTreshold}::GetIntersection
-__device__ bool line_plane(const Plane& pl, const D3& n0, const D3& n1, double ortho_treshold, double& depth) {
-    D3 dir = normalized3(n1 - n0);  // ParametrizedLine::Through
-    if (ortho_treshold > 0) {
-        D3 lineNormal = normalized3(n1);
-        D3 planeNormal = normalized3(pl.n);
-        if (!(fabs(dot3(planeNormal, lineNormal)) >= ortho_treshold)) return false;
-    }
-    double t = -(pl.off + dot3(pl.n, n0)) / dot3(pl.n, dir);
-    D3 pt = n0 + dir * t;
-    depth = pt.z;
-    return true;
-}
-
-// A9 CameraPinhole::getViewingRays (+ the caller's z flip, DepthEstimator.cpp:938-939)
-__device__ D3 viewing_ray(const DevParams& P, double u, double v) {
-    D3 d = D3{(P.Kinv[0] * u + P.Kinv[1] * v) + P.Kinv[2] * 1.0, (P.Kinv[3] * u + P.Kinv[4] * v) + P.Kinv[5] * 1.0,
-              (P.Kinv[6] * u + P.Kinv[7] * v) + P.Kinv[8] * 1.0};
-    d = normalized3(d);
-    if (d.z < 0) d = d * -1.0;
-    return d;
-}
-
-// A11 thresholds; returns 0 or the failing status, may clamp depth in Adjust mode
-__device__ int apply_tresholds(const DevParams& P, double& depth, double minZ, double maxZ) {
-    if (P.glob_en) {  // TresholdDepthGlobal::CheckInDepth
-        if (depth < P.glob_min) {
-            if (P.glob_mode == 0) return ST_TresholdDepthGlobalSmallerMin;
-            depth = P.glob_min;
-        } else if (depth > P.glob_max) {
-            if (P.glob_mode == 0) return ST_TresholdDepthGlobalGreaterMax;
-            depth = P.glob_max;
-        }
-    }
-    if (P.loc_en) {  // TresholdDepthLocal::CheckInBounds
-        double depthInterval = maxZ - minZ;
-        double lo, hi;
-        if (P.loc_type == 1) {
-            double r = depthInterval * P.loc_val;
-            lo = minZ - r;
-            hi = maxZ + r;
-        } else {
-            lo = minZ - P.loc_val;
-            hi = maxZ + P.loc_val;
-        }
-        if (depth < lo) {
-            if (P.loc_mode == 0) return ST_TresholdDepthLocalSmallerMin;
-            depth = lo;
-        } else if (depth > hi) {
-            if (P.loc_mode == 0) return ST_TresholdDepthLocalGreaterMax;
-            depth = hi;
-        }
-    }
-    return 0;
-}
-
 __device__ void slab_z_range(int n, int lane, const WarpSlab& s, double& minZ, double& maxZ) {
     double lo = 1.7976931348623157e308, hi = -1.7976931348623157e308;
     for (int i = lane; i < n; i += 32) {
@@ -524,12 +436,12 @@ __device__ int road_depth(const DevParams& P, double u, double v, int k2, int la
 
 // ---- per-feature driver (DepthEstimator.cpp:491-600) --------------------------------------------
 template <int KCAP>
-__device__ void feature_depth(const DevParams& P, const unsigned int* __restrict__ map, const float* __restrict__ pts,
+__device__ void feature_depth(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map, const float* __restrict__ pts,
                               int stride_f, double u, double v, const float* plane_coeffs,
                               const unsigned int* __restrict__ inlier_bits, int lane, const WarpSlab& s, int& status_out,
                               double& depth_out) {
     depth_out = -1;
-    int k = gather_window<KCAP>(P, map, pts, stride_f, u, v, P.hx1, P.hy1, lane, s);
+    int k = gather_window<KCAP>(P, mc, map, pts, stride_f, u, v, P.hx1, P.hy1, lane, s);
     if ((unsigned)k < (unsigned)P.count_min) {  // neighbors.size() < (uint)radiusSearch_count_min (:680)
         status_out = ST_RadiusSearchInsufficientPoints;
         return;
@@ -551,7 +463,7 @@ __device__ void feature_depth(const DevParams& P, const unsigned int* __restrict
     }
     if (plane_coeffs != nullptr && P.road_mode != ROAD_NONE) {
         __syncwarp();
-        int k2 = gather_window<KCAP>(P, map, pts, stride_f, u, v, P.hx2, P.hy2, lane, s);
+        int k2 = gather_window<KCAP>(P, mc, map, pts, stride_f, u, v, P.hx2, P.hy2, lane, s);
         if ((unsigned)k2 < (unsigned)P.count_min) {
             status_out = ST_RadiusSearchInsufficientPoints;
             return;
@@ -565,44 +477,59 @@ __device__ void feature_depth(const DevParams& P, const unsigned int* __restrict
 
 template <int KCAP, int K2_WARPS>
 __global__ void __launch_bounds__(K2_WARPS * 32)
-feature_depth_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+feature_depth_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
                      const unsigned int* __restrict__ maps, const double* __restrict__ uv, int F,
                      double* __restrict__ depth, int* __restrict__ status, const float* __restrict__ plane_coeffs,
-                     const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame) {
+                     const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame,
+                     const int* __restrict__ list, const int* __restrict__ list_count) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long frame = blockIdx.y;
-    const int fi = blockIdx.x * K2_WARPS + warp;
-    if (fi >= F) return;
-
     double* sx = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 3 * KCAP;
     WarpSlab s{sx, sx + KCAP, sx + 2 * KCAP,
                reinterpret_cast<int*>(reinterpret_cast<double*>(smem_raw) + (size_t)K2_WARPS * 3 * KCAP) + (size_t)warp * KCAP};
 
-    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
-    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
-    const long long o = frame * (long long)F + fi;
-    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
-        if (lane == 0) {
-            status[o] = 1;
-            depth[o] = -1;
-        }
-        return;
+    // direct mode: grid = (ceil(F / warps), frames), one feature per warp.
+    // list mode (overflow of the thread-per-feature kernel): warps stride a list of global feature ids.
+    long long item, item_end, item_step;
+    if (list != nullptr) {
+        item = (long long)blockIdx.x * K2_WARPS + warp;
+        item_end = *list_count;
+        item_step = (long long)gridDim.x * K2_WARPS;
+    } else {
+        const int fi = blockIdx.x * K2_WARPS + warp;
+        if (fi >= F) return;
+        item = (long long)blockIdx.y * F + fi;
+        item_end = item + 1;
+        item_step = 1;
     }
-    double u = uv[o * 2], v = uv[o * 2 + 1];
-    const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
-    const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
-    int st;
-    double dp;
-    feature_depth<KCAP>(P, map, fp, stride_f, u, v, pc, bits, lane, s, st, dp);
-    if (lane == 0) {
-        status[o] = st;
-        depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
+    for (; item < item_end; item += item_step) {
+        const long long o = list ? (long long)list[item] : item;
+        const long long frame = o / F;
+        const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+        const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+        if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
+            if (lane == 0) {
+                status[o] = 1;
+                depth[o] = -1;
+            }
+            continue;
+        }
+        double u = uv[o * 2], v = uv[o * 2 + 1];
+        const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
+        const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
+        int st;
+        double dp;
+        feature_depth<KCAP>(P, mc, map, fp, stride_f, u, v, pc, bits, lane, s, st, dp);
+        if (lane == 0) {
+            status[o] = st;
+            depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
+        }
+        __syncwarp();
     }
 }
 
 // debug: neighbour list of one feature in scan order (raw indices)
-__global__ void neighbors_debug_kernel(DevParams P, const unsigned int* __restrict__ map, double u, double v, double hx,
+__global__ void neighbors_debug_kernel(DevParams P, MapCode mc, const unsigned int* __restrict__ map, double u, double v, double hx,
                                        double hy, int* __restrict__ out, int cap, int* __restrict__ k_out) {
     const int lane = threadIdx.x;
     if (!(fabs(u) < 1e9) || !(fabs(v) < 1e9)) {
@@ -623,10 +550,11 @@ __global__ void neighbors_debug_kernel(DevParams P, const unsigned int* __restri
                 int ry = idx / wc, rx = idx - (idx / wc) * wc;
                 cell = map[(long long)(y0 + ry) * P.W + (x0 + rx)];
             }
-            unsigned m = __ballot_sync(MLD_FULL_MASK, cell != MLD_EMPTY);
-            if (cell != MLD_EMPTY) {
+            const bool hit = (idx < area) && map_cell_valid(mc, cell);
+            unsigned m = __ballot_sync(MLD_FULL_MASK, hit);
+            if (hit) {
                 int pos = k + __popc(m & lt);
-                if (pos < cap) out[pos] = (int)cell;
+                if (pos < cap) out[pos] = (int)map_cell_index(mc, cell);
             }
             k += __popc(m);
         }
@@ -635,14 +563,15 @@ __global__ void neighbors_debug_kernel(DevParams P, const unsigned int* __restri
 }
 
 template <int KCAP, int K2_WARPS>
-cudaError_t launch_feature(const DevParams& P, const float* d_pts, int stride_f, long long pitch_pts,
+cudaError_t launch_feature(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long pitch_pts,
                            const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
                            const float* d_plane_coeffs, const unsigned int* d_inlier_bits, long long words_per_frame,
-                           int nframes, cudaStream_t stream) {
+                           int nframes, const int* d_list, const int* d_list_count, int list_blocks, cudaStream_t stream) {
     constexpr size_t smem = (size_t)K2_WARPS * KCAP * (3 * sizeof(double) + sizeof(int));
-    dim3 grid((unsigned)((F + K2_WARPS - 1) / K2_WARPS), (unsigned)nframes);
+    dim3 grid = d_list ? dim3((unsigned)list_blocks, 1) : dim3((unsigned)((F + K2_WARPS - 1) / K2_WARPS), (unsigned)nframes);
     feature_depth_kernel<KCAP, K2_WARPS><<<grid, K2_WARPS * 32, smem, stream>>>(
-        P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs, d_inlier_bits, words_per_frame);
+        P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs, d_inlier_bits, words_per_frame,
+        d_list, d_list_count);
     return cudaGetLastError();
 }
 
@@ -661,21 +590,22 @@ int mld_feature_capacity_for(int max_area) {
     return -1;
 }
 
-cudaError_t mld_launch_feature_depth(const DevParams& P, int kcap, const float* d_pts, int stride_f, long long pitch_pts,
-                                     const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
-                                     const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
-                                     long long words_per_frame, int nframes, cudaStream_t stream) {
+cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int kcap, const float* d_pts, int stride_f,
+                                     long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F, double* d_depth,
+                                     int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, const int* d_list, const int* d_list_count,
+                                     int list_blocks, cudaStream_t stream) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
     switch (kcap) {
         case 96:
-            return launch_feature<96, 8>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                      d_inlier_bits, words_per_frame, nframes, stream);
+            return launch_feature<96, 8>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                         d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
         case 256:
-            return launch_feature<256, 8>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                       d_inlier_bits, words_per_frame, nframes, stream);
+            return launch_feature<256, 8>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                          d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
         case 1024:
-            return launch_feature<1024, 4>(P, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                        d_inlier_bits, words_per_frame, nframes, stream);
+            return launch_feature<1024, 4>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                           d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
         default:
             return cudaErrorInvalidValue;
     }
@@ -691,8 +621,8 @@ cudaError_t mld_configure_feature_depth(int kcap) {
     }
 }
 
-cudaError_t mld_launch_neighbors_debug(const DevParams& P, const unsigned int* d_map, double u, double v, double hx, double hy,
-                                       int* d_out, int cap, int* d_k, cudaStream_t stream) {
-    neighbors_debug_kernel<<<1, 32, 0, stream>>>(P, d_map, u, v, hx, hy, d_out, cap, d_k);
+cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, const unsigned int* d_map, double u, double v,
+                                       double hx, double hy, int* d_out, int cap, int* d_k, cudaStream_t stream) {
+    neighbors_debug_kernel<<<1, 32, 0, stream>>>(P, mc, d_map, u, v, hx, hy, d_out, cap, d_k);
     return cudaGetLastError();
 }

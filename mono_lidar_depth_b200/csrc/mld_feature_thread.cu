@@ -1,0 +1,388 @@
+// mld_feature_thread.cu -- K2 fast path: per-feature depth estimation, one THREAD per feature.
+//
+// Same reference routines as mld_feature.cu (DepthEstimator.cpp:491-600 and the helpers it calls);
+// the difference is the mapping. On lidar data the search window of a feature holds a handful of
+// points (KITTI shape: 7x10 pixels, ~2.4 x 5.3 pixels between returns => k ~ 2-8), so a warp per
+// feature leaves most lanes idle and executes the scalar FP64 tail 32 times redundantly (ncu of the
+// warp kernel: ~800 warp instructions per feature, 17 % occupancy). Here every lane owns a feature
+// and runs the reference's sequential algorithm on a small per-thread slab in shared memory
+// (interleaved [entry][thread], conflict free), which is also the order the oracle uses -- sums,
+// first-maximum scans and tie-breaks are literally sequential.
+//
+// Features whose window holds more than TCAP points (dense clouds / large windows) are not handled
+// here: they are appended to an overflow list and finished by the warp-per-feature kernel.
+#include "mld_common.cuh"
+#include "mld_geometry.cuh"
+#include "mld_kernels.h"
+
+namespace {
+
+constexpr int TCAP = 16;  // neighbours per thread
+constexpr int TBT = 64;   // threads (= features) per block
+
+struct TSlab {
+    double* x;
+    double* y;
+    double* z;
+    int* aux;  // raw indices during the gather, bin ids during the histogram
+    __device__ __forceinline__ D3 pt(int i) const { return D3{x[i * TBT], y[i * TBT], z[i * TBT]}; }
+    __device__ __forceinline__ void set(int i, const D3& p) const {
+        x[i * TBT] = p.x;
+        y[i * TBT] = p.y;
+        z[i * TBT] = p.z;
+    }
+};
+
+// A5: window scan (reference order: rows outer, columns inner) + gather. Returns k, or -1 when the
+// window holds more than TCAP points. inlier_mask (bit i = neighbour i is a plane inlier) is filled
+// when inlier_bits != nullptr.
+__device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map,
+                               const float* __restrict__ pts, int stride_f, double u, double v, double hx, double hy,
+                               const TSlab& s, const unsigned int* __restrict__ inlier_bits, unsigned int& inlier_mask) {
+    inlier_mask = 0u;
+    if (!(fabs(u) < 1e9) || !(fabs(v) < 1e9)) return 0;  // see mld_feature.cu: UB upstream, empty window here
+    double leftEdgeX = fmax(u - hx, 0.);
+    double rightEdgeX = fmin(u + hx, (double)(P.W - 1));
+    double topEdgeY = fmax(v - hy, 0.);
+    double bottomEdgeY = fmin(v + hy, (double)(P.H - 1));
+    int x0 = (int)leftEdgeX, x1 = (int)rightEdgeX, y0 = (int)topEdgeY, y1 = (int)bottomEdgeY;
+    int k = 0;
+    for (int y = y0; y <= y1; y++) {
+        const unsigned int* row = map + (long long)y * P.W;
+#pragma unroll 4
+        for (int x = x0; x <= x1; x++) {
+            unsigned int cell = __ldg(row + x);
+            if (map_cell_valid(mc, cell)) {
+                if (k < TCAP) s.aux[k * TBT] = (int)map_cell_index(mc, cell);
+                k++;
+            }
+        }
+    }
+    if (k > TCAP) return -1;
+    for (int i = 0; i < k; i++) {
+        int raw = s.aux[i * TBT];
+        float4 q = __ldg(reinterpret_cast<const float4*>(pts + (long long)raw * stride_f));
+        s.set(i, lidar_to_cam(P, q.x, q.y, q.z));
+        if (inlier_bits && ((inlier_bits[raw >> 5] >> (raw & 31)) & 1u)) inlier_mask |= 1u << i;
+    }
+    return k;
+}
+
+// A6: PointHistogram::FilterPointsMinDistBlob, sequential like the reference. Returns the segmented
+// count (slab compacted in place, order kept) or -1.
+__device__ int t_histogram_segment(const DevParams& P, int k, const TSlab& s) {
+    int maxDist = 0;
+    for (int i = 0; i < k; i++) {
+        double d = fmin(s.z[i * TBT], 999.);
+        if (d > maxDist) maxDist = (int)ceil(d);  // HistogramPointDepth.cpp:38-41
+    }
+    int binCount = (int)((maxDist) / P.bin_w + 1);  // :43
+    if (binCount <= 1) return -1;
+    int bmin = binCount;
+    for (int i = 0; i < k; i++) {
+        double value = fmin(fmin(s.z[i * TBT], 999.), 1e10);  // Histogram.cpp:29
+        int b = (int)fmin(fabs(value / P.bin_w), (double)binCount - 1.);
+        s.aux[i * TBT] = b;
+        bmin = min(bmin, b);
+    }
+    // first-local-maximum scan (:66-85); only the first run of occupied bins can decide it
+    int binMaxId = -1, binMaxVal = -1, binValue = 0;
+    if (bmin > 0 && 0 >= P.hist_min) {
+        binMaxVal = 0;
+        binMaxId = 0;
+    }
+    bool fail = false;
+    for (int b = bmin; b < binCount; b++) {
+        int lastBinValue = binValue;
+        int cnt = 0;
+        for (int i = 0; i < k; i++) cnt += (s.aux[i * TBT] == b) ? 1 : 0;
+        binValue = cnt;
+        if ((binValue > binMaxVal) && (binValue >= P.hist_min)) {
+            binMaxVal = binValue;
+            binMaxId = b;
+        } else if (binValue < binMaxVal)
+            break;
+        if ((lastBinValue > 0) && (binValue == 0)) {
+            fail = true;
+            break;
+        }
+        if (binValue == 0) break;
+    }
+    if (fail || binMaxId < 0) return -1;
+    double lowerBorder = binMaxId * P.bin_w - 0.0 * P.bin_w;   // :99
+    double higherBorder = (binMaxId)*P.bin_w + 1.0 * P.bin_w;  // :100
+    int n = 0;
+    for (int i = 0; i < k; i++) {
+        D3 p = s.pt(i);
+        double d = fmin(p.z, 999.);
+        if ((d >= lowerBorder) && (d < higherBorder)) {  // :116
+            if (n != i) s.set(n, p);
+            n++;
+        }
+    }
+    return n;
+}
+
+// A7: PlaneEstimationCalcMaxSpanningTriangle::CalculatePlaneCorners, sequential
+__device__ bool t_max_spanning_triangle(int n, const TSlab& s, int& ci, int& cj, int& ck) {
+    if (n < 3) return false;
+    int mi = -1, mj = -1;
+    double maxdist = -1;
+    for (int i = 0; i < n - 1; i++) {
+        D3 pi = s.pt(i);
+        for (int j = i + 1; j < n; j++) {
+            double dist = sqnorm3(pi - s.pt(j));
+            if (dist > maxdist) {
+                maxdist = dist;
+                mi = i;
+                mj = j;
+            }
+        }
+    }
+    if (maxdist <= 0.0) return false;
+    D3 pi = s.pt(mi), pj = s.pt(mj);
+    double maxdist2 = -1;
+    int mk = -1;
+    for (int k = 0; k < n - 1; k++) {  // the last point is never eligible (:71)
+        if (k == mi || k == mj) continue;
+        D3 pk = s.pt(k);
+        double dist1 = sqnorm3(pk - pi);
+        if (dist1 <= 0.0) continue;
+        double dist2 = sqnorm3(pk - pj);
+        if (dist2 <= 0.0) continue;
+        double dist = dist1 + dist2;
+        if (dist > maxdist2) {
+            maxdist2 = dist;
+            mk = k;
+        }
+    }
+    if (mi == -1 || mj == -1 || mk == -1) return false;
+    ci = mi;
+    cj = mj;
+    ck = mk;
+    return true;
+}
+
+__device__ void t_z_range(int n, const TSlab& s, double& minZ, double& maxZ) {
+    minZ = 1.7976931348623157e308;
+    maxZ = -1.7976931348623157e308;
+    for (int i = 0; i < n; i++) {
+        double z = s.z[i * TBT];
+        if (z < minZ) minZ = z;
+        if (z > maxZ) maxZ = z;
+    }
+}
+
+// weighted centroid + scatter in the reference's sequential order
+__device__ void t_weighted_scatter(int n, const TSlab& s, bool weighted, const Plane& prior, D3& center, double c[6]) {
+    D3 acc = D3{0, 0, 0};
+    double wsum = 0;
+    for (int i = 0; i < n; i++) {
+        D3 p = s.pt(i);
+        double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
+        acc = acc + p * w;
+        wsum += w;
+    }
+    center = acc / wsum;
+    c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0;
+    for (int i = 0; i < n; i++) {
+        D3 p = s.pt(i);
+        double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
+        D3 d = p - center;
+        c[0] += w * d.x * d.x; c[1] += w * d.x * d.y; c[2] += w * d.x * d.z;
+        c[3] += w * d.y * d.y; c[4] += w * d.y * d.z; c[5] += w * d.z * d.z;
+    }
+}
+
+// A12: CalculateDepthSegmented
+__device__ int t_depth_segmented(const DevParams& P, double u, double v, int n, const TSlab& s, double& depth_out) {
+    depth_out = -1;
+    D3 c1{}, c2{}, c3{};
+    if (!P.use_pca && P.use_tri_max) {
+        int i, j, k;
+        if (!t_max_spanning_triangle(n, s, i, j, k)) return ST_TriangleNotPlanarInsufficientPoints;
+        c1 = s.pt(i); c2 = s.pt(j); c3 = s.pt(k);
+    } else {
+        if (n < 3) return ST_HistogramNoLocalMax;
+        c1 = s.pt(0); c2 = s.pt(1); c3 = s.pt(2);
+    }
+    if (!P.use_pca && P.check_planar)
+        if (!check_planar(c1, c2, c3, P.crossnorm_thr)) return ST_TriangleNotPlanar;
+    D3 support = D3{0, 0, 0};
+    D3 dir = viewing_ray(P, u, v);
+    double depth;
+    if (P.use_pca) {
+        D3 mean;
+        double c[6];
+        Plane none{};
+        t_weighted_scatter(n, s, false, none, mean, c);
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs(c[0], c[1], c[2], c[3], c[4], c[5], w, ev);
+        int i0 = 0, i1 = 1, i2 = 2, tmp;
+        if (w[i1] < w[i0]) { tmp = i0; i0 = i1; i1 = tmp; }
+        if (w[i2] < w[i1]) { tmp = i1; i1 = i2; i2 = tmp; }
+        if (w[i1] < w[i0]) { tmp = i0; i0 = i1; i1 = tmp; }
+        double ev1 = w[i0], ev2 = w[i1], ev3 = w[i2];
+        float planarity = (float)((ev2 - ev1) / ev3);
+        float linearity = (float)((ev3 - ev2) / ev3);
+        if (planarity < P.pca_2_1_rel_min) return ST_PcaIsCubic;
+        if (linearity > P.pca_3_2_rel_max) return ST_PcaIsLine;
+        if (ev3 < P.pca_3_abs_min) return ST_PcaIsPoint;
+        D3 e0 = (i0 == 0) ? ev[0] : (i0 == 1 ? ev[1] : ev[2]);
+        D3 normal = e0 / norm3(e0);
+        Plane pl{normal, -dot3(normal, mean)};
+        if (!line_plane(pl, support, dir, P.ortho_thr, depth)) return ST_PlaneViewrayNotOrthogonal;
+    } else {
+        Plane pl = plane_through(c1, c2, c3);
+        if (!line_plane(pl, support, dir, P.ortho_thr, depth)) return ST_PlaneViewrayNotOrthogonal;
+    }
+    double minZ, maxZ;
+    t_z_range(n, s, minZ, maxZ);
+    int r = apply_tresholds(P, depth, minZ, maxZ);
+    if (r) return r;
+    if (depth < 0 && P.cut_behind) return ST_CornerBehindCamera;
+    depth_out = depth;
+    return ST_Success;
+}
+
+// R2 + R3/R4/R5
+__device__ int t_road_depth(const DevParams& P, double u, double v, int k2, const TSlab& s, const float* coeffs,
+                            unsigned int inlier_mask, int old_status, double& depth_out) {
+    depth_out = -1;
+    const float a = coeffs[0], b = coeffs[1], c = coeffs[2], d = coeffs[3];
+    for (int i = 0; i < k2; i++) {
+        D3 p = s.pt(i);
+        double lx = ((P.Ri[0] * p.x + P.Ri[1] * p.y) + P.Ri[2] * p.z) + P.ti[0];
+        double ly = ((P.Ri[3] * p.x + P.Ri[4] * p.y) + P.Ri[5] * p.z) + P.ti[1];
+        double lz = ((P.Ri[6] * p.x + P.Ri[7] * p.y) + P.Ri[8] * p.z) + P.ti[2];
+        float fx = (float)lx, fy = (float)ly, fz = (float)lz;
+        float sd = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, fx), __fmul_rn(b, fy)), __fmul_rn(c, fz)), d);
+        if (fabs((double)sd) > P.road_dist_thr) return old_status;  // DepthEstimator.cpp:814-815
+    }
+    int n = 0;
+    for (int i = 0; i < k2; i++) {
+        if ((inlier_mask >> i) & 1u) {
+            if (n != i) s.set(n, s.pt(i));
+            n++;
+        }
+    }
+    if (n < 3) return old_status;
+    Plane pl;
+    if (P.road_mode == ROAD_TRIANGLE) {
+        int i, j, k;
+        if (!t_max_spanning_triangle(n, s, i, j, k)) return ST_RadiusSearchInsufficientPoints;
+        double loX = 1.7976931348623157e308, hiX = -1.7976931348623157e308, loZ = loX, hiZ = hiX;
+        for (int q = 0; q < n; q++) {
+            double x = s.x[q * TBT], z = s.z[q * TBT];
+            if (x < loX) loX = x;
+            if (x > hiX) hiX = x;
+            if (z < loZ) loZ = z;
+            if (z > hiZ) hiZ = z;
+        }
+        double relation = (hiZ - loZ) / (hiX - loX);
+        if (!(relation >= P.zx_min_rel)) return ST_InsufficientRoadPoints;
+        pl = plane_through(s.pt(i), s.pt(j), s.pt(k));
+    } else {
+        Plane prior{normalized3(D3{(double)a, (double)b, (double)c}), (double)d};
+        D3 center;
+        double cv[6];
+        t_weighted_scatter(n, s, P.road_mode == ROAD_MESTIMATOR, prior, center, cv);
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs(cv[0], cv[1], cv[2], cv[3], cv[4], cv[5], w, ev);
+        int bi = 0;
+        if (w[1] < w[bi]) bi = 1;
+        if (w[2] < w[bi]) bi = 2;
+        D3 nrm = normalized3((bi == 0) ? ev[0] : (bi == 1 ? ev[1] : ev[2]));
+        pl = Plane{nrm, -dot3(nrm, center)};
+    }
+    D3 support = D3{0, 0, 0};
+    D3 dir = viewing_ray(P, u, v);
+    double depth;
+    line_plane(pl, dir, support, 0.0, depth);
+    double minZ, maxZ;
+    t_z_range(n, s, minZ, maxZ);
+    int r = apply_tresholds(P, depth, minZ, maxZ);
+    if (r) return r;
+    depth_out = depth;
+    return ST_SuccessRoad;
+}
+
+constexpr int ST_OVERFLOW = -1;
+
+__global__ void __launch_bounds__(TBT)
+feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                            const unsigned int* __restrict__ maps, const double* __restrict__ uv, int F,
+                            double* __restrict__ depth, int* __restrict__ status, const float* __restrict__ plane_coeffs,
+                            const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame,
+                            int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
+    __shared__ double sx[TCAP * TBT], sy[TCAP * TBT], sz[TCAP * TBT];
+    __shared__ int saux[TCAP * TBT];
+    const int fi = blockIdx.x * TBT + threadIdx.x;
+    if (fi >= F) return;
+    const long long frame = blockIdx.y;
+    const long long o = frame * (long long)F + fi;
+    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
+        status[o] = 1;
+        depth[o] = -1;
+        return;
+    }
+    TSlab s{sx + threadIdx.x, sy + threadIdx.x, sz + threadIdx.x, saux + threadIdx.x};
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+    const double u = f2.x, v = f2.y;
+    const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
+    const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
+
+    int st = ST_Unspecified;
+    double dp = -1;
+    unsigned int mask;
+    int k = t_gather_window(P, mc, map, fp, stride_f, u, v, P.hx1, P.hy1, s, nullptr, mask);
+    if (k < 0) {
+        st = ST_OVERFLOW;
+    } else if ((unsigned)k < (unsigned)P.count_min) {
+        st = ST_RadiusSearchInsufficientPoints;
+    } else {
+        int n = k;
+        if (P.use_hist) {
+            n = t_histogram_segment(P, k, s);
+            if (n < 0) st = ST_HistogramNoLocalMax;
+        }
+        if (st != ST_HistogramNoLocalMax) st = t_depth_segmented(P, u, v, n, s, dp);
+        if (st != ST_Success && pc != nullptr && P.road_mode != ROAD_NONE) {
+            int k2 = t_gather_window(P, mc, map, fp, stride_f, u, v, P.hx2, P.hy2, s, bits, mask);
+            if (k2 < 0)
+                st = ST_OVERFLOW;
+            else if ((unsigned)k2 < (unsigned)P.count_min)
+                st = ST_RadiusSearchInsufficientPoints;
+            else
+                st = t_road_depth(P, u, v, k2, s, pc, mask, st, dp);
+        }
+    }
+    if (st == ST_OVERFLOW) {
+        int slot = atomicAdd(overflow_count, 1);
+        overflow_list[slot] = (int)o;  // finished by the warp-per-feature kernel
+        return;
+    }
+    status[o] = st;
+    depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
+}
+
+}  // namespace
+
+int mld_thread_feature_capacity(void) { return TCAP; }
+
+cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
+                                            long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F,
+                                            double* d_depth, int* d_status, const float* d_plane_coeffs,
+                                            const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
+                                            int* d_overflow_list, int* d_overflow_count, cudaStream_t stream) {
+    if (F <= 0 || nframes <= 0) return cudaSuccess;
+    dim3 grid((unsigned)((F + TBT - 1) / TBT), (unsigned)nframes);
+    feature_depth_thread_kernel<<<grid, TBT, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status,
+                                                         d_plane_coeffs, d_inlier_bits, words_per_frame, d_overflow_list,
+                                                         d_overflow_count);
+    return cudaGetLastError();
+}

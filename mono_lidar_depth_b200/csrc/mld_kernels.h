@@ -7,22 +7,35 @@
 #include "mld_c_api.h"
 
 struct DevParams;
+struct MapCode;
 
 // K1 (mld_project.cu)
-cudaError_t mld_launch_project_scatter(const DevParams& P, const float* d_pts, int stride_f, long long n,
+void mld_setup_prefilter(DevParams& P);
+cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, int nframes, cudaStream_t stream);
 cudaError_t mld_launch_visible_debug(const DevParams& P, const float* d_pts, int stride_f, long long n,
                                      unsigned char* d_visible, double* d_cam, cudaStream_t stream);
 
-// K2/K3 (mld_feature.cu)
+// K2/K3, warp per feature (mld_feature.cu). d_list == nullptr: every feature of every frame;
+// otherwise the warps of list_blocks blocks stride the *d_list_count global feature ids in d_list.
 int mld_feature_capacity_for(int max_area);
 cudaError_t mld_configure_feature_depth(int kcap);
-cudaError_t mld_launch_feature_depth(const DevParams& P, int kcap, const float* d_pts, int stride_f, long long pitch_pts,
-                                     const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
-                                     const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
-                                     long long words_per_frame, int nframes, cudaStream_t stream);
-cudaError_t mld_launch_neighbors_debug(const DevParams& P, const unsigned int* d_map, double u, double v, double hx, double hy,
-                                       int* d_out, int cap, int* d_k, cudaStream_t stream);
+cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int kcap, const float* d_pts, int stride_f,
+                                     long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F, double* d_depth,
+                                     int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, const int* d_list, const int* d_list_count,
+                                     int list_blocks, cudaStream_t stream);
+cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, const unsigned int* d_map, double u, double v,
+                                       double hx, double hy, int* d_out, int cap, int* d_k, cudaStream_t stream);
+
+// K2/K3, thread per feature (mld_feature_thread.cu): features whose window holds more than
+// mld_thread_feature_capacity() points are appended to d_overflow_list (global feature ids).
+int mld_thread_feature_capacity(void);
+cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
+                                            long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F,
+                                            double* d_depth, int* d_status, const float* d_plane_coeffs,
+                                            const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
+                                            int* d_overflow_list, int* d_overflow_count, cudaStream_t stream);
 
 // K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
 struct RansacConfig {

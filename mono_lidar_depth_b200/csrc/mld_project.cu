@@ -9,11 +9,13 @@
 // The reference walks the visible points in cloud order and writes a pixel only while it is still
 // empty and the point has z_cam > 0 (NeighborFinderPixel.cpp:51): the winner of a pixel is the point
 // with the smallest raw index among those that qualify. That is an order-independent reduction, so
-// it is done with atomicMin(raw index) on a map pre-filled with 0xFFFFFFFF -- deterministic and
-// bit-exact whatever the thread schedule.
+// it is done with atomicMin on the (epoch-tagged) raw index -- deterministic and bit-exact whatever
+// the thread schedule.
 //
-// HBM traffic per frame: 16 B (float4) per point read once, streaming; the 4*W*H-byte map is cleared
-// by a memset node and touched by ~N_visible L2 atomics.
+// Roofline: HBM. 16 B (float4) per point are read once, streaming; ~80 % of a 360-degree sweep
+// never reaches the image, so each point first goes through an FP32 pre-filter (5 linear forms with
+// rigorous error bounds, ~25 FP32 ops) and only the survivors pay the exact FP64 transform and the
+// two FP64 divisions whose truncated results index the map.
 #include "mld_common.cuh"
 #include "mld_kernels.h"
 
@@ -22,11 +24,10 @@ namespace {
 constexpr int K1_THREADS = 256;
 constexpr int K1_PPT = 4;  // points per thread: four independent 16-byte loads in flight
 
-// projection of one point; returns the pixel offset or -1 when the point does not enter the map
+// exact projection of one point; returns the pixel offset or -1 when the point does not enter the map
 __device__ __forceinline__ int project_pixel(const DevParams& P, float x, float y, float z, bool need_front) {
     D3 c = lidar_to_cam(P, x, y, z);
-    // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51); testing it
-    // first skips both divisions for everything behind the image plane
+    // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51)
     if (need_front && !(c.z > 0.0)) return -1;
     // K * p with K = [f 0 cx; 0 f cy; 0 0 1] evaluated term by term like Eigen's product
     // (camera_pinhole.h:88), then colwise().hnormalized() = division by the third row (:90)
@@ -42,13 +43,32 @@ __device__ __forceinline__ int project_pixel(const DevParams& P, float x, float 
     return (int)v * P.W + (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
 }
 
+// FP32 pre-filter: true when the point certainly fails one of  z_cam > 0, u > 0, u < W, v > 0, v < H
+// (or is not finite, which fails all of them in the exact path as well).
+__device__ __forceinline__ bool surely_outside(const DevParams& P, float x, float y, float z) {
+    float S = fabsf(x) + fabsf(y) + fabsf(z);
+    if (!(S < 3.0e38f)) return true;  // NaN or inf coordinate: never visible
+    float val[5], err[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        val[k] = fmaf(P.pf_g[k][0], x, fmaf(P.pf_g[k][1], y, fmaf(P.pf_g[k][2], z, P.pf_h[k])));
+        err[k] = fmaf(P.pf_G[k], S, P.pf_H[k]);
+    }
+    return (val[0] + err[0] < 0.f) ||  // z_cam < 0
+           (val[1] + err[1] < 0.f) ||  // f*X + cx*Z < 0          <=> u < 0
+           (val[2] - err[2] > 0.f) ||  // f*X + (cx-W)*Z > 0      <=> u > W
+           (val[3] + err[3] < 0.f) ||  // f*Y + cy*Z < 0          <=> v < 0
+           (val[4] - err[4] > 0.f);    // f*Y + (cy-H)*Z > 0      <=> v > H
+}
+
 __global__ void __launch_bounds__(K1_THREADS)
-project_scatter_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
+project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
                        unsigned int* __restrict__ maps) {
     const long long frame = blockIdx.y;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
     const long long base = (long long)blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
+    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
 
     float4 p[K1_PPT];
 #pragma unroll
@@ -57,14 +77,15 @@ project_scatter_kernel(DevParams P, const float* __restrict__ pts, int stride_f,
         if (i < n)
             p[j] = ld_stream_f4(fp + i * stride_f);
         else
-            p[j] = make_float4(0.f, 0.f, -1.f, 0.f);
+            p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int j = 0; j < K1_PPT; j++) {
         long long i = base + (long long)j * K1_THREADS;
         if (i >= n) continue;
+        if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
         int off = project_pixel(P, p[j].x, p[j].y, p[j].z, true);
-        if (off >= 0) atomicMin(&map[off], (unsigned int)i);
+        if (off >= 0) atomicMin(&map[off], hi | (unsigned int)i);
     }
 }
 
@@ -86,11 +107,54 @@ __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts,
 
 }  // namespace
 
-cudaError_t mld_launch_project_scatter(const DevParams& P, const float* d_pts, int stride_f, long long n,
+// Host side of the pre-filter: the five linear forms in double, rounded to float, with bounds that
+// cover (a) rounding the coefficients to float, (b) the four float operations of the evaluation and
+// (c) the (far smaller) rounding of the exact FP64 path itself. 16 * 2^-24 leaves a factor > 2 of slack.
+void mld_setup_prefilter(DevParams& P) {
+    const double W = (double)P.W, H = (double)P.H;
+    double g[5][3], h[5];
+    for (int j = 0; j < 3; j++) {
+        g[0][j] = P.R[6 + j];
+        g[1][j] = P.f * P.R[0 + j] + P.cx * P.R[6 + j];
+        g[2][j] = P.f * P.R[0 + j] + (P.cx - W) * P.R[6 + j];
+        g[3][j] = P.f * P.R[3 + j] + P.cy * P.R[6 + j];
+        g[4][j] = P.f * P.R[3 + j] + (P.cy - H) * P.R[6 + j];
+    }
+    h[0] = P.t[2];
+    h[1] = P.f * P.t[0] + P.cx * P.t[2];
+    h[2] = P.f * P.t[0] + (P.cx - W) * P.t[2];
+    h[3] = P.f * P.t[1] + P.cy * P.t[2];
+    h[4] = P.f * P.t[1] + (P.cy - H) * P.t[2];
+    const double eps = 16.0 / 16777216.0;
+    for (int k = 0; k < 5; k++) {
+        double gmax = 0;
+        for (int j = 0; j < 3; j++) {
+            P.pf_g[k][j] = (float)g[k][j];
+            // the exact path evaluates f*X + c*Z from separately rounded terms: bound with the parts' magnitudes
+            gmax = fmax(gmax, fabs(g[k][j]));
+        }
+        // |f*R0j| + |c*R2j| can exceed |f*R0j + c*R2j| when the terms cancel; use the un-cancelled magnitude
+        double gabs = gmax;
+        if (k > 0) {
+            const double c = (k == 1) ? P.cx : (k == 2) ? (P.cx - W) : (k == 3) ? P.cy : (P.cy - H);
+            const int row = (k <= 2) ? 0 : 3;
+            double m = 0;
+            for (int j = 0; j < 3; j++) m = fmax(m, fabs(P.f * P.R[row + j]) + fabs(c * P.R[6 + j]));
+            gabs = m;
+            P.pf_H[k] = (float)(eps * (fabs(P.f * P.t[row / 3]) + fabs(c * P.t[2])) * 1.0000002 + 1e-30);
+        } else {
+            P.pf_H[k] = (float)(eps * fabs(h[0]) * 1.0000002 + 1e-30);
+        }
+        P.pf_h[k] = (float)h[k];
+        P.pf_G[k] = (float)(eps * gabs * 1.0000002 + 1e-30);
+    }
+}
+
+cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, int nframes, cudaStream_t stream) {
     if (n <= 0 || nframes <= 0) return cudaSuccess;
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
-    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, d_pts, stride_f, n, pitch_pts, d_maps);
+    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, n, pitch_pts, d_maps);
     return cudaGetLastError();
 }
 

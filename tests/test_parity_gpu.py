@@ -324,3 +324,74 @@ def test_batched_device_and_host_paths_match_per_frame():
         d1, s1 = est.CalculateDepth(uv_h[i])
         assert np.array_equal(s1, s_dev[i]) and np.array_equal(d1, d_dev[i])
     assert est.kernelLaunchCount() > 0
+
+
+@pytest.mark.parametrize("mode", ["warp", "untagged"])
+def test_alternative_kernel_modes(mode, monkeypatch):
+    """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp) and cleared (un-tagged) pixel maps
+    (MLD_TAGGED_MAPS=0) give the same results as the default thread-per-feature + epoch-tag path."""
+    if mode == "warp":
+        monkeypatch.setenv("MLD_FEATURE_MODE", "warp")
+    else:
+        monkeypatch.setenv("MLD_TAGGED_MAPS", "0")
+    p = O.yaml_params()
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    cloud = synth.points_host(cfg, 13, 0)
+    uv = synth.features_host(cfg, 13, 0, 2000)
+    dist = np.abs(cloud[:, 2] + 1.73)
+    inl = np.nonzero(np.isfinite(dist) & (dist < 0.1))[0].astype(np.int32)
+    PU.compare_frame(est, orc, cloud, uv, plane=(np.array([0, 0, 1, 1.73], np.float32), inl), what=mode)
+    rng = np.random.RandomState(5)
+    W, H, f, cx, cy = 320, 240, 300.0, 160.3, 119.6
+    q = O.yaml_params()
+    q.do_use_ransac_plane = 0
+    est2, orc2 = PU.make_pair(q, CameraPinhole(W, H, f, cx, cy), KT)
+    cloud2 = PU.random_scene_cloud(rng, 14000, W, H, f, cx, cy, KT, dense_patches=60)
+    uv2 = np.stack([rng.uniform(-10, W + 10, 3000), rng.uniform(-10, H + 10, 3000)], 1)
+    PU.compare_frame(est2, orc2, cloud2, uv2, what=mode + " dense")
+
+
+def test_overflow_features_finish_on_the_warp_kernel():
+    """Windows with more neighbours than the thread-per-feature kernel holds (16) fall through to the
+    warp-per-feature pass; a dense wall makes most windows overflow."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    W, H, f = 160, 120, 200.0
+    cam = CameraPinhole(W, H, f, 80.0, 60.0)
+    est, orc = PU.make_pair(p, cam, np.eye(4)[:3])
+    us, vs = np.meshgrid(np.arange(1, W - 1) + 0.5, np.arange(1, H - 1) + 0.5)
+    rng = np.random.RandomState(3)
+    z = 9.0 + 0.002 * us.ravel() + rng.normal(0, 0.003, us.size)
+    cloud = np.stack([(us.ravel() - 80.0) / f * z, (vs.ravel() - 60.0) / f * z, z, np.zeros_like(z)], 1).astype(np.float32)
+    uv = np.stack([rng.uniform(0, W, 1500), rng.uniform(0, H, 1500)], 1)
+    d, s = PU.compare_frame(est, orc, cloud, uv, what="overflow")
+    ks = [len(orc.neighbors(u, v)) for u, v in uv[:50]]
+    assert max(ks) > 16
+    assert (s == 1).mean() > 0.5
+
+
+def test_epoch_tag_wraparound():
+    """The pixel map is cleared only when the 14-bit epoch tag is exhausted (16383 uses): run past the
+    wrap on a tiny image and check the map after every few hundred clouds and around the wrap."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    W, H, f = 48, 32, 60.0
+    cam = CameraPinhole(W, H, f, 24.0, 16.0)
+    est, orc = PU.make_pair(p, cam, np.eye(4)[:3])
+    rng = np.random.RandomState(0)
+    clouds = []
+    for i in range(7):
+        n = 40 + 10 * i
+        us, vs = rng.uniform(0, W, n), rng.uniform(0, H, n)
+        z = rng.uniform(2, 20, n)
+        clouds.append(np.stack([(us - 24.0) / f * z, (vs - 16.0) / f * z, z, np.zeros(n)], 1).astype(np.float32))
+    refs = []
+    for c in clouds:
+        orc.set_cloud(c)
+        refs.append(orc.pixel_map_raw())
+    for it in range(16500):
+        j = it % 7
+        est.setInputCloud(clouds[j])
+        if it % 997 == 0 or 16370 <= it <= 16400:
+            assert np.array_equal(est.getPixelMap(), refs[j]), it

@@ -1,0 +1,57 @@
+"""The source-compatible C++ DepthEstimator shim (shim/) driven the way tracklets_depth drives the
+reference, diffed against the oracle."""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity_util as PU
+from mono_lidar_depth_b200 import synth
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_shim_builds_against_stub_headers():
+    subprocess.check_call(["make", "-C", str(ROOT / "shim")])
+    assert (ROOT / "shim" / "libmonolidar_fusion_b200.so").exists()
+    assert (ROOT / "shim" / "shim_selftest").exists()
+    out = subprocess.check_output(["nm", "-DC", str(ROOT / "shim" / "libmonolidar_fusion_b200.so")], text=True)
+    for sym in ("Mono_Lidar::DepthEstimator::Initialize", "Mono_Lidar::DepthEstimator::InitConfig",
+                "Mono_Lidar::DepthEstimator::setInputCloud", "Mono_Lidar::DepthEstimator::CalculateDepth",
+                "Mono_Lidar::RansacPlane::CalculateInliersPlane"):
+        assert sym in out, sym
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_plane", [0, 1])
+def test_shim_matches_oracle(tmp_path, use_plane):
+    subprocess.check_call(["make", "-C", str(ROOT / "shim")])
+    cfg = synth.default_config()
+    cloud = synth.points_host(cfg, 77, 0)
+    uv = synth.features_host(cfg, 77, 0, 2000)
+    cloud.tofile(tmp_path / "pts.f32")
+    uv.tofile(tmp_path / "uv.f64")
+    r = subprocess.run([str(ROOT / "shim" / "shim_selftest"), str(tmp_path / "pts.f32"), str(tmp_path / "uv.f64"),
+                        str(tmp_path / "d.f64"), str(tmp_path / "s.i32"), str(use_plane), str(tmp_path / "plane.bin")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    d = np.fromfile(tmp_path / "d.f64", np.float64)
+    s = np.fromfile(tmp_path / "s.i32", np.int32)
+    p = O.yaml_params()
+    p.do_use_ransac_plane = use_plane
+    orc = O.Oracle(p)
+    cam = synth.kitti_camera()
+    orc.initialize(1241, 376, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
+    orc.set_cloud(cloud)
+    plane = None
+    if use_plane:
+        raw = np.fromfile(tmp_path / "plane.bin", np.uint8)
+        coeffs = raw[:16].view(np.float32)
+        inl = raw[16:].view(np.int32)
+        plane = (coeffs, inl)
+        rc, c_ref, inl_ref, _ = O.ransac_plane(p, cloud, 99)
+        assert rc == 0 and np.array_equal(inl, inl_ref)
+    d_ref, s_ref = orc.calculate_depth(uv, plane)
+    PU.assert_depth_status_equal(d, s, d_ref, s_ref, f"shim plane={use_plane}")
