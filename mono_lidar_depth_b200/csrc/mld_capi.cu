@@ -38,6 +38,7 @@ struct Slot {
     void* d_scratch = nullptr;  size_t scratch_bytes = 0;
     int* d_small = nullptr;     size_t small_bytes = 0;  // n_inliers | iterations | rc, per frame
     int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
+    unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
     unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
     MapCode mc = {0u, 0u};      // encoding of the maps currently held by this slot
 };
@@ -159,6 +160,7 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
     CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int), &maps_changed));
     if (maps_changed) s.epoch = 0;  // fresh memory holds no valid tags
     CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)frames * (size_t)std::max(F, 1) + 1) * sizeof(int)));
+    CK(ensure(s.d_occ, s.occ_bytes, (size_t)frames * (size_t)occ_words_per_row(h->dp.W) * (size_t)h->dp.H * sizeof(unsigned int)));
     if (road) {
         const size_t words = (size_t)((n_points + 31) / 32);
         CK(ensure(s.d_bits, s.bits_bytes, (size_t)frames * words * sizeof(unsigned int)));
@@ -188,6 +190,8 @@ int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStrea
         mc = MapCode{1u, MLD_TAG_MAX_EPOCH - s.epoch};
     }
     s.mc = mc;
+    if (h->feature_mode == 1)
+        CK(cudaMemsetAsync(s.d_occ, 0, (size_t)frames * (size_t)occ_words_per_row(h->dp.W) * (size_t)h->dp.H * sizeof(unsigned int), st));
     return MLD_OK;
 }
 
@@ -198,7 +202,7 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
     if (F <= 0 || frames <= 0) return MLD_OK;
     if (h->feature_mode == 1) {
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
-        CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs, bits,
+        CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
                                            words, frames, s.d_ovf + 1, s.d_ovf, st));
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
                                     bits, words, frames, s.d_ovf + 1, s.d_ovf, h->overflow_blocks, st));
@@ -235,7 +239,7 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     int rcm = begin_maps(h, s, frames, n_points, st, mc);
     if (rcm) return rcm;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, frames, st));
+    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode == 1 ? s.d_occ : nullptr, frames, st));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
     const float* coeffs = nullptr;
@@ -489,7 +493,7 @@ int mld_destroy(mld_handle* h) {
     for (auto& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
-        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -665,7 +669,8 @@ int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_
     MapCode mc;
     rc = begin_maps(h, s, 1, n, s.stream, mc);
     if (rc) return rc;
-    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps, 1, s.stream));
+    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps,
+                                  h->feature_mode == 1 ? s.d_occ : nullptr, 1, s.stream));
     if (n > 0) h->launches++;
     h->cur_n = n;
     h->cur_stride_f = stride_bytes / 4;

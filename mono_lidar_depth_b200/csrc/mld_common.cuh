@@ -91,6 +91,13 @@ __host__ __device__ __forceinline__ unsigned int map_cell_index(const MapCode& m
     return mc.tagged ? (cell & MLD_TAG_IDX_MASK) : cell;
 }
 
+// Occupancy bitmap of the pixel map (one per in-flight frame, cleared per chunk): word j of a row
+// covers pixels [16 j, 16 j + 32), i.e. consecutive words overlap by 16 pixels, so every window row of
+// up to 17 pixels is one 32-bit load (word x0 >> 4); wider rows walk words j, j+2, ... K1 sets the
+// (at most two) bits of every pixel it writes; K2 reads window rows from here instead of loading
+// every pixel cell of the 4-byte map.
+__host__ __device__ __forceinline__ int occ_words_per_row(int W) { return ((W + 15) >> 4) + 1; }
+
 struct D3 {
     double x, y, z;
 };

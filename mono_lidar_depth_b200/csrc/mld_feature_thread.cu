@@ -36,29 +36,72 @@ struct TSlab {
 // A5: window scan (reference order: rows outer, columns inner) + gather. Returns k, or -1 when the
 // window holds more than TCAP points. inlier_mask (bit i = neighbour i is a plane inlier) is filled
 // when inlier_bits != nullptr.
+//
+// Three phases, each a batch of independent loads: (1) one occupancy word per window row (rows of up
+// to 17 pixels; wider rows walk further words), set bits -> pixel offsets in scan order; (2) the map
+// cells of the occupied pixels -> raw point indices; (3) the points themselves -> FP64 camera frame.
+constexpr int T_ROWS = 16;  // window rows whose occupancy words are fetched up front
+
+__device__ __forceinline__ unsigned int row_mask(unsigned int w, int base_px, int x0, int x1) {
+    // keep the bits of word `w` (covering pixels base_px .. base_px+31) that lie in [x0, x1]
+    int lo = x0 - base_px, hi = x1 - base_px;
+    if (lo < 0) lo = 0;
+    if (hi > 31) hi = 31;
+    if (hi < lo) return 0u;
+    return w & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+}
+
 __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map,
-                               const float* __restrict__ pts, int stride_f, double u, double v, double hx, double hy,
-                               const TSlab& s, const unsigned int* __restrict__ inlier_bits, unsigned int& inlier_mask) {
+                               const unsigned int* __restrict__ occ, const float* __restrict__ pts, int stride_f, double u,
+                               double v, double hx, double hy, const TSlab& s, const unsigned int* __restrict__ inlier_bits,
+                               unsigned int& inlier_mask) {
     inlier_mask = 0u;
     if (!(fabs(u) < 1e9) || !(fabs(v) < 1e9)) return 0;  // see mld_feature.cu: UB upstream, empty window here
     double leftEdgeX = fmax(u - hx, 0.);
     double rightEdgeX = fmin(u + hx, (double)(P.W - 1));
     double topEdgeY = fmax(v - hy, 0.);
     double bottomEdgeY = fmin(v + hy, (double)(P.H - 1));
-    int x0 = (int)leftEdgeX, x1 = (int)rightEdgeX, y0 = (int)topEdgeY, y1 = (int)bottomEdgeY;
+    const int x0 = (int)leftEdgeX, x1 = (int)rightEdgeX, y0 = (int)topEdgeY, y1 = (int)bottomEdgeY;
+    if (x1 < x0 || y1 < y0) return 0;
+    const int pitch = occ_words_per_row(P.W);
+    const int wj0 = x0 >> 4;
     int k = 0;
-    for (int y = y0; y <= y1; y++) {
-        const unsigned int* row = map + (long long)y * P.W;
-#pragma unroll 4
-        for (int x = x0; x <= x1; x++) {
-            unsigned int cell = __ldg(row + x);
-            if (map_cell_valid(mc, cell)) {
-                if (k < TCAP) s.aux[k * TBT] = (int)map_cell_index(mc, cell);
-                k++;
+    // ---- phase 1: occupancy words -> pixel offsets (row-major order) ----
+    for (int yb = y0; yb <= y1; yb += T_ROWS) {
+        unsigned int w[T_ROWS];
+#pragma unroll
+        for (int r = 0; r < T_ROWS; r++) {
+            const int y = yb + r;
+            w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < T_ROWS; r++) {
+            const int y = yb + r;
+            if (y > y1) break;
+            unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
+            int wj = wj0;
+            while (true) {
+                while (m) {
+                    const int b = __ffs(m) - 1;
+                    m &= m - 1;
+                    if (k < TCAP) s.aux[k * TBT] = y * P.W + (wj << 4) + b;
+                    k++;
+                }
+                wj += 2;  // next non-overlapping 32-pixel span of a wide row
+                if ((wj << 4) > x1) break;
+                m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
             }
         }
     }
     if (k > TCAP) return -1;
+    // ---- phase 2: map cells -> raw indices ----
+#pragma unroll 4
+    for (int i = 0; i < k; i++) {
+        unsigned int cell = __ldg(map + s.aux[i * TBT]);
+        s.aux[i * TBT] = (int)map_cell_index(mc, cell);
+    }
+    // ---- phase 3: points -> camera frame ----
+#pragma unroll 2
     for (int i = 0; i < k; i++) {
         int raw = s.aux[i * TBT];
         float4 q = __ldg(reinterpret_cast<const float4*>(pts + (long long)raw * stride_f));
@@ -313,10 +356,10 @@ constexpr int ST_OVERFLOW = -1;
 
 __global__ void __launch_bounds__(TBT)
 feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
-                            const unsigned int* __restrict__ maps, const double* __restrict__ uv, int F,
-                            double* __restrict__ depth, int* __restrict__ status, const float* __restrict__ plane_coeffs,
-                            const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame,
-                            int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
+                            const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
+                            const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                            const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ inlier_bits,
+                            long long inlier_words_per_frame, int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
     __shared__ double sx[TCAP * TBT], sy[TCAP * TBT], sz[TCAP * TBT];
     __shared__ int saux[TCAP * TBT];
     const int fi = blockIdx.x * TBT + threadIdx.x;
@@ -331,6 +374,7 @@ feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ p
     TSlab s{sx + threadIdx.x, sy + threadIdx.x, sz + threadIdx.x, saux + threadIdx.x};
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
     const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
     const double u = f2.x, v = f2.y;
     const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
@@ -339,7 +383,7 @@ feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ p
     int st = ST_Unspecified;
     double dp = -1;
     unsigned int mask;
-    int k = t_gather_window(P, mc, map, fp, stride_f, u, v, P.hx1, P.hy1, s, nullptr, mask);
+    int k = t_gather_window(P, mc, map, occ, fp, stride_f, u, v, P.hx1, P.hy1, s, nullptr, mask);
     if (k < 0) {
         st = ST_OVERFLOW;
     } else if ((unsigned)k < (unsigned)P.count_min) {
@@ -352,7 +396,7 @@ feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ p
         }
         if (st != ST_HistogramNoLocalMax) st = t_depth_segmented(P, u, v, n, s, dp);
         if (st != ST_Success && pc != nullptr && P.road_mode != ROAD_NONE) {
-            int k2 = t_gather_window(P, mc, map, fp, stride_f, u, v, P.hx2, P.hy2, s, bits, mask);
+            int k2 = t_gather_window(P, mc, map, occ, fp, stride_f, u, v, P.hx2, P.hy2, s, bits, mask);
             if (k2 < 0)
                 st = ST_OVERFLOW;
             else if ((unsigned)k2 < (unsigned)P.count_min)
@@ -375,13 +419,13 @@ feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ p
 int mld_thread_feature_capacity(void) { return TCAP; }
 
 cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
-                                            long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F,
-                                            double* d_depth, int* d_status, const float* d_plane_coeffs,
+                                            long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
+                                            const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,
                                             const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                             int* d_overflow_list, int* d_overflow_count, cudaStream_t stream) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
     dim3 grid((unsigned)((F + TBT - 1) / TBT), (unsigned)nframes);
-    feature_depth_thread_kernel<<<grid, TBT, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status,
+    feature_depth_thread_kernel<<<grid, TBT, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
                                                          d_plane_coeffs, d_inlier_bits, words_per_frame, d_overflow_list,
                                                          d_overflow_count);
     return cudaGetLastError();

@@ -11,8 +11,10 @@ struct MapCode;
 
 // K1 (mld_project.cu)
 void mld_setup_prefilter(DevParams& P);
+// d_occ: occupancy bitmaps (occ_words_per_row(W) * H words per frame, zeroed by the caller) or nullptr
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
-                                       long long pitch_pts, unsigned int* d_maps, int nframes, cudaStream_t stream);
+                                       long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
+                                       cudaStream_t stream);
 cudaError_t mld_launch_visible_debug(const DevParams& P, const float* d_pts, int stride_f, long long n,
                                      unsigned char* d_visible, double* d_cam, cudaStream_t stream);
 
@@ -32,7 +34,8 @@ cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, co
 // mld_thread_feature_capacity() points are appended to d_overflow_list (global feature ids).
 int mld_thread_feature_capacity(void);
 cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
-                                            long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F,
+                                            long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
+                                            const double* d_uv, int F,
                                             double* d_depth, int* d_status, const float* d_plane_coeffs,
                                             const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                             int* d_overflow_list, int* d_overflow_count, cudaStream_t stream);

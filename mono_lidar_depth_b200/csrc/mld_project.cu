@@ -45,28 +45,30 @@ __device__ __forceinline__ int project_pixel(const DevParams& P, float x, float 
 
 // FP32 pre-filter: true when the point certainly fails one of  z_cam > 0, u > 0, u < W, v > 0, v < H
 // (or is not finite, which fails all of them in the exact path as well).
+__device__ __forceinline__ float pf_form(const DevParams& P, int k, float x, float y, float z) {
+    return fmaf(P.pf_g[k][0], x, fmaf(P.pf_g[k][1], y, fmaf(P.pf_g[k][2], z, P.pf_h[k])));
+}
 __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, float y, float z) {
     float S = fabsf(x) + fabsf(y) + fabsf(z);
     if (!(S < 3.0e38f)) return true;  // NaN or inf coordinate: never visible
-    float val[5], err[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) {
-        val[k] = fmaf(P.pf_g[k][0], x, fmaf(P.pf_g[k][1], y, fmaf(P.pf_g[k][2], z, P.pf_h[k])));
-        err[k] = fmaf(P.pf_G[k], S, P.pf_H[k]);
-    }
-    return (val[0] + err[0] < 0.f) ||  // z_cam < 0
-           (val[1] + err[1] < 0.f) ||  // f*X + cx*Z < 0          <=> u < 0
-           (val[2] - err[2] > 0.f) ||  // f*X + (cx-W)*Z > 0      <=> u > W
-           (val[3] + err[3] < 0.f) ||  // f*Y + cy*Z < 0          <=> v < 0
-           (val[4] - err[4] > 0.f);    // f*Y + (cy-H)*Z > 0      <=> v > H
+    // tests ordered by how much of a 360-degree sweep they remove; a sweep is azimuth ordered, so the
+    // early exits are nearly warp uniform
+    if (pf_form(P, 0, x, y, z) + fmaf(P.pf_G[0], S, P.pf_H[0]) < 0.f) return true;  // z_cam < 0
+    if (pf_form(P, 1, x, y, z) + fmaf(P.pf_G[1], S, P.pf_H[1]) < 0.f) return true;  // f*X + cx*Z < 0      <=> u < 0
+    if (pf_form(P, 2, x, y, z) - fmaf(P.pf_G[2], S, P.pf_H[2]) > 0.f) return true;  // f*X + (cx-W)*Z > 0  <=> u > W
+    if (pf_form(P, 3, x, y, z) + fmaf(P.pf_G[3], S, P.pf_H[3]) < 0.f) return true;  // f*Y + cy*Z < 0      <=> v < 0
+    if (pf_form(P, 4, x, y, z) - fmaf(P.pf_G[4], S, P.pf_H[4]) > 0.f) return true;  // f*Y + (cy-H)*Z > 0  <=> v > H
+    return false;
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
 project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
-                       unsigned int* __restrict__ maps) {
+                       unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
     const long long frame = blockIdx.y;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const int occ_pitch = occ_words_per_row(P.W);
+    unsigned int* ob = occ ? occ + frame * (long long)occ_pitch * (long long)P.H : nullptr;
     const long long base = (long long)blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
     const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
 
@@ -85,7 +87,16 @@ project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, i
         if (i >= n) continue;
         if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
         int off = project_pixel(P, p[j].x, p[j].y, p[j].z, true);
-        if (off >= 0) atomicMin(&map[off], hi | (unsigned int)i);
+        if (off >= 0) {
+            atomicMin(&map[off], hi | (unsigned int)i);
+            if (ob) {
+                const int y = off / P.W, x = off - y * P.W;
+                unsigned int* orow = ob + (long long)y * occ_pitch;
+                const int wj = x >> 4, b = x & 15;
+                atomicOr(orow + wj, 1u << b);
+                if (wj > 0) atomicOr(orow + wj - 1, 1u << (16 + b));
+            }
+        }
     }
 }
 
@@ -151,10 +162,11 @@ void mld_setup_prefilter(DevParams& P) {
 }
 
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
-                                       long long pitch_pts, unsigned int* d_maps, int nframes, cudaStream_t stream) {
+                                       long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
+                                       cudaStream_t stream) {
     if (n <= 0 || nframes <= 0) return cudaSuccess;
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
-    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, n, pitch_pts, d_maps);
+    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, n, pitch_pts, d_maps, d_occ);
     return cudaGetLastError();
 }
 
