@@ -75,6 +75,8 @@ struct mld_handle {
     int feature_mode = 1;  // 1: thread per feature + warp-per-feature overflow pass; 0: warp per feature only
     int overflow_blocks = 296;
     bool use_tagged_maps = true;
+    int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
+    cudaEvent_t ev_fork = nullptr;
     long long cur_n = 0;
     int cur_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
@@ -470,10 +472,17 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "warp") == 0) h->feature_mode = 0;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
+    env = getenv("MLD_OVERLAP");       // "1": run the chunks of a sequence on one stream (no K1/K2 overlap), up to 3
+    if (env && atoi(env) >= 1 && atoi(env) <= MLD_PIPE_SLOTS) h->overlap_slots = atoi(env);
     DeviceGuard g(device);
     if (!g.ok) {
         delete h;
         return fail(nullptr, MLD_ERR_CUDA, "mld_create: cudaSetDevice failed");
+    }
+    e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete h;
+        return fail_cuda(nullptr, e, "event creation");
     }
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
         e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
@@ -500,6 +509,7 @@ int mld_destroy(mld_handle* h) {
     cudaFree(h->d_dbg);
     cudaFree(h->d_synth_tables);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return MLD_OK;
 }
@@ -569,6 +579,7 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     mld_setup_prefilter(d);
     DeviceGuard g(h->device);
     CK(mld_configure_feature_depth(h->kcap));
+    CK(mld_configure_feature_depth_thread());
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->overflow_blocks = 2 * sms;
     for (auto& sl : h->slots) sl.epoch = 0;  // image size may have changed
@@ -758,19 +769,37 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
     if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     DeviceGuard g(h->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    Slot& s = h->slots[0];
-    const int chunk = h->chunk_frames;
+    // short sequences are cut into at least `overlap_slots` chunks so that the streams still overlap
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(h->chunk_frames, std::max<int64_t>(8, (nframes + h->overlap_slots - 1) / h->overlap_slots)));
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
-    rc = slot_reserve(h, s, std::max<int64_t>(n_points, 1), stride_bytes, F, chunk, false, use_road);
-    if (rc) return rc;
+    const int64_t nchunks = (nframes + chunk - 1) / chunk;
+    // K1 is issue/DRAM bound, K2 latency bound: chunks alternate over `nslots` slots (own maps + stream) so
+    // that K1 of one chunk runs under K2 of the previous one. Fork from / join into the caller's stream.
+    const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(h->overlap_slots, nchunks));
+    for (int i = 0; i < nslots; i++) {
+        rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_bytes, F, chunk, false, use_road);
+        if (rc) return rc;
+    }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
-    for (int64_t f0 = 0; f0 < nframes; f0 += chunk) {
+    if (nslots > 1) {
+        CK(cudaEventRecord(h->ev_fork, st));
+        for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
+    }
+    int64_t ci = 0;
+    for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
         int c = (int)std::min<int64_t>(chunk, nframes - f0);
-        rc = enqueue_chunk(h, s, st, pts + f0 * frame_pitch_points * stride_f, n_points, frame_pitch_points, stride_f,
-                           d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F, d_status + f0 * (int64_t)F, c, use_road, seed,
-                           f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr);
+        Slot& s = h->slots[ci % nslots];
+        rc = enqueue_chunk(h, s, nslots > 1 ? s.stream : st, pts + f0 * frame_pitch_points * stride_f, n_points, frame_pitch_points,
+                           stride_f, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F, d_status + f0 * (int64_t)F, c, use_road,
+                           seed, f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr);
         if (rc) return rc;
+    }
+    if (nslots > 1) {
+        for (int i = 0; i < nslots; i++) {
+            CK(cudaEventRecord(h->slots[i].done, h->slots[i].stream));
+            CK(cudaStreamWaitEvent(st, h->slots[i].done, 0));
+        }
     }
     h->have_cloud = false;  // slot 0's map now belongs to the batch
     return MLD_OK;

@@ -17,10 +17,11 @@
 
 namespace {
 
-constexpr int TCAP = 16;  // neighbours per thread
-constexpr int TBT = 64;   // threads (= features) per block
-
-struct TSlab {
+// TCAP = neighbours a thread can hold, TBT = threads (= features) per block
+template <int TCAP_, int TBT_>
+struct TSlabT {
+    static constexpr int TCAP = TCAP_;
+    static constexpr int TBT = TBT_;
     double* x;
     double* y;
     double* z;
@@ -31,6 +32,9 @@ struct TSlab {
         y[i * TBT] = p.y;
         z[i * TBT] = p.z;
     }
+    __device__ __forceinline__ double& Z(int i) const { return z[i * TBT]; }
+    __device__ __forceinline__ double& X(int i) const { return x[i * TBT]; }
+    __device__ __forceinline__ int& A(int i) const { return aux[i * TBT]; }
 };
 
 // A5: window scan (reference order: rows outer, columns inner) + gather. Returns k, or -1 when the
@@ -51,6 +55,7 @@ __device__ __forceinline__ unsigned int row_mask(unsigned int w, int base_px, in
     return w & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
 }
 
+template <typename TSlab>
 __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map,
                                const unsigned int* __restrict__ occ, const float* __restrict__ pts, int stride_f, double u,
                                double v, double hx, double hy, const TSlab& s, const unsigned int* __restrict__ inlier_bits,
@@ -84,7 +89,7 @@ __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsi
                 while (m) {
                     const int b = __ffs(m) - 1;
                     m &= m - 1;
-                    if (k < TCAP) s.aux[k * TBT] = y * P.W + (wj << 4) + b;
+                    if (k < TSlab::TCAP) s.A(k) = y * P.W + (wj << 4) + b;
                     k++;
                 }
                 wj += 2;  // next non-overlapping 32-pixel span of a wide row
@@ -93,17 +98,17 @@ __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsi
             }
         }
     }
-    if (k > TCAP) return -1;
+    if (k > TSlab::TCAP) return -1;
     // ---- phase 2: map cells -> raw indices ----
 #pragma unroll 4
     for (int i = 0; i < k; i++) {
-        unsigned int cell = __ldg(map + s.aux[i * TBT]);
-        s.aux[i * TBT] = (int)map_cell_index(mc, cell);
+        unsigned int cell = __ldg(map + s.A(i));
+        s.A(i) = (int)map_cell_index(mc, cell);
     }
     // ---- phase 3: points -> camera frame ----
 #pragma unroll 2
     for (int i = 0; i < k; i++) {
-        int raw = s.aux[i * TBT];
+        int raw = s.A(i);
         float4 q = __ldg(reinterpret_cast<const float4*>(pts + (long long)raw * stride_f));
         s.set(i, lidar_to_cam(P, q.x, q.y, q.z));
         if (inlier_bits && ((inlier_bits[raw >> 5] >> (raw & 31)) & 1u)) inlier_mask |= 1u << i;
@@ -113,19 +118,20 @@ __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsi
 
 // A6: PointHistogram::FilterPointsMinDistBlob, sequential like the reference. Returns the segmented
 // count (slab compacted in place, order kept) or -1.
+template <typename TSlab>
 __device__ int t_histogram_segment(const DevParams& P, int k, const TSlab& s) {
     int maxDist = 0;
     for (int i = 0; i < k; i++) {
-        double d = fmin(s.z[i * TBT], 999.);
+        double d = fmin(s.Z(i), 999.);
         if (d > maxDist) maxDist = (int)ceil(d);  // HistogramPointDepth.cpp:38-41
     }
     int binCount = (int)((maxDist) / P.bin_w + 1);  // :43
     if (binCount <= 1) return -1;
     int bmin = binCount;
     for (int i = 0; i < k; i++) {
-        double value = fmin(fmin(s.z[i * TBT], 999.), 1e10);  // Histogram.cpp:29
+        double value = fmin(fmin(s.Z(i), 999.), 1e10);  // Histogram.cpp:29
         int b = (int)fmin(fabs(value / P.bin_w), (double)binCount - 1.);
-        s.aux[i * TBT] = b;
+        s.A(i) = b;
         bmin = min(bmin, b);
     }
     // first-local-maximum scan (:66-85); only the first run of occupied bins can decide it
@@ -138,7 +144,7 @@ __device__ int t_histogram_segment(const DevParams& P, int k, const TSlab& s) {
     for (int b = bmin; b < binCount; b++) {
         int lastBinValue = binValue;
         int cnt = 0;
-        for (int i = 0; i < k; i++) cnt += (s.aux[i * TBT] == b) ? 1 : 0;
+        for (int i = 0; i < k; i++) cnt += (s.A(i) == b) ? 1 : 0;
         binValue = cnt;
         if ((binValue > binMaxVal) && (binValue >= P.hist_min)) {
             binMaxVal = binValue;
@@ -167,6 +173,7 @@ __device__ int t_histogram_segment(const DevParams& P, int k, const TSlab& s) {
 }
 
 // A7: PlaneEstimationCalcMaxSpanningTriangle::CalculatePlaneCorners, sequential
+template <typename TSlab>
 __device__ bool t_max_spanning_triangle(int n, const TSlab& s, int& ci, int& cj, int& ck) {
     if (n < 3) return false;
     int mi = -1, mj = -1;
@@ -206,17 +213,19 @@ __device__ bool t_max_spanning_triangle(int n, const TSlab& s, int& ci, int& cj,
     return true;
 }
 
+template <typename TSlab>
 __device__ void t_z_range(int n, const TSlab& s, double& minZ, double& maxZ) {
     minZ = 1.7976931348623157e308;
     maxZ = -1.7976931348623157e308;
     for (int i = 0; i < n; i++) {
-        double z = s.z[i * TBT];
+        double z = s.Z(i);
         if (z < minZ) minZ = z;
         if (z > maxZ) maxZ = z;
     }
 }
 
 // weighted centroid + scatter in the reference's sequential order
+template <typename TSlab>
 __device__ void t_weighted_scatter(int n, const TSlab& s, bool weighted, const Plane& prior, D3& center, double c[6]) {
     D3 acc = D3{0, 0, 0};
     double wsum = 0;
@@ -237,18 +246,25 @@ __device__ void t_weighted_scatter(int n, const TSlab& s, bool weighted, const P
     }
 }
 
-// A12: CalculateDepthSegmented
-__device__ int t_depth_segmented(const DevParams& P, double u, double v, int n, const TSlab& s, double& depth_out) {
-    depth_out = -1;
-    D3 c1{}, c2{}, c3{};
+// A12 (first half): corner selection of CalculateDepthSegmented (DepthEstimator.cpp:915-926).
+// Returns 0 and the corner indices, or the failing status.
+template <typename TSlab>
+__device__ int t_select_corners(const DevParams& P, int n, const TSlab& s, int& ci, int& cj, int& ck) {
+    ci = 0; cj = 1; ck = 2;
     if (!P.use_pca && P.use_tri_max) {
-        int i, j, k;
-        if (!t_max_spanning_triangle(n, s, i, j, k)) return ST_TriangleNotPlanarInsufficientPoints;
-        c1 = s.pt(i); c2 = s.pt(j); c3 = s.pt(k);
+        if (!t_max_spanning_triangle(n, s, ci, cj, ck)) return ST_TriangleNotPlanarInsufficientPoints;
     } else {
         if (n < 3) return ST_HistogramNoLocalMax;
-        c1 = s.pt(0); c2 = s.pt(1); c3 = s.pt(2);
     }
+    return 0;
+}
+
+// A12 (second half): planarity, viewing ray, plane intersection, thresholds (DepthEstimator.cpp:928-1036)
+template <typename TSlab>
+__device__ int t_depth_from_corners(const DevParams& P, double u, double v, int n, const TSlab& s, int ci, int cj, int ck,
+                                    double& depth_out) {
+    depth_out = -1;
+    D3 c1 = s.pt(ci), c2 = s.pt(cj), c3 = s.pt(ck);
     if (!P.use_pca && P.check_planar)
         if (!check_planar(c1, c2, c3, P.crossnorm_thr)) return ST_TriangleNotPlanar;
     D3 support = D3{0, 0, 0};
@@ -290,6 +306,7 @@ __device__ int t_depth_segmented(const DevParams& P, double u, double v, int n, 
 }
 
 // R2 + R3/R4/R5
+template <typename TSlab>
 __device__ int t_road_depth(const DevParams& P, double u, double v, int k2, const TSlab& s, const float* coeffs,
                             unsigned int inlier_mask, int old_status, double& depth_out) {
     depth_out = -1;
@@ -317,7 +334,7 @@ __device__ int t_road_depth(const DevParams& P, double u, double v, int k2, cons
         if (!t_max_spanning_triangle(n, s, i, j, k)) return ST_RadiusSearchInsufficientPoints;
         double loX = 1.7976931348623157e308, hiX = -1.7976931348623157e308, loZ = loX, hiZ = hiX;
         for (int q = 0; q < n; q++) {
-            double x = s.x[q * TBT], z = s.z[q * TBT];
+            double x = s.X(q), z = s.Z(q);
             if (x < loX) loX = x;
             if (x > hiX) hiX = x;
             if (z < loZ) loZ = z;
@@ -354,69 +371,195 @@ __device__ int t_road_depth(const DevParams& P, double u, double v, int k2, cons
 
 constexpr int ST_OVERFLOW = -1;
 
+// order-preserving block-wide compaction: threads with `flag` append `value` to list; returns the count
+template <int TBT>
+__device__ int block_compact(bool flag, int value, short* list, int* warp_tot) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(MLD_FULL_MASK, flag);
+    if (lane == 0) warp_tot[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < TBT / 32; w++) {
+        const int c = warp_tot[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (flag) list[base + __popc(m & ((1u << lane) - 1u))] = (short)value;
+    __syncthreads();
+    return total;
+}
+
+// Phases (a block owns TBT consecutive features of one frame; between phases the surviving features are
+// compacted onto the low lanes so that the expensive later phases run on dense warps):
+//   P1 every thread: window scan + gather of its own feature          -> status 2 / overflow / survivor
+//   P2 survivors:    histogram segmentation + corner selection        -> status 3 / 9 / survivor
+//   P3 survivors:    planarity, ray/plane intersection, thresholds    -> final status of the normal path
+//   P4 (plane given) features without Success: road path (wide window, plane gate, M-estimator ...)
+template <int TCAP, int TBT>
 __global__ void __launch_bounds__(TBT)
 feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
                             const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
                             const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
                             const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ inlier_bits,
                             long long inlier_words_per_frame, int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
-    __shared__ double sx[TCAP * TBT], sy[TCAP * TBT], sz[TCAP * TBT];
-    __shared__ int saux[TCAP * TBT];
-    const int fi = blockIdx.x * TBT + threadIdx.x;
-    if (fi >= F) return;
+    using TSlab = TSlabT<TCAP, TBT>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double* sx = reinterpret_cast<double*>(smem_raw);
+    double* sy = sx + TCAP * TBT;
+    double* sz = sy + TCAP * TBT;
+    int* saux = reinterpret_cast<int*>(sz + TCAP * TBT);
+    __shared__ double s_u[TBT], s_v[TBT], s_dp[TBT];
+    __shared__ short s_list[TBT];
+    __shared__ short s_cnt[TBT];
+    __shared__ signed char s_st[TBT], s_ci[TBT], s_cj[TBT], s_ck[TBT];
+    __shared__ int s_wtot[TBT / 32];
+
+    const int tid = threadIdx.x;
+    const int fi = blockIdx.x * TBT + tid;
+    const bool valid = fi < F;
     const long long frame = blockIdx.y;
-    const long long o = frame * (long long)F + fi;
-    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
-        status[o] = 1;
-        depth[o] = -1;
-        return;
-    }
-    TSlab s{sx + threadIdx.x, sy + threadIdx.x, sz + threadIdx.x, saux + threadIdx.x};
+    const long long obase = frame * (long long)F + (long long)blockIdx.x * TBT;  // global id of this block's feature 0
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
     const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
-    const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
-    const double u = f2.x, v = f2.y;
     const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
     const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
+    const bool road = pc != nullptr && P.road_mode != ROAD_NONE;
+    auto slab_of = [&](int owner) { return TSlab{sx + owner, sy + owner, sz + owner, saux + owner}; };
 
-    int st = ST_Unspecified;
-    double dp = -1;
-    unsigned int mask;
-    int k = t_gather_window(P, mc, map, occ, fp, stride_f, u, v, P.hx1, P.hy1, s, nullptr, mask);
-    if (k < 0) {
-        st = ST_OVERFLOW;
-    } else if ((unsigned)k < (unsigned)P.count_min) {
-        st = ST_RadiusSearchInsufficientPoints;
-    } else {
-        int n = k;
-        if (P.use_hist) {
-            n = t_histogram_segment(P, k, s);
-            if (n < 0) st = ST_HistogramNoLocalMax;
+    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
+        if (valid) {
+            status[obase + tid] = 1;
+            depth[obase + tid] = -1;
         }
-        if (st != ST_HistogramNoLocalMax) st = t_depth_segmented(P, u, v, n, s, dp);
-        if (st != ST_Success && pc != nullptr && P.road_mode != ROAD_NONE) {
-            int k2 = t_gather_window(P, mc, map, occ, fp, stride_f, u, v, P.hx2, P.hy2, s, bits, mask);
-            if (k2 < 0)
-                st = ST_OVERFLOW;
-            else if ((unsigned)k2 < (unsigned)P.count_min)
-                st = ST_RadiusSearchInsufficientPoints;
-            else
-                st = t_road_depth(P, u, v, k2, s, pc, mask, st, dp);
-        }
-    }
-    if (st == ST_OVERFLOW) {
-        int slot = atomicAdd(overflow_count, 1);
-        overflow_list[slot] = (int)o;  // finished by the warp-per-feature kernel
         return;
     }
-    status[o] = st;
-    depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
+
+    // ---- P1: gather ----
+    bool surv = false;
+    s_st[tid] = ST_Unspecified;
+    s_dp[tid] = -1;
+    if (valid) {
+        const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + obase + tid);
+        s_u[tid] = f2.x;
+        s_v[tid] = f2.y;
+        unsigned int mask;
+        const int k = t_gather_window(P, mc, map, occ, fp, stride_f, f2.x, f2.y, P.hx1, P.hy1, slab_of(tid), nullptr, mask);
+        if (k < 0) {
+            s_st[tid] = ST_OVERFLOW;
+        } else if ((unsigned)k < (unsigned)P.count_min) {  // neighbors.size() < (uint)radiusSearch_count_min (:680)
+            s_st[tid] = ST_RadiusSearchInsufficientPoints;
+        } else {
+            s_cnt[tid] = (short)k;
+            surv = true;
+        }
+    }
+    int n1 = block_compact<TBT>(surv, tid, s_list, s_wtot);
+
+    // ---- P2: histogram + corner selection ----
+    surv = false;
+    int owner = -1;
+    if (tid < n1) {
+        owner = s_list[tid];
+        const TSlab s = slab_of(owner);
+        int n = s_cnt[owner];
+        int st = ST_Unspecified;
+        if (P.use_hist) {
+            n = t_histogram_segment(P, n, s);
+            if (n < 0) st = ST_HistogramNoLocalMax;
+        }
+        if (st != ST_HistogramNoLocalMax) {
+            int ci, cj, ck;
+            st = t_select_corners(P, n, s, ci, cj, ck);
+            if (st == 0) {
+                s_cnt[owner] = (short)n;
+                s_ci[owner] = (signed char)ci;
+                s_cj[owner] = (signed char)cj;
+                s_ck[owner] = (signed char)ck;
+                surv = true;
+            }
+        }
+        if (!surv) s_st[owner] = (signed char)st;
+    }
+    __syncthreads();
+    int n2 = block_compact<TBT>(surv, owner, s_list, s_wtot);
+
+    // ---- P3: geometry tail ----
+    if (tid < n2) {
+        owner = s_list[tid];
+        double dp;
+        const int st = t_depth_from_corners(P, s_u[owner], s_v[owner], (int)s_cnt[owner], slab_of(owner), (int)s_ci[owner],
+                                            (int)s_cj[owner], (int)s_ck[owner], dp);
+        s_st[owner] = (signed char)st;
+        s_dp[owner] = dp;
+    }
+    __syncthreads();
+
+    // ---- P4: road path for features the normal path could not solve (DepthEstimator.cpp:579-597) ----
+    if (road) {
+        const int st0 = s_st[tid];
+        const bool want = valid && st0 != ST_Success && st0 != ST_OVERFLOW && st0 != ST_RadiusSearchInsufficientPoints;
+        const int n3 = block_compact<TBT>(want, tid, s_list, s_wtot);
+        if (tid < n3) {
+            owner = s_list[tid];
+            const TSlab s = slab_of(owner);
+            unsigned int mask;
+            const int k2 = t_gather_window(P, mc, map, occ, fp, stride_f, s_u[owner], s_v[owner], P.hx2, P.hy2, s, bits, mask);
+            if (k2 < 0) {
+                s_st[owner] = ST_OVERFLOW;
+            } else if ((unsigned)k2 < (unsigned)P.count_min) {
+                s_st[owner] = ST_RadiusSearchInsufficientPoints;
+                s_dp[owner] = -1;
+            } else {
+                double dp;
+                const int st = t_road_depth(P, s_u[owner], s_v[owner], k2, s, pc, mask, (int)s_st[owner], dp);
+                s_st[owner] = (signed char)st;
+                s_dp[owner] = dp;
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- results ----
+    if (valid) {
+        const int st = s_st[tid];
+        const long long o = obase + tid;
+        if (st == ST_OVERFLOW) {
+            const int slot = atomicAdd(overflow_count, 1);
+            overflow_list[slot] = (int)o;  // finished by the warp-per-feature kernel
+        } else {
+            status[o] = st;
+            depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? s_dp[tid] : -1.0;
+        }
+    }
+}
+
+template <int TCAP, int TBT>
+cudaError_t launch_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long pitch_pts,
+                          const unsigned int* d_maps, const unsigned int* d_occ, const double* d_uv, int F, double* d_depth,
+                          int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits, long long words_per_frame,
+                          int nframes, int* d_overflow_list, int* d_overflow_count, cudaStream_t stream) {
+    constexpr size_t smem = (size_t)TCAP * TBT * (3 * sizeof(double) + sizeof(int));
+    dim3 grid((unsigned)((F + TBT - 1) / TBT), (unsigned)nframes);
+    feature_depth_thread_kernel<TCAP, TBT><<<grid, TBT, smem, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F,
+                                                                       d_depth, d_status, d_plane_coeffs, d_inlier_bits,
+                                                                       words_per_frame, d_overflow_list, d_overflow_count);
+    return cudaGetLastError();
 }
 
 }  // namespace
 
-int mld_thread_feature_capacity(void) { return TCAP; }
+// two builds: 12 neighbours x 128 features per block when only the normal window is scanned, 24 x 64 when the
+// road path (window scale 2.0 x 1.5) may run
+int mld_thread_feature_capacity(int road) { return road ? 24 : 12; }
+
+cudaError_t mld_configure_feature_depth_thread(void) {
+    cudaError_t e = cudaFuncSetAttribute(feature_depth_thread_kernel<12, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         12 * 128 * 28);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(feature_depth_thread_kernel<24, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 64 * 28);
+}
 
 cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
                                             long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
@@ -424,9 +567,10 @@ cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& m
                                             const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                             int* d_overflow_list, int* d_overflow_count, cudaStream_t stream) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
-    dim3 grid((unsigned)((F + TBT - 1) / TBT), (unsigned)nframes);
-    feature_depth_thread_kernel<<<grid, TBT, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
-                                                         d_plane_coeffs, d_inlier_bits, words_per_frame, d_overflow_list,
-                                                         d_overflow_count);
-    return cudaGetLastError();
+    const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
+    if (road)
+        return launch_thread<24, 64>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                     d_inlier_bits, words_per_frame, nframes, d_overflow_list, d_overflow_count, stream);
+    return launch_thread<12, 128>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                  d_inlier_bits, words_per_frame, nframes, d_overflow_list, d_overflow_count, stream);
 }

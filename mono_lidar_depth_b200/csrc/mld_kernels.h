@@ -32,7 +32,8 @@ cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, co
 
 // K2/K3, thread per feature (mld_feature_thread.cu): features whose window holds more than
 // mld_thread_feature_capacity() points are appended to d_overflow_list (global feature ids).
-int mld_thread_feature_capacity(void);
+int mld_thread_feature_capacity(int road);
+cudaError_t mld_configure_feature_depth_thread(void);
 cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
                                             long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
                                             const double* d_uv, int F,

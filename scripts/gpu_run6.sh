@@ -1,0 +1,8 @@
+python -m pytest tests -m gpu -q --no-header -rf -x --timeout 900 > gpurun_out/test6.log 2>&1; tail -8 gpurun_out/test6.log
+for ov in 1 2 3; do for c in 32 64 128; do MLD_OVERLAP=$ov MLD_CHUNK_FRAMES=$c MLD_BENCH_CPU_SECONDS=1 MLD_BENCH_E2E_FRAMES=256 python bench.py --steps 3 --warmup 3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('overlap $ov chunk',d['config']['chunk_frames_per_launch'],'fps',round(d['value']),'e2e',round(d['e2e']['value']),{k:(round(v['avg_launch_ms']*1000,1) if v['avg_launch_ms'] else None) for k,v in d['roofline']['per_kernel'].items()})
+    elif 'Error' in l or 'error' in l: print(l)
+"; done; done
