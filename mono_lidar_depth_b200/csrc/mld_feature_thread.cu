@@ -550,13 +550,19 @@ cudaError_t launch_thread(const DevParams& P, const MapCode& mc, const float* d_
 
 }  // namespace
 
-// two builds: 12 neighbours x 128 features per block when only the normal window is scanned, 24 x 64 when the
-// road path (window scale 2.0 x 1.5) may run
-int mld_thread_feature_capacity(int road) { return road ? 24 : 12; }
+// two builds: MLD_T_TCAP neighbours x MLD_T_TBT features per block when only the normal window is scanned,
+// 24 x 64 when the road path (window scale 2.0 x 1.5) may run
+#ifndef MLD_T_TCAP
+#define MLD_T_TCAP 12
+#endif
+#ifndef MLD_T_TBT
+#define MLD_T_TBT 128
+#endif
+int mld_thread_feature_capacity(int road) { return road ? 24 : MLD_T_TCAP; }
 
 cudaError_t mld_configure_feature_depth_thread(void) {
-    cudaError_t e = cudaFuncSetAttribute(feature_depth_thread_kernel<12, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         12 * 128 * 28);
+    cudaError_t e = cudaFuncSetAttribute(feature_depth_thread_kernel<MLD_T_TCAP, MLD_T_TBT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         MLD_T_TCAP * MLD_T_TBT * 28);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(feature_depth_thread_kernel<24, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, 24 * 64 * 28);
 }
@@ -571,6 +577,6 @@ cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& m
     if (road)
         return launch_thread<24, 64>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs,
                                      d_inlier_bits, words_per_frame, nframes, d_overflow_list, d_overflow_count, stream);
-    return launch_thread<12, 128>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs,
+    return launch_thread<MLD_T_TCAP, MLD_T_TBT>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs,
                                   d_inlier_bits, words_per_frame, nframes, d_overflow_list, d_overflow_count, stream);
 }

@@ -21,8 +21,14 @@
 
 namespace {
 
-constexpr int K1_THREADS = 256;
-constexpr int K1_PPT = 4;  // points per thread: four independent 16-byte loads in flight
+#ifndef MLD_K1_THREADS
+#define MLD_K1_THREADS 128
+#endif
+#ifndef MLD_K1_PPT
+#define MLD_K1_PPT 4
+#endif
+constexpr int K1_THREADS = MLD_K1_THREADS;
+constexpr int K1_PPT = MLD_K1_PPT;  // points per thread: independent 16-byte loads in flight
 
 // exact projection of one point; returns the pixel offset or -1 when the point does not enter the map
 __device__ __forceinline__ int project_pixel(const DevParams& P, float x, float y, float z, bool need_front) {

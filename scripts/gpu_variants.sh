@@ -1,0 +1,11 @@
+run() { MLD_BENCH_CPU_SECONDS=1 MLD_BENCH_E2E_FRAMES=128 python bench.py --steps 3 --warmup 3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('$1 overlap',os.environ.get('MLD_OVERLAP','3') if False else '', 'chunk',d['config']['chunk_frames_per_launch'],'fps',round(d['value']),{k:(round(v['avg_launch_ms']*1000,1) if v['avg_launch_ms'] else None) for k,v in d['roofline']['per_kernel'].items()})
+    elif 'Error' in l or 'error' in l: print(l)
+"; }
+echo "== default lib"; MLD_OVERLAP=1 run base_serial; run base
+for v in tbt64 tbt256 tcap8 tcap8_tbt64 ppt8 ppt2 k1t128; do
+  echo "== $v"; export MLD_CUDA_LIB=$PWD/build/variants/libmld_$v.so; MLD_OVERLAP=1 run ${v}_serial; run $v; unset MLD_CUDA_LIB
+done
