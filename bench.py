@@ -31,6 +31,27 @@ if str(ROOT) not in sys.path:
 N_POINTS, IMG_W, IMG_H, N_FEATURES = 120000, 1241, 376, 2000
 ALGO_BYTES_PER_FRAME = 16 * N_POINTS + 4 * IMG_W * IMG_H + 28 * N_FEATURES  # 3 842 464 B
 SEED = 20261017
+WORKLOAD = "kitti"
+
+# BASELINE.json configs: "kitti" = configs[1] (the headline, default), "road" = configs[2] (RANSAC ground
+# plane per frame + road path), "dense" = configs[3] (128-beam sweep, 2048x1024 image, 20000 features)
+WORKLOADS = {
+    "kitti": dict(dense=False, road=False, frames=10000, features=2000, desc="BASELINE.json configs[1]: non-road features"),
+    "road": dict(dense=False, road=True, frames=10000, features=2000,
+                 desc="BASELINE.json configs[2]: RANSAC ground plane fitted per frame on the GPU + road-depth path"),
+    "dense": dict(dense=True, road=False, frames=2000, features=20000,
+                  desc="BASELINE.json configs[3]: 128-beam sweep (260096 pts), 2048x1024 image, 20000 features"),
+}
+
+
+def set_workload(name):
+    global N_POINTS, IMG_W, IMG_H, N_FEATURES, ALGO_BYTES_PER_FRAME
+    w = WORKLOADS[name]
+    if w["dense"]:
+        N_POINTS, IMG_W, IMG_H = 260096, 2048, 1024
+    N_FEATURES = w["features"]
+    ALGO_BYTES_PER_FRAME = 16 * N_POINTS + 4 * IMG_W * IMG_H + 28 * N_FEATURES
+    return w
 
 
 def env_int(name, default):
@@ -123,39 +144,53 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
     from mono_lidar_depth_b200 import synth
 
     cores = os.cpu_count() or 1
+    wl = WORKLOADS[WORKLOAD]
     p = O.yaml_params()
-    p.do_use_ransac_plane = 0
-    cam = synth.kitti_camera()
-    cfg = synth.default_config()
+    p.do_use_ransac_plane = 1 if wl["road"] else 0
+    cam = synth.dense_camera() if wl["dense"] else synth.kitti_camera()
+    cfg = synth.default_config(wl["dense"])
 
     def make():
         o = O.Oracle(p)
         o.initialize(IMG_W, IMG_H, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
         return o
 
-    nsample = 32
+    nsample = 32 if not wl["dense"] else 8
     if frames_host is None:
         frames_host = [synth.points_host(cfg, SEED, f) for f in range(nsample)]
         uv_host = [synth.features_host(cfg, SEED, f, N_FEATURES) for f in range(nsample)]
     nsample = len(frames_host)
 
+    def run_frame(o, i):
+        # the reference's per-frame sequence: setInputCloud (+ RANSAC when the plane is not segmented) + CalculateDepth
+        o.set_cloud(frames_host[i])
+        plane = None
+        if wl["road"]:
+            rc, coeffs, inl, _ = O.ransac_plane(p, frames_host[i], SEED + i)
+            plane = (coeffs, inl) if rc == 0 else None
+        o.calculate_depth(uv_host[i], plane)
+
     # native: OpenMP inside the frame
     O.lib().orc_set_num_threads(cores)
     o = make()
-    o.set_cloud(frames_host[0])
-    o.calculate_depth(uv_host[0])  # warm-up
+    run_frame(o, 0)  # warm-up
     t0 = time.perf_counter()
     done = 0
     t_set = t_calc = 0.0
     while time.perf_counter() - t0 < budget_s * 0.4 or done < 8:
         i = done % nsample
         a = time.perf_counter()
-        o.set_cloud(frames_host[i])
-        b = time.perf_counter()
-        o.calculate_depth(uv_host[i])
-        c = time.perf_counter()
-        t_set += b - a
-        t_calc += c - b
+        if wl["road"]:
+            run_frame(o, i)
+            b = c = time.perf_counter()
+            t_set += b - a
+        else:
+            o.set_cloud(frames_host[i])
+            b = time.perf_counter()
+            o.calculate_depth(uv_host[i])
+            c = time.perf_counter()
+            t_set += b - a
+            t_calc += c - b
         done += 1
     native = done / (time.perf_counter() - t0)
     native_detail = {"frames": done, "ms_set_input_cloud": 1e3 * t_set / done, "ms_calculate_depth": 1e3 * t_calc / done}
@@ -169,9 +204,7 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
         ow = make()
         k = w
         while time.perf_counter() < stop:
-            i = k % nsample
-            ow.set_cloud(frames_host[i])
-            ow.calculate_depth(uv_host[i])
+            run_frame(ow, k % nsample)
             counts[w] += 1
             k += cores
 
@@ -192,7 +225,7 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
         "sample": (f"{done} frames native (OpenMP over features, {cores} threads: {native:.1f} frames/s, "
                    f"setInputCloud {native_detail['ms_set_input_cloud']:.2f} ms + CalculateDepth {native_detail['ms_calculate_depth']:.2f} ms) and "
                    f"{sum(counts)} frames frame-parallel ({cores} single-thread estimators: {frame_parallel:.1f} frames/s) of the same "
-                   f"KITTI-shaped workload, {nsample} distinct frames cycled; the better figure is reported"),
+                   f"{WORKLOAD} workload, {nsample} distinct frames cycled; the better figure is reported"),
         "native_frames_per_s": native,
         "frame_parallel_frames_per_s": frame_parallel,
     }
@@ -218,8 +251,8 @@ def run_reference(args, rank, world):
         "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": ngpu, "steps": steps, "warmup": warm,
         "ms_per_step": 1e3 * per, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "KITTI-shaped frames (120000 pts, 1241x376, 2000 features), yaml parameters, ground plane off; "
-                               f"each step is a bounded {per:.1f} s sample (~{frames_per_step:.0f} frames) of the 10k-frame sequence on the host cores",
+        "config": {"workload": f"{WORKLOAD}: {WORKLOADS[WORKLOAD]['desc']} ({N_POINTS} pts, {IMG_W}x{IMG_H}, {N_FEATURES} features), yaml parameters; "
+                               f"each step is a bounded {per:.1f} s sample (~{frames_per_step:.0f} frames) of the sequence on the host cores",
                    "points_per_frame": N_POINTS, "features_per_frame": N_FEATURES, "image": [IMG_W, IMG_H]},
         "feature_depths_per_sec": v * N_FEATURES,
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
@@ -244,21 +277,25 @@ def run_gpu(args, rank, local_rank, world):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    frames_total = env_int("MLD_BENCH_FRAMES", 10000) * world  # weak scaling: 10k frames per GPU
+    wl = WORKLOADS[WORKLOAD]
+    frames_total = env_int("MLD_BENCH_FRAMES", wl["frames"]) * world  # weak scaling: the same block per GPU
     f0, nframes = sharding.frame_block(frames_total, world, rank)
-    cfg = synth.default_config()
+    cfg = synth.default_config(wl["dense"])
     n = synth.points_per_frame(cfg)
     F = N_FEATURES
     assert n == N_POINTS
+    use_road = bool(wl["road"])
+    cam = synth.dense_camera() if wl["dense"] else synth.kitti_camera()
 
     est = DepthEstimator(device=local_rank)
-    est.InitConfig(DepthEstimatorParameters.reference_yaml(do_use_ransac_plane=0))
-    est.Initialize(synth.kitti_camera(), synth.KITTI_T_LIDAR_TO_CAM)
+    est.InitConfig(DepthEstimatorParameters.reference_yaml(do_use_ransac_plane=1 if use_road else 0))
+    est.Initialize(cam, synth.KITTI_T_LIDAR_TO_CAM)
 
     pts = torch.empty((nframes, n, 4), dtype=torch.float32, device=dev)
     uv = torch.empty((nframes, F, 2), dtype=torch.float64, device=dev)
     depth = torch.empty((nframes, F), dtype=torch.float64, device=dev)
     status = torch.empty((nframes, F), dtype=torch.int32, device=dev)
+    coeffs = torch.zeros((nframes, 4), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     synth.points_device(est, cfg, SEED, f0, nframes, pts.data_ptr(), stream=stream)
     synth.features_device(est, cfg, SEED, f0, nframes, F, uv.data_ptr(), stream=stream)
@@ -270,7 +307,8 @@ def run_gpu(args, rank, local_rank, world):
         g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev)
 
     def step():
-        est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes, stream=stream)
+        est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes,
+                                road=use_road, seed=SEED + f0, d_plane_coeffs_out=coeffs.data_ptr() if use_road else 0, stream=stream)
         if world > 1:  # gather the per-frame results (the only inter-GPU traffic of the path)
             dist.all_gather_into_tensor(g_depth, depth)
             dist.all_gather_into_tensor(g_status, status)
@@ -322,22 +360,28 @@ def run_gpu(args, rank, local_rank, world):
         import parity_util as PU
 
         p = O.yaml_params()
-        p.do_use_ransac_plane = 0
+        p.do_use_ransac_plane = 1 if use_road else 0
         orc = O.Oracle(p)
-        cam = synth.kitti_camera()
         orc.initialize(IMG_W, IMG_H, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
         checked = 0
         for i in sorted({0, nframes // 2, nframes - 1}):
-            orc.set_cloud(pts[i].cpu().numpy())
-            d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy())
+            cloud_i = pts[i].cpu().numpy()
+            orc.set_cloud(cloud_i)
+            plane_i = None
+            if use_road:  # the oracle's RANSAC with the same per-frame seed gives the inlier set; coefficients from the GPU
+                rc_i, c_ref, inl_i, _ = O.ransac_plane(p, cloud_i, SEED + f0 + i)
+                c_gpu = coeffs[i].cpu().numpy()
+                assert rc_i == 0 and np.allclose(c_gpu, c_ref, rtol=1e-5, atol=1e-6), (c_gpu, c_ref)
+                plane_i = (c_gpu, inl_i)
+            d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy(), plane_i)
             PU.assert_depth_status_equal(depth[i].cpu().numpy(), status[i].cpu().numpy(), d_ref, s_ref, f"bench frame {i}")
             checked += 1
         s_all = status.cpu().numpy()
         parity = {"frames_checked_vs_oracle": checked, "status_exact": True, "depth_rtol": PU.DEPTH_RTOL,
-                  "success_fraction": float((s_all == 1).mean())}
+                  "success_fraction": float((s_all == 1).mean()), "success_road_fraction": float((s_all == 16).mean())}
 
     # ---- e2e: host buffers through mld_process_frames_host ----
-    ne = min(nframes, env_int("MLD_BENCH_E2E_FRAMES", 1024))
+    ne = min(nframes, env_int("MLD_BENCH_E2E_FRAMES", 256 if wl["dense"] else 1024))
     h_pts = torch.empty((ne, n, 4), dtype=torch.float32).pin_memory()
     h_uv = torch.empty((ne, F, 2), dtype=torch.float64).pin_memory()
     h_depth = torch.empty((ne, F), dtype=torch.float64).pin_memory()
@@ -347,7 +391,8 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
 
     def e2e_step():
-        est.processFramesHostPtr(h_pts.data_ptr(), n, n, 16, h_uv.data_ptr(), F, h_depth.data_ptr(), h_status.data_ptr(), ne)
+        est.processFramesHostPtr(h_pts.data_ptr(), n, n, 16, h_uv.data_ptr(), F, h_depth.data_ptr(), h_status.data_ptr(), ne,
+                                 road=use_road, seed=SEED + f0)
 
     for _ in range(2):
         e2e_step()
@@ -384,14 +429,18 @@ def run_gpu(args, rank, local_rank, world):
             per_class[name] = {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None}
         # dominant kernel of the step and its algorithmic bytes per launch (DESIGN.md "roofline")
         kernels = {k: v for k, v in per_class.items() if k in ("project_scatter", "feature_depth") and v["launches"]}
+        per_class["note"] = ("durations are bracketed by CUDA events on each chunk's stream inside the timed region; chunks run on "
+                             "3 overlapping streams, so a kernel's duration includes time shared with the other chunks' kernels")
         dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
         roof = None
         if dom:
             frames_per_launch = prof_frames / per_class[dom]["launches"]
+            # K1 owns the point stream and the pixel map (written once per frame in the reference's accounting; the
+            # epoch-tagged map makes the actual clear traffic ~0), K2 the feature reads and the result writes
             per_frame_bytes = {"project_scatter": 16 * N_POINTS + 4 * IMG_W * IMG_H, "feature_depth": 28 * N_FEATURES}[dom]
             avg_s = per_class[dom]["avg_launch_ms"] * 1e-3
             achieved = per_frame_bytes * frames_per_launch / avg_s / 1e9
-            sampled_ms = sum(v["ms_total"] for v in per_class.values())
+            sampled_ms = sum(v["ms_total"] for v in per_class.values() if isinstance(v, dict))
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,
@@ -412,9 +461,9 @@ def run_gpu(args, rank, local_rank, world):
             "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"KITTI-shaped sequence of {frames_total // world} synthetic frames per GPU, batched, non-road features "
-                                   "(BASELINE.json configs[1]); HDL-64-like 120000 pts, 1241x376, 2000 features, monolidar_fusion/parameters.yaml "
-                                   "with do_use_depth_segmentation 0 and the ground plane off",
+            "config": {"workload": f"{WORKLOAD}: sequence of {frames_total // world} synthetic frames per GPU, batched; {wl['desc']}; "
+                                   f"{N_POINTS} pts, {IMG_W}x{IMG_H}, {N_FEATURES} features, monolidar_fusion/parameters.yaml "
+                                   "with do_use_depth_segmentation 0",
                        "frames_per_gpu": frames_total // world, "points_per_frame": N_POINTS, "features_per_frame": N_FEATURES,
                        "image": [IMG_W, IMG_H], "chunk_frames_per_launch": chunk,
                        "l2": f"inputs of one step ({nframes * n * 16 / 1e9:.1f} GB of points per GPU) are far larger than the 126 MB L2; no flush needed",
@@ -439,7 +488,11 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="kitti", choices=sorted(WORKLOADS))
     args = ap.parse_args()
+    global WORKLOAD
+    WORKLOAD = args.workload
+    set_workload(WORKLOAD)
     rank = env_int("RANK", 0)
     local_rank = env_int("LOCAL_RANK", 0)
     world = env_int("WORLD_SIZE", 1)
