@@ -136,6 +136,14 @@ RansacConfig ransac_config(const mld_params& p) {
     c.use_refinement = p.ransac_plane_use_refinement;
     c.cos_eps = cos(M_PI / 18.);
     c.log_probability = log(1.0 - p.ransac_plane_probability);
+    // (double)dist < threshold  <=>  dist <= largest float strictly below the threshold (dist is a float)
+    auto below = [](double thr) {
+        float f = (float)thr;
+        if (!((double)f < thr)) f = nextafterf(f, -INFINITY);
+        return f;
+    };
+    c.thr_lt = below(p.ransac_plane_distance_treshold);
+    c.refine_lt = below(p.ransac_plane_refinement_treshold);
     return c;
 }
 
@@ -522,7 +530,7 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
         return fail(h, MLD_ERR_BAD_SEARCH_MODE, "neighbor_search_mode has the invalid value: " + std::to_string(p.neighbor_search_mode));
     DevParams& d = h->dp;
     memset(&d, 0, sizeof(d));
-    d.W = W; d.H = H; d.f = f; d.cx = cx; d.cy = cy;
+    d.W = W; d.H = H; d.Wd = (double)W; d.Hd = (double)H; d.f = f; d.cx = cx; d.cy = cy;
     for (int r = 0; r < 3; r++) {
         for (int c = 0; c < 3; c++) d.R[r * 3 + c] = T[r * 4 + c];
         d.t[r] = T[r * 4 + 3];

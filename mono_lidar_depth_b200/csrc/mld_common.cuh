@@ -41,6 +41,7 @@ enum MldRoadMode : int { ROAD_NONE = 0, ROAD_TRIANGLE = 1, ROAD_LEASTSQUARES = 2
 // monolidar_fusion/src/DepthEstimator.cpp:35-127, flattened into flags).
 struct DevParams {
     int W, H;
+    double Wd, Hd;        // (double)W, (double)H
     double f, cx, cy;
     double R[9], t[3];    // transform_lidar_to_cam
     double Ri[9], ti[3];  // transform_cam_to_lidar (Affine3d::inverse(), :44)

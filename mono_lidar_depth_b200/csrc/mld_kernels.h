@@ -51,6 +51,7 @@ struct RansacConfig {
     int use_refinement;           // ransac_plane_use_refinement
     double cos_eps;               // cos(M_PI / 18.): SampleConsensusModelPerpendicularPlane eps angle (RansacPlane.cpp:99)
     double log_probability;       // log(1 - probability)
+    float thr_lt, refine_lt;      // largest floats whose double value is < distance / refinement threshold
 };
 constexpr int MLD_RANSAC_SAMPLE = 6000;  // _numberRandomSamplePoints, RansacPlane.cpp:32
 

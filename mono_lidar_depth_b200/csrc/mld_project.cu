@@ -25,16 +25,16 @@ namespace {
 #define MLD_K1_THREADS 128
 #endif
 #ifndef MLD_K1_PPT
-#define MLD_K1_PPT 4
+#define MLD_K1_PPT 8
 #endif
 constexpr int K1_THREADS = MLD_K1_THREADS;
 constexpr int K1_PPT = MLD_K1_PPT;  // points per thread: independent 16-byte loads in flight
 
-// exact projection of one point; returns the pixel offset or -1 when the point does not enter the map
-__device__ __forceinline__ int project_pixel(const DevParams& P, float x, float y, float z, bool need_front) {
+// exact projection of one point; returns false when the point does not enter the map, else its pixel
+__device__ __forceinline__ bool project_pixel(const DevParams& P, float x, float y, float z, bool need_front, int& px, int& py) {
     D3 c = lidar_to_cam(P, x, y, z);
     // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51)
-    if (need_front && !(c.z > 0.0)) return -1;
+    if (need_front && !(c.z > 0.0)) return false;
     // K * p with K = [f 0 cx; 0 f cy; 0 0 1] evaluated term by term like Eigen's product
     // (camera_pinhole.h:88), then colwise().hnormalized() = division by the third row (:90)
     double q0 = __dadd_rn(__dadd_rn(__dmul_rn(P.f, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(P.cx, c.z));
@@ -42,11 +42,12 @@ __device__ __forceinline__ int project_pixel(const DevParams& P, float x, float 
     double q2 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(1.0, c.z));
     double u = __ddiv_rn(q0, q2);
     double v = __ddiv_rn(q1, q2);
-    double Wd = (double)P.W, Hd = (double)P.H;
-    bool in_range = (u >= 0.) && (u <= Wd) && (v >= 0.) && (v <= Hd);  // camera_pinhole.h:93-96
-    bool visible = (u > 0.) && (u < Wd) && (v > 0.) && (v < Hd);       // DepthEstimator.cpp:186-187
-    if (!(in_range && visible)) return -1;
-    return (int)v * P.W + (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
+    bool in_range = (u >= 0.) && (u <= P.Wd) && (v >= 0.) && (v <= P.Hd);  // camera_pinhole.h:93-96
+    bool visible = (u > 0.) && (u < P.Wd) && (v > 0.) && (v < P.Hd);       // DepthEstimator.cpp:186-187
+    if (!(in_range && visible)) return false;
+    px = (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
+    py = (int)v;
+    return true;
 }
 
 // FP32 pre-filter: true when the point certainly fails one of  z_cam > 0, u > 0, u < W, v > 0, v < H
@@ -68,40 +69,38 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
 }
 
 __global__ void __launch_bounds__(K1_THREADS)
-project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
+project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                        unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
-    const long long frame = blockIdx.y;
-    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
-    unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const unsigned int frame = blockIdx.y;
     const int occ_pitch = occ_words_per_row(P.W);
-    unsigned int* ob = occ ? occ + frame * (long long)occ_pitch * (long long)P.H : nullptr;
-    const long long base = (long long)blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
+    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
+    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
+    const int base = blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
+    const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
+    const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
     const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
 
     float4 p[K1_PPT];
 #pragma unroll
     for (int j = 0; j < K1_PPT; j++) {
-        long long i = base + (long long)j * K1_THREADS;
-        if (i < n)
-            p[j] = ld_stream_f4(fp + i * stride_f);
+        if (base + j * K1_THREADS < n)
+            p[j] = ld_stream_f4(src + j * step);
         else
             p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
     for (int j = 0; j < K1_PPT; j++) {
-        long long i = base + (long long)j * K1_THREADS;
-        if (i >= n) continue;
+        const int i = base + j * K1_THREADS;
+        if (i >= n) break;
         if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
-        int off = project_pixel(P, p[j].x, p[j].y, p[j].z, true);
-        if (off >= 0) {
-            atomicMin(&map[off], hi | (unsigned int)i);
-            if (ob) {
-                const int y = off / P.W, x = off - y * P.W;
-                unsigned int* orow = ob + (long long)y * occ_pitch;
-                const int wj = x >> 4, b = x & 15;
-                atomicOr(orow + wj, 1u << b);
-                if (wj > 0) atomicOr(orow + wj - 1, 1u << (16 + b));
-            }
+        int x, y;
+        if (!project_pixel(P, p[j].x, p[j].y, p[j].z, true, x, y)) continue;
+        atomicMin(&map[y * P.W + x], hi | (unsigned int)i);
+        if (ob) {
+            unsigned int* orow = ob + y * occ_pitch;
+            const int wj = x >> 4, b = x & 15;
+            atomicOr(orow + wj, 1u << b);
+            if (wj > 0) atomicOr(orow + wj - 1, 1u << (16 + b));
         }
     }
 }
@@ -113,7 +112,8 @@ __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts,
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float x = pts[i * stride_f], y = pts[i * stride_f + 1], z = pts[i * stride_f + 2];
-    if (visible) visible[i] = project_pixel(P, x, y, z, false) >= 0 ? 1 : 0;
+    int px, py;
+    if (visible) visible[i] = project_pixel(P, x, y, z, false, px, py) ? 1 : 0;
     if (cam) {
         D3 c = lidar_to_cam(P, x, y, z);
         cam[i * 3] = c.x;
@@ -171,8 +171,9 @@ cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, co
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
                                        cudaStream_t stream) {
     if (n <= 0 || nframes <= 0) return cudaSuccess;
+    if (n > 0x7fffffffLL / 8) return cudaErrorInvalidValue;  // 32-bit point indexing inside a frame
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
-    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, n, pitch_pts, d_maps, d_occ);
+    project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps, d_occ);
     return cudaGetLastError();
 }
 

@@ -32,6 +32,10 @@ constexpr int RS_CLUSTER = 8;
 constexpr int RS_THREADS = 256;
 constexpr int RS_SLICE = (MLD_RANSAC_SAMPLE + RS_CLUSTER - 1) / RS_CLUSTER;  // 750
 constexpr int RS_MAX_SAMPLE_CHECKS = 1000;  // pcl::SampleConsensusModel::max_sample_checks_
+// PCL's adaptive loop usually stops after 50-250 iterations, so a round scores only RS_HYP hypotheses;
+// the RS_THREADS / RS_HYP threads that share a hypothesis split the CTA's slice of the sample.
+constexpr int RS_HYP = 64;
+constexpr int RS_PARTS = RS_THREADS / RS_HYP;
 
 struct F3 {
     float x, y, z;
@@ -66,9 +70,11 @@ __device__ __forceinline__ bool model_valid(const float c[4], double cos_eps) {
     if (z > 0) nz = __fdiv_rn(c[2], __fsqrt_rn(z));
     return fabs((double)nz) >= cos_eps;
 }
-__device__ __forceinline__ double plane_dist(float a, float b, float c, float d, float x, float y, float z) {
-    float s = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d);
-    return fabs((double)s);
+// |a x + b y + c z + d| evaluated in float, left to right, no contraction (PCL's Vector4f arithmetic).
+// PCL compares (double)dist < (double)threshold; with thr_lt = the largest float whose double value is
+// below the threshold this is exactly  dist <= thr_lt  in float (see ransac_config()).
+__device__ __forceinline__ float plane_dist(float a, float b, float c, float d, float x, float y, float z) {
+    return fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d));
 }
 
 struct FrameView {
@@ -155,10 +161,10 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
     const long long frame = blockIdx.y;
 
     __shared__ float4 s_pts[RS_SLICE];         // x, y, z, raw index bits
-    __shared__ int s_partial[RS_THREADS];      // this CTA's counts for the round's hypotheses
-    __shared__ int s_total[RS_THREADS];
-    __shared__ float s_hyp[RS_THREADS][4];
-    __shared__ unsigned char s_nosample[RS_THREADS];
+    __shared__ int s_partial[RS_HYP];          // this CTA's counts for the round's hypotheses
+    __shared__ int s_total[RS_HYP];
+    __shared__ float s_hyp[RS_HYP][4];
+    __shared__ unsigned char s_nosample[RS_HYP], s_valid[RS_HYP];
     __shared__ float s_best[4];
     __shared__ int s_state[4];                 // done, have_model, iterations, n_best
     __shared__ double s_k;
@@ -203,59 +209,70 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
     __syncthreads();
 
     const double cos_eps = cfg.cos_eps;  // cos(M_PI / 18.), evaluated on the host
-    const double threshold = cfg.distance_treshold;
     const double log_probability = cfg.log_probability;  // log(1 - probability), evaluated on the host
     const unsigned max_skip = (unsigned)cfg.max_iterations * 10u;
     const double one_over_indices = 1.0 / (double)M;
 
+    const float thr_lt = cfg.thr_lt;
+    const int hyp = tid & (RS_HYP - 1), part = tid / RS_HYP;
+    const int per_part = (slice_n + RS_PARTS - 1) / RS_PARTS;
+    const int q_begin = part * per_part, q_end = min(slice_n, q_begin + per_part);
     for (int round = 0;; round++) {
-        // ---- hypothesis (round*256 + tid): draw, model, validity -------------------------------
-        const uint64_t draw = (uint64_t)round * RS_THREADS + (uint64_t)tid;
-        bool got = false;
-        F3 p0{}, p1{}, p2{};
-        for (int a = 0; a < RS_MAX_SAMPLE_CHECKS && !got; a++) {
-            uint64_t h0 = mld_hash3(fv.seed, draw, (uint64_t)a, 0), h1 = mld_hash3(fv.seed, draw, (uint64_t)a, 1),
-                     h2 = mld_hash3(fv.seed, draw, (uint64_t)a, 2);
-            long long i0 = (long long)(h0 % (uint64_t)M);
-            long long i1 = (long long)(h1 % (uint64_t)(M - 1));
-            if (i1 >= i0) i1++;
-            long long i2 = (long long)(h2 % (uint64_t)(M - 2));
-            long long lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
-            if (i2 >= lo) i2++;
-            if (i2 >= hi) i2++;
-            p0 = load_pt(fv, sub_raw(fv, i0));
-            p1 = load_pt(fv, sub_raw(fv, i1));
-            p2 = load_pt(fv, sub_raw(fv, i2));
-            got = sample_good(p0, p1, p2);
-        }
-        float c[4] = {0.f, 0.f, 0.f, 0.f};
-        bool valid = false;
-        if (got) {
-            plane_from_sample(p0, p1, p2, c);
-            valid = model_valid(c, cos_eps);
-        }
-        s_nosample[tid] = got ? 0 : 1;
-        s_hyp[tid][0] = c[0]; s_hyp[tid][1] = c[1]; s_hyp[tid][2] = c[2]; s_hyp[tid][3] = c[3];
-        // ---- score against this CTA's slice (countWithinDistance) -----------------------------
-        int count = 0;
-        if (valid) {
-            for (int q = 0; q < slice_n; q++) {
-                float4 p = s_pts[q];  // broadcast
-                if (plane_dist(c[0], c[1], c[2], c[3], p.x, p.y, p.z) < threshold) count++;
+        // ---- hypothesis (round*RS_HYP + tid), tid < RS_HYP: draw, model, validity ------------------
+        if (tid < RS_HYP) {
+            const uint64_t draw = (uint64_t)round * RS_HYP + (uint64_t)tid;
+            bool got = false;
+            F3 p0{}, p1{}, p2{};
+            for (int a = 0; a < RS_MAX_SAMPLE_CHECKS && !got; a++) {
+                uint64_t h0 = mld_hash3(fv.seed, draw, (uint64_t)a, 0), h1 = mld_hash3(fv.seed, draw, (uint64_t)a, 1),
+                         h2 = mld_hash3(fv.seed, draw, (uint64_t)a, 2);
+                long long i0 = (long long)(h0 % (uint64_t)M);
+                long long i1 = (long long)(h1 % (uint64_t)(M - 1));
+                if (i1 >= i0) i1++;
+                long long i2 = (long long)(h2 % (uint64_t)(M - 2));
+                long long lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
+                if (i2 >= lo) i2++;
+                if (i2 >= hi) i2++;
+                p0 = load_pt(fv, sub_raw(fv, i0));
+                p1 = load_pt(fv, sub_raw(fv, i1));
+                p2 = load_pt(fv, sub_raw(fv, i2));
+                got = sample_good(p0, p1, p2);
             }
+            float c[4] = {0.f, 0.f, 0.f, 0.f};
+            bool valid = false;
+            if (got) {
+                plane_from_sample(p0, p1, p2, c);
+                valid = model_valid(c, cos_eps);
+            }
+            s_nosample[tid] = got ? 0 : 1;
+            s_valid[tid] = valid ? 1 : 0;
+            s_hyp[tid][0] = c[0]; s_hyp[tid][1] = c[1]; s_hyp[tid][2] = c[2]; s_hyp[tid][3] = c[3];
+            s_partial[tid] = 0;
         }
-        s_partial[tid] = count;
+        __syncthreads();
+        // ---- score against this CTA's slice (countWithinDistance); RS_PARTS threads share a hypothesis ----
+        if (s_valid[hyp]) {
+            const float c0 = s_hyp[hyp][0], c1 = s_hyp[hyp][1], c2 = s_hyp[hyp][2], c3 = s_hyp[hyp][3];
+            int count = 0;
+            for (int q = q_begin; q < q_end; q++) {
+                float4 p = s_pts[q];
+                if (plane_dist(c0, c1, c2, c3, p.x, p.y, p.z) <= thr_lt) count++;
+            }
+            if (count) atomicAdd(&s_partial[hyp], count);
+        }
         cluster.sync();
-        int total = 0;
+        if (tid < RS_HYP) {
+            int total = 0;
 #pragma unroll
-        for (unsigned r = 0; r < RS_CLUSTER; r++) total += *cluster.map_shared_rank(&s_partial[tid], r);
-        s_total[tid] = total;
+            for (unsigned r = 0; r < RS_CLUSTER; r++) total += *cluster.map_shared_rank(&s_partial[tid], r);
+            s_total[tid] = total;
+        }
         __syncthreads();
         // ---- PCL's sequential update over the round (RandomSampleConsensus::computeModel) ------
         if (tid == 0) {
             int iterations = s_state[2], n_best = s_state[3], have = s_state[1], done = 0;
             double k = s_k;
-            for (int t = 0; t < RS_THREADS; t++) {
+            for (int t = 0; t < RS_HYP; t++) {
                 if (!((double)iterations < k) || !(0u < max_skip)) { done = 1; break; }
                 if (s_nosample[t]) { done = 1; break; }  // "No samples could be selected!"
                 int cnt = s_total[t];
@@ -302,7 +319,7 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
         if (best_valid) {
             for (int q = tid; q < slice_n; q += RS_THREADS) {
                 float4 p = s_pts[q];
-                if (plane_dist(b0, b1, b2, b3, p.x, p.y, p.z) < threshold) {
+                if (plane_dist(b0, b1, b2, b3, p.x, p.y, p.z) <= thr_lt) {
                     double x = p.x, y = p.y, z = p.z;
                     v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
                     v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
@@ -341,13 +358,13 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
         }
     }
     // final inlier set: selectWithinDistance with the UN-refined coefficients (RansacPlane.cpp:121)
-    const double final_thr = cfg.use_refinement ? cfg.refinement_treshold : threshold;
+    const float final_lt = cfg.use_refinement ? cfg.refine_lt : thr_lt;
     unsigned int* bits = out_bits + frame * words_per_frame;
     int my_inl = 0;
     if (best_valid) {
         for (int q = tid; q < slice_n; q += RS_THREADS) {
             float4 p = s_pts[q];
-            if (plane_dist(b0, b1, b2, b3, p.x, p.y, p.z) < final_thr) {
+            if (plane_dist(b0, b1, b2, b3, p.x, p.y, p.z) <= final_lt) {
                 int raw = __float_as_int(p.w);
                 atomicOr(&bits[raw >> 5], 1u << (raw & 31));
                 my_inl++;
