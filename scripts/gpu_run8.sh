@@ -1,0 +1,11 @@
+python -m pytest tests -m gpu -q --no-header -rf -x --timeout 900 > gpurun_out/test8.log 2>&1; tail -5 gpurun_out/test8.log
+run() { MLD_BENCH_CPU_SECONDS=1 MLD_BENCH_E2E_FRAMES=128 python bench.py --workload ${2:-kitti} --steps 3 --warmup 3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('$1 ${2:-kitti} chunk',d['config']['chunk_frames_per_launch'],'fps',round(d['value']),{k:(round(v['avg_launch_ms']*1000,1) if isinstance(v,dict) and v['avg_launch_ms'] else None) for k,v in d['roofline']['per_kernel'].items()})
+    elif 'Error' in l or 'error' in l: print(l)
+"; }
+for c in 32 64; do MLD_CHUNK_FRAMES=$c MLD_OVERLAP=1 run serial; done
+for ov in 2 3; do for c in 24 32 48 64; do MLD_CHUNK_FRAMES=$c MLD_OVERLAP=$ov run ov$ov; done; done
+MLD_CHUNK_FRAMES=32 run ov3 road; MLD_CHUNK_FRAMES=64 run ov3 road; MLD_CHUNK_FRAMES=32 run ov3 dense
