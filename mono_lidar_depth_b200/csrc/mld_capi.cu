@@ -39,6 +39,7 @@ struct Slot {
     int* d_small = nullptr;     size_t small_bytes = 0;  // n_inliers | iterations | rc, per frame
     int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
     unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
+    void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
     unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
     MapCode mc = {0u, 0u};      // encoding of the maps currently held by this slot
 };
@@ -72,7 +73,9 @@ struct mld_handle {
     bool have_cloud = false;
     int kcap = 0;
     int chunk_frames = 64;
-    int feature_mode = 1;  // 1: thread per feature + warp-per-feature overflow pass; 0: warp per feature only
+    // 2: split gather/solve(/road) thread-per-feature kernels + warp-per-feature overflow pass (default)
+    // 1: fused thread-per-feature kernel + overflow pass; 0: warp per feature only
+    int feature_mode = 2;
     int overflow_blocks = 296;
     bool use_tagged_maps = true;
     int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
@@ -200,7 +203,7 @@ int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStrea
         mc = MapCode{1u, MLD_TAG_MAX_EPOCH - s.epoch};
     }
     s.mc = mc;
-    if (h->feature_mode == 1)
+    if (h->feature_mode >= 1)
         CK(cudaMemsetAsync(s.d_occ, 0, (size_t)frames * (size_t)occ_words_per_row(h->dp.W) * (size_t)h->dp.H * sizeof(unsigned int), st));
     return MLD_OK;
 }
@@ -210,7 +213,16 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
                     const double* d_uv, int F, double* d_depth, int* d_status, const float* coeffs, const unsigned int* bits,
                     long long words, int frames) {
     if (F <= 0 || frames <= 0) return MLD_OK;
-    if (h->feature_mode == 1) {
+    if (h->feature_mode == 2) {
+        CK(ensure(s.d_split, s.split_bytes, mld_split_scratch_bytes((long long)frames * F)));
+        CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
+        int nl = 0;
+        CK(mld_launch_feature_depth_split(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
+                                          words, frames, s.d_ovf + 1, s.d_ovf, s.d_split, st, &nl));
+        CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
+                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, h->overflow_blocks, st));
+        h->launches += nl + 1;
+    } else if (h->feature_mode == 1) {
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
         CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
                                            words, frames, s.d_ovf + 1, s.d_ovf, st));
@@ -249,7 +261,7 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     int rcm = begin_maps(h, s, frames, n_points, st, mc);
     if (rcm) return rcm;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode == 1 ? s.d_occ : nullptr, frames, st));
+    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
     const float* coeffs = nullptr;
@@ -476,8 +488,10 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     h->device = device;
     const char* env = getenv("MLD_CHUNK_FRAMES");
     if (env && atoi(env) > 0) h->chunk_frames = atoi(env);
-    env = getenv("MLD_FEATURE_MODE");  // "warp": warp-per-feature kernel only (A/B measurements)
+    env = getenv("MLD_FEATURE_MODE");  // "warp" / "fused" / "split": K2 variants (A/B measurements)
     if (env && strcmp(env, "warp") == 0) h->feature_mode = 0;
+    if (env && strcmp(env, "fused") == 0) h->feature_mode = 1;
+    if (env && strcmp(env, "split") == 0) h->feature_mode = 2;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
     env = getenv("MLD_OVERLAP");       // "1": run the chunks of a sequence on one stream (no K1/K2 overlap), up to 3
@@ -510,7 +524,7 @@ int mld_destroy(mld_handle* h) {
     for (auto& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
-        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -689,7 +703,7 @@ int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_
     rc = begin_maps(h, s, 1, n, s.stream, mc);
     if (rc) return rc;
     CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps,
-                                  h->feature_mode == 1 ? s.d_occ : nullptr, 1, s.stream));
+                                  h->feature_mode >= 1 ? s.d_occ : nullptr, 1, s.stream));
     if (n > 0) h->launches++;
     h->cur_n = n;
     h->cur_stride_f = stride_bytes / 4;

@@ -1,0 +1,330 @@
+// mld_feature_split.cu -- K2 as two (three with a ground plane) thread-per-feature kernels with a
+// chunk-wide compaction in between.
+//
+// ncu of the fused thread-per-feature kernel (profiles/r1_v4_*): 45 % of the stall samples wait on the
+// three dependent load rounds of the window gather, 23 % on the block barriers of the in-block
+// compaction, occupancy pinned at 16 warps/SM by the per-thread XYZ slabs that only the later phases
+// need, and 44 % of the features (empty windows) idle through those phases. Splitting fixes all three:
+//
+//   K2a gather  every feature: occupancy words -> pixel offsets -> map cells -> points -> FP64 camera
+//               frame. No XYZ slab (8 KB of shared memory per block), so it runs at register-limited
+//               occupancy where the load latency is hidden. Features with k >= radiusSearch_count_min are
+//               appended to a chunk-wide survivor list (one atomic per block) with their points in SoA
+//               form [entry][xyz][slot]; empty windows get status 2 right here.
+//   K2b solve   one thread per SURVIVOR (dense warps over the whole chunk): histogram segmentation,
+//               corner selection, in-block compaction, geometry tail. With a plane, unsolved features go
+//               to a second list.
+//   K2c road    one thread per road candidate: wide-window gather + plane gate + road estimator.
+//
+// Reference routines restated: see mld_feature.cu / mld_thread_helpers.cuh (DepthEstimator.cpp:491-600).
+#include "mld_common.cuh"
+#include "mld_geometry.cuh"
+#include "mld_kernels.h"
+#include "mld_thread_helpers.cuh"
+
+namespace {
+
+constexpr int SCAP = 16;    // neighbours per feature in the normal window (more -> warp-kernel overflow list)
+constexpr int SBT_A = 128;  // threads per block, gather
+constexpr int SBT_B = 64;   // threads per block, solve
+constexpr int RCAP = 24;    // neighbours per feature in the road window
+constexpr int SBT_C = 64;   // threads per block, road
+
+// survivor record: (k << 27) | global feature id
+__device__ __forceinline__ unsigned int pack_rec(int k, long long o) { return ((unsigned int)k << 27) | (unsigned int)o; }
+
+// ---- K2a ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SBT_A)
+feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                      const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
+                      const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                      int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
+                      double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap) {
+    __shared__ int s_aux[SCAP * SBT_A];
+    __shared__ int s_wtot[SBT_A / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const int fi = blockIdx.x * SBT_A + tid;
+    const bool valid = fi < F;
+    const long long frame = blockIdx.y;
+    const long long o = frame * (long long)F + fi;
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+    int* aux = s_aux + tid;
+
+    if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
+        if (valid) {
+            status[o] = 1;
+            depth[o] = -1;
+        }
+        return;
+    }
+
+    // phase 1: occupancy words -> pixel offsets of the window's points in scan order
+    int k = 0;
+    if (valid) {
+        const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+        const double u = f2.x, v = f2.y;
+        if ((fabs(u) < 1e9) && (fabs(v) < 1e9)) {  // NaN / huge coordinates: empty window (see mld_feature.cu)
+            const int x0 = (int)fmax(u - P.hx1, 0.), x1 = (int)fmin(u + P.hx1, (double)(P.W - 1));
+            const int y0 = (int)fmax(v - P.hy1, 0.), y1 = (int)fmin(v + P.hy1, (double)(P.H - 1));
+            if (x1 >= x0 && y1 >= y0) {
+                const int pitch = occ_words_per_row(P.W);
+                const int wj0 = x0 >> 4;
+                for (int yb = y0; yb <= y1; yb += T_ROWS) {
+                    unsigned int w[T_ROWS];
+#pragma unroll
+                    for (int r = 0; r < T_ROWS; r++) {
+                        const int y = yb + r;
+                        w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
+                    }
+#pragma unroll
+                    for (int r = 0; r < T_ROWS; r++) {
+                        const int y = yb + r;
+                        if (y > y1) break;
+                        unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
+                        int wj = wj0;
+                        while (true) {
+                            while (m) {
+                                const int b = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (k < SCAP) aux[k * SBT_A] = y * P.W + (wj << 4) + b;
+                                k++;
+                            }
+                            wj += 2;
+                            if ((wj << 4) > x1) break;
+                            m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    const bool overflow = valid && k > SCAP;
+    const bool surv = valid && !overflow && (unsigned)k >= (unsigned)P.count_min;
+    if (valid && !surv) {
+        if (overflow) {
+            overflow_list[atomicAdd(overflow_count, 1)] = (int)o;  // finished by the warp-per-feature kernel
+        } else {  // neighbors.size() < (uint)radiusSearch_count_min (DepthEstimator.cpp:680)
+            status[o] = ST_RadiusSearchInsufficientPoints;
+            depth[o] = -1;
+        }
+    }
+    // chunk-wide survivor slot: rank inside the block + one atomic per block
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned bm = __ballot_sync(MLD_FULL_MASK, surv);
+    if (lane == 0) s_wtot[warp] = __popc(bm);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SBT_A / 32; w++) {
+        const int c = s_wtot[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (tid == 0) s_base = total ? atomicAdd(surv_count, total) : 0;
+    __syncthreads();
+    if (!surv) return;
+    const long long slot = (long long)s_base + base + __popc(bm & ((1u << lane) - 1u));
+    surv_rec[slot] = pack_rec(k, o);
+    // phase 2: map cells -> raw indices; phase 3: points -> FP64 camera frame, stored [entry][xyz][slot]
+#pragma unroll 4
+    for (int i = 0; i < k; i++) aux[i * SBT_A] = (int)map_cell_index(mc, __ldg(map + aux[i * SBT_A]));
+#pragma unroll 2
+    for (int i = 0; i < k; i++) {
+        const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)aux[i * SBT_A] * stride_f));
+        const D3 c = lidar_to_cam(P, q.x, q.y, q.z);
+        double* dst = surv_xyz + (long long)i * 3 * cap + slot;
+        dst[0] = c.x;
+        dst[cap] = c.y;
+        dst[2 * cap] = c.z;
+    }
+}
+
+// ---- K2b ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SBT_B)
+feature_solve_kernel(DevParams P, const double* __restrict__ uv, double* __restrict__ depth, int* __restrict__ status,
+                     const unsigned int* __restrict__ surv_rec, const double* __restrict__ surv_xyz,
+                     const int* __restrict__ surv_count, long long cap, int road, int* __restrict__ road_list,
+                     int* __restrict__ road_count) {
+    using TSlab = TSlabT<SCAP, SBT_B>;
+    __shared__ double sx[SCAP * SBT_B], sy[SCAP * SBT_B], sz[SCAP * SBT_B];
+    __shared__ int saux[SCAP * SBT_B];
+    __shared__ double s_u[SBT_B], s_v[SBT_B];
+    __shared__ int s_o[SBT_B];
+    __shared__ short s_list[SBT_B], s_cnt[SBT_B];
+    __shared__ signed char s_st[SBT_B], s_ci[SBT_B], s_cj[SBT_B], s_ck[SBT_B];
+    __shared__ int s_wtot[SBT_B / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const int count = *surv_count;
+    const long long slot = (long long)blockIdx.x * SBT_B + tid;
+    if ((long long)blockIdx.x * SBT_B >= count) return;  // uniform per block
+    const bool valid = slot < count;
+    auto slab_of = [&](int owner) { return TSlab{sx + owner, sy + owner, sz + owner, saux + owner}; };
+
+    // P2: histogram segmentation + corner selection
+    bool surv = false;
+    s_st[tid] = ST_Unspecified;
+    if (valid) {
+        const unsigned int rec = surv_rec[slot];
+        const int k = (int)(rec >> 27);
+        const int o = (int)(rec & 0x7FFFFFFu);
+        s_o[tid] = o;
+        const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+        s_u[tid] = f2.x;
+        s_v[tid] = f2.y;
+        const TSlab s = slab_of(tid);
+        for (int i = 0; i < k; i++) {
+            const double* src = surv_xyz + (long long)i * 3 * cap + slot;
+            s.set(i, D3{src[0], src[cap], src[2 * cap]});
+        }
+        int n = k;
+        int st = ST_Unspecified;
+        if (P.use_hist) {
+            n = t_histogram_segment(P, k, s);
+            if (n < 0) st = ST_HistogramNoLocalMax;
+        }
+        if (st != ST_HistogramNoLocalMax) {
+            int ci, cj, ck;
+            st = t_select_corners(P, n, s, ci, cj, ck);
+            if (st == 0) {
+                s_cnt[tid] = (short)n;
+                s_ci[tid] = (signed char)ci;
+                s_cj[tid] = (signed char)cj;
+                s_ck[tid] = (signed char)ck;
+                surv = true;
+            }
+        }
+        if (!surv) s_st[tid] = (signed char)st;
+    }
+    __syncthreads();
+    const int n2 = block_compact<SBT_B>(surv, tid, s_list, s_wtot);
+
+    // P3: geometry tail on dense lanes
+    double dp_mine = -1;
+    if (tid < n2) {
+        const int owner = s_list[tid];
+        double dp;
+        const int st = t_depth_from_corners(P, s_u[owner], s_v[owner], (int)s_cnt[owner], slab_of(owner), (int)s_ci[owner],
+                                            (int)s_cj[owner], (int)s_ck[owner], dp);
+        s_st[owner] = (signed char)st;
+        // park the depth in the owner's slab (entry 0 is no longer needed once the tail is done)
+        sx[owner] = dp;
+    }
+    __syncthreads();
+    if (valid) {
+        const int st = s_st[tid];
+        const int o = s_o[tid];
+        if (st == ST_Success) dp_mine = sx[tid];
+        // the road path overwrites status/depth of its candidates later; everything gets a normal-path result first
+        status[o] = st;
+        depth[o] = (st == ST_Success) ? dp_mine : -1.0;
+    }
+    if (road) {
+        const bool want = valid && s_st[tid] != ST_Success;
+        const int lane = tid & 31, warp = tid >> 5;
+        const unsigned bm = __ballot_sync(MLD_FULL_MASK, want);
+        if (lane == 0) s_wtot[warp] = __popc(bm);
+        __syncthreads();
+        int base = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < SBT_B / 32; w++) {
+            const int c = s_wtot[w];
+            if (w < warp) base += c;
+            total += c;
+        }
+        if (tid == 0) s_base = total ? atomicAdd(road_count, total) : 0;
+        __syncthreads();
+        if (want) road_list[s_base + base + __popc(bm & ((1u << lane) - 1u))] = s_o[tid];
+    }
+}
+
+// ---- K2c ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(SBT_C)
+feature_road_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                    const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
+                    const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                    const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ inlier_bits,
+                    long long inlier_words_per_frame, const int* __restrict__ road_list, const int* __restrict__ road_count,
+                    int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
+    using TSlab = TSlabT<RCAP, SBT_C>;
+    __shared__ double sx[RCAP * SBT_C], sy[RCAP * SBT_C], sz[RCAP * SBT_C];
+    __shared__ int saux[RCAP * SBT_C];
+    const int tid = threadIdx.x;
+    const int count = *road_count;
+    const long long item = (long long)blockIdx.x * SBT_C + tid;
+    if (item >= count) return;
+    const long long o = road_list[item];
+    const long long frame = o / F;
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
+    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+    const float* pc = plane_coeffs + frame * 4;
+    const unsigned int* bits = inlier_bits + frame * inlier_words_per_frame;
+    const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+    const TSlab s{sx + tid, sy + tid, sz + tid, saux + tid};
+    unsigned int mask;
+    const int k2 = t_gather_window(P, mc, map, occ, fp, stride_f, f2.x, f2.y, P.hx2, P.hy2, s, bits, mask);
+    if (k2 < 0) {
+        overflow_list[atomicAdd(overflow_count, 1)] = (int)o;  // the warp kernel redoes the feature from scratch
+        return;
+    }
+    if ((unsigned)k2 < (unsigned)P.count_min) {  // DepthEstimator.cpp:585-586
+        status[o] = ST_RadiusSearchInsufficientPoints;
+        depth[o] = -1;
+        return;
+    }
+    double dp;
+    const int st = t_road_depth(P, f2.x, f2.y, k2, s, pc, mask, status[o], dp);
+    status[o] = st;
+    depth[o] = (st == ST_SuccessRoad) ? dp : -1.0;
+}
+
+}  // namespace
+
+size_t mld_split_scratch_bytes(long long features) {
+    // counters (64 B) + survivor records + road list + survivor points [SCAP][3][features]
+    return 64 + (size_t)features * (sizeof(unsigned int) + sizeof(int)) + (size_t)features * SCAP * 3 * sizeof(double) + 256;
+}
+
+cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
+                                           long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
+                                           const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,
+                                           const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
+                                           int* d_overflow_list, int* d_overflow_count, void* d_scratch, cudaStream_t stream,
+                                           int* launches) {
+    if (F <= 0 || nframes <= 0) return cudaSuccess;
+    const long long features = (long long)nframes * F;
+    if (features >= (1ll << 27)) return cudaErrorInvalidValue;  // survivor records hold 27-bit feature ids
+    unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
+    int* surv_count = reinterpret_cast<int*>(base);
+    int* road_count = surv_count + 1;
+    unsigned int* surv_rec = reinterpret_cast<unsigned int*>(base + 64);
+    int* road_list = reinterpret_cast<int*>(surv_rec + features);
+    size_t off = 64 + (size_t)features * 8;
+    off = (off + 255) & ~(size_t)255;
+    double* surv_xyz = reinterpret_cast<double*>(base + off);
+    const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
+    cudaError_t e = cudaMemsetAsync(surv_count, 0, 2 * sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    dim3 ga((unsigned)((F + SBT_A - 1) / SBT_A), (unsigned)nframes);
+    feature_gather_kernel<<<ga, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
+                                                   d_overflow_list, d_overflow_count, surv_rec, surv_xyz, surv_count, features);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
+    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, surv_rec, surv_xyz, surv_count, features, road ? 1 : 0,
+                                                  road_list, road_count);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) *launches += 2;
+    if (road) {
+        const unsigned gc = (unsigned)((features + SBT_C - 1) / SBT_C);
+        feature_road_kernel<<<gc, SBT_C, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
+                                                     d_plane_coeffs, d_inlier_bits, words_per_frame, road_list, road_count,
+                                                     d_overflow_list, d_overflow_count);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 1;
+    }
+    return cudaSuccess;
+}

@@ -41,6 +41,15 @@ cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& m
                                             const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                             int* d_overflow_list, int* d_overflow_count, cudaStream_t stream);
 
+// K2/K3 split into gather / solve / road kernels with a chunk-wide compaction (mld_feature_split.cu)
+size_t mld_split_scratch_bytes(long long features);
+cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
+                                           long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
+                                           const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,
+                                           const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
+                                           int* d_overflow_list, int* d_overflow_count, void* d_scratch, cudaStream_t stream,
+                                           int* launches);
+
 // K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
 struct RansacConfig {
     double distance_treshold;     // ransac_plane_distance_treshold

@@ -27,6 +27,9 @@ namespace {
 #ifndef MLD_K1_PPT
 #define MLD_K1_PPT 8
 #endif
+#ifndef MLD_K1_MINBLOCKS
+#define MLD_K1_MINBLOCKS 1
+#endif
 constexpr int K1_THREADS = MLD_K1_THREADS;
 constexpr int K1_PPT = MLD_K1_PPT;  // points per thread: independent 16-byte loads in flight
 
@@ -68,7 +71,7 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
     return false;
 }
 
-__global__ void __launch_bounds__(K1_THREADS)
+__global__ void __launch_bounds__(K1_THREADS, MLD_K1_MINBLOCKS)
 project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                        unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
     const unsigned int frame = blockIdx.y;

@@ -326,12 +326,13 @@ def test_batched_device_and_host_paths_match_per_frame():
     assert est.kernelLaunchCount() > 0
 
 
-@pytest.mark.parametrize("mode", ["warp", "untagged"])
+@pytest.mark.parametrize("mode", ["warp", "fused", "untagged"])
 def test_alternative_kernel_modes(mode, monkeypatch):
-    """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp) and cleared (un-tagged) pixel maps
-    (MLD_TAGGED_MAPS=0) give the same results as the default thread-per-feature + epoch-tag path."""
-    if mode == "warp":
-        monkeypatch.setenv("MLD_FEATURE_MODE", "warp")
+    """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp), the fused thread-per-feature kernel (=fused)
+    and cleared (un-tagged) pixel maps (MLD_TAGGED_MAPS=0) give the same results as the default path (split
+    gather/solve/road kernels + epoch tags)."""
+    if mode in ("warp", "fused"):
+        monkeypatch.setenv("MLD_FEATURE_MODE", mode)
     else:
         monkeypatch.setenv("MLD_TAGGED_MAPS", "0")
     p = O.yaml_params()
