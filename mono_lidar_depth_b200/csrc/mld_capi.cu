@@ -22,7 +22,8 @@ namespace {
 
 thread_local std::string g_create_error;
 
-constexpr int MLD_PIPE_SLOTS = 3;
+constexpr int MLD_PIPE_SLOTS = 6;   // slots (streams + buffers) a handle owns
+constexpr int MLD_HOST_SLOTS = 3;   // of which the host-buffer pipeline uses
 
 // everything one in-flight chunk of frames needs on the device
 struct Slot {
@@ -40,6 +41,7 @@ struct Slot {
     int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
     unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
     void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
+    int* h_ovf_seen = nullptr;  // pinned: overflow count of this slot's previous chunk (sizes the next overflow launch)
     unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
     MapCode mc = {0u, 0u};      // encoding of the maps currently held by this slot
 };
@@ -72,7 +74,7 @@ struct mld_handle {
     bool initialized = false;
     bool have_cloud = false;
     int kcap = 0;
-    int chunk_frames = 64;
+    int chunk_frames = 128;
     // 2: split gather/solve(/road) thread-per-feature kernels + warp-per-feature overflow pass (default)
     // 1: fused thread-per-feature kernel + overflow pass; 0: warp per feature only
     int feature_mode = 2;
@@ -208,6 +210,16 @@ int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStrea
     return MLD_OK;
 }
 
+// The overflow pass runs the (slow) warp-per-feature kernel over a list whose length is only known on the
+// device. Its grid is sized from the overflow count this slot saw on its previous chunk (read back
+// asynchronously into pinned memory, never waited for): an empty list costs a 4-block launch instead of a
+// machine-filling one. Any grid size is correct -- the warps stride the list.
+int overflow_grid(mld_handle* h, Slot& s) {
+    const int seen = *reinterpret_cast<volatile int*>(s.h_ovf_seen);
+    const long long want = ((long long)seen * 2 + 7) / 8 + 4;  // 8 warps per block, 2x head-room
+    return (int)std::min<long long>(h->overflow_blocks, std::max<long long>(4, want));
+}
+
 // K2: thread-per-feature kernel + warp-per-feature pass over its overflow list, or warp-per-feature only
 int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, const float* d_pts, int stride_f, long long pitch_pts,
                     const double* d_uv, int F, double* d_depth, int* d_status, const float* coeffs, const unsigned int* bits,
@@ -220,14 +232,16 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
         CK(mld_launch_feature_depth_split(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
                                           words, frames, s.d_ovf + 1, s.d_ovf, s.d_split, st, &nl));
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
-                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, h->overflow_blocks, st));
+                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, overflow_grid(h, s), st));
+        CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         h->launches += nl + 1;
     } else if (h->feature_mode == 1) {
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
         CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
                                            words, frames, s.d_ovf + 1, s.d_ovf, st));
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
-                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, h->overflow_blocks, st));
+                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, overflow_grid(h, s), st));
+        CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         h->launches += 2;
     } else {
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
@@ -509,6 +523,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
         e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->slots[i].h_ovf_seen), sizeof(int), cudaHostAllocDefault);
+        if (e == cudaSuccess) *h->slots[i].h_ovf_seen = 1 << 30;  // unknown yet: launch the full overflow grid
         if (e != cudaSuccess) {
             mld_destroy(h);
             return fail_cuda(nullptr, e, "stream/event creation");
@@ -526,6 +542,7 @@ int mld_destroy(mld_handle* h) {
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
         cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.h_ovf_seen) cudaFreeHost(s.h_ovf_seen);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(h->d_dbg);
@@ -847,13 +864,13 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
     const int stride_f = stride_bytes / 4;
     const size_t frame_bytes = (size_t)n_points * (size_t)stride_bytes;
     const unsigned char* src = reinterpret_cast<const unsigned char*>(points_host);
-    for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
+    for (int i = 0; i < MLD_HOST_SLOTS; i++) {
         rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_bytes, std::max(F, 1), chunk, true, use_road);
         if (rc) return rc;
     }
     int64_t ci = 0;
     for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
-        Slot& s = h->slots[ci % MLD_PIPE_SLOTS];
+        Slot& s = h->slots[ci % MLD_HOST_SLOTS];
         int c = (int)std::min<int64_t>(chunk, nframes - f0);
         // stream order makes the slot's buffers safe to reuse: the previous chunk on this stream is complete
         // (its D2H copies included) before these copies start
@@ -877,7 +894,7 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
             CK(cudaMemcpyAsync(plane_coeffs_out_host + f0 * 4, s.d_coeffs, (size_t)c * 4 * sizeof(float), cudaMemcpyDeviceToHost,
                                s.stream));
     }
-    for (int i = 0; i < MLD_PIPE_SLOTS; i++) CK(cudaStreamSynchronize(h->slots[i].stream));
+    for (int i = 0; i < MLD_HOST_SLOTS; i++) CK(cudaStreamSynchronize(h->slots[i].stream));
     h->have_cloud = false;
     return MLD_OK;
 }

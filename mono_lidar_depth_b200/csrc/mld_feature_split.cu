@@ -24,9 +24,15 @@
 
 namespace {
 
-constexpr int SCAP = 16;    // neighbours per feature in the normal window (more -> warp-kernel overflow list)
+#ifndef MLD_SCAP
+#define MLD_SCAP 12
+#endif
+#ifndef MLD_SBT_B
+#define MLD_SBT_B 128
+#endif
+constexpr int SCAP = MLD_SCAP;  // neighbours per feature in the normal window (more -> warp-kernel overflow list)
 constexpr int SBT_A = 128;  // threads per block, gather
-constexpr int SBT_B = 64;   // threads per block, solve
+constexpr int SBT_B = MLD_SBT_B;  // threads per block, solve
 constexpr int RCAP = 24;    // neighbours per feature in the road window
 constexpr int SBT_C = 64;   // threads per block, road
 
