@@ -164,6 +164,27 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
                             int stride_bytes, const double* uv_host, int F, double* depth_host, int32_t* status_host,
                             int64_t nframes, int road, uint64_t seed, float* plane_coeffs_out_host);
 
+/* ---- tracklets_depth batch adaptor ----
+ * TrackletDepthModule::process calls CalculateDepth twice per frame, for the previous and the current cloud
+ * with different feature sets (tracklets_depth/src/tracklet_depth_module.cpp:318, :330). Both clouds go through
+ * the device concurrently (own streams, maps and staging buffers); a NULL cloud (no previous frame yet,
+ * :97-100) yields depth -1 for its features. Planes follow mld_set_cloud / mld_calculate_depth semantics;
+ * the status outputs may be NULL (the 4-argument overload discards them). After the call the handle's
+ * current cloud is the `cur` cloud. */
+int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev, const double* uv_prev, int F_prev,
+                             double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur,
+                             int64_t n_cur, const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur,
+                             mld_plane* plane_cur, int stride_bytes, uint64_t ransac_seed);
+
+/* ---- DepthCalculationStatistics (DepthEstimator.cpp:1039-1090): counters per DepthResultType (0..20) ---- */
+int mld_status_histogram_host(mld_handle* h, const int32_t* status_host, int64_t n, int64_t* hist21_out);
+int mld_status_histogram_device(mld_handle* h, const int32_t* d_status, int64_t n, int64_t* hist21_out_host, void* stream);
+
+/* ---- matches_msg_depth_ros/FeaturePoint {float32 u, v, d} packing (FeaturePoint.msg:1-5) ----
+ * device buffers in, device buffer of 3 floats per feature out; enqueued on `stream`. */
+int mld_pack_feature_points_device(mld_handle* h, const double* d_uv, const double* d_depth, int64_t n, float* d_out_uvd,
+                                   void* stream);
+
 /* number of kernels this handle has launched since creation (for bench.py's gpu_launches) */
 int64_t mld_kernel_launch_count(const mld_handle* h);
 /* per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figures).

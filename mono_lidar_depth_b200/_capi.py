@@ -145,6 +145,14 @@ SYMBOLS = {
         [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
          C.c_uint64, C.c_void_p],
     ),
+    "mld_calculate_depth_pair": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _PL, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+         C.c_void_p, C.c_void_p, _PL, C.c_int, C.c_uint64],
+    ),
+    "mld_status_histogram_host": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "mld_status_histogram_device": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
+    "mld_pack_feature_points_device": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mld_kernel_launch_count": (C.c_int64, [_H]),
     "mld_neighbor_capacity": (C.c_int, []),
     "mld_profile_enable": (C.c_int, [_H, C.c_int]),

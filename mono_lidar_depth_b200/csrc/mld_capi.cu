@@ -859,7 +859,9 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
         return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
     if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     DeviceGuard g(h->device);
-    const int chunk = h->chunk_frames;
+    // H2D copies, kernels and D2H copies of different chunks overlap: chunks are kept small (<= 32 frames, ~1 ms of
+    // PCIe time each) and a sequence is cut into at least two chunks per slot
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(h->chunk_frames, 32), std::max<int64_t>(8, (nframes + 2 * MLD_HOST_SLOTS - 1) / (2 * MLD_HOST_SLOTS))));
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
     const int stride_f = stride_bytes / 4;
     const size_t frame_bytes = (size_t)n_points * (size_t)stride_bytes;
@@ -896,6 +898,153 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
     }
     for (int i = 0; i < MLD_HOST_SLOTS; i++) CK(cudaStreamSynchronize(h->slots[i].stream));
     h->have_cloud = false;
+    return MLD_OK;
+}
+
+// ---- tracklets_depth batch adaptor: previous + current cloud in one call ----
+static int pair_side_begin(mld_handle* h, Slot& s, const void* pts, int64_t n, int stride_bytes, const double* uv, int F,
+                           const mld_plane* plane, bool want_ransac, uint64_t seed, std::vector<unsigned int>& hb) {
+    int rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, std::max(F, 1), 1, true, want_ransac || plane != nullptr);
+    if (rc) return rc;
+    const int stride_f = stride_bytes / 4;
+    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, pts, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    if (F > 0) CK(cudaMemcpyAsync(s.d_uv, uv, (size_t)F * 2 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
+    MapCode mc;
+    rc = begin_maps(h, s, 1, n, s.stream, mc);
+    if (rc) return rc;
+    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, s.d_maps,
+                                  h->feature_mode >= 1 ? s.d_occ : nullptr, 1, s.stream));
+    if (n > 0) h->launches++;
+    const long long words = (n + 31) / 32;
+    const float* coeffs = nullptr;
+    const unsigned int* bits = nullptr;
+    if (want_ransac) {
+        int nl = 0;
+        CK(mld_launch_ransac(ransac_config(h->params), reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, 1, seed, 0, s.d_scratch,
+                             s.d_coeffs, s.d_bits, words, s.d_small, s.d_small + 1, s.d_small + 2, s.stream, &nl));
+        h->launches += nl;
+        coeffs = s.d_coeffs;
+        bits = s.d_bits;
+    } else if (plane != nullptr && h->dp.road_mode != ROAD_NONE) {
+        hb.assign((size_t)std::max<long long>(words, 1), 0u);
+        for (int64_t i = 0; i < plane->n_inliers; i++) {
+            int32_t r = plane->inlier_idx[i];
+            if (r >= 0 && r < n) hb[(size_t)(r >> 5)] |= 1u << (r & 31);
+        }
+        CK(cudaMemcpyAsync(s.d_bits, hb.data(), hb.size() * sizeof(unsigned int), cudaMemcpyHostToDevice, s.stream));
+        CK(cudaMemcpyAsync(s.d_coeffs, plane->coeffs, 4 * sizeof(float), cudaMemcpyHostToDevice, s.stream));
+        coeffs = s.d_coeffs;
+        bits = s.d_bits;
+    }
+    if (F > 0) {
+        rc = launch_features(h, s, mc, s.stream, reinterpret_cast<const float*>(s.d_pts), stride_f, n, s.d_uv, F, s.d_depth, s.d_status,
+                             coeffs, bits, words, 1);
+        if (rc) return rc;
+    }
+    return MLD_OK;
+}
+
+int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev, const double* uv_prev, int F_prev,
+                             double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur, int64_t n_cur,
+                             const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur, mld_plane* plane_cur,
+                             int stride_bytes, uint64_t ransac_seed) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (n_prev < 0 || n_cur < 0 || F_prev < 0 || F_cur < 0 || !pts_cur || (F_prev > 0 && (!uv_prev || !depth_prev)) ||
+        (F_cur > 0 && (!uv_cur || !depth_cur)))
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_calculate_depth_pair: bad arguments");
+    if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
+        return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
+    DeviceGuard g(h->device);
+    const bool have_prev = pts_prev != nullptr;
+    const bool road = h->params.do_use_ransac_plane != 0;
+    const bool ransac_prev = have_prev && road && plane_prev && !plane_prev->segmented;
+    const bool ransac_cur = road && plane_cur && !plane_cur->segmented;
+    if ((ransac_prev && n_prev < 3) || (ransac_cur && n_cur < 3)) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    Slot& sc = h->slots[0];  // current cloud stays the handle's cloud
+    Slot& sp = h->slots[1];
+    std::vector<unsigned int> hb_prev, hb_cur;
+    std::vector<int32_t> st_prev_tmp, st_cur_tmp;
+    if (have_prev) {
+        rc = pair_side_begin(h, sp, pts_prev, n_prev, stride_bytes, uv_prev, F_prev, (road && plane_prev && !ransac_prev) ? plane_prev : nullptr,
+                             ransac_prev, ransac_seed, hb_prev);
+        if (rc) return rc;
+    } else {
+        for (int i = 0; i < F_prev; i++) {  // depths.setConstant(-1) (tracklet_depth_module.cpp:97-100)
+            depth_prev[i] = -1;
+            if (status_prev) status_prev[i] = 0;
+        }
+    }
+    rc = pair_side_begin(h, sc, pts_cur, n_cur, stride_bytes, uv_cur, F_cur, (road && plane_cur && !ransac_cur) ? plane_cur : nullptr, ransac_cur,
+                         ransac_seed + 1, hb_cur);
+    if (rc) return rc;
+    auto finish = [&](Slot& s, int64_t n, int F, double* depth, int32_t* status, mld_plane* plane, bool ransac) -> int {
+        if (F > 0) {
+            CK(cudaMemcpyAsync(depth, s.d_depth, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
+            if (status) CK(cudaMemcpyAsync(status, s.d_status, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+        }
+        if (ransac) {
+            const long long words = (n + 31) / 32;
+            std::vector<unsigned int> bits((size_t)words);
+            int small[3] = {0, 0, 0};
+            CK(cudaMemcpyAsync(plane->coeffs, s.d_coeffs, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(bits.data(), s.d_bits, (size_t)words * sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaMemcpyAsync(small, s.d_small, 3 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+            CK(cudaStreamSynchronize(s.stream));
+            if (small[2] != 0) return fail(h, MLD_ERR_NO_MODEL, "RANSAC found no plane model");
+            bits_to_plane(bits, n, plane);
+            plane->segmented = 1;
+        } else {
+            CK(cudaStreamSynchronize(s.stream));
+        }
+        return MLD_OK;
+    };
+    if (have_prev) {
+        rc = finish(sp, n_prev, F_prev, depth_prev, status_prev, plane_prev, ransac_prev);
+        if (rc) return rc;
+    }
+    rc = finish(sc, n_cur, F_cur, depth_cur, status_cur, plane_cur, ransac_cur);
+    if (rc) return rc;
+    h->cur_n = n_cur;
+    h->cur_stride_f = stride_bytes / 4;
+    h->have_cloud = true;
+    return MLD_OK;
+}
+
+// ---- DepthCalculationStatistics / FeaturePoint packing ----
+int mld_status_histogram_device(mld_handle* h, const int32_t* d_status, int64_t n, int64_t* hist21_out_host, void* stream) {
+    if (!h || !hist21_out_host || n < 0 || (n > 0 && !d_status)) return MLD_ERR_INVALID_ARG;
+    DeviceGuard g(h->device);
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    unsigned long long* d_hist = nullptr;
+    CK(cudaMalloc(&d_hist, 21 * sizeof(unsigned long long)));
+    cudaError_t e = mld_launch_status_histogram(d_status, n, d_hist, st);
+    h->launches++;
+    unsigned long long hh[21];
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hh, d_hist, sizeof(hh), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(d_hist);
+    if (e != cudaSuccess) return fail_cuda(h, e, "mld_status_histogram_device");
+    for (int i = 0; i < 21; i++) hist21_out_host[i] = (int64_t)hh[i];
+    return MLD_OK;
+}
+
+int mld_status_histogram_host(mld_handle* h, const int32_t* status_host, int64_t n, int64_t* hist21_out) {
+    if (!h || !hist21_out || n < 0 || (n > 0 && !status_host)) return MLD_ERR_INVALID_ARG;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[2];
+    CK(ensure(s.d_status, s.status_bytes, (size_t)std::max<int64_t>(n, 1) * sizeof(int)));
+    if (n > 0) CK(cudaMemcpyAsync(s.d_status, status_host, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, s.stream));
+    return mld_status_histogram_device(h, s.d_status, n, hist21_out, s.stream);
+}
+
+int mld_pack_feature_points_device(mld_handle* h, const double* d_uv, const double* d_depth, int64_t n, float* d_out_uvd, void* stream) {
+    if (!h || n < 0 || (n > 0 && (!d_uv || !d_depth || !d_out_uvd))) return MLD_ERR_INVALID_ARG;
+    DeviceGuard g(h->device);
+    CK(mld_launch_pack_feature_points(d_uv, d_depth, n, d_out_uvd, reinterpret_cast<cudaStream_t>(stream)));
+    if (n > 0) h->launches++;
     return MLD_OK;
 }
 

@@ -72,6 +72,10 @@ cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int s
                               long long pitch_pts, int nframes, uint64_t seed, long long frame0, void* d_scratch,
                               float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame, int* d_n_inliers,
                               int* d_iterations, int* d_rc, cudaStream_t stream, int* launches);
+// extras (mld_extras.cu)
+cudaError_t mld_launch_status_histogram(const int* d_status, long long n, unsigned long long* d_hist21, cudaStream_t stream);
+cudaError_t mld_launch_pack_feature_points(const double* d_uv, const double* d_depth, long long n, float* d_out, cudaStream_t stream);
+
 // synthetic data (mld_synth.cu)
 cudaError_t mld_launch_synth_points(const mld_synth_config& c, uint64_t seed, long long frame0, long long nframes,
                                     long long pitch_pts, const float* d_tables, float* d_out, cudaStream_t stream);

@@ -230,6 +230,77 @@ class DepthEstimator:
                                                   C.byref(pl_c) if pl_c is not None else None))
         return depths, status
 
+    # -- tracklets_depth batch adaptor (TrackletDepthModule::process, tracklet_depth_module.cpp:318,330) ---------
+    def CalculateDepthPair(self, cloud_last, feats_last, plane_last, cloud_cur, feats_cur, plane_cur):
+        """Previous and current cloud with their own feature sets in one call (both clouds are on the device
+        concurrently). cloud_last may be None (first frame): its depths are -1. Planes follow setInputCloud:
+        with do_use_ransac_plane a None / un-segmented plane is fitted on the GPU and returned.
+        Returns (depths_last, depths_cur, plane_last, plane_cur)."""
+        if not self._isInitialized:
+            raise RuntimeError("call of 'setInputCloud' without 'initialize'")
+
+        def prep(feats):
+            f = np.asarray(feats, np.float64)
+            if f.ndim == 2 and f.shape[0] == 2 and f.shape[1] != 2:
+                f = f.T
+            return np.ascontiguousarray(f.reshape(-1, 2))
+
+        fl, fc = prep(feats_last), prep(feats_cur)
+        dl, dc = np.empty(len(fl), np.float64), np.empty(len(fc), np.float64)
+        use_plane = bool(self._parameters.do_use_ransac_plane)
+        a_cur, n_cur, stride = _cloud_buffer(cloud_cur)
+        if cloud_last is not None:
+            a_last, n_last, stride_l = _cloud_buffer(cloud_last)
+            if stride_l != stride:
+                raise ValueError("both clouds must use the same point layout")
+        else:
+            a_last, n_last = None, 0
+        planes, cplanes = [plane_last, plane_cur], [None, None]
+        sizes = [n_last, n_cur]
+        if use_plane:
+            for i in range(2):
+                if i == 0 and cloud_last is None:
+                    continue
+                if planes[i] is None:
+                    planes[i] = RansacPlane(self._parameters, self.ransac_seed)
+                cplanes[i] = planes[i]._as_c(capacity=max(sizes[i], 1) if not planes[i].isSegmented() else 0)
+        self._check(self._lib.mld_calculate_depth_pair(
+            self._h, a_last.ctypes.data if a_last is not None else None, n_last,
+            fl.ctypes.data if len(fl) else None, len(fl), dl.ctypes.data if len(fl) else None, None,
+            C.byref(cplanes[0]) if cplanes[0] is not None else None,
+            a_cur.ctypes.data, n_cur, fc.ctypes.data if len(fc) else None, len(fc), dc.ctypes.data if len(fc) else None, None,
+            C.byref(cplanes[1]) if cplanes[1] is not None else None, stride, self.ransac_seed))
+        for i in range(2):
+            if cplanes[i] is not None:
+                planes[i]._from_c(cplanes[i])
+        self._n = n_cur
+        self._isInitializedPointCloud = True
+        return dl, dc, planes[0], planes[1]
+
+    # -- DepthCalculationStatistics (DepthEstimator.cpp:1039-1090) ---------------------------------------------
+    def getDepthCalcStats(self, status) -> dict:
+        """Counters per DepthResultType of a status array, computed on the GPU."""
+        s = np.ascontiguousarray(status, np.int32).ravel()
+        hist = (C.c_int64 * 21)()
+        self._check(self._lib.mld_status_histogram_host(self._h, s.ctypes.data if len(s) else None, len(s), hist))
+        names = {v: k for k, v in {
+            "Unspecified": 0, "Success": 1, "RadiusSearchInsufficientPoints": 2, "HistogramNoLocalMax": 3,
+            "TresholdDepthGlobalGreaterMax": 4, "TresholdDepthGlobalSmallerMin": 5, "TresholdDepthLocalGreaterMax": 6,
+            "TresholdDepthLocalSmallerMin": 7, "TriangleNotPlanar": 8, "TriangleNotPlanarInsufficientPoints": 9,
+            "CornerBehindCamera": 10, "PlaneViewrayNotOrthogonal": 11, "PcaIsPoint": 12, "PcaIsLine": 13, "PcaIsCubic": 14,
+            "InsufficientRoadPoints": 15, "SuccessRoad": 16, "RegionGrowingNearestSeedNotAvailable": 17,
+            "RegionGrowingSeedsOutOfRange": 18, "RegionGrowingInsufficientPoints": 19, "SuccessRegionGrowing": 20}.items()}
+        return {names[i]: int(hist[i]) for i in range(21)}
+
+    def statusHistogramDevice(self, d_status: int, n: int, stream: int = 0) -> np.ndarray:
+        hist = (C.c_int64 * 21)()
+        self._check(self._lib.mld_status_histogram_device(self._h, d_status, n, hist, stream or None))
+        return np.array(list(hist), np.int64)
+
+    def packFeaturePointsDevice(self, d_uv: int, d_depth: int, n: int, d_out: int, stream: int = 0) -> None:
+        """matches_msg_depth_ros/FeaturePoint {float32 u, v, d} for n features, device buffers."""
+        self._check(self._lib.mld_pack_feature_points_device(self._h, d_uv, d_depth, n, d_out, stream or None))
+
     # -- stand-alone RansacPlane::CalculateInliersPlane -------------------------------------------
     def estimateGroundPlane(self, cloud, seed: int = 0) -> RansacPlane:
         a, n, stride = _cloud_buffer(cloud)

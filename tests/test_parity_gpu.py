@@ -396,3 +396,62 @@ def test_epoch_tag_wraparound():
         est.setInputCloud(clouds[j])
         if it % 997 == 0 or 16370 <= it <= 16400:
             assert np.array_equal(est.getPixelMap(), refs[j]), it
+
+
+def test_pair_adaptor_matches_two_single_calls():
+    """mld_calculate_depth_pair (tracklets_depth's previous + current cloud per frame) == two single calls == oracle."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    c0, c1 = synth.points_host(cfg, 41, 0), synth.points_host(cfg, 41, 1)
+    f0, f1 = synth.features_host(cfg, 41, 0, 1500), synth.features_host(cfg, 41, 1, 2100)
+    d0, d1, pl0, pl1 = est.CalculateDepthPair(c0, f0, None, c1, f1, None)
+    assert pl0 is None and pl1 is None
+    for cloud, feats, d in ((c0, f0, d0), (c1, f1, d1)):
+        orc.set_cloud(cloud)
+        d_ref, s_ref = orc.calculate_depth(feats)
+        assert np.array_equal(np.isnan(d), np.isnan(d_ref))
+        np.testing.assert_allclose(d, d_ref, rtol=PU.DEPTH_RTOL)
+    # the current cloud stays the estimator's cloud
+    d1b, _ = est.CalculateDepth(f1)
+    assert np.array_equal(d1b, d1)
+    # first frame: no previous cloud -> -1 (tracklet_depth_module.cpp:97-100)
+    dl, dc, _, _ = est.CalculateDepthPair(None, f0, None, c1, f1, None)
+    assert np.all(dl == -1) and np.array_equal(dc, d1)
+    # with RANSAC planes fitted on the GPU for both clouds
+    q = O.yaml_params()
+    est2, orc2 = kitti_pair(q)
+    est2.ransac_seed = 7
+    d0, d1, pl0, pl1 = est2.CalculateDepthPair(c0, f0, None, c1, f1, None)
+    assert pl0.isSegmented() and pl1.isSegmented()
+    for cloud, feats, d, pl in ((c0, f0, d0, pl0), (c1, f1, d1, pl1)):
+        orc2.set_cloud(cloud)
+        d_ref, s_ref = orc2.calculate_depth(feats, (pl.getModelCoeffs(), pl.getInlinersIndex()))
+        np.testing.assert_allclose(d, d_ref, rtol=PU.DEPTH_RTOL)
+
+
+def test_status_statistics_and_feature_point_packing():
+    import torch
+
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    cloud, uv = synth.points_host(cfg, 43, 0), synth.features_host(cfg, 43, 0, 2000)
+    est.setInputCloud(cloud)
+    d, s = est.CalculateDepth(uv)
+    stats = est.getDepthCalcStats(s)
+    counts = collections.Counter(s.tolist())
+    assert stats["Success"] == counts[1] and stats["RadiusSearchInsufficientPoints"] == counts[2]
+    assert sum(stats.values()) == len(s)
+    t_uv = torch.from_numpy(uv).cuda()
+    t_d = torch.from_numpy(d).cuda()
+    t_s = torch.from_numpy(s).cuda()
+    out = torch.empty((len(d), 3), dtype=torch.float32, device="cuda")
+    est.packFeaturePointsDevice(t_uv.data_ptr(), t_d.data_ptr(), len(d), out.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    hist = est.statusHistogramDevice(t_s.data_ptr(), len(s), torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    o = out.cpu().numpy()
+    assert np.array_equal(o[:, 0], uv[:, 0].astype(np.float32)) and np.array_equal(o[:, 2], d.astype(np.float32))
+    assert hist[1] == counts[1] and hist.sum() == len(s)
