@@ -136,6 +136,9 @@ __device__ __forceinline__ D3 lidar_to_cam(const DevParams& P, float x, float y,
 // streaming 16-byte load that does not pollute L1 (points are read once per kernel)
 __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     float4 v;
+#ifdef MLD_DIAG_LDG
+    return __ldg(reinterpret_cast<const float4*>(p));
+#endif
     asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
                  : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                  : "l"(p));

@@ -96,8 +96,16 @@ project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, i
         const int i = base + j * K1_THREADS;
         if (i >= n) break;
         if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
+#ifdef MLD_DIAG_NOFP64
+        if (p[j].x == 123456.f) map[0] = 1;  // diagnostic build: keep the loads alive, skip the exact path
+        continue;
+#endif
         int x, y;
         if (!project_pixel(P, p[j].x, p[j].y, p[j].z, true, x, y)) continue;
+#ifdef MLD_DIAG_NOATOM
+        if (x == -5) map[0] = 1;  // diagnostic build: no scatter
+        continue;
+#endif
         atomicMin(&map[y * P.W + x], hi | (unsigned int)i);
         if (ob) {
             unsigned int* orow = ob + y * occ_pitch;

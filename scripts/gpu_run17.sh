@@ -1,0 +1,11 @@
+run() { MLD_BENCH_CPU_SECONDS=1 MLD_BENCH_E2E_FRAMES=128 python bench.py --workload ${2:-kitti} --steps 4 --warmup 3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); print('$1 ${2:-kitti} chunk',d['config']['chunk_frames_per_launch'],'fps',round(d['value']),{k:(round(v['avg_launch_ms']*1000,1) if isinstance(v,dict) and v['avg_launch_ms'] else None) for k,v in d['roofline']['per_kernel'].items()})
+    elif 'Error' in l or 'error' in l: print(l)
+"; }
+MLD_OVERLAP=1 run base_serial; run base
+for v in k1p8 k1p12 k1p16 k1p8t256; do export MLD_CUDA_LIB=$PWD/build/variants/libmld_$v.so; MLD_OVERLAP=1 run ${v}_serial; run $v; unset MLD_CUDA_LIB; done
+export MLD_CUDA_LIB=$PWD/build/variants/libmld_k1p8.so
+python -m pytest tests/test_parity_gpu.py -m gpu -q --no-header -x -k "kitti_shape or dense_random or edge" 2>&1 | tail -2
