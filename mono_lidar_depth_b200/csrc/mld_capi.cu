@@ -226,7 +226,7 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
                     long long words, int frames) {
     if (F <= 0 || frames <= 0) return MLD_OK;
     if (h->feature_mode == 2) {
-        CK(ensure(s.d_split, s.split_bytes, mld_split_scratch_bytes((long long)frames * F)));
+        CK(ensure(s.d_split, s.split_bytes, mld_split_scratch_bytes((long long)frames * F, coeffs != nullptr)));
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
         int nl = 0;
         CK(mld_launch_feature_depth_split(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,

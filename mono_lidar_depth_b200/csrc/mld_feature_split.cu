@@ -247,52 +247,165 @@ feature_solve_kernel(DevParams P, const double* __restrict__ uv, double* __restr
     }
 }
 
-// ---- K2c ------------------------------------------------------------------------------------------
+// ---- K2c: road gather ---------------------------------------------------------------------------------
+// One thread per unsolved survivor. Most candidates die at the plane gate or have fewer than 3 plane inliers
+// (the inlier set is restricted to the 6000-point RANSAC subsample, RansacPlane.cpp:100), so nothing is parked
+// in shared memory here: the gate is evaluated while the neighbours stream by, and only the rare candidates
+// that pass get their inlier points written to the road-survivor arrays for K2d.
+__global__ void __launch_bounds__(SBT_A)
+feature_road_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                           const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
+                           const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                           const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ inlier_bits,
+                           long long inlier_words_per_frame, const int* __restrict__ road_list, const int* __restrict__ road_count,
+                           int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ rs_rec,
+                           double* __restrict__ rs_xyz, int* __restrict__ rs_count, long long cap) {
+    __shared__ int s_aux[RCAP * SBT_A];
+    __shared__ int s_wtot[SBT_A / 32];
+    __shared__ int s_base;
+    const int tid = threadIdx.x;
+    const int count = *road_count;
+    const long long item = (long long)blockIdx.x * SBT_A + tid;
+    if ((long long)blockIdx.x * SBT_A >= count) return;  // uniform per block
+    const bool valid = item < count;
+    int* aux = s_aux + tid;
+    bool surv = false;
+    int n_inl = 0;
+    unsigned int inl_mask = 0u;
+    long long o = 0;
+    const float* fp = nullptr;
+    const unsigned int* map = nullptr;
+    if (valid) {
+        o = road_list[item];
+        const long long frame = o / F;
+        fp = pts + frame * pitch_pts * (long long)stride_f;
+        map = maps + frame * (long long)P.W * (long long)P.H;
+        const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+        const float* pc = plane_coeffs + frame * 4;
+        const unsigned int* bits = inlier_bits + frame * inlier_words_per_frame;
+        const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+        const double u = f2.x, v = f2.y;
+        // wide window (scale 2.0 x 1.5): occupancy words -> pixel offsets in scan order
+        int k2 = 0;
+        if ((fabs(u) < 1e9) && (fabs(v) < 1e9)) {
+            const int x0 = (int)fmax(u - P.hx2, 0.), x1 = (int)fmin(u + P.hx2, (double)(P.W - 1));
+            const int y0 = (int)fmax(v - P.hy2, 0.), y1 = (int)fmin(v + P.hy2, (double)(P.H - 1));
+            if (x1 >= x0 && y1 >= y0) {
+                const int pitch = occ_words_per_row(P.W);
+                const int wj0 = x0 >> 4;
+                for (int yb = y0; yb <= y1; yb += T_ROWS) {
+                    unsigned int w[T_ROWS];
+#pragma unroll
+                    for (int r = 0; r < T_ROWS; r++) {
+                        const int y = yb + r;
+                        w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
+                    }
+#pragma unroll
+                    for (int r = 0; r < T_ROWS; r++) {
+                        const int y = yb + r;
+                        if (y > y1) break;
+                        unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
+                        int wj = wj0;
+                        while (true) {
+                            while (m) {
+                                const int b = __ffs(m) - 1;
+                                m &= m - 1;
+                                if (k2 < RCAP) aux[k2 * SBT_A] = y * P.W + (wj << 4) + b;
+                                k2++;
+                            }
+                            wj += 2;
+                            if ((wj << 4) > x1) break;
+                            m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
+                        }
+                    }
+                }
+            }
+        }
+        if (k2 > RCAP) {
+            overflow_list[atomicAdd(overflow_count, 1)] = (int)o;  // the warp kernel redoes the feature from scratch
+        } else if ((unsigned)k2 < (unsigned)P.count_min) {           // DepthEstimator.cpp:585-586
+            status[o] = ST_RadiusSearchInsufficientPoints;
+            depth[o] = -1;
+        } else {
+            const float a = pc[0], b = pc[1], c = pc[2], d = pc[3];
+#pragma unroll 4
+            for (int i = 0; i < k2; i++) aux[i * SBT_A] = (int)map_cell_index(mc, __ldg(map + aux[i * SBT_A]));
+            bool far = false;
+            for (int i = 0; i < k2 && !far; i++) {
+                const int raw = aux[i * SBT_A];
+                const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)raw * stride_f));
+                far = road_point_far(P, lidar_to_cam(P, q.x, q.y, q.z), a, b, c, d);
+                if ((bits[raw >> 5] >> (raw & 31)) & 1u) {
+                    inl_mask |= 1u << i;
+                    n_inl++;
+                }
+            }
+            // a far neighbour or fewer than 3 inliers: the normal path's status stands (already written by K2b)
+            surv = !far && n_inl >= 3;
+        }
+    }
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned bm = __ballot_sync(MLD_FULL_MASK, surv);
+    if (lane == 0) s_wtot[warp] = __popc(bm);
+    __syncthreads();
+    int base = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SBT_A / 32; w++) {
+        const int c = s_wtot[w];
+        if (w < warp) base += c;
+        total += c;
+    }
+    if (tid == 0) s_base = total ? atomicAdd(rs_count, total) : 0;
+    __syncthreads();
+    if (!surv) return;
+    const long long slot = (long long)s_base + base + __popc(bm & ((1u << lane) - 1u));
+    rs_rec[slot] = pack_rec(n_inl, o);
+    int e = 0;
+    for (int i = 0; inl_mask; i++, inl_mask >>= 1) {
+        if (!(inl_mask & 1u)) continue;
+        const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)aux[i * SBT_A] * stride_f));
+        const D3 c = lidar_to_cam(P, q.x, q.y, q.z);
+        double* dst = rs_xyz + (long long)e * 3 * cap + slot;
+        dst[0] = c.x;
+        dst[cap] = c.y;
+        dst[2 * cap] = c.z;
+        e++;
+    }
+}
+
+// ---- K2d: road solve ----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SBT_C)
-feature_road_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
-                    const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
-                    const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
-                    const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ inlier_bits,
-                    long long inlier_words_per_frame, const int* __restrict__ road_list, const int* __restrict__ road_count,
-                    int* __restrict__ overflow_list, int* __restrict__ overflow_count) {
+feature_road_solve_kernel(DevParams P, const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                          const float* __restrict__ plane_coeffs, const unsigned int* __restrict__ rs_rec,
+                          const double* __restrict__ rs_xyz, const int* __restrict__ rs_count, long long cap) {
     using TSlab = TSlabT<RCAP, SBT_C>;
     __shared__ double sx[RCAP * SBT_C], sy[RCAP * SBT_C], sz[RCAP * SBT_C];
     __shared__ int saux[RCAP * SBT_C];
     const int tid = threadIdx.x;
-    const int count = *road_count;
-    const long long item = (long long)blockIdx.x * SBT_C + tid;
-    if (item >= count) return;
-    const long long o = road_list[item];
-    const long long frame = o / F;
-    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
-    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
-    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
-    const float* pc = plane_coeffs + frame * 4;
-    const unsigned int* bits = inlier_bits + frame * inlier_words_per_frame;
-    const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
+    const long long slot = (long long)blockIdx.x * SBT_C + tid;
+    if (slot >= *rs_count) return;
+    const unsigned int rec = rs_rec[slot];
+    const int n = (int)(rec >> 27);
+    const long long o = (long long)(rec & 0x7FFFFFFu);
     const TSlab s{sx + tid, sy + tid, sz + tid, saux + tid};
-    unsigned int mask;
-    const int k2 = t_gather_window(P, mc, map, occ, fp, stride_f, f2.x, f2.y, P.hx2, P.hy2, s, bits, mask);
-    if (k2 < 0) {
-        overflow_list[atomicAdd(overflow_count, 1)] = (int)o;  // the warp kernel redoes the feature from scratch
-        return;
+    for (int i = 0; i < n; i++) {
+        const double* src = rs_xyz + (long long)i * 3 * cap + slot;
+        s.set(i, D3{src[0], src[cap], src[2 * cap]});
     }
-    if ((unsigned)k2 < (unsigned)P.count_min) {  // DepthEstimator.cpp:585-586
-        status[o] = ST_RadiusSearchInsufficientPoints;
-        depth[o] = -1;
-        return;
-    }
+    const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
     double dp;
-    const int st = t_road_depth(P, f2.x, f2.y, k2, s, pc, mask, status[o], dp);
+    const int st = t_road_estimate(P, f2.x, f2.y, n, s, plane_coeffs + (o / F) * 4, dp);
     status[o] = st;
     depth[o] = (st == ST_SuccessRoad) ? dp : -1.0;
 }
 
 }  // namespace
 
-size_t mld_split_scratch_bytes(long long features) {
-    // counters (64 B) + survivor records + road list + survivor points [SCAP][3][features]
-    return 64 + (size_t)features * (sizeof(unsigned int) + sizeof(int)) + (size_t)features * SCAP * 3 * sizeof(double) + 256;
+size_t mld_split_scratch_bytes(long long features, int road) {
+    // counters (64 B) + survivor records + road list + survivor points [entries][3][features]; the road pass
+    // reuses the arrays for its own (rarer, up to RCAP-entry) survivors
+    const int entries = road ? (SCAP > RCAP ? SCAP : RCAP) : SCAP;
+    return 64 + (size_t)features * (sizeof(unsigned int) + sizeof(int)) + (size_t)features * entries * 3 * sizeof(double) + 256;
 }
 
 cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
@@ -307,13 +420,14 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
     unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
     int* surv_count = reinterpret_cast<int*>(base);
     int* road_count = surv_count + 1;
+    int* rs_count = surv_count + 2;
     unsigned int* surv_rec = reinterpret_cast<unsigned int*>(base + 64);
     int* road_list = reinterpret_cast<int*>(surv_rec + features);
     size_t off = 64 + (size_t)features * 8;
     off = (off + 255) & ~(size_t)255;
     double* surv_xyz = reinterpret_cast<double*>(base + off);
     const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
-    cudaError_t e = cudaMemsetAsync(surv_count, 0, 2 * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(surv_count, 0, 3 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     dim3 ga((unsigned)((F + SBT_A - 1) / SBT_A), (unsigned)nframes);
     feature_gather_kernel<<<ga, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
@@ -325,12 +439,17 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) *launches += 2;
     if (road) {
-        const unsigned gc = (unsigned)((features + SBT_C - 1) / SBT_C);
-        feature_road_kernel<<<gc, SBT_C, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
-                                                     d_plane_coeffs, d_inlier_bits, words_per_frame, road_list, road_count,
-                                                     d_overflow_list, d_overflow_count);
+        // the survivor arrays are free again once K2b has finished: the road pass reuses them
+        const unsigned gc = (unsigned)((features + SBT_A - 1) / SBT_A);
+        feature_road_gather_kernel<<<gc, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
+                                                            d_plane_coeffs, d_inlier_bits, words_per_frame, road_list, road_count,
+                                                            d_overflow_list, d_overflow_count, surv_rec, surv_xyz, rs_count, features);
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (launches) *launches += 1;
+        const unsigned gd = (unsigned)((features + SBT_C - 1) / SBT_C);
+        feature_road_solve_kernel<<<gd, SBT_C, 0, stream>>>(P, d_uv, F, d_depth, d_status, d_plane_coeffs, surv_rec, surv_xyz, rs_count,
+                                                           features);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 2;
     }
     return cudaSuccess;
 }

@@ -42,7 +42,7 @@ cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& m
                                             int* d_overflow_list, int* d_overflow_count, cudaStream_t stream);
 
 // K2/K3 split into gather / solve / road kernels with a chunk-wide compaction (mld_feature_split.cu)
-size_t mld_split_scratch_bytes(long long features);
+size_t mld_split_scratch_bytes(long long features, int road);
 cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
                                            long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
                                            const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,

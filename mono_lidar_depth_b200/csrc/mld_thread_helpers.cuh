@@ -295,36 +295,19 @@ __device__ int t_depth_from_corners(const DevParams& P, double u, double v, int 
     return ST_Success;
 }
 
-// R2 + R3/R4/R5
+// R3/R4/R5: road estimators on the n plane-inlier points held in the slab (RoadDepthEstimator*.cpp)
 template <typename TSlab>
-__device__ int t_road_depth(const DevParams& P, double u, double v, int k2, const TSlab& s, const float* coeffs,
-                            unsigned int inlier_mask, int old_status, double& depth_out) {
+__device__ int t_road_estimate(const DevParams& P, double u, double v, int n, const TSlab& s, const float* coeffs, double& depth_out) {
+    constexpr int TBT = TSlab::TBT;
     depth_out = -1;
     const float a = coeffs[0], b = coeffs[1], c = coeffs[2], d = coeffs[3];
-    for (int i = 0; i < k2; i++) {
-        D3 p = s.pt(i);
-        double lx = ((P.Ri[0] * p.x + P.Ri[1] * p.y) + P.Ri[2] * p.z) + P.ti[0];
-        double ly = ((P.Ri[3] * p.x + P.Ri[4] * p.y) + P.Ri[5] * p.z) + P.ti[1];
-        double lz = ((P.Ri[6] * p.x + P.Ri[7] * p.y) + P.Ri[8] * p.z) + P.ti[2];
-        float fx = (float)lx, fy = (float)ly, fz = (float)lz;
-        float sd = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, fx), __fmul_rn(b, fy)), __fmul_rn(c, fz)), d);
-        if (fabs((double)sd) > P.road_dist_thr) return old_status;  // DepthEstimator.cpp:814-815
-    }
-    int n = 0;
-    for (int i = 0; i < k2; i++) {
-        if ((inlier_mask >> i) & 1u) {
-            if (n != i) s.set(n, s.pt(i));
-            n++;
-        }
-    }
-    if (n < 3) return old_status;
     Plane pl;
     if (P.road_mode == ROAD_TRIANGLE) {
         int i, j, k;
         if (!t_max_spanning_triangle(n, s, i, j, k)) return ST_RadiusSearchInsufficientPoints;
         double loX = 1.7976931348623157e308, hiX = -1.7976931348623157e308, loZ = loX, hiZ = hiX;
         for (int q = 0; q < n; q++) {
-            double x = s.X(q), z = s.Z(q);
+            double x = s.x[q * TBT], z = s.z[q * TBT];
             if (x < loX) loX = x;
             if (x > hiX) hiX = x;
             if (z < loZ) loZ = z;
@@ -357,6 +340,35 @@ __device__ int t_road_depth(const DevParams& P, double u, double v, int k2, cons
     if (r) return r;
     depth_out = depth;
     return ST_SuccessRoad;
+}
+
+// R2 gate: |a x + b y + c z + d| of the lidar-frame point, in float like pcl::pointToPlaneDistance(PointXYZ, Vector4f)
+__device__ __forceinline__ bool road_point_far(const DevParams& P, const D3& p, float a, float b, float c, float d) {
+    double lx = ((P.Ri[0] * p.x + P.Ri[1] * p.y) + P.Ri[2] * p.z) + P.ti[0];
+    double ly = ((P.Ri[3] * p.x + P.Ri[4] * p.y) + P.Ri[5] * p.z) + P.ti[1];
+    double lz = ((P.Ri[6] * p.x + P.Ri[7] * p.y) + P.Ri[8] * p.z) + P.ti[2];
+    float fx = (float)lx, fy = (float)ly, fz = (float)lz;
+    float sd = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, fx), __fmul_rn(b, fy)), __fmul_rn(c, fz)), d);
+    return fabs((double)sd) > P.road_dist_thr;  // DepthEstimator.cpp:814-815
+}
+
+// R2 + R3/R4/R5 on a slab holding all k2 neighbours of the wide window
+template <typename TSlab>
+__device__ int t_road_depth(const DevParams& P, double u, double v, int k2, const TSlab& s, const float* coeffs,
+                            unsigned int inlier_mask, int old_status, double& depth_out) {
+    depth_out = -1;
+    const float a = coeffs[0], b = coeffs[1], c = coeffs[2], d = coeffs[3];
+    for (int i = 0; i < k2; i++)
+        if (road_point_far(P, s.pt(i), a, b, c, d)) return old_status;
+    int n = 0;
+    for (int i = 0; i < k2; i++) {
+        if ((inlier_mask >> i) & 1u) {
+            if (n != i) s.set(n, s.pt(i));
+            n++;
+        }
+    }
+    if (n < 3) return old_status;
+    return t_road_estimate(P, u, v, n, s, coeffs, depth_out);
 }
 
 constexpr int ST_OVERFLOW = -1;
