@@ -59,6 +59,16 @@ public:
                         const GroundPlane::Ptr& ransacPlane);
     std::pair<DepthResultType, double> CalculateDepth(const Eigen::Vector2d& point_image_cs, const GroundPlane::Ptr& ransacPlane);
 
+    // tracklets_depth batch adaptor: previous + current cloud of one frame in a single call
+    // (TrackletDepthModule::process issues them back to back, tracklet_depth_module.cpp:318, :330). A null
+    // pointCloudLast (first frame) sets depthsLast to -1 like CalculateFeatureDepthsLastFrame (:97-100).
+    void CalculateDepthPair(const Cloud::ConstPtr& pointCloudLast, const Eigen::Matrix2Xd& featuresLast, Eigen::VectorXd& depthsLast,
+                            GroundPlane::Ptr& planeLast, const Cloud::ConstPtr& pointCloudCur, const Eigen::Matrix2Xd& featuresCur,
+                            Eigen::VectorXd& depthsCur, GroundPlane::Ptr& planeCur);
+
+    // DepthCalculationStatistics counters (one per DepthResultType value) of a result vector
+    void getDepthCalcStats(const Eigen::VectorXi& resultType, long long counters[21]);
+
     // debug views served from device buffers on demand
     void getPointsCloudImageCs(Eigen::Matrix2Xd& visiblePointsImageCs);
     void getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs);

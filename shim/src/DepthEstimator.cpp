@@ -227,6 +227,52 @@ std::pair<DepthResultType, double> DepthEstimator::CalculateDepth(const Eigen::V
     return std::pair<DepthResultType, double>((DepthResultType)t(0), d(0));
 }
 
+void DepthEstimator::CalculateDepthPair(const Cloud::ConstPtr& cloudLast, const Eigen::Matrix2Xd& featuresLast, Eigen::VectorXd& depthsLast,
+                                        GroundPlane::Ptr& planeLast, const Cloud::ConstPtr& cloudCur, const Eigen::Matrix2Xd& featuresCur,
+                                        Eigen::VectorXd& depthsCur, GroundPlane::Ptr& planeCur) {
+    if (!_isInitialized) throw "call of 'setInputCloud' without 'initialize'";
+    depthsLast.resize(featuresLast.cols());
+    depthsCur.resize(featuresCur.cols());
+    const bool road = _parameters->do_use_ransac_plane != 0;
+    GroundPlane::Ptr* planes[2] = {&planeLast, &planeCur};
+    const Cloud::ConstPtr* clouds[2] = {&cloudLast, &cloudCur};
+    PlaneView views[2];
+    mld_plane* cp[2] = {nullptr, nullptr};
+    for (int i = 0; i < 2; i++) {
+        if (!road || *clouds[i] == nullptr) continue;
+        if (*planes[i] == nullptr) *planes[i] = std::make_shared<RansacPlane>(_parameters);  // DepthEstimator.cpp:275-278
+        GroundPlane& gp = **planes[i];
+        if (!gp.isSegmented() && dynamic_cast<RansacPlane*>(&gp) == nullptr)  // e.g. SemanticPlane: segments itself on the host
+            gp.CalculateInliersPlane(*clouds[i], _parameters->ransac_plane_min_z, _parameters->ransac_plane_max_z);
+        fill_plane(views[i], gp._modelCoeffs, gp._inliersIndex, gp.isSegmented(), gp.isSegmented() ? 0 : (int64_t)(*clouds[i])->points.size());
+        cp[i] = &views[i].c;
+    }
+    const bool have_last = cloudLast != nullptr;
+    int rc = mld_calculate_depth_pair(_handle, have_last ? cloudLast->points.data() : nullptr, have_last ? (int64_t)cloudLast->points.size() : 0,
+                                      featuresLast.data(), featuresLast.cols(), depthsLast.data(), nullptr, cp[0], cloudCur->points.data(),
+                                      (int64_t)cloudCur->points.size(), featuresCur.data(), featuresCur.cols(), depthsCur.data(), nullptr, cp[1],
+                                      (int)sizeof(Point), _ransacSeed);
+    if (rc != MLD_OK) rethrow(rc);
+    for (int i = 0; i < 2; i++) {
+        if (!cp[i] || (*planes[i])->isSegmented()) continue;
+        GroundPlane& gp = **planes[i];
+        for (int q = 0; q < 4; q++) gp._modelCoeffs[q] = cp[i]->coeffs[q];
+        gp._inliersIndex.assign(views[i].idx.begin(), views[i].idx.begin() + cp[i]->n_inliers);
+        gp._pointIsInPlane.clear();
+        for (const auto& index : gp._inliersIndex) gp._pointIsInPlane.insert(std::pair<int, bool>(index, true));
+        gp.is_segmented_ = true;
+    }
+    _pointCount = (long long)cloudCur->points.size();
+    _isInitializedPointCloud = true;
+}
+
+void DepthEstimator::getDepthCalcStats(const Eigen::VectorXi& resultType, long long counters[21]) {
+    int64_t hist[21];
+    int rc = mld_status_histogram_host(_handle, reinterpret_cast<const int32_t*>(resultType.data()), resultType.size(), hist);
+    if (rc != MLD_OK) rethrow(rc);
+    for (int i = 0; i < 21; i++) counters[i] = (long long)hist[i];
+}
+
 void DepthEstimator::getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs) {
     std::vector<double> cam((size_t)std::max<long long>(_pointCount, 1) * 3);
     int rc = mld_get_points_camera(_handle, cam.data());

@@ -96,6 +96,23 @@ int main(int argc, char** argv) {
         auto pr = est.CalculateDepth(one, plane);
         if ((int)pr.first != types(0)) return 7;
 
+        // batch adaptor: previous + current cloud in one call gives the same depths; statistics add up
+        {
+            Eigen::VectorXd dl, dc;
+            GroundPlane::Ptr pl_last = plane, pl_cur = plane;
+            est.CalculateDepthPair(ccloud, feats, dl, pl_last, ccloud, feats, dc, pl_cur);
+            for (int i = 0; i < F; i++) {
+                const bool same_l = (dl(i) == depths(i)) || (dl(i) != dl(i) && depths(i) != depths(i));
+                const bool same_c = (dc(i) == depths(i)) || (dc(i) != dc(i) && depths(i) != depths(i));
+                if (!same_l || !same_c) return 8;
+            }
+            long long counters[21];
+            est.getDepthCalcStats(types, counters);
+            long long total = 0;
+            for (int i = 0; i < 21; i++) total += counters[i];
+            if (total != F) return 9;
+        }
+
         std::ofstream(argv[3], std::ios::binary).write(reinterpret_cast<const char*>(depths.data()), (std::streamsize)(F * sizeof(double)));
         std::ofstream(argv[4], std::ios::binary).write(reinterpret_cast<const char*>(types.data()), (std::streamsize)(F * sizeof(int)));
         std::ofstream po(argv[6], std::ios::binary);
