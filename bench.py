@@ -75,7 +75,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -99,7 +99,7 @@ class ClockSampler:
     def summary(self, t0=None, t1=None):
         sm, smax, reasons = [], [], set()
         for t, line in self.rows:
-            if t0 is not None and not (t0 <= t <= t1 + 0.2):
+            if t0 is not None and not (t0 - 0.03 <= t <= t1 + 0.03):
                 continue
             parts = [x.strip() for x in line.split(",")]
             if len(parts) < 9:
@@ -293,8 +293,10 @@ def run_gpu(args, rank, local_rank, world):
 
     pts = torch.empty((nframes, n, 4), dtype=torch.float32, device=dev)
     uv = torch.empty((nframes, F, 2), dtype=torch.float64, device=dev)
-    depth = torch.empty((nframes, F), dtype=torch.float64, device=dev)
-    status = torch.empty((nframes, F), dtype=torch.int32, device=dev)
+    # two result sets: with N > 1 the NCCL gather of step i overlaps the kernels of step i+1
+    depths = [torch.empty((nframes, F), dtype=torch.float64, device=dev) for _ in range(2 if world > 1 else 1)]
+    statuses = [torch.empty((nframes, F), dtype=torch.int32, device=dev) for _ in range(2 if world > 1 else 1)]
+    depth, status = depths[0], statuses[0]
     coeffs = torch.zeros((nframes, 4), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream().cuda_stream
     synth.points_device(est, cfg, SEED, f0, nframes, pts.data_ptr(), stream=stream)
@@ -306,12 +308,26 @@ def run_gpu(args, rank, local_rank, world):
         g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev)
         g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev)
 
+    pending = [[], []]
+    step_no = [0]
+
     def step():
-        est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes,
+        b = step_no[0] % len(depths)
+        step_no[0] += 1
+        for w in pending[b]:  # the gather that last read this result set must be done before it is overwritten
+            w.wait()
+        pending[b] = []
+        est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depths[b].data_ptr(), statuses[b].data_ptr(), nframes,
                                 road=use_road, seed=SEED + f0, d_plane_coeffs_out=coeffs.data_ptr() if use_road else 0, stream=stream)
-        if world > 1:  # gather the per-frame results (the only inter-GPU traffic of the path)
-            dist.all_gather_into_tensor(g_depth, depth)
-            dist.all_gather_into_tensor(g_status, status)
+        if world > 1:  # gather the per-frame results (the only inter-GPU traffic of the path), asynchronously
+            pending[b] = [dist.all_gather_into_tensor(g_depth, depths[b], async_op=True),
+                          dist.all_gather_into_tensor(g_status, statuses[b], async_op=True)]
+
+    def drain():
+        for b in range(len(pending)):
+            for w in pending[b]:
+                w.wait()
+            pending[b] = []
 
     def barrier():
         if world > 1:
@@ -321,6 +337,7 @@ def run_gpu(args, rank, local_rank, world):
     steps, warm = max(1, args.steps), max(3, args.warmup)
     for _ in range(warm):
         step()
+    drain()
     barrier()
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -334,9 +351,11 @@ def run_gpu(args, rank, local_rank, world):
     e0.record()
     for _ in range(steps):
         step()
+    drain()  # every gather has completed inside the timed region
     e1.record()
     barrier()
     tw1 = time.perf_counter()
+    depth, status = depths[(step_no[0] - 1) % len(depths)], statuses[(step_no[0] - 1) % len(depths)]
     est.profileEnable(False)
     prof, prof_frames = est.profileRead()
     launches = est.kernelLaunchCount() - launches0

@@ -29,6 +29,7 @@ constexpr int MLD_HOST_SLOTS = 3;   // of which the host-buffer pipeline uses
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
+    cudaEvent_t ev_k1 = nullptr, ev_k2 = nullptr;  // priority mode: K1 of the slot's chunk finished / its K2 finished
     void* d_pts = nullptr;      size_t pts_bytes = 0;
     double* d_uv = nullptr;     size_t uv_bytes = 0;
     double* d_depth = nullptr;  size_t depth_bytes = 0;
@@ -82,6 +83,11 @@ struct mld_handle {
     bool use_tagged_maps = true;
     int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
     cudaEvent_t ev_fork = nullptr;
+    // priority mode: every K1 of a sequence runs on a low-priority stream, every K2 on a high-priority one, so the
+    // latency-bound K2 blocks are placed first and the streaming K1 fills what is left
+    int overlap_mode = 0;           // 0: whole chunks alternate over slot streams (faster, measured), 1: priority streams
+    cudaStream_t st_lo = nullptr, st_hi = nullptr;
+    cudaEvent_t ev_join = nullptr;
     long long cur_n = 0;
     int cur_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
@@ -254,11 +260,14 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
 // one chunk of frames on one stream: [clear maps], K1, [K4], K2
 int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, long long n_points, long long pitch_pts,
                   int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
-                  long long frame0, float* d_coeffs_out) {
+                  long long frame0, float* d_coeffs_out, cudaStream_t st_k2 = nullptr) {
+    // st: stream of the map clear + K1 (and of everything when st_k2 is null); st_k2: stream of K4 + K2
+    const bool two = st_k2 != nullptr && st_k2 != st;
+    cudaStream_t sb = two ? st_k2 : st;
     cudaEvent_t* ev = nullptr;
     if (h->prof_on && h->prof_used < MLD_PROF_MAX_CHUNKS) {
-        if (h->prof_events.size() < (h->prof_used + 1) * 5) {
-            for (int q = 0; q < 5; q++) {
+        if (h->prof_events.size() < (h->prof_used + 1) * 6) {
+            for (int q = 0; q < 6; q++) {
                 cudaEvent_t e;
                 CK(cudaEventCreate(&e));
                 h->prof_events.push_back(e);
@@ -266,10 +275,11 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
             h->prof_frames.push_back(0);
             h->prof_ransac_launches.push_back(0);
         }
-        ev = &h->prof_events[h->prof_used * 5];
+        ev = &h->prof_events[h->prof_used * 6];
         h->prof_frames[h->prof_used] = frames;
         h->prof_ransac_launches[h->prof_used] = 0;
     }
+    if (two) CK(cudaStreamWaitEvent(st, s.ev_k2, 0));  // the slot's maps are free once its previous chunk's K2 has finished
     if (ev) CK(cudaEventRecord(ev[0], st));
     MapCode mc;
     int rcm = begin_maps(h, s, frames, n_points, st, mc);
@@ -278,6 +288,11 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
+    if (two) {
+        CK(cudaEventRecord(s.ev_k1, st));
+        CK(cudaStreamWaitEvent(sb, s.ev_k1, 0));
+    }
+    if (ev) CK(cudaEventRecord(ev[3], sb));
     const float* coeffs = nullptr;
     const unsigned int* bits = nullptr;
     const long long words = (n_points + 31) / 32;
@@ -285,17 +300,18 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         float* cdst = d_coeffs_out ? d_coeffs_out : s.d_coeffs;
         int nl = 0;
         CK(mld_launch_ransac(ransac_config(h->params), d_pts, stride_f, n_points, pitch_pts, frames, seed, frame0, s.d_scratch,
-                             cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, st, &nl));
+                             cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, sb, &nl));
         h->launches += nl;
         if (ev) h->prof_ransac_launches[h->prof_used] = nl;
         coeffs = cdst;
         bits = s.d_bits;
     }
-    if (ev) CK(cudaEventRecord(ev[3], st));
-    int rcf = launch_features(h, s, mc, st, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames);
+    if (ev) CK(cudaEventRecord(ev[4], sb));
+    int rcf = launch_features(h, s, mc, sb, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames);
     if (rcf) return rcf;
+    if (two) CK(cudaEventRecord(s.ev_k2, sb));
     if (ev) {
-        CK(cudaEventRecord(ev[4], st));
+        CK(cudaEventRecord(ev[5], sb));
         h->prof_used++;
     }
     return MLD_OK;
@@ -508,12 +524,26 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "split") == 0) h->feature_mode = 2;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
+    env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
+    if (env && strcmp(env, "slots") == 0) h->overlap_mode = 0;
+    if (env && strcmp(env, "prio") == 0) h->overlap_mode = 1;
     env = getenv("MLD_OVERLAP");       // "1": run the chunks of a sequence on one stream (no K1/K2 overlap), up to 3
     if (env && atoi(env) >= 1 && atoi(env) <= MLD_PIPE_SLOTS) h->overlap_slots = atoi(env);
     DeviceGuard g(device);
     if (!g.ok) {
         delete h;
         return fail(nullptr, MLD_ERR_CUDA, "mld_create: cudaSetDevice failed");
+    }
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);  // lo = least priority (numerically greatest)
+        e = cudaStreamCreateWithPriority(&h->st_lo, cudaStreamNonBlocking, lo);
+        if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->st_hi, cudaStreamNonBlocking, hi);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            delete h;
+            return fail_cuda(nullptr, e, "priority stream creation");
+        }
     }
     e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
     if (e != cudaSuccess) {
@@ -523,6 +553,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
         e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k1, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k2, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->slots[i].h_ovf_seen), sizeof(int), cudaHostAllocDefault);
         if (e == cudaSuccess) *h->slots[i].h_ovf_seen = 1 << 30;  // unknown yet: launch the full overflow grid
         if (e != cudaSuccess) {
@@ -542,6 +574,8 @@ int mld_destroy(mld_handle* h) {
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
         cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split);
         if (s.done) cudaEventDestroy(s.done);
+        if (s.ev_k1) cudaEventDestroy(s.ev_k1);
+        if (s.ev_k2) cudaEventDestroy(s.ev_k2);
         if (s.h_ovf_seen) cudaFreeHost(s.h_ovf_seen);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -549,6 +583,9 @@ int mld_destroy(mld_handle* h) {
     cudaFree(h->d_synth_tables);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->st_lo) cudaStreamDestroy(h->st_lo);
+    if (h->st_hi) cudaStreamDestroy(h->st_hi);
     delete h;
     return MLD_OK;
 }
@@ -645,11 +682,12 @@ int mld_profile_read(mld_handle* h, double* ms4, int64_t* launches4, int64_t* fr
     }
     int64_t frames = 0;
     for (size_t c = 0; c < h->prof_used; c++) {
-        cudaEvent_t* ev = &h->prof_events[c * 5];
-        CK(cudaEventSynchronize(ev[4]));
+        cudaEvent_t* ev = &h->prof_events[c * 6];
+        CK(cudaEventSynchronize(ev[5]));
+        const int from[4] = {0, 1, 3, 4}, to[4] = {1, 2, 4, 5};  // clear, K1, K4, K2
         for (int q = 0; q < 4; q++) {
             float ms = 0.f;
-            CK(cudaEventElapsedTime(&ms, ev[q], ev[q + 1]));
+            CK(cudaEventElapsedTime(&ms, ev[from[q]], ev[to[q]]));
             ms4[q] += (double)ms;
         }
         launches4[0] += 1;
@@ -821,20 +859,31 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
     }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
+    const bool prio = nslots > 1 && h->overlap_mode == 1;
     if (nslots > 1) {
         CK(cudaEventRecord(h->ev_fork, st));
-        for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
+        if (prio) {
+            CK(cudaStreamWaitEvent(h->st_lo, h->ev_fork, 0));
+            CK(cudaStreamWaitEvent(h->st_hi, h->ev_fork, 0));
+        } else {
+            for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
+        }
     }
     int64_t ci = 0;
     for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
         int c = (int)std::min<int64_t>(chunk, nframes - f0);
         Slot& s = h->slots[ci % nslots];
-        rc = enqueue_chunk(h, s, nslots > 1 ? s.stream : st, pts + f0 * frame_pitch_points * stride_f, n_points, frame_pitch_points,
-                           stride_f, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F, d_status + f0 * (int64_t)F, c, use_road,
-                           seed, f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr);
+        rc = enqueue_chunk(h, s, prio ? h->st_lo : (nslots > 1 ? s.stream : st), pts + f0 * frame_pitch_points * stride_f, n_points,
+                           frame_pitch_points, stride_f, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F,
+                           d_status + f0 * (int64_t)F, c, use_road, seed, f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr,
+                           prio ? h->st_hi : nullptr);
         if (rc) return rc;
     }
-    if (nslots > 1) {
+    if (prio) {
+        // every K1 precedes a K2 on st_hi, so the end of st_hi is the end of the sequence
+        CK(cudaEventRecord(h->ev_join, h->st_hi));
+        CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    } else if (nslots > 1) {
         for (int i = 0; i < nslots; i++) {
             CK(cudaEventRecord(h->slots[i].done, h->slots[i].stream));
             CK(cudaStreamWaitEvent(st, h->slots[i].done, 0));
