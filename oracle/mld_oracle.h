@@ -12,11 +12,16 @@
  * PCL expression is restated by hand; see the function headers in mld_oracle.cpp
  * for the reference file:line each one follows.
  *
- * Parity status: A6 (histogram) is pinned by the reference's golden vector
- * (test_monolidar_fusion.cpp:306-374); A4/A5 by its window-extent property test
- * (:82-171); R1 (RANSAC) only by its +-0.2 coefficient test (:376-441) -> the
- * RANSAC hypotheses are "parity unpinned". A2/A3/A7-A12/R2/R3/R5 have no golden
- * data in the reference: they are pinned only by this restatement.
+ * Parity status: pinned against the reference itself. oracle/_ref/libmld_ref.so is the
+ * reference's own sources compiled on stand-in Eigen/PCL headers (oracle/ref_standin,
+ * oracle/ref_bridge.cpp); tests/test_ref_pin.py diffs this restatement against it on
+ * seeded inputs (visible set, pixel map, neighbour lists, status codes bit-exact; depths
+ * bit-exact on the main path, <= 1e-9 on the M-estimator road path) for every parameter
+ * variant, and tests/golden/ref_golden.npz freezes reference outputs for the GPU box.
+ * Also pinned by the reference's own KATs: A6 golden vector (test_monolidar_fusion.cpp:
+ * 306-374), A4/A5 window property (:82-171), R1 +-0.2 coefficient test (:376-441).
+ * NOT pinned: arithmetic inside Eigen/PCL calls (the stand-in's, same assumptions as
+ * here), the RANSAC hypothesis stream (PCL is time-seeded), R4 (undefined upstream).
  */
 #ifndef MLD_ORACLE_H
 #define MLD_ORACLE_H

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Regenerates tests/golden/ref_golden.npz: outputs of the REFERENCE ITSELF (oracle/_ref/libmld_ref.so = the
+reference's own monolidar_fusion sources compiled on the stand-in headers of oracle/ref_standin) on seeded inputs.
+
+/root/reference does not exist on the GPU box, so these fixtures are how reference outputs travel: the GPU tests
+(tests/test_ref_golden.py) compare the CUDA path with them directly, without the oracle in between.
+Run from the repo root in a container that has /root/reference:  make -C oracle && python tests/golden/make_ref_golden.py
+
+Cases
+  small_*  320x240 random scene with a road (the inputs of golden_small.npz), yaml parameters, plane nullptr and an
+           injected plane (M-estimator road path)
+  kitti_*  two KITTI-shaped synthetic frames (inputs are regenerated from the seed by mono_lidar_depth_b200.synth, only
+           the reference's outputs are stored), plane nullptr; frame 1 also with an injected plane
+  var_*    the 256x192 scene of the parameter-variant tests under every variant of parity_util.VARIANTS except pca
+"""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests"))
+
+import oracle_lib as O  # noqa: E402
+import parity_util as PU  # noqa: E402
+import ref_lib as R  # noqa: E402
+from mono_lidar_depth_b200 import synth  # noqa: E402
+
+KCAM = (1241, 376, 718.856, 607.1928, 185.2157)
+KITTI_SEED, KITTI_FRAMES, KITTI_F = 4242, (0, 1), 2000
+VAR_CAM = (256, 192, 250.0, 128.0, 96.0)
+
+
+def variant_inputs():
+    rng = np.random.RandomState(42)
+    W, H, f, cx, cy = VAR_CAM
+    cloud = PU.random_scene_cloud(rng, 10000, W, H, f, cx, cy, synth.KITTI_T_LIDAR_TO_CAM, dense_patches=45)
+    uv = np.stack([rng.uniform(0, W, 2000), rng.uniform(0, H, 2000)], 1)
+    return cloud, uv
+
+
+def kitti_plane(cloud):
+    coeffs = np.array([0.0, 0.0, 1.0, 1.73], np.float32)
+    dist = np.abs(cloud[:, 2] + 1.73)
+    return coeffs, np.nonzero(np.isfinite(dist) & (dist < 0.1))[0].astype(np.int32)
+
+
+def main():
+    assert R.available(), "build oracle/_ref first (make -C oracle in a container with /root/reference)"
+    T = synth.KITTI_T_LIDAR_TO_CAM
+    out = {}
+    # ---- small scene: same inputs as golden_small.npz ----
+    G = np.load(Path(__file__).with_name("golden_small.npz"))
+    cam = tuple(G["camera"])
+    cam = (int(cam[0]), int(cam[1]), float(cam[2]), float(cam[3]), float(cam[4]))
+    p = O.yaml_params()
+    r = R.Reference(p)
+    r.initialize(*cam, G["T"])
+    r.set_cloud(G["cloud"], (G["plane_coeffs"], G["plane_inliers"]))
+    out["small_pixel_map"] = r.pixel_map_raw()
+    out["small_point_index"] = r.point_index()
+    out["small_depth_noplane"], out["small_status_noplane"] = r.calculate_depth(G["uv"], with_plane=False)
+    out["small_depth_plane"], out["small_status_plane"] = r.calculate_depth(G["uv"], with_plane=True)
+    nb = [r.neighbors(float(u), float(v), sw, sh) for u, v in G["uv"][:64] for sw, sh in ((1.0, 1.0), (2.0, 1.5))]
+    out["small_neighbors_flat"] = np.concatenate(nb) if nb else np.zeros(0, np.int32)
+    out["small_neighbors_len"] = np.array([len(x) for x in nb], np.int32)
+    # ---- KITTI-shaped frames ----
+    cfg = synth.default_config()
+    r = R.Reference(p)
+    r.initialize(*KCAM, T)
+    for fr in KITTI_FRAMES:
+        cloud = synth.points_host(cfg, KITTI_SEED, fr)
+        uv = synth.features_host(cfg, KITTI_SEED, fr, KITTI_F)
+        plane = kitti_plane(cloud)
+        r.set_cloud(cloud, plane)
+        out[f"kitti{fr}_pixel_map"] = r.pixel_map_raw()
+        out[f"kitti{fr}_point_index"] = r.point_index()
+        out[f"kitti{fr}_depth_noplane"], out[f"kitti{fr}_status_noplane"] = r.calculate_depth(uv, with_plane=False)
+        if fr == 1:
+            rng = np.random.RandomState(1)
+            uvr = np.stack([rng.randint(0, 1241, 3000), rng.randint(180, 376, 3000)], 1).astype(np.float64)
+            out["kitti1_uv_road"] = uvr
+            out["kitti1_depth_plane"], out["kitti1_status_plane"] = r.calculate_depth(uvr, with_plane=True)
+    # ---- parameter variants ----
+    cloud, uv = variant_inputs()
+    for v in PU.VARIANTS:
+        if v == "pca":
+            continue
+        r = R.Reference(PU.variant_params(v))
+        r.initialize(*VAR_CAM, T)
+        r.set_cloud(cloud)
+        out[f"var_{v}_depth"], out[f"var_{v}_status"] = r.calculate_depth(uv)
+    np.savez_compressed(Path(__file__).with_name("ref_golden.npz"), **out)
+    for k in ("small_status_noplane", "small_status_plane", "kitti0_status_noplane", "kitti1_status_plane"):
+        print(k, np.bincount(out[k], minlength=17))
+    print("written", Path(__file__).with_name("ref_golden.npz").stat().st_size, "bytes")
+
+
+if __name__ == "__main__":
+    main()

@@ -91,3 +91,56 @@ def random_scene_cloud(rng, n, W, H, f, cx, cy, T, zmin=2.0, zmax=60.0, dense_pa
     out = np.zeros((len(lid), 4), np.float32)
     out[:, :3] = lid.astype(np.float32)
     return out
+
+
+VARIANTS = ["defaults", "no_hist", "no_trimax", "no_planar_check", "no_ortho", "adjust_mode", "absolute_local", "no_thresholds", "count_min3",
+            "pca", "big_window", "hist_min0", "no_cut_behind", "cut_behind_only"]
+
+
+def variant_params(variant) -> MldParams:
+    """Parameter sets that switch every optional module of DepthEstimator::Initialize (DepthEstimator.cpp:46-124) on and off."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    if variant == "defaults":
+        p = O.default_params()
+        p.do_use_ransac_plane = 0
+        p.viewray_plane_orthoganality_treshold = 0.05
+    elif variant == "no_hist":
+        p.do_use_histogram_segmentation = 0
+    elif variant == "no_trimax":
+        p.do_use_triangle_size_maximation = 0
+    elif variant == "no_planar_check":
+        p.do_check_triangleplanar_condition = 0
+    elif variant == "no_ortho":
+        p.viewray_plane_orthoganality_treshold = 0.0
+    elif variant == "adjust_mode":
+        p.treshold_depth_mode = 1
+        p.treshold_depth_local_mode = 1
+        p.treshold_depth_max = 20
+        p.treshold_depth_min = 5
+    elif variant == "absolute_local":
+        p.treshold_depth_local_valuetype = 0
+        p.treshold_depth_local_value = 0.05
+    elif variant == "no_thresholds":
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+    elif variant == "count_min3":
+        p.radiusSearch_count_min = 3
+    elif variant == "pca":
+        p.do_use_PCA = 1
+        p.pca_treshold_2_1_rel_min = 0.5
+    elif variant == "big_window":
+        p.pixelarea_search_witdh = 14
+        p.pixelarea_search_height = 17
+    elif variant == "hist_min0":
+        p.histogram_segmentation_min_pointcount = 0
+    elif variant == "no_cut_behind":
+        p.do_use_cut_behind_camera = 0
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+    elif variant == "cut_behind_only":
+        p.treshold_depth_enabled = 0
+        p.treshold_depth_local_enabled = 0
+        p.do_check_triangleplanar_condition = 0
+        p.viewray_plane_orthoganality_treshold = 0.0
+    return p

@@ -68,59 +68,12 @@ def test_dense_random_scenes_all_branches(seed):
     assert len(hist) >= 5, hist
 
 
-@pytest.mark.parametrize(
-    "variant",
-    ["defaults", "no_hist", "no_trimax", "no_planar_check", "no_ortho", "adjust_mode", "absolute_local", "no_thresholds", "count_min3",
-     "pca", "big_window", "hist_min0", "no_cut_behind", "cut_behind_only"],
-)
+@pytest.mark.parametrize("variant", PU.VARIANTS)
 def test_parameter_variants(variant):
     rng = np.random.RandomState(42)
     W, H, f, cx, cy = 256, 192, 250.0, 128.0, 96.0
     cam = CameraPinhole(W, H, f, cx, cy)
-    p = O.yaml_params()
-    p.do_use_ransac_plane = 0
-    if variant == "defaults":
-        p = O.default_params()
-        p.do_use_ransac_plane = 0
-        p.viewray_plane_orthoganality_treshold = 0.05
-    elif variant == "no_hist":
-        p.do_use_histogram_segmentation = 0
-    elif variant == "no_trimax":
-        p.do_use_triangle_size_maximation = 0
-    elif variant == "no_planar_check":
-        p.do_check_triangleplanar_condition = 0
-    elif variant == "no_ortho":
-        p.viewray_plane_orthoganality_treshold = 0.0
-    elif variant == "adjust_mode":
-        p.treshold_depth_mode = 1
-        p.treshold_depth_local_mode = 1
-        p.treshold_depth_max = 20
-        p.treshold_depth_min = 5
-    elif variant == "absolute_local":
-        p.treshold_depth_local_valuetype = 0
-        p.treshold_depth_local_value = 0.05
-    elif variant == "no_thresholds":
-        p.treshold_depth_enabled = 0
-        p.treshold_depth_local_enabled = 0
-    elif variant == "count_min3":
-        p.radiusSearch_count_min = 3
-    elif variant == "pca":
-        p.do_use_PCA = 1
-        p.pca_treshold_2_1_rel_min = 0.5
-    elif variant == "big_window":
-        p.pixelarea_search_witdh = 14
-        p.pixelarea_search_height = 17
-    elif variant == "hist_min0":
-        p.histogram_segmentation_min_pointcount = 0
-    elif variant == "no_cut_behind":
-        p.do_use_cut_behind_camera = 0
-        p.treshold_depth_enabled = 0
-        p.treshold_depth_local_enabled = 0
-    elif variant == "cut_behind_only":
-        p.treshold_depth_enabled = 0
-        p.treshold_depth_local_enabled = 0
-        p.do_check_triangleplanar_condition = 0
-        p.viewray_plane_orthoganality_treshold = 0.0
+    p = PU.variant_params(variant)
     est, orc = PU.make_pair(p, cam, KT)
     cloud = PU.random_scene_cloud(rng, 10000, W, H, f, cx, cy, KT, dense_patches=45)
     uv = np.stack([rng.uniform(0, W, 2000), rng.uniform(0, H, 2000)], 1)

@@ -1,0 +1,138 @@
+"""Reference-generated golden fixture (tests/golden/ref_golden.npz, made by tests/golden/make_ref_golden.py from
+oracle/_ref = the reference's own sources compiled on stand-in Eigen/PCL headers). The fixture travels to the GPU box,
+where /root/reference does not exist: the CUDA path is compared with the reference's outputs directly.
+
+Contract: pixel map, visible indices, neighbour lists, status codes bit-exact; depths within 1e-4 relative (north_star)."""
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+import parity_util as PU
+from mono_lidar_depth_b200 import CameraPinhole, DepthEstimator, GroundPlane, synth
+
+sys_path_golden = Path(__file__).resolve().parent / "golden"
+G = np.load(sys_path_golden / "ref_golden.npz")
+S = np.load(sys_path_golden / "golden_small.npz")
+
+import importlib.util  # noqa: E402
+
+_spec = importlib.util.spec_from_file_location("make_ref_golden", sys_path_golden / "make_ref_golden.py")
+MK = importlib.util.module_from_spec(_spec)
+_spec.loader.exec_module(MK)
+
+KT = synth.KITTI_T_LIDAR_TO_CAM
+
+
+def _small_cam():
+    W, H, f, cx, cy = S["camera"]
+    return int(W), int(H), float(f), float(cx), float(cy)
+
+
+def _close(d, ref, rtol):
+    return np.all(np.abs(d - ref) <= rtol * np.abs(ref))
+
+
+# ---------------------------------------------------------------- CPU: the oracle against the reference's outputs
+def test_oracle_reproduces_reference_small_scene():
+    o = O.Oracle(O.yaml_params())
+    o.initialize(*_small_cam(), S["T"])
+    o.set_cloud(S["cloud"])
+    assert np.array_equal(o.pixel_map_raw(), G["small_pixel_map"])
+    assert np.array_equal(o.point_index(), G["small_point_index"])
+    d, s = o.calculate_depth(S["uv"])
+    assert np.array_equal(s, G["small_status_noplane"]) and np.array_equal(d, G["small_depth_noplane"])
+    d, s = o.calculate_depth(S["uv"], (S["plane_coeffs"], S["plane_inliers"]))
+    assert np.array_equal(s, G["small_status_plane"]) and _close(d, G["small_depth_plane"], 1e-9)
+    nb = [o.neighbors(float(u), float(v), sw, sh) for u, v in S["uv"][:64] for sw, sh in ((1.0, 1.0), (2.0, 1.5))]
+    assert np.array_equal(np.array([len(x) for x in nb]), G["small_neighbors_len"])
+    assert np.array_equal(np.concatenate(nb), G["small_neighbors_flat"])
+    # the older oracle-generated fixture agrees with the reference-generated one
+    assert np.array_equal(S["status_noplane"], G["small_status_noplane"]) and np.array_equal(S["status_plane"], G["small_status_plane"])
+
+
+def test_oracle_reproduces_reference_kitti_frames():
+    o = O.Oracle(O.yaml_params())
+    o.initialize(*MK.KCAM, KT)
+    cfg = synth.default_config()
+    for fr in MK.KITTI_FRAMES:
+        cloud = synth.points_host(cfg, MK.KITTI_SEED, fr)
+        o.set_cloud(cloud)
+        assert np.array_equal(o.pixel_map_raw(), G[f"kitti{fr}_pixel_map"])
+        assert np.array_equal(o.point_index(), G[f"kitti{fr}_point_index"])
+        d, s = o.calculate_depth(synth.features_host(cfg, MK.KITTI_SEED, fr, MK.KITTI_F))
+        assert np.array_equal(s, G[f"kitti{fr}_status_noplane"]) and np.array_equal(d, G[f"kitti{fr}_depth_noplane"])
+        if fr == 1:
+            d, s = o.calculate_depth(G["kitti1_uv_road"], MK.kitti_plane(cloud))
+            assert np.array_equal(s, G["kitti1_status_plane"]) and _close(d, G["kitti1_depth_plane"], 1e-9)
+
+
+def test_oracle_reproduces_reference_parameter_variants():
+    cloud, uv = MK.variant_inputs()
+    for v in PU.VARIANTS:
+        if v == "pca":
+            continue
+        o = O.Oracle(PU.variant_params(v))
+        o.initialize(*MK.VAR_CAM, KT)
+        o.set_cloud(cloud)
+        d, s = o.calculate_depth(uv)
+        assert np.array_equal(s, G[f"var_{v}_status"]), v
+        assert np.array_equal(d, G[f"var_{v}_depth"]), v
+
+
+# ---------------------------------------------------------------- GPU: the CUDA path against the reference's outputs
+def _gpu_estimator(c_params, cam):
+    est = DepthEstimator()
+    est.InitConfig(PU.params_from_c(c_params))
+    est.Initialize(CameraPinhole(*cam), KT)
+    return est
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_small_scene():
+    est = _gpu_estimator(O.yaml_params(), _small_cam())
+    gp = GroundPlane(S["plane_coeffs"], S["plane_inliers"])
+    est.setInputCloud(S["cloud"], gp)
+    assert np.array_equal(est.getPixelMap(), G["small_pixel_map"])
+    assert np.array_equal(np.nonzero(est.getVisible())[0].astype(np.int32), G["small_point_index"])
+    d, s = est.CalculateDepth(S["uv"])
+    PU.assert_depth_status_equal(d, s, G["small_depth_noplane"], G["small_status_noplane"], "ref small no plane")
+    d, s = est.CalculateDepth(S["uv"], gp)
+    PU.assert_depth_status_equal(d, s, G["small_depth_plane"], G["small_status_plane"], "ref small plane")
+    lens = G["small_neighbors_len"]
+    flat = G["small_neighbors_flat"]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    k = 0
+    for u, v in S["uv"][:64]:
+        for sw, sh in ((1.0, 1.0), (2.0, 1.5)):
+            assert np.array_equal(est.getNeighbors(float(u), float(v), sw, sh), flat[off[k]:off[k + 1]])
+            k += 1
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_kitti_frames():
+    est = _gpu_estimator(O.yaml_params(), MK.KCAM)
+    cfg = synth.default_config()
+    for fr in MK.KITTI_FRAMES:
+        cloud = synth.points_host(cfg, MK.KITTI_SEED, fr)
+        coeffs, inl = MK.kitti_plane(cloud)
+        gp = GroundPlane(coeffs, inl)
+        est.setInputCloud(cloud, gp)
+        assert np.array_equal(est.getPixelMap(), G[f"kitti{fr}_pixel_map"])
+        assert np.array_equal(np.nonzero(est.getVisible())[0].astype(np.int32), G[f"kitti{fr}_point_index"])
+        d, s = est.CalculateDepth(synth.features_host(cfg, MK.KITTI_SEED, fr, MK.KITTI_F))
+        PU.assert_depth_status_equal(d, s, G[f"kitti{fr}_depth_noplane"], G[f"kitti{fr}_status_noplane"], f"ref kitti {fr}")
+        if fr == 1:
+            d, s = est.CalculateDepth(G["kitti1_uv_road"], gp)
+            PU.assert_depth_status_equal(d, s, G["kitti1_depth_plane"], G["kitti1_status_plane"], "ref kitti road")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", [v for v in PU.VARIANTS if v != "pca"])
+def test_gpu_matches_reference_parameter_variants(variant):
+    cloud, uv = MK.variant_inputs()
+    est = _gpu_estimator(PU.variant_params(variant), MK.VAR_CAM)
+    est.setInputCloud(cloud)
+    d, s = est.CalculateDepth(uv)
+    PU.assert_depth_status_equal(d, s, G[f"var_{variant}_depth"], G[f"var_{variant}_status"], f"ref variant {variant}")
