@@ -217,6 +217,25 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
     frame_parallel = sum(counts) / (time.perf_counter() - t1)
     O.lib().orc_set_num_threads(cores)
     best = max(native, frame_parallel)
+    # the reference's OWN sources (oracle/_ref: compiled against stand-in Eigen/PCL headers) on a short
+    # sample, reported for information only: the stand-in linear algebra is not Eigen, so the (faster) port stays the baseline
+    ref_sources = None
+    try:
+        import ref_lib as R
+
+        if R.available():
+            r = R.Reference(p)
+            r.initialize(IMG_W, IMG_H, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
+            t2 = time.perf_counter()
+            nref = 0
+            while time.perf_counter() - t2 < min(2.0, 0.1 * budget_s) or nref < 2:
+                r.set_cloud(frames_host[nref % nsample], None)  # with do_use_ransac_plane the reference fits its own RansacPlane
+                r.has_plane = bool(wl["road"])
+                r.calculate_depth(uv_host[nref % nsample])
+                nref += 1
+            ref_sources = nref / (time.perf_counter() - t2)
+    except Exception as ex:  # the checker build is optional on the GPU box
+        ref_sources = f"unavailable: {ex}"
     return {
         "value": best,
         "unit": "frames/s",
@@ -228,6 +247,7 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
                    f"{WORKLOAD} workload, {nsample} distinct frames cycled; the better figure is reported"),
         "native_frames_per_s": native,
         "frame_parallel_frames_per_s": frame_parallel,
+        "reference_sources_frames_per_s": ref_sources,
     }
 
 
@@ -255,7 +275,7 @@ def run_reference(args, rank, world):
                                f"each step is a bounded {per:.1f} s sample (~{frames_per_step:.0f} frames) of the sequence on the host cores",
                    "points_per_frame": N_POINTS, "features_per_frame": N_FEATURES, "image": [IMG_W, IMG_H]},
         "feature_depths_per_sec": v * N_FEATURES,
-        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "reference_sources_frames_per_s")},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }

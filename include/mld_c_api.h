@@ -146,6 +146,27 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
 int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, uint64_t seed,
                               mld_plane* out_plane, int32_t* iterations_out);
 
+/* ---- SemanticPlane::CalculateInliersPlane (RansacPlane.cpp:159-274), stand-alone ----
+ * The ground plane the production caller builds from a semantic label image
+ * (tracklets_depth/src/tracklet_depth_module.cpp:269-284): points whose projection carries a ground label ->
+ * least-squares plane -> inliers within inlier_threshold over the whole cloud -> refit.
+ * labels_host: label_h x label_w uint8, row-major (the cv::Mat); f/cu/cv and T_cam_lidar (row-major 3x4) are
+ * SemanticPlane::Camera; ground_labels: the std::set<int> (values outside 0..255 never match a uint8 pixel).
+ * Fails with MLD_ERR_PCL_INVALID when fewer than 3 points carry a ground label (ExceptionPclInvalid, :224-227).
+ * out_plane receives getModelCoeffs() / getInlinersIndex() and segmented = 1; it can be passed to mld_set_cloud /
+ * mld_calculate_depth like any GroundPlane. Does not disturb the handle's current cloud. */
+int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
+                              int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
+                              const int32_t* ground_labels, int n_ground_labels, double inlier_threshold, mld_plane* out_plane);
+/* Device-resident, batched form: nframes clouds (frame_pitch_points apart) and nframes label images back to back.
+ * Outputs per frame: 4 coefficients, an inlier bitmask over raw indices ((n_points + 31) / 32 words, the format the
+ * road path consumes), the inlier count and a return code (0 or MLD_ERR_PCL_INVALID). Enqueued on `stream`. */
+int mld_semantic_ground_plane_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
+                                     int stride_bytes, const uint8_t* d_labels, int label_w, int label_h, double f, double cu,
+                                     double cv, const double* T_cam_lidar, const int32_t* ground_labels, int n_ground_labels,
+                                     double inlier_threshold, int64_t nframes, float* d_coeffs_out, uint32_t* d_inlier_bits_out,
+                                     int32_t* d_n_inliers_out, int32_t* d_rc_out, void* stream);
+
 /* ---- batched, device-resident sequence (the benchmark path; frames are independent) ----
  * d_points: nframes clouds, frame_pitch_points elements apart, n_points valid in each.
  * d_uv: nframes x (2 x F) doubles; d_depth: nframes x F; d_status: nframes x F.
@@ -210,6 +231,13 @@ int mld_get_neighbors(mld_handle* h, double u, double v, double scale_w, double 
 /* visible flags per raw point (Transform_Cloud_LidarToCamera's cull, DepthEstimator.cpp:184-207):
  * out_visible_host[n] bytes; *n_visible_out = count. */
 int mld_get_visible(mld_handle* h, uint8_t* out_visible_host, int64_t* n_visible_out);
+/* visible-order views, compacted on the device in cloud order:
+ *   point_index_out[j]  = raw index of visible point j                  (_pointIndex, DepthEstimator.cpp:197-207)
+ *   image_points_out    = 2 x nvis doubles, column-major (u_j, v_j)     (getPointsCloudImageCs / _points_cs_image_visible)
+ *   depth_cam_out[j]    = camera-frame z of visible point j              (getPointDepthCamVisible(j))
+ * Any output may be NULL; at most `capacity` entries are written; *n_visible_out = number of visible points. */
+int mld_get_visible_points(mld_handle* h, int32_t* point_index_out, double* image_points_out, double* depth_cam_out,
+                           int64_t capacity, int64_t* n_visible_out);
 /* camera-frame coordinates of raw point i (3 doubles each), _points_cs_camera */
 int mld_get_points_camera(mld_handle* h, double* out_host);
 

@@ -12,6 +12,7 @@ from .depth_estimator import (  # noqa: F401
     ExceptionPclInvalid,
     GroundPlane,
     RansacPlane,
+    SemanticPlane,
 )
 from . import sharding, synth  # noqa: F401
 

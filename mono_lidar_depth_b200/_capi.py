@@ -135,6 +135,17 @@ SYMBOLS = {
     "mld_set_cloud": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int, _PL, C.c_uint64]),
     "mld_calculate_depth": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _PL]),
     "mld_estimate_ground_plane": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_int, C.c_uint64, _PL, C.POINTER(C.c_int32)]),
+    "mld_semantic_ground_plane": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+         C.c_int, C.c_double, _PL],
+    ),
+    "mld_semantic_ground_plane_device": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
+         C.c_void_p, C.c_int, C.c_double, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "mld_get_visible_points": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "mld_process_frames_device": (
         C.c_int,
         [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

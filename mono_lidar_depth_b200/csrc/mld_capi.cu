@@ -40,6 +40,8 @@ struct Slot {
     void* d_scratch = nullptr;  size_t scratch_bytes = 0;
     int* d_small = nullptr;     size_t small_bytes = 0;  // n_inliers | iterations | rc, per frame
     int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
+    unsigned char* d_labels = nullptr; size_t labels_bytes = 0; // semantic label image (mld_semantic_ground_plane)
+    unsigned char* d_sem = nullptr; size_t sem_bytes = 0;       // SemanticPlane scratch
     unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
     void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
     int* h_ovf_seen = nullptr;  // pinned: overflow count of this slot's previous chunk (sizes the next overflow launch)
@@ -81,6 +83,8 @@ struct mld_handle {
     int feature_mode = 2;
     int overflow_blocks = 296;
     bool use_tagged_maps = true;
+    int k1_persist_per_sm = 0;
+    int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
     int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
     cudaEvent_t ev_fork = nullptr;
     // priority mode: every K1 of a sequence runs on a low-priority stream, every K2 on a high-priority one, so the
@@ -285,7 +289,8 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     int rcm = begin_maps(h, s, frames, n_points, st, mc);
     if (rcm) return rcm;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st));
+    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st,
+                                  h->k1_persistent_blocks));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
     if (two) {
@@ -524,6 +529,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "split") == 0) h->feature_mode = 2;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
+    env = getenv("MLD_K1_PERSIST");    // blocks per SM of the persistent K1 grid (0 = one block per tile)
+    if (env && atoi(env) >= 0) h->k1_persist_per_sm = atoi(env);
     env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
     if (env && strcmp(env, "slots") == 0) h->overlap_mode = 0;
     if (env && strcmp(env, "prio") == 0) h->overlap_mode = 1;
@@ -572,7 +579,7 @@ int mld_destroy(mld_handle* h) {
     for (auto& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
-        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split); cudaFree(s.d_labels); cudaFree(s.d_sem);
         if (s.done) cudaEventDestroy(s.done);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_k2) cudaEventDestroy(s.ev_k2);
@@ -657,7 +664,10 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     CK(mld_configure_feature_depth(h->kcap));
     CK(mld_configure_feature_depth_thread());
     int sms = 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) h->overflow_blocks = 2 * sms;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) {
+        h->overflow_blocks = 2 * sms;
+        h->k1_persistent_blocks = h->k1_persist_per_sm * sms;
+    }
     for (auto& sl : h->slots) sl.epoch = 0;  // image size may have changed
     h->initialized = true;
     h->have_cloud = false;
@@ -783,6 +793,71 @@ int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n,
     CK(ensure(s.d_pts, s.pts_bytes, (size_t)n * (size_t)stride_bytes));
     CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
     return run_ransac_single(h, s, n, stride_bytes / 4, seed, out_plane, iterations_out);
+}
+
+static void ground_label_set(const int32_t* labels, int n, unsigned int set8[8]) {
+    for (int i = 0; i < 8; i++) set8[i] = 0u;
+    for (int i = 0; i < n; i++)
+        if (labels[i] >= 0 && labels[i] <= 255) set8[labels[i] >> 5] |= 1u << (labels[i] & 31);
+}
+
+int mld_semantic_ground_plane_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
+                                     int stride_bytes, const uint8_t* d_labels, int label_w, int label_h, double f, double cu,
+                                     double cv, const double* T_cam_lidar, const int32_t* ground_labels, int n_ground_labels,
+                                     double inlier_threshold, int64_t nframes, float* d_coeffs_out, uint32_t* d_inlier_bits_out,
+                                     int32_t* d_n_inliers_out, int32_t* d_rc_out, void* stream) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (nframes < 0 || n_points < 0 || label_w <= 0 || label_h <= 0 || !T_cam_lidar || (n_ground_labels > 0 && !ground_labels) ||
+        (nframes > 0 && (!d_labels || !d_coeffs_out || !d_inlier_bits_out || !d_n_inliers_out || !d_rc_out || (n_points > 0 && !d_points))))
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_semantic_ground_plane_device: bad arguments");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (nframes == 0) return MLD_OK;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[1];
+    CK(ensure(s.d_sem, s.sem_bytes, mld_semantic_state_bytes((int)nframes)));
+    unsigned int set8[8];
+    ground_label_set(ground_labels, n_ground_labels, set8);
+    int nl = 0;
+    CK(mld_launch_semantic_plane(T_cam_lidar, f, cu, cv, label_w, label_h, set8, inlier_threshold, reinterpret_cast<const float*>(d_points),
+                                 stride_bytes / 4, n_points, frame_pitch_points, d_labels, (int)nframes, s.d_sem, d_coeffs_out,
+                                 d_inlier_bits_out, (n_points + 31) / 32, d_n_inliers_out, d_rc_out, reinterpret_cast<cudaStream_t>(stream), &nl));
+    h->launches += nl;
+    return MLD_OK;
+}
+
+int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
+                              int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
+                              const int32_t* ground_labels, int n_ground_labels, double inlier_threshold, mld_plane* out_plane) {
+    if (!h || !out_plane) return MLD_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && !points_host) || !labels_host || label_w <= 0 || label_h <= 0)
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_semantic_ground_plane: bad arguments");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[1];  // does not disturb the current cloud of slot 0
+    const long long words = (n + 31) / 32;
+    CK(ensure(s.d_pts, s.pts_bytes, (size_t)std::max<int64_t>(n, 1) * (size_t)stride_bytes));
+    CK(ensure(s.d_labels, s.labels_bytes, (size_t)label_w * (size_t)label_h));
+    CK(ensure(s.d_bits, s.bits_bytes, (size_t)std::max<long long>(words, 1) * sizeof(unsigned int)));
+    CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
+    CK(ensure(s.d_small, s.small_bytes, 3 * sizeof(int)));
+    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_labels, labels_host, (size_t)label_w * (size_t)label_h, cudaMemcpyHostToDevice, s.stream));
+    rc = mld_semantic_ground_plane_device(h, s.d_pts, n, n, stride_bytes, s.d_labels, label_w, label_h, f, cu, cv, T_cam_lidar,
+                                          ground_labels, n_ground_labels, inlier_threshold, 1, s.d_coeffs, s.d_bits, s.d_small,
+                                          s.d_small + 2, s.stream);
+    if (rc) return rc;
+    std::vector<unsigned int> bits((size_t)words);
+    int small[3] = {0, 0, 0};
+    CK(cudaMemcpyAsync(out_plane->coeffs, s.d_coeffs, 4 * sizeof(float), cudaMemcpyDeviceToHost, s.stream));
+    if (words > 0) CK(cudaMemcpyAsync(bits.data(), s.d_bits, (size_t)words * sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaMemcpyAsync(small, s.d_small, 3 * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    if (small[2] == MLD_ERR_PCL_INVALID) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    bits_to_plane(bits, n, out_plane);
+    out_plane->segmented = 1;
+    return MLD_OK;
 }
 
 int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* depth_host, int32_t* status_host,
@@ -1165,6 +1240,40 @@ static int debug_views(mld_handle* h, uint8_t* vis_host, int64_t* n_vis, double*
 int mld_get_visible(mld_handle* h, uint8_t* out_visible_host, int64_t* n_visible_out) {
     if (!h || !out_visible_host) return MLD_ERR_INVALID_ARG;
     return debug_views(h, out_visible_host, n_visible_out, nullptr);
+}
+int mld_get_visible_points(mld_handle* h, int32_t* point_index_out, double* image_points_out, double* depth_cam_out,
+                           int64_t capacity, int64_t* n_visible_out) {
+    if (!h || capacity < 0) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    const long long n = h->cur_n;
+    const long long cap = std::min<long long>(capacity, n);
+    unsigned char* d_buf = nullptr;
+    const size_t scratch = (mld_visible_scratch_bytes(n) + 15) / 16 * 16;
+    const size_t idx_b = point_index_out ? ((size_t)cap * sizeof(int) + 15) / 16 * 16 : 0;
+    const size_t img_b = image_points_out ? (size_t)cap * 2 * sizeof(double) : 0;
+    const size_t dep_b = depth_cam_out ? (size_t)cap * sizeof(double) : 0;
+    CK(cudaMalloc(&d_buf, scratch + idx_b + img_b + dep_b + 16));
+    int* d_idx = point_index_out ? reinterpret_cast<int*>(d_buf + scratch) : nullptr;
+    double* d_img = image_points_out ? reinterpret_cast<double*>(d_buf + scratch + idx_b) : nullptr;
+    double* d_dep = depth_cam_out ? reinterpret_cast<double*>(d_buf + scratch + idx_b + img_b) : nullptr;
+    const unsigned int* d_count = nullptr;
+    int nl = 0;
+    cudaError_t e = mld_launch_visible_compact(h->dp, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, n, d_buf, cap, d_idx, d_img,
+                                               d_dep, &d_count, s.stream, &nl);
+    h->launches += nl;
+    unsigned int nvis = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&nvis, d_count, sizeof(unsigned int), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    const size_t w = (size_t)std::min<long long>(cap, (long long)nvis);
+    if (e == cudaSuccess && d_idx && w) e = cudaMemcpy(point_index_out, d_idx, w * sizeof(int), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && d_img && w) e = cudaMemcpy(image_points_out, d_img, w * 2 * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && d_dep && w) e = cudaMemcpy(depth_cam_out, d_dep, w * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(d_buf);
+    if (e != cudaSuccess) return fail_cuda(h, e, "mld_get_visible_points");
+    if (n_visible_out) *n_visible_out = (int64_t)nvis;
+    return MLD_OK;
 }
 int mld_get_points_camera(mld_handle* h, double* out_host) {
     if (!h || !out_host) return MLD_ERR_INVALID_ARG;

@@ -47,8 +47,10 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
                       int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
                       double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap) {
     __shared__ int s_aux[SCAP * SBT_A];
-    __shared__ int s_wtot[SBT_A / 32];
+    __shared__ int s_hist[SCAP + 1], s_start[SCAP + 2], s_off[SCAP + 1];
+    __shared__ unsigned char s_order[SBT_A];
     __shared__ int s_base;
+    static_assert(SBT_A <= 256, "s_order holds thread ids in a byte");
     const int tid = threadIdx.x;
     const int fi = blockIdx.x * SBT_A + tid;
     const bool valid = fi < F;
@@ -117,31 +119,53 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
             depth[o] = -1;
         }
     }
-    // chunk-wide survivor slot: rank inside the block + one atomic per block
-    const int lane = tid & 31, warp = tid >> 5;
-    const unsigned bm = __ballot_sync(MLD_FULL_MASK, surv);
-    if (lane == 0) s_wtot[warp] = __popc(bm);
+    // chunk-wide survivor slots, ordered by neighbour count inside the block (counting sort over k): the solve
+    // kernel's warps then hold features of (nearly) equal k, so its per-thread loops over the neighbours stop
+    // diverging; one global atomic per block reserves the block's slots.
+    if (tid <= SCAP) s_hist[tid] = 0;
     __syncthreads();
-    int base = 0, total = 0;
-#pragma unroll
-    for (int w = 0; w < SBT_A / 32; w++) {
-        const int c = s_wtot[w];
-        if (w < warp) base += c;
-        total += c;
+    int r = 0;
+    if (surv) r = atomicAdd(&s_hist[k], 1);  // rank among the block's survivors with the same k
+    __syncthreads();
+    if (tid == 0) {
+        // s_start[j] = survivors with k < j; s_off[i] = (entry, survivor) pairs with entry < i
+        int acc = 0;
+        for (int j = 0; j <= SCAP; j++) {
+            s_start[j] = acc;
+            acc += s_hist[j];
+        }
+        s_start[SCAP + 1] = acc;
+        int pairs = 0;
+        for (int i = 0; i < SCAP; i++) {
+            s_off[i] = pairs;
+            pairs += acc - s_start[i + 1];  // survivors with k > i own an entry i
+        }
+        s_off[SCAP] = pairs;
+        s_base = acc ? atomicAdd(surv_count, acc) : 0;
     }
-    if (tid == 0) s_base = total ? atomicAdd(surv_count, total) : 0;
     __syncthreads();
-    if (!surv) return;
-    const long long slot = (long long)s_base + base + __popc(bm & ((1u << lane) - 1u));
-    surv_rec[slot] = pack_rec(k, o);
-    // phase 2: map cells -> raw indices; phase 3: points -> FP64 camera frame, stored [entry][xyz][slot]
-#pragma unroll 4
-    for (int i = 0; i < k; i++) aux[i * SBT_A] = (int)map_cell_index(mc, __ldg(map + aux[i * SBT_A]));
-#pragma unroll 2
-    for (int i = 0; i < k; i++) {
-        const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)aux[i * SBT_A] * stride_f));
+    const int S = s_start[SCAP + 1];
+    if (S == 0) return;  // uniform per block
+    if (surv) {
+        const int rank = s_start[k] + r;
+        s_order[rank] = (unsigned char)tid;
+        surv_rec[(long long)s_base + rank] = pack_rec(k, o);
+    }
+    __syncthreads();
+    // phases 2 and 3 over the flattened (entry i, survivor rank) pairs, entry-major: every lane owns one neighbour
+    // (dense warps whatever the spread of k), lanes of equal i store to consecutive slots.
+    // map cell -> raw index -> point -> FP64 camera frame, stored [entry][xyz][slot]
+    const int T = s_off[SCAP];
+    for (int p = tid; p < T; p += SBT_A) {
+        int i = 0;
+#pragma unroll
+        for (int j = 1; j < SCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
+        const int rank = s_start[i + 1] + (p - s_off[i]);
+        const int owner = s_order[rank];
+        const unsigned int raw = map_cell_index(mc, __ldg(map + s_aux[i * SBT_A + owner]));
+        const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)raw * stride_f));
         const D3 c = lidar_to_cam(P, q.x, q.y, q.z);
-        double* dst = surv_xyz + (long long)i * 3 * cap + slot;
+        double* dst = surv_xyz + (long long)i * 3 * cap + ((long long)s_base + rank);
         dst[0] = c.x;
         dst[cap] = c.y;
         dst[2 * cap] = c.z;

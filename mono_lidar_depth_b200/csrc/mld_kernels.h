@@ -14,7 +14,12 @@ void mld_setup_prefilter(DevParams& P);
 // d_occ: occupancy bitmaps (occ_words_per_row(W) * H words per frame, zeroed by the caller) or nullptr
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
-                                       cudaStream_t stream);
+                                       cudaStream_t stream, int persistent_blocks = 0);
+// visible-order compaction: _pointIndex, _points_cs_image_visible (2 x nvis), camera-frame depth
+size_t mld_visible_scratch_bytes(long long n);
+cudaError_t mld_launch_visible_compact(const DevParams& P, const float* d_pts, int stride_f, long long n, void* d_scratch, long long capacity,
+                                       int* d_point_index, double* d_image_points, double* d_depth_cam, const unsigned int** d_count_out,
+                                       cudaStream_t stream, int* launches);
 cudaError_t mld_launch_visible_debug(const DevParams& P, const float* d_pts, int stride_f, long long n,
                                      unsigned char* d_visible, double* d_cam, cudaStream_t stream);
 
@@ -66,6 +71,13 @@ constexpr int MLD_RANSAC_SAMPLE = 6000;  // _numberRandomSamplePoints, RansacPla
 
 // Scratch per frame (device): see mld_ransac.cu. Sizes in bytes for nframes.
 size_t mld_ransac_scratch_bytes(long long n_points, int nframes);
+// SemanticPlane (mld_semantic.cu): d_state holds mld_semantic_state_bytes(nframes) bytes of scratch
+size_t mld_semantic_state_bytes(int nframes);
+cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, double cu, double cv, int label_w, int label_h,
+                                      const unsigned int* ground_set8, double inlier_threshold, const float* d_pts, int stride_f,
+                                      long long n_points, long long pitch_pts, const unsigned char* d_labels, int nframes,
+                                      void* d_state, float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame,
+                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches);
 // Fits one plane per frame. Outputs per frame: coeffs[4] (float), inlier bitmask over raw indices
 // (words_per_frame uint32), n_inliers, iterations, rc (0 ok, MLD_ERR_PCL_INVALID, MLD_ERR_NO_MODEL).
 cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int stride_f, long long n_points,

@@ -33,9 +33,21 @@ namespace {
 constexpr int K1_THREADS = MLD_K1_THREADS;
 constexpr int K1_PPT = MLD_K1_PPT;  // points per thread: independent 16-byte loads in flight
 
+// exact projection of one point; returns false when the point is culled, else its image coordinates and camera-frame point
+__device__ __forceinline__ bool project_uv(const DevParams& P, float x, float y, float z, bool need_front, double& u, double& v, D3& c);
+
 // exact projection of one point; returns false when the point does not enter the map, else its pixel
 __device__ __forceinline__ bool project_pixel(const DevParams& P, float x, float y, float z, bool need_front, int& px, int& py) {
-    D3 c = lidar_to_cam(P, x, y, z);
+    double u, v;
+    D3 c;
+    if (!project_uv(P, x, y, z, need_front, u, v, c)) return false;
+    px = (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
+    py = (int)v;
+    return true;
+}
+
+__device__ __forceinline__ bool project_uv(const DevParams& P, float x, float y, float z, bool need_front, double& u, double& v, D3& c) {
+    c = lidar_to_cam(P, x, y, z);
     // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51)
     if (need_front && !(c.z > 0.0)) return false;
     // K * p with K = [f 0 cx; 0 f cy; 0 0 1] evaluated term by term like Eigen's product
@@ -43,14 +55,11 @@ __device__ __forceinline__ bool project_pixel(const DevParams& P, float x, float
     double q0 = __dadd_rn(__dadd_rn(__dmul_rn(P.f, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(P.cx, c.z));
     double q1 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, c.x), __dmul_rn(P.f, c.y)), __dmul_rn(P.cy, c.z));
     double q2 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(1.0, c.z));
-    double u = __ddiv_rn(q0, q2);
-    double v = __ddiv_rn(q1, q2);
+    u = __ddiv_rn(q0, q2);
+    v = __ddiv_rn(q1, q2);
     bool in_range = (u >= 0.) && (u <= P.Wd) && (v >= 0.) && (v <= P.Hd);  // camera_pinhole.h:93-96
     bool visible = (u > 0.) && (u < P.Wd) && (v > 0.) && (v < P.Hd);       // DepthEstimator.cpp:186-187
-    if (!(in_range && visible)) return false;
-    px = (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
-    py = (int)v;
-    return true;
+    return in_range && visible;
 }
 
 // FP32 pre-filter: true when the point certainly fails one of  z_cam > 0, u > 0, u < W, v > 0, v < H
@@ -71,26 +80,9 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
     return false;
 }
 
-__global__ void __launch_bounds__(K1_THREADS, MLD_K1_MINBLOCKS)
-project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
-                       unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
-    const unsigned int frame = blockIdx.y;
-    const int occ_pitch = occ_words_per_row(P.W);
-    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
-    const int base = blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
-    const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
-    const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
-    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
-
-    float4 p[K1_PPT];
-#pragma unroll
-    for (int j = 0; j < K1_PPT; j++) {
-        if (base + j * K1_THREADS < n)
-            p[j] = ld_stream_f4(src + j * step);
-        else
-            p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+// pre-filter, exact projection and scatter of the K1_PPT points a thread holds in registers
+__device__ __forceinline__ void scatter_points(const DevParams& P, const float4 (&p)[K1_PPT], int base, int n, unsigned int hi,
+                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch) {
 #pragma unroll
     for (int j = 0; j < K1_PPT; j++) {
         const int i = base + j * K1_THREADS;
@@ -116,6 +108,69 @@ project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, i
     }
 }
 
+__global__ void __launch_bounds__(K1_THREADS, MLD_K1_MINBLOCKS)
+project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
+                       unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
+    const unsigned int frame = blockIdx.y;
+    const int occ_pitch = occ_words_per_row(P.W);
+    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
+    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
+    const int base = blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
+    const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
+    const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
+    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
+
+    float4 p[K1_PPT];
+#pragma unroll
+    for (int j = 0; j < K1_PPT; j++) {
+        if (base + j * K1_THREADS < n)
+            p[j] = ld_stream_f4(src + j * step);
+        else
+            p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    scatter_points(P, p, base, n, hi, map, ob, occ_pitch);
+}
+
+// Persistent variant: gridDim.x blocks loop over the (frame, tile) pairs of the chunk with the next tile's loads
+// already in flight. Launched with a grid of (SM count x blocks-per-SM) it holds only part of every SM for the
+// whole chunk, so the latency-bound K2 blocks of the previous chunk (other stream) stay co-resident with the
+// DRAM-bound stream instead of queueing behind a full-machine grid.
+__global__ void __launch_bounds__(K1_THREADS)
+project_scatter_persistent_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
+                                  unsigned int* __restrict__ maps, unsigned int* __restrict__ occ, int tiles_per_frame, int total_tiles) {
+    const int occ_pitch = occ_words_per_row(P.W);
+    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
+    const int step = K1_THREADS * stride_f;
+    auto load_tile = [&](int t, float4 (&q)[K1_PPT]) {
+        const int frame = t / tiles_per_frame, tile = t - frame * tiles_per_frame;
+        const int base = tile * (K1_THREADS * K1_PPT) + threadIdx.x;
+        const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; j++) {
+            if (base + j * K1_THREADS < n)
+                q[j] = ld_stream_f4(src + j * step);
+            else
+                q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    };
+    int t = blockIdx.x;
+    if (t >= total_tiles) return;
+    float4 cur[K1_PPT], nxt[K1_PPT];
+    load_tile(t, cur);
+    while (true) {
+        const int tn = t + gridDim.x;
+        if (tn < total_tiles) load_tile(tn, nxt);
+        const int frame = t / tiles_per_frame, tile = t - frame * tiles_per_frame;
+        unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
+        unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
+        scatter_points(P, cur, tile * (K1_THREADS * K1_PPT) + threadIdx.x, n, hi, map, ob, occ_pitch);
+        if (tn >= total_tiles) break;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; j++) cur[j] = nxt[j];
+        t = tn;
+    }
+}
+
 // debug view: Transform_Cloud_LidarToCamera's visibility cull (no z > 0 test, DepthEstimator.cpp:184-207)
 // and the camera-frame coordinates (_points_cs_camera). Not on the hot path.
 __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n,
@@ -133,7 +188,126 @@ __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts,
     }
 }
 
+// ---- visible-order views: _pointIndex, _points_cs_image_visible, getPointDepthCamVisible ----
+// Transform_Cloud_LidarToCamera compacts the visible points in cloud order (DepthEstimator.cpp:189-207). On the GPU
+// that is an order-preserving stream compaction: per-block counts, an exclusive scan of the counts, and a second
+// pass that ranks the visible points inside each block with warp ballots. Off the hot path (debug publishers).
+constexpr int VC_THREADS = 256;
+constexpr int VC_PPT = 4;  // thread t of a block owns points base + 4 t .. + 3 (contiguous, so ranks follow cloud order)
+
+__device__ __forceinline__ int vc_flags(const DevParams& P, const float* __restrict__ pts, int stride_f, long long n, long long first,
+                                        double (&u)[VC_PPT], double (&v)[VC_PPT], double (&zc)[VC_PPT]) {
+    int m = 0;
+#pragma unroll
+    for (int j = 0; j < VC_PPT; j++) {
+        const long long i = first + j;
+        if (i >= n) break;
+        const float* q = pts + i * stride_f;
+        D3 c;
+        if (project_uv(P, q[0], q[1], q[2], false, u[j], v[j], c)) {  // no z > 0 test here (DepthEstimator.cpp:184-207)
+            m |= 1 << j;
+            zc[j] = c.z;
+        }
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(VC_THREADS)
+visible_count_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n, unsigned int* __restrict__ block_counts) {
+    __shared__ int s_w[VC_THREADS / 32];
+    double u[VC_PPT], v[VC_PPT], zc[VC_PPT];
+    const long long first = ((long long)blockIdx.x * VC_THREADS + threadIdx.x) * VC_PPT;
+    int c = __popc(vc_flags(P, pts, stride_f, n, first, u, v, zc));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_down_sync(MLD_FULL_MASK, c, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < VC_THREADS / 32; w++) t += s_w[w];
+        block_counts[blockIdx.x] = (unsigned int)t;
+    }
+}
+
+// exclusive scan of the block counts in place (one block; nblocks is N / 1024, i.e. small), total -> counts[nblocks]
+__global__ void __launch_bounds__(1024) visible_scan_kernel(unsigned int* __restrict__ counts, int nblocks) {
+    __shared__ unsigned int s_part[1024];
+    const int per = (nblocks + 1023) / 1024;
+    const int lo = threadIdx.x * per, hi = min(lo + per, nblocks);
+    unsigned int t = 0;
+    for (int i = lo; i < hi; i++) t += counts[i];
+    s_part[threadIdx.x] = t;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan of the per-thread sums
+        const unsigned int add = (threadIdx.x >= o) ? s_part[threadIdx.x - o] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += add;
+        __syncthreads();
+    }
+    unsigned int run = s_part[threadIdx.x] - t;
+    for (int i = lo; i < hi; i++) {
+        const unsigned int c = counts[i];
+        counts[i] = run;
+        run += c;
+    }
+    if (threadIdx.x == 1023) counts[nblocks] = s_part[1023];
+}
+
+__global__ void __launch_bounds__(VC_THREADS)
+visible_compact_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n, const unsigned int* __restrict__ block_offsets,
+                       long long capacity, int* __restrict__ point_index, double* __restrict__ image_points, double* __restrict__ depth_cam) {
+    __shared__ int s_w[VC_THREADS / 32];
+    double u[VC_PPT], v[VC_PPT], zc[VC_PPT];
+    const long long first = ((long long)blockIdx.x * VC_THREADS + threadIdx.x) * VC_PPT;
+    const int m = vc_flags(P, pts, stride_f, n, first, u, v, zc);
+    const int c = __popc(m);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int incl = c;  // inclusive scan of the per-thread counts inside the warp
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(MLD_FULL_MASK, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < warp; w++) base += s_w[w];
+    long long slot = (long long)block_offsets[blockIdx.x] + base + (incl - c);
+#pragma unroll
+    for (int j = 0; j < VC_PPT; j++) {
+        if (!((m >> j) & 1)) continue;
+        if (slot < capacity) {
+            if (point_index) point_index[slot] = (int)(first + j);
+            if (image_points) {
+                image_points[2 * slot] = u[j];
+                image_points[2 * slot + 1] = v[j];
+            }
+            if (depth_cam) depth_cam[slot] = zc[j];
+        }
+        slot++;
+    }
+}
+
 }  // namespace
+
+size_t mld_visible_scratch_bytes(long long n) { return (size_t)((n + VC_THREADS * VC_PPT - 1) / (VC_THREADS * VC_PPT) + 2) * sizeof(unsigned int); }
+
+// d_scratch: mld_visible_scratch_bytes(n); the visible count ends up in d_scratch[nblocks] (returned through d_count_out)
+cudaError_t mld_launch_visible_compact(const DevParams& P, const float* d_pts, int stride_f, long long n, void* d_scratch, long long capacity,
+                                       int* d_point_index, double* d_image_points, double* d_depth_cam, const unsigned int** d_count_out,
+                                       cudaStream_t stream, int* launches) {
+    unsigned int* counts = reinterpret_cast<unsigned int*>(d_scratch);
+    const long long nb = (n + VC_THREADS * VC_PPT - 1) / (VC_THREADS * VC_PPT);
+    if (nb > 0x7fffffffLL) return cudaErrorInvalidValue;
+    if (d_count_out) *d_count_out = counts + nb;
+    if (n <= 0) return cudaMemsetAsync(counts, 0, sizeof(unsigned int), stream);
+    visible_count_kernel<<<(unsigned)nb, VC_THREADS, 0, stream>>>(P, d_pts, stride_f, n, counts);
+    visible_scan_kernel<<<1, 1024, 0, stream>>>(counts, (int)nb);
+    visible_compact_kernel<<<(unsigned)nb, VC_THREADS, 0, stream>>>(P, d_pts, stride_f, n, counts, capacity, d_point_index, d_image_points,
+                                                                  d_depth_cam);
+    if (launches) *launches += 3;
+    return cudaGetLastError();
+}
 
 // Host side of the pre-filter: the five linear forms in double, rounded to float, with bounds that
 // cover (a) rounding the coefficients to float, (b) the four float operations of the evaluation and
@@ -180,9 +354,15 @@ void mld_setup_prefilter(DevParams& P) {
 
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
-                                       cudaStream_t stream) {
+                                       cudaStream_t stream, int persistent_blocks) {
     if (n <= 0 || nframes <= 0) return cudaSuccess;
     if (n > 0x7fffffffLL / 8) return cudaErrorInvalidValue;  // 32-bit point indexing inside a frame
+    const long long tiles = (n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT);
+    if (persistent_blocks > 0 && tiles * nframes > persistent_blocks && tiles * nframes < 0x7fffffffLL) {
+        project_scatter_persistent_kernel<<<persistent_blocks, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps,
+                                                                                        d_occ, (int)tiles, (int)(tiles * nframes));
+        return cudaGetLastError();
+    }
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
     project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps, d_occ);
     return cudaGetLastError();

@@ -1,0 +1,234 @@
+// mld_semantic.cu -- SemanticPlane::CalculateInliersPlane on the GPU: the ground plane the
+// production caller actually uses (tracklets_depth/src/tracklet_depth_module.cpp:269-284).
+//
+// Replaces (reference, /root/reference/monolidar_fusion/src/RansacPlane.cpp:159-274):
+//   pcl::transformPointCloud(cloud, transformed, cam_.transform_cam_lidar)        :198
+//   project(): p = K * (x,y,z); p /= p[2]; cv::Point(p[0], p[1])                  :170-181
+//   keep points whose pixel carries a ground label                                 :201-222
+//   < 3 kept -> ExceptionPclInvalid                                                :224-227
+//   SampleConsensusModelPlane::optimizeModelCoefficients(kept, (0,0,1,0))          :236-242
+//   selectWithinDistance(coeffs, inlier_threshold) over the WHOLE cloud            :248
+//   optimizeModelCoefficients(inliers, coeffs)                                     :249
+//   _modelCoeffs = refined, _inliersIndex = inliers                                :254-265
+//
+// Two streaming passes over the cloud (16 B per point each, HBM bound) with the 3x3 fit done by the last block of
+// each pass (ticket counter), so a frame costs two launches and no host round trip. Thread i owns point i, hence
+// a warp's ballot IS word i/32 of the inlier bitmask: plain coalesced stores, no atomics, no clear.
+//
+// Arithmetic: the transform is evaluated in double and rounded to float per coordinate (PCL 1.8 computes
+// transform(i,0)*x + ... in the transform's scalar and casts), the projection in double with true division and
+// (int) truncation like cv::Point_<int>(double, double); the point-to-plane distance in float (PCL). The moments of
+// the least-squares fit are accumulated in double (PCL: sequential float), so coefficients agree with the reference
+// to ~1e-4 and the inlier sets differ only for points within that margin of the threshold (tests state both).
+// Deviation: a pixel with x == cols or y == rows passes the reference's validity test ('>' instead of '>=',
+// :205-206) and is then read out of bounds (undefined); here such a pixel is "not ground".
+#include "mld_common.cuh"
+#include "mld_kernels.h"
+
+namespace {
+
+constexpr int SP_THREADS = 256;
+constexpr int SP_PPT = 4;
+constexpr int SP_NSUM = 10;  // n, x, y, z, xx, xy, xz, yy, yz, zz
+
+__device__ __forceinline__ double sp_warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(MLD_FULL_MASK, v, o);
+    return v;
+}
+
+// block-reduce the 10 moments and add them to acc (double atomics); returns true in the LAST block of the frame
+__device__ bool sp_commit(double (&v)[SP_NSUM], double* __restrict__ acc, unsigned int* __restrict__ ticket, unsigned int nblocks) {
+    __shared__ double s_red[SP_NSUM][SP_THREADS / 32];
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int q = 0; q < SP_NSUM; q++) {
+        const double t = sp_warp_sum(v[q]);
+        if (lane == 0) s_red[q][warp] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < SP_NSUM) {
+        double t = 0;
+#pragma unroll
+        for (int w = 0; w < SP_THREADS / 32; w++) t += s_red[threadIdx.x][w];
+        if (t != 0.0) atomicAdd(&acc[threadIdx.x], t);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == nblocks - 1);
+    __syncthreads();
+    return s_last;
+}
+
+// SampleConsensusModelPlane::optimizeModelCoefficients: centroid + eigenvector of the smallest eigenvalue of the
+// covariance; returns the input model unchanged when there are not more than 3 inliers.
+__device__ void sp_fit(const double* __restrict__ acc, const float in[4], float out[4]) {
+    out[0] = in[0]; out[1] = in[1]; out[2] = in[2]; out[3] = in[3];
+    const double m = acc[0];
+    if (!(m > 3.0)) return;
+    const double mx = acc[1] / m, my = acc[2] / m, mz = acc[3] / m;
+    double w[3];
+    D3 ev[3];
+    eig3_sym_regs(acc[4] / m - mx * mx, acc[5] / m - mx * my, acc[6] / m - mx * mz, acc[7] / m - my * my, acc[8] / m - my * mz,
+                  acc[9] / m - mz * mz, w, ev);
+    int bi = 0;
+    if (w[1] < w[bi]) bi = 1;
+    if (w[2] < w[bi]) bi = 2;
+    const D3 e = (bi == 0) ? ev[0] : (bi == 1 ? ev[1] : ev[2]);
+    const float ex = (float)e.x, ey = (float)e.y, ez = (float)e.z;
+    out[0] = ex; out[1] = ey; out[2] = ez;
+    out[3] = -1 * __fadd_rn(__fadd_rn(__fmul_rn(ex, (float)mx), __fmul_rn(ey, (float)my)), __fmul_rn(ez, (float)mz));
+}
+
+struct SemCam {
+    double T[12];  // cam <- lidar, row-major 3x4
+    double f, cu, cv;
+    int W, H;      // label image size
+    unsigned int ground[8];  // 256-bit set of ground labels
+};
+
+// pass 1: label lookup -> moments of the labelled points; the last block fits the first model.
+// state per frame: acc1[10], acc2[10] doubles | coeffs1[4], coeffs2[4] floats | tickets[2], n_labelled, n_inliers, rc
+__global__ void __launch_bounds__(SP_THREADS)
+semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
+                      const unsigned char* __restrict__ labels, double* __restrict__ acc_all, float* __restrict__ coeff_all,
+                      unsigned int* __restrict__ ctl_all) {
+    const long long frame = blockIdx.y;
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    const unsigned char* lab = labels + frame * (long long)C.W * (long long)C.H;
+    double* acc = acc_all + frame * 2 * SP_NSUM;
+    float* coeff = coeff_all + frame * 8;
+    unsigned int* ctl = ctl_all + frame * 8;
+    double v[SP_NSUM] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int base = blockIdx.x * (SP_THREADS * SP_PPT) + threadIdx.x;
+    float4 p[SP_PPT];
+#pragma unroll
+    for (int j = 0; j < SP_PPT; j++) {
+        const int i = base + j * SP_THREADS;
+        p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < SP_PPT; j++) {
+        const int i = base + j * SP_THREADS;
+        if (i >= n) break;
+        const double x = p[j].x, y = p[j].y, z = p[j].z;
+        // pcl::transformPointCloud: per coordinate in double, left to right, rounded to float
+        const float tx = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[0], x), __dmul_rn(C.T[1], y)), __dmul_rn(C.T[2], z)), C.T[3]);
+        const float ty = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[4], x), __dmul_rn(C.T[5], y)), __dmul_rn(C.T[6], z)), C.T[7]);
+        const float tz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[8], x), __dmul_rn(C.T[9], y)), __dmul_rn(C.T[10], z)), C.T[11]);
+        // project(): intrin * Vector3d{x,y,z}, p /= p[2], cv::Point(p[0], p[1]) (RansacPlane.cpp:174-177)
+        const double X = tx, Y = ty, Z = tz;
+        const double q0 = __dadd_rn(__dadd_rn(__dmul_rn(C.f, X), __dmul_rn(0.0, Y)), __dmul_rn(C.cu, Z));
+        const double q1 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, X), __dmul_rn(C.f, Y)), __dmul_rn(C.cv, Z));
+        const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, X), __dmul_rn(0.0, Y)), __dmul_rn(1.0, Z));
+        const double u = __ddiv_rn(q0, q2), w = __ddiv_rn(q1, q2);
+        // double -> int like cvttsd2si: NaN and out-of-range values become INT_MIN, i.e. "x < 0" -> invalid
+        if (!(fabs(u) < 2147483648.0) || !(fabs(w) < 2147483648.0)) continue;
+        const int px = (int)u, py = (int)w;
+        if (px < 0 || px >= C.W || py < 0 || py >= C.H) continue;  // see the deviation note in the header
+        const unsigned int l = __ldg(lab + (long long)py * C.W + px);
+        if (!((C.ground[l >> 5] >> (l & 31)) & 1u)) continue;
+        // the fit runs on the ORIGINAL cloud (model_p is built on `cloud`, RansacPlane.cpp:236); PCL skips non-finite points
+        if (!(fabs(x) <= 3.4e38 && fabs(y) <= 3.4e38 && fabs(z) <= 3.4e38)) { v[0] += 0.0; continue; }
+        v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
+        v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
+    }
+    if (sp_commit(v, acc, ctl + 0, gridDim.x) && threadIdx.x == 0) {
+        volatile double* va = acc;
+        double a[SP_NSUM];
+        for (int q = 0; q < SP_NSUM; q++) a[q] = va[q];
+        ctl[2] = (unsigned int)a[0];                 // labelled points
+        const float dummy[4] = {0.f, 0.f, 1.f, 0.f};  // dummy_model_coeffs (RansacPlane.cpp:239-240)
+        float c[4];
+        sp_fit(a, dummy, c);
+        for (int q = 0; q < 4; q++) coeff[q] = c[q];
+        ctl[4] = (a[0] < 3.0) ? 1u : 0u;  // ExceptionPclInvalid (RansacPlane.cpp:224-227)
+    }
+}
+
+// pass 2: selectWithinDistance over the whole cloud -> inlier bitmask + moments; the last block refits.
+__global__ void __launch_bounds__(SP_THREADS)
+semantic_select_kernel(const float* __restrict__ pts, int stride_f, int n, long long pitch_pts, double threshold,
+                       double* __restrict__ acc_all, float* __restrict__ coeff_all, unsigned int* __restrict__ ctl_all,
+                       unsigned int* __restrict__ bits_all, long long words_per_frame, float* __restrict__ coeffs_out,
+                       int* __restrict__ n_inliers_out, int* __restrict__ rc_out) {
+    const long long frame = blockIdx.y;
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    double* acc = acc_all + frame * 2 * SP_NSUM + SP_NSUM;
+    float* coeff = coeff_all + frame * 8;
+    unsigned int* ctl = ctl_all + frame * 8;
+    unsigned int* bits = bits_all + frame * words_per_frame;
+    const float a = coeff[0], b = coeff[1], c = coeff[2], d = coeff[3];
+    const bool invalid = ctl[4] != 0u;
+    double v[SP_NSUM] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    const int base = blockIdx.x * (SP_THREADS * SP_PPT) + threadIdx.x;
+    float4 p[SP_PPT];
+#pragma unroll
+    for (int j = 0; j < SP_PPT; j++) {
+        const int i = base + j * SP_THREADS;
+        p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < SP_PPT; j++) {
+        const int i = base + j * SP_THREADS;  // warp-uniform tail: i - lane is a multiple of 32
+        bool in = false;
+        if (i < n && !invalid) {
+            // pcl::SampleConsensusModelPlane::selectWithinDistance: fabs(dot((x,y,z,1), coeffs)) < threshold, float dot
+            const float dist = fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p[j].x), __fmul_rn(b, p[j].y)), __fmul_rn(c, p[j].z)), d));
+            in = (double)dist < threshold;
+            if (in) {
+                const double x = p[j].x, y = p[j].y, z = p[j].z;
+                v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
+                v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
+            }
+        }
+        const unsigned int m = __ballot_sync(MLD_FULL_MASK, in);
+        if ((threadIdx.x & 31) == 0 && (i - (int)(threadIdx.x & 31)) < n) bits[i >> 5] = m;
+    }
+    if (sp_commit(v, acc, ctl + 1, gridDim.x) && threadIdx.x == 0) {
+        volatile double* va = acc;
+        double s[SP_NSUM];
+        for (int q = 0; q < SP_NSUM; q++) s[q] = va[q];
+        const float first[4] = {a, b, c, d};
+        float r[4];
+        sp_fit(s, first, r);
+        for (int q = 0; q < 4; q++) {
+            coeff[4 + q] = r[q];
+            coeffs_out[frame * 4 + q] = invalid ? 0.f : r[q];
+        }
+        n_inliers_out[frame] = invalid ? 0 : (int)s[0];
+        rc_out[frame] = invalid ? MLD_ERR_PCL_INVALID : 0;
+    }
+}
+
+}  // namespace
+
+size_t mld_semantic_state_bytes(int nframes) { return (size_t)nframes * (2 * SP_NSUM * sizeof(double) + 8 * sizeof(float) + 8 * sizeof(unsigned int)); }
+
+cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, double cu, double cv, int label_w, int label_h,
+                                      const unsigned int* ground_set8, double inlier_threshold, const float* d_pts, int stride_f,
+                                      long long n_points, long long pitch_pts, const unsigned char* d_labels, int nframes,
+                                      void* d_state, float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame,
+                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches) {
+    if (nframes <= 0) return cudaSuccess;
+    if (n_points > 0x7fffffffLL / 8) return cudaErrorInvalidValue;
+    SemCam C;
+    for (int i = 0; i < 12; i++) C.T[i] = T_cam_lidar[i];
+    C.f = f; C.cu = cu; C.cv = cv; C.W = label_w; C.H = label_h;
+    for (int i = 0; i < 8; i++) C.ground[i] = ground_set8[i];
+    cudaError_t e = cudaMemsetAsync(d_state, 0, mld_semantic_state_bytes(nframes), stream);
+    if (e != cudaSuccess) return e;
+    double* acc = reinterpret_cast<double*>(d_state);
+    float* coeff = reinterpret_cast<float*>(acc + (size_t)nframes * 2 * SP_NSUM);
+    unsigned int* ctl = reinterpret_cast<unsigned int*>(coeff + (size_t)nframes * 8);
+    const unsigned int gx = (unsigned int)std::max<long long>(1, (n_points + SP_THREADS * SP_PPT - 1) / (SP_THREADS * SP_PPT));
+    dim3 grid(gx, (unsigned)nframes);
+    semantic_label_kernel<<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    semantic_select_kernel<<<grid, SP_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, inlier_threshold, acc, coeff, ctl,
+                                                           d_inlier_bits, words_per_frame, d_coeffs, d_n_inliers, d_rc);
+    if (launches) *launches += 2;
+    return cudaGetLastError();
+}

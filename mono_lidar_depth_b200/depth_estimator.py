@@ -92,6 +92,37 @@ class RansacPlane(GroundPlane):
         self.iterations = 0
 
 
+class SemanticPlane(GroundPlane):
+    """Mono_Lidar::SemanticPlane (RansacPlane.h:166-216, RansacPlane.cpp:159-274): the ground plane fitted to the lidar
+    points whose projection carries a ground label in a semantic image; the fit runs on the GPU
+    (mld_semantic_ground_plane). Same constructor arguments as the reference plus the estimator whose device handle is
+    used: SemanticPlane(img, cam, groundplane_label, inlier_threshold, estimator)."""
+
+    class Camera:
+        """SemanticPlane::Camera: f, cu, cv and transform_cam_lidar (3x4 or 4x4, camera <- lidar)."""
+
+        def __init__(self, f: float, cu: float, cv: float, transform_cam_lidar):
+            self.f, self.cu, self.cv = float(f), float(cu), float(cv)
+            self.transform_cam_lidar = np.ascontiguousarray(np.asarray(transform_cam_lidar, np.float64)[:3, :4])
+
+    def __init__(self, img, cam: "SemanticPlane.Camera", groundplane_label=(6, 7, 8, 9), inlier_threshold: float = 0.1, estimator=None):
+        super().__init__()
+        self.semantic_image_ = np.ascontiguousarray(img, np.uint8)
+        if self.semantic_image_.ndim != 2:
+            raise ValueError("semantic image must be a single-channel 8-bit image (H, W)")
+        self.cam_ = cam
+        self.groundplane_label_ = sorted(int(x) for x in set(groundplane_label))
+        self.inlier_threshold_ = float(inlier_threshold)
+        self._estimator = estimator
+
+    def CalculateInliersPlane(self, cloud, min_z: float = -1000.0, max_z: float = 1000.0) -> None:
+        """RansacPlane.cpp:195-274 (min_z / max_z are ignored by the reference's override too, RansacPlane.h:205-207).
+        Raises ExceptionPclInvalid when fewer than 3 points carry a ground label."""
+        if self._estimator is None:
+            raise RuntimeError("SemanticPlane needs the DepthEstimator whose GPU handle it runs on")
+        self._estimator._semantic_plane(self, cloud)
+
+
 def _cloud_buffer(cloud) -> Tuple[np.ndarray, int, int]:
     """Accepts (n,4) float32 [x,y,z,i] (float4) or (n,8) float32 (pcl::PointXYZI's 32-byte layout)."""
     a = np.ascontiguousarray(cloud, dtype=np.float32)
@@ -312,6 +343,23 @@ class DepthEstimator:
         plane.iterations = it.value
         return plane
 
+    def _semantic_plane(self, plane: SemanticPlane, cloud) -> None:
+        a, n, stride = _cloud_buffer(cloud)
+        pl_c = plane._as_c(capacity=max(n, 1))
+        lab = plane.semantic_image_
+        gl = np.ascontiguousarray(plane.groundplane_label_, np.int32)
+        T = plane.cam_.transform_cam_lidar
+        self._check(self._lib.mld_semantic_ground_plane(self._handle_for_plane(), a.ctypes.data if n else None, n, stride, lab.ctypes.data,
+                                                        lab.shape[1], lab.shape[0], plane.cam_.f, plane.cam_.cu, plane.cam_.cv,
+                                                        T.ctypes.data, gl.ctypes.data if len(gl) else None, len(gl),
+                                                        plane.inlier_threshold_, C.byref(pl_c)))
+        plane._from_c(pl_c)
+
+    def _handle_for_plane(self):
+        if not self._h:
+            raise RuntimeError("Call 'InitConfig' before fitting a ground plane")
+        return self._h
+
     # -- debug views (DepthEstimator.h:116-164) ------------------------------------------------
     def getPixelMap(self) -> np.ndarray:
         W, H = self._camera.getImageSize()
@@ -337,16 +385,29 @@ class DepthEstimator:
         self._check(self._lib.mld_get_points_camera(self._h, out.ctypes.data))
         return out[: self._n]
 
+    def getVisiblePoints(self):
+        """(_pointIndex, _points_cs_image_visible as (nvis, 2), camera-frame depth per visible point), compacted on the
+        device in cloud order (DepthEstimator.cpp:189-207)."""
+        cap = max(self._n, 1)
+        idx = np.empty(cap, np.int32)
+        img = np.empty((cap, 2), np.float64)
+        dep = np.empty(cap, np.float64)
+        nv = C.c_int64(0)
+        self._check(self._lib.mld_get_visible_points(self._h, idx.ctypes.data, img.ctypes.data, dep.ctypes.data, cap, C.byref(nv)))
+        k = nv.value
+        return idx[:k].copy(), img[:k].copy(), dep[:k].copy()
+
+    def getPointIndex(self) -> np.ndarray:
+        """_pointIndex: raw index of every visible point, cloud order."""
+        return self.getVisiblePoints()[0]
+
     def getPointsCloudImageCs(self) -> np.ndarray:
-        """_points_cs_image_visible as (nvis, 2): projection of the visible points, cloud order."""
-        cam = self.getPointsCloudCameraCs()
-        vis = self.getVisible()
-        c = cam[vis]
-        f, cx, cy = self._camera.focal_length_, self._camera.principal_point_x_, self._camera.principal_point_y_
-        with np.errstate(all="ignore"):
-            u = ((f * c[:, 0] + 0.0 * c[:, 1]) + cx * c[:, 2]) / c[:, 2]
-            v = ((0.0 * c[:, 0] + f * c[:, 1]) + cy * c[:, 2]) / c[:, 2]
-        return np.stack([u, v], 1)
+        """_points_cs_image_visible as (nvis, 2): projection of the visible points, cloud order (DepthEstimator.h:139)."""
+        return self.getVisiblePoints()[1]
+
+    def getPointDepthCamVisible(self, index: int) -> float:
+        """_points_cs_camera(2, _pointIndex[index]) (DepthEstimator.h:116-118)."""
+        return float(self.getVisiblePoints()[2][index])
 
     # -- batched sequences (frames are independent; see bench.py) ---------------------------------
     def processFramesDevice(self, d_points: int, n_points: int, frame_pitch_points: int, stride_bytes: int, d_uv: int, F: int,

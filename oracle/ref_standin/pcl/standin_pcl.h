@@ -79,18 +79,20 @@ inline double pointToPlaneDistance(const Point& p, const Eigen::Vector4f& c) {
     return std::fabs(c[0] * p.x + c[1] * p.y + c[2] * p.z + c[3]);
 }
 
-// pcl::transformPointCloud(cloud_in, cloud_out, Affine3d): PCL converts the transform to the cloud's scalar
-// (float) and applies x' = m00 x + m01 y + m02 z + m03 per point in float.
+// pcl::transformPointCloud(cloud_in, cloud_out, Transform<Scalar,3,Affine>) (PCL 1.8 common/impl/transforms.hpp): per
+// point and coordinate  static_cast<float>(t(i,0) * x + t(i,1) * y + t(i,2) * z + t(i,3))  evaluated in the transform's
+// Scalar (double for the Affine3d the reference passes), left to right; non-finite points of a non-dense cloud are
+// copied unchanged (they stay non-finite either way).
 template <class PointT, class Scalar>
 void transformPointCloud(const PointCloud<PointT>& in, PointCloud<PointT>& out, const Eigen::Transform<Scalar, 3, Eigen::Affine>& tf) {
     out = in;
-    float m[3][4];
-    for (int i = 0; i < 3; i++) for (int j = 0; j < 4; j++) m[i][j] = float(tf.matrix()(i, j));
+    const auto& m = tf.matrix();
     for (size_t k = 0; k < in.points.size(); k++) {
         const PointT& p = in.points[k];
-        out.points[k].x = m[0][0] * p.x + m[0][1] * p.y + m[0][2] * p.z + m[0][3];
-        out.points[k].y = m[1][0] * p.x + m[1][1] * p.y + m[1][2] * p.z + m[1][3];
-        out.points[k].z = m[2][0] * p.x + m[2][1] * p.y + m[2][2] * p.z + m[2][3];
+        const Scalar x = p.x, y = p.y, z = p.z;
+        out.points[k].x = static_cast<float>(m(0, 0) * x + m(0, 1) * y + m(0, 2) * z + m(0, 3));
+        out.points[k].y = static_cast<float>(m(1, 0) * x + m(1, 1) * y + m(1, 2) * z + m(1, 3));
+        out.points[k].z = static_cast<float>(m(2, 0) * x + m(2, 1) * y + m(2, 2) * z + m(2, 3));
     }
 }
 

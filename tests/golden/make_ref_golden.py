@@ -11,6 +11,7 @@ Cases
            injected plane (M-estimator road path)
   kitti_*  two KITTI-shaped synthetic frames (inputs are regenerated from the seed by mono_lidar_depth_b200.synth, only
            the reference's outputs are stored), plane nullptr; frame 1 also with an injected plane
+  sem*_    SemanticPlane coefficients and inlier indices for three label images over KITTI-shaped sweeps
   var_*    the 256x192 scene of the parameter-variant tests under every variant of parity_util.VARIANTS except pca
 """
 import sys
@@ -44,6 +45,24 @@ def kitti_plane(cloud):
     coeffs = np.array([0.0, 0.0, 1.0, 1.73], np.float32)
     dist = np.abs(cloud[:, 2] + 1.73)
     return coeffs, np.nonzero(np.isfinite(dist) & (dist < 0.1))[0].astype(np.int32)
+
+
+def semantic_case(case):
+    """(cloud, label image, ground labels, inlier threshold) of the SemanticPlane fixtures."""
+    cfg = synth.default_config()
+    cloud = synth.points_host(cfg, 77, case)
+    W, H = 1241, 376
+    lab = np.zeros((H, W), np.uint8)
+    rng = np.random.RandomState(100 + case)
+    lab[200 + 10 * case:, :] = 7                      # road
+    lab[300:, 400:800] = 9                            # another ground class
+    lab[250:280, 100:300] = 2                         # a non-ground object on the road
+    lab[:40, :] = 6                                   # ground label in the sky: only stray / behind-camera projections
+    noise = rng.rand(H, W) < 0.01
+    lab[noise] = rng.randint(0, 12, int(noise.sum())).astype(np.uint8)
+    gl = [6, 7, 8, 9] if case != 2 else [7, 300, -1]  # labels outside 0..255 never match a pixel
+    thr = (0.1, 0.25, 0.05)[case]
+    return cloud, lab, gl, thr
 
 
 def main():
@@ -91,6 +110,13 @@ def main():
         r.initialize(*VAR_CAM, T)
         r.set_cloud(cloud)
         out[f"var_{v}_depth"], out[f"var_{v}_status"] = r.calculate_depth(uv)
+    # ---- SemanticPlane (RansacPlane.cpp:159-274) run by the reference's own code ----
+    for case in (0, 1, 2):
+        cloud, lab, gl, thr = semantic_case(case)
+        rc, c, inl = R.semantic_plane(lab, KCAM[2], KCAM[3], KCAM[4], T, gl, thr, cloud)
+        assert rc == 0
+        out[f"sem{case}_coeffs"], out[f"sem{case}_inliers"] = c, inl
+        print("semantic case", case, c, len(inl))
     np.savez_compressed(Path(__file__).with_name("ref_golden.npz"), **out)
     for k in ("small_status_noplane", "small_status_plane", "kitti0_status_noplane", "kitti1_status_plane"):
         print(k, np.bincount(out[k], minlength=17))

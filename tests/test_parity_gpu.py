@@ -48,6 +48,22 @@ def test_visible_and_camera_points_views():
     assert np.array_equal(cam_gpu[~np.isnan(cam_gpu)], cam_ref[~np.isnan(cam_ref)])  # bit-exact FP64 transform
     img = est.getPointsCloudImageCs()
     assert np.array_equal(img, orc.image_points_visible())
+    # visible-order compaction on the device: _pointIndex, image points, getPointDepthCamVisible
+    idx, img2, dep = est.getVisiblePoints()
+    assert np.array_equal(idx, orc.point_index()) and np.array_equal(img2, orc.image_points_visible())
+    assert np.array_equal(dep, cam_ref[orc.point_index(), 2])
+    assert est.getPointDepthCamVisible(17) == cam_ref[orc.point_index()[17], 2]
+    # capacity smaller than the visible count: the count is still reported, only `capacity` entries are written
+    import ctypes as C
+    small = np.full(8, -1, np.int32)
+    nv = C.c_int64(0)
+    est._check(est._lib.mld_get_visible_points(est._h, small.ctypes.data, None, None, 5, C.byref(nv)))
+    assert nv.value == len(idx) and np.array_equal(small[:5], idx[:5]) and np.all(small[5:] == -1)
+    # empty and all-invisible clouds
+    est.setInputCloud(np.zeros((0, 4), np.float32))
+    assert len(est.getPointIndex()) == 0
+    est.setInputCloud(np.full((3000, 4), np.nan, np.float32))
+    assert len(est.getPointIndex()) == 0
 
 
 @pytest.mark.parametrize("seed", [0, 1, 2])

@@ -121,6 +121,7 @@ def test_gpu_matches_reference_kitti_frames():
         est.setInputCloud(cloud, gp)
         assert np.array_equal(est.getPixelMap(), G[f"kitti{fr}_pixel_map"])
         assert np.array_equal(np.nonzero(est.getVisible())[0].astype(np.int32), G[f"kitti{fr}_point_index"])
+        assert np.array_equal(est.getPointIndex(), G[f"kitti{fr}_point_index"])  # device compaction, cloud order
         d, s = est.CalculateDepth(synth.features_host(cfg, MK.KITTI_SEED, fr, MK.KITTI_F))
         PU.assert_depth_status_equal(d, s, G[f"kitti{fr}_depth_noplane"], G[f"kitti{fr}_status_noplane"], f"ref kitti {fr}")
         if fr == 1:
