@@ -468,7 +468,9 @@ def run_gpu(args, rank, local_rank, world):
         for name, (ms, ln) in prof.items():
             per_class[name] = {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None}
         # dominant kernel of the step and its algorithmic bytes per launch (DESIGN.md "roofline")
-        kernels = {k: v for k, v in per_class.items() if k in ("project_scatter", "feature_depth") and v["launches"]}
+        # single kernels only: feature_depth is the sum of feature_gather + feature_solve + feature_rest (road kernels and the
+        # overflow pass), listed for the share of the step but not a kernel of its own
+        kernels = {k: v for k, v in per_class.items() if k in ("project_scatter", "feature_gather", "feature_solve") and v["launches"]}
         per_class["note"] = ("durations are bracketed by CUDA events on each chunk's stream inside the timed region; chunks run on "
                              "3 overlapping streams, so a kernel's duration includes time shared with the other chunks' kernels")
         dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
@@ -477,15 +479,19 @@ def run_gpu(args, rank, local_rank, world):
             frames_per_launch = prof_frames / per_class[dom]["launches"]
             # K1 owns the point stream and the pixel map (written once per frame in the reference's accounting; the
             # epoch-tagged map makes the actual clear traffic ~0), K2 the feature reads and the result writes
-            per_frame_bytes = {"project_scatter": 16 * N_POINTS + 4 * IMG_W * IMG_H, "feature_depth": 28 * N_FEATURES}[dom]
+            per_frame_bytes = {"project_scatter": 16 * N_POINTS + 4 * IMG_W * IMG_H, "feature_gather": 16 * N_FEATURES,
+                               "feature_solve": 12 * N_FEATURES}[dom]
             avg_s = per_class[dom]["avg_launch_ms"] * 1e-3
             achieved = per_frame_bytes * frames_per_launch / avg_s / 1e9
-            sampled_ms = sum(v["ms_total"] for v in per_class.values() if isinstance(v, dict))
+            sampled_ms = sum(v["ms_total"] for k, v in per_class.items() if isinstance(v, dict) and k in ("map_clear", "project_scatter", "ransac", "feature_depth"))
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,
                     "share_of_step": per_class[dom]["ms_total"] / sampled_ms if sampled_ms else None,
                     "per_kernel": per_class,
+                    "algorithmic_bytes_split": "SURVEY.md 8(d): B = 16 N + 4 W H + 28 F per frame; project_scatter owns 16 N + 4 W H (point stream + "
+                                               "one write per map cell; the epoch-tagged map replaces the physical clear, so its DRAM traffic is "
+                                               "below this figure), feature_gather 16 F (feature reads), feature_solve 12 F (result writes)",
                     "path": {"algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
                              "achieved": ALGO_BYTES_PER_FRAME * (value / world) / 1e9, "frac": ALGO_BYTES_PER_FRAME * (value / world) / 1e9 / peak,
                              "note": "whole hot path per GPU: B * frames/s against the same peak"}}

@@ -209,12 +209,13 @@ int mld_pack_feature_points_device(mld_handle* h, const double* d_uv, const doub
 /* number of kernels this handle has launched since creation (for bench.py's gpu_launches) */
 int64_t mld_kernel_launch_count(const mld_handle* h);
 /* per-kernel device timing with CUDA events on the launching stream (bench.py's roofline figures).
- * Classes: 0 = pixel-map clear (memset node), 1 = project_scatter, 2 = ransac, 3 = feature_depth.
+ * Classes (7): 0 = pixel-map / occupancy clear (memset nodes), 1 = project_scatter, 2 = ransac, 3 = feature_depth (all
+ * K2 kernels of the chunk), 4 = feature_gather, 5 = feature_solve, 6 = the rest of K2 (road kernels + overflow pass).
  * While enabled, every chunk of frames records events around each class (bounded pool; chunks beyond
  * the pool are not sampled). mld_profile_read synchronises, returns the accumulated milliseconds,
  * launch counts and frames covered per class since the last read, and resets the accumulators. */
 int mld_profile_enable(mld_handle* h, int on);
-int mld_profile_read(mld_handle* h, double* ms4, int64_t* launches4, int64_t* frames_sampled);
+int mld_profile_read(mld_handle* h, double* ms7, int64_t* launches7, int64_t* frames_sampled);
 /* frames processed per kernel launch in the batched paths (env MLD_CHUNK_FRAMES, default 16) */
 int mld_chunk_frames(const mld_handle* h);
 /* largest neighbour count per feature the kernels were built for */

@@ -109,6 +109,7 @@ struct mld_handle {
     size_t prof_used = 0;                  // sampled chunks
 };
 constexpr size_t MLD_PROF_MAX_CHUNKS = 2048;
+constexpr int MLD_PROF_EVENTS = 8;  // per sampled chunk: start, clear, K1, K2-stream start, K4, end, gather end, solve end
 
 namespace {
 
@@ -233,19 +234,29 @@ int overflow_grid(mld_handle* h, Slot& s) {
 // K2: thread-per-feature kernel + warp-per-feature pass over its overflow list, or warp-per-feature only
 int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, const float* d_pts, int stride_f, long long pitch_pts,
                     const double* d_uv, int F, double* d_depth, int* d_status, const float* coeffs, const unsigned int* bits,
-                    long long words, int frames) {
-    if (F <= 0 || frames <= 0) return MLD_OK;
+                    long long words, int frames, cudaEvent_t* ev_mid = nullptr) {
+    if (F <= 0 || frames <= 0) {
+        if (ev_mid) {
+            CK(cudaEventRecord(ev_mid[0], st));
+            CK(cudaEventRecord(ev_mid[1], st));
+        }
+        return MLD_OK;
+    }
     if (h->feature_mode == 2) {
         CK(ensure(s.d_split, s.split_bytes, mld_split_scratch_bytes((long long)frames * F, coeffs != nullptr)));
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
         int nl = 0;
         CK(mld_launch_feature_depth_split(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
-                                          words, frames, s.d_ovf + 1, s.d_ovf, s.d_split, st, &nl));
+                                          words, frames, s.d_ovf + 1, s.d_ovf, s.d_split, st, &nl, ev_mid));
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
                                     bits, words, frames, s.d_ovf + 1, s.d_ovf, overflow_grid(h, s), st));
         CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         h->launches += nl + 1;
     } else if (h->feature_mode == 1) {
+        if (ev_mid) {
+            CK(cudaEventRecord(ev_mid[0], st));
+            CK(cudaEventRecord(ev_mid[1], st));
+        }
         CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
         CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
                                            words, frames, s.d_ovf + 1, s.d_ovf, st));
@@ -254,6 +265,10 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
         CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         h->launches += 2;
     } else {
+        if (ev_mid) {
+            CK(cudaEventRecord(ev_mid[0], st));
+            CK(cudaEventRecord(ev_mid[1], st));
+        }
         CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
                                     bits, words, frames, nullptr, nullptr, 0, st));
         h->launches++;
@@ -270,8 +285,8 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     cudaStream_t sb = two ? st_k2 : st;
     cudaEvent_t* ev = nullptr;
     if (h->prof_on && h->prof_used < MLD_PROF_MAX_CHUNKS) {
-        if (h->prof_events.size() < (h->prof_used + 1) * 6) {
-            for (int q = 0; q < 6; q++) {
+        if (h->prof_events.size() < (h->prof_used + 1) * MLD_PROF_EVENTS) {
+            for (int q = 0; q < MLD_PROF_EVENTS; q++) {
                 cudaEvent_t e;
                 CK(cudaEventCreate(&e));
                 h->prof_events.push_back(e);
@@ -279,7 +294,7 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
             h->prof_frames.push_back(0);
             h->prof_ransac_launches.push_back(0);
         }
-        ev = &h->prof_events[h->prof_used * 6];
+        ev = &h->prof_events[h->prof_used * MLD_PROF_EVENTS];
         h->prof_frames[h->prof_used] = frames;
         h->prof_ransac_launches[h->prof_used] = 0;
     }
@@ -312,7 +327,8 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         bits = s.d_bits;
     }
     if (ev) CK(cudaEventRecord(ev[4], sb));
-    int rcf = launch_features(h, s, mc, sb, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames);
+    int rcf = launch_features(h, s, mc, sb, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames,
+                              ev ? ev + 6 : nullptr);
     if (rcf) return rcf;
     if (two) CK(cudaEventRecord(s.ev_k2, sb));
     if (ev) {
@@ -683,27 +699,25 @@ int mld_profile_enable(mld_handle* h, int on) {
     return MLD_OK;
 }
 
-int mld_profile_read(mld_handle* h, double* ms4, int64_t* launches4, int64_t* frames_sampled) {
-    if (!h || !ms4 || !launches4) return MLD_ERR_INVALID_ARG;
+int mld_profile_read(mld_handle* h, double* ms7, int64_t* launches7, int64_t* frames_sampled) {
+    if (!h || !ms7 || !launches7) return MLD_ERR_INVALID_ARG;
     DeviceGuard g(h->device);
-    for (int q = 0; q < 4; q++) {
-        ms4[q] = 0.0;
-        launches4[q] = 0;
+    for (int q = 0; q < 7; q++) {
+        ms7[q] = 0.0;
+        launches7[q] = 0;
     }
     int64_t frames = 0;
     for (size_t c = 0; c < h->prof_used; c++) {
-        cudaEvent_t* ev = &h->prof_events[c * 6];
+        cudaEvent_t* ev = &h->prof_events[c * MLD_PROF_EVENTS];
         CK(cudaEventSynchronize(ev[5]));
-        const int from[4] = {0, 1, 3, 4}, to[4] = {1, 2, 4, 5};  // clear, K1, K4, K2
-        for (int q = 0; q < 4; q++) {
+        // clear, K1, K4, K2 (all of it), K2 gather, K2 solve, K2 rest (road kernels + overflow pass)
+        const int from[7] = {0, 1, 3, 4, 4, 6, 7}, to[7] = {1, 2, 4, 5, 6, 7, 5};
+        for (int q = 0; q < 7; q++) {
             float ms = 0.f;
             CK(cudaEventElapsedTime(&ms, ev[from[q]], ev[to[q]]));
-            ms4[q] += (double)ms;
+            ms7[q] += (double)ms;
         }
-        launches4[0] += 1;
-        launches4[1] += 1;
-        launches4[2] += h->prof_ransac_launches[c];
-        launches4[3] += 1;
+        for (int q = 0; q < 7; q++) launches7[q] += (q == 2) ? h->prof_ransac_launches[c] : 1;
         frames += h->prof_frames[c];
     }
     if (frames_sampled) *frames_sampled = frames;

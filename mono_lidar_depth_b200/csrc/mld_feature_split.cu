@@ -437,7 +437,7 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
                                            const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,
                                            const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                            int* d_overflow_list, int* d_overflow_count, void* d_scratch, cudaStream_t stream,
-                                           int* launches) {
+                                           int* launches, cudaEvent_t* ev_mid) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
     const long long features = (long long)nframes * F;
     if (features >= (1ll << 27)) return cudaErrorInvalidValue;  // survivor records hold 27-bit feature ids
@@ -457,10 +457,12 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
     feature_gather_kernel<<<ga, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
                                                    d_overflow_list, d_overflow_count, surv_rec, surv_xyz, surv_count, features);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (ev_mid && (e = cudaEventRecord(ev_mid[0], stream)) != cudaSuccess) return e;  // profiling: end of the gather
     const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
     feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, surv_rec, surv_xyz, surv_count, features, road ? 1 : 0,
                                                   road_list, road_count);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (ev_mid && (e = cudaEventRecord(ev_mid[1], stream)) != cudaSuccess) return e;  // profiling: end of the solve
     if (launches) *launches += 2;
     if (road) {
         // the survivor arrays are free again once K2b has finished: the road pass reuses them

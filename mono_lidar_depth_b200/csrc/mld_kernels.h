@@ -53,7 +53,7 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
                                            const double* d_uv, int F, double* d_depth, int* d_status, const float* d_plane_coeffs,
                                            const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
                                            int* d_overflow_list, int* d_overflow_count, void* d_scratch, cudaStream_t stream,
-                                           int* launches);
+                                           int* launches, cudaEvent_t* ev_mid = nullptr);
 
 // K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
 struct RansacConfig {

@@ -50,13 +50,14 @@ __device__ __forceinline__ bool project_uv(const DevParams& P, float x, float y,
     c = lidar_to_cam(P, x, y, z);
     // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51)
     if (need_front && !(c.z > 0.0)) return false;
-    // K * p with K = [f 0 cx; 0 f cy; 0 0 1] evaluated term by term like Eigen's product
-    // (camera_pinhole.h:88), then colwise().hnormalized() = division by the third row (:90)
-    double q0 = __dadd_rn(__dadd_rn(__dmul_rn(P.f, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(P.cx, c.z));
-    double q1 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, c.x), __dmul_rn(P.f, c.y)), __dmul_rn(P.cy, c.z));
-    double q2 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, c.x), __dmul_rn(0.0, c.y)), __dmul_rn(1.0, c.z));
-    u = __ddiv_rn(q0, q2);
-    v = __ddiv_rn(q1, q2);
+    // K * p with K = [f 0 cx; 0 f cy; 0 0 1] (camera_pinhole.h:88), then colwise().hnormalized() = division by the third
+    // row (:90). Eigen's product also adds the terms 0*X, 0*Y: they are +-0 for finite coordinates and change no value
+    // (at most the sign of a zero numerator, which fails u > 0 / v > 0 either way); for non-finite coordinates they make
+    // the quotient NaN, and so does the division below (inf/inf) or the point fails the bounds as +-inf. Left out.
+    const double q0 = __dadd_rn(__dmul_rn(P.f, c.x), __dmul_rn(P.cx, c.z));
+    const double q1 = __dadd_rn(__dmul_rn(P.f, c.y), __dmul_rn(P.cy, c.z));
+    u = __ddiv_rn(q0, c.z);
+    v = __ddiv_rn(q1, c.z);
     bool in_range = (u >= 0.) && (u <= P.Wd) && (v >= 0.) && (v <= P.Hd);  // camera_pinhole.h:93-96
     bool visible = (u > 0.) && (u < P.Wd) && (v > 0.) && (v < P.Hd);       // DepthEstimator.cpp:186-187
     return in_range && visible;
@@ -68,15 +69,15 @@ __device__ __forceinline__ float pf_form(const DevParams& P, int k, float x, flo
     return fmaf(P.pf_g[k][0], x, fmaf(P.pf_g[k][1], y, fmaf(P.pf_g[k][2], z, P.pf_h[k])));
 }
 __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, float y, float z) {
-    float S = fabsf(x) + fabsf(y) + fabsf(z);
-    if (!(S < 3.0e38f)) return true;  // NaN or inf coordinate: never visible
-    // tests ordered by how much of a 360-degree sweep they remove; a sweep is azimuth ordered, so the
-    // early exits are nearly warp uniform
-    if (pf_form(P, 0, x, y, z) + fmaf(P.pf_G[0], S, P.pf_H[0]) < 0.f) return true;  // z_cam < 0
-    if (pf_form(P, 1, x, y, z) + fmaf(P.pf_G[1], S, P.pf_H[1]) < 0.f) return true;  // f*X + cx*Z < 0      <=> u < 0
-    if (pf_form(P, 2, x, y, z) - fmaf(P.pf_G[2], S, P.pf_H[2]) > 0.f) return true;  // f*X + (cx-W)*Z > 0  <=> u > W
-    if (pf_form(P, 3, x, y, z) + fmaf(P.pf_G[3], S, P.pf_H[3]) < 0.f) return true;  // f*Y + cy*Z < 0      <=> v < 0
-    if (pf_form(P, 4, x, y, z) - fmaf(P.pf_G[4], S, P.pf_H[4]) > 0.f) return true;  // f*Y + (cy-H)*Z > 0  <=> v > H
+    const float S = fabsf(x) + fabsf(y) + fabsf(z);
+    // tests ordered by how much of a 360-degree sweep they remove; a sweep is azimuth ordered, so the early exits are
+    // nearly warp uniform. Each test is written so that a NaN (dropout) is rejected by the first one; an infinite
+    // coordinate is rejected here or, failing that, by the exact path -- a rejection is only ever a shortcut.
+    if (!(pf_form(P, 0, x, y, z) + fmaf(P.pf_G[0], S, P.pf_H[0]) >= 0.f)) return true;  // z_cam < 0
+    if (!(pf_form(P, 1, x, y, z) + fmaf(P.pf_G[1], S, P.pf_H[1]) >= 0.f)) return true;  // f*X + cx*Z < 0      <=> u < 0
+    if (!(pf_form(P, 2, x, y, z) - fmaf(P.pf_G[2], S, P.pf_H[2]) <= 0.f)) return true;  // f*X + (cx-W)*Z > 0  <=> u > W
+    if (!(pf_form(P, 3, x, y, z) + fmaf(P.pf_G[3], S, P.pf_H[3]) >= 0.f)) return true;  // f*Y + cy*Z < 0      <=> v < 0
+    if (!(pf_form(P, 4, x, y, z) - fmaf(P.pf_G[4], S, P.pf_H[4]) <= 0.f)) return true;  // f*Y + (cy-H)*Z > 0  <=> v > H
     return false;
 }
 

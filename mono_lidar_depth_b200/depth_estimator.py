@@ -435,12 +435,13 @@ class DepthEstimator:
         self._check(self._lib.mld_profile_enable(self._h, int(on)))
 
     def profileRead(self):
-        """{class: (total ms, launches)} for clear / project_scatter / ransac / feature_depth, frames sampled."""
-        ms = (C.c_double * 4)()
-        ln = (C.c_int64 * 4)()
+        """{class: (total ms, launches)} for clear / project_scatter / ransac / feature_depth (= gather + solve + rest) and
+        its three parts, frames sampled."""
+        ms = (C.c_double * 7)()
+        ln = (C.c_int64 * 7)()
         fr = C.c_int64(0)
         self._check(self._lib.mld_profile_read(self._h, ms, ln, C.byref(fr)))
-        names = ("map_clear", "project_scatter", "ransac", "feature_depth")
+        names = ("map_clear", "project_scatter", "ransac", "feature_depth", "feature_gather", "feature_solve", "feature_rest")
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}, fr.value
 
     def chunkFrames(self) -> int:

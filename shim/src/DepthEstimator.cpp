@@ -92,6 +92,40 @@ void RansacPlane::CalculateInliersPlane(const Cloud::ConstPtr& pointCloud, doubl
 }
 
 // ---------------------------------------------------------------------------------------------
+// SemanticPlane (monolidar_fusion/src/RansacPlane.cpp:159-274) on mld_semantic_ground_plane
+SemanticPlane::SemanticPlane(const cv::Mat& img, Camera cam, std::set<int> groundplane_label, double inlier_threshold)
+        : rows_(img.rows), cols_(img.cols), cam_(cam), inlier_threshold_(inlier_threshold), groundplane_label_(groundplane_label) {
+    labels_.resize((size_t)rows_ * (size_t)cols_);
+    for (int y = 0; y < rows_; y++) std::memcpy(labels_.data() + (size_t)y * (size_t)cols_, img.ptr<unsigned char>(y), (size_t)cols_);
+}
+
+SemanticPlane::~SemanticPlane() { mld_destroy(handle_); }
+
+void SemanticPlane::CalculateInliersPlane(const Cloud::ConstPtr& cloud) {
+    if (!handle_) {
+        DepthEstimatorParameters p;
+        if (mld_create(&p, -1, &handle_) != MLD_OK) throw std::runtime_error(mld_last_error(nullptr));
+    }
+    double T[12];
+    for (int r = 0; r < 3; r++)
+        for (int c = 0; c < 4; c++) T[r * 4 + c] = cam_.transform_cam_lidar.matrix()(r, c);
+    std::vector<int32_t> labels(groundplane_label_.begin(), groundplane_label_.end());
+    PlaneView v;
+    std::vector<int> none;
+    const int64_t n = (int64_t)cloud->points.size();
+    fill_plane(v, _modelCoeffs, none, false, n);
+    int rc = mld_semantic_ground_plane(handle_, cloud->points.data(), n, (int)sizeof(Point), labels_.data(), cols_, rows_, cam_.f, cam_.cu,
+                                       cam_.cv, T, labels.data(), (int)labels.size(), inlier_threshold_, &v.c);
+    if (rc == MLD_ERR_PCL_INVALID) throw ExceptionPclInvalid();
+    if (rc != MLD_OK) throw std::runtime_error(mld_last_error(handle_));
+    for (int i = 0; i < 4; i++) _modelCoeffs[i] = v.c.coeffs[i];
+    _inliersIndex.assign(v.idx.begin(), v.idx.begin() + v.c.n_inliers);
+    _pointIsInPlane.clear();
+    for (const auto& index : _inliersIndex) _pointIsInPlane.insert(std::pair<int, bool>(index, true));
+    is_segmented_ = true;
+}
+
+// ---------------------------------------------------------------------------------------------
 DepthEstimator::DepthEstimator() {
     for (int s = 1; s <= 15; s++) DepthResultTypeMap[(DepthResultType)s] = mld_status_name(s);
 }
@@ -170,7 +204,7 @@ void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Pt
                 _isInitializedPointCloud = true;
                 return;
             }
-            // any other GroundPlane (e.g. the reference's SemanticPlane) segments itself on the host
+            // any other GroundPlane segments itself (SemanticPlane: on the GPU through mld_semantic_ground_plane)
             groundPlane->CalculateInliersPlane(cloud, _parameters->ransac_plane_min_z, _parameters->ransac_plane_max_z);
         }
     }
@@ -242,7 +276,7 @@ void DepthEstimator::CalculateDepthPair(const Cloud::ConstPtr& cloudLast, const 
         if (!road || *clouds[i] == nullptr) continue;
         if (*planes[i] == nullptr) *planes[i] = std::make_shared<RansacPlane>(_parameters);  // DepthEstimator.cpp:275-278
         GroundPlane& gp = **planes[i];
-        if (!gp.isSegmented() && dynamic_cast<RansacPlane*>(&gp) == nullptr)  // e.g. SemanticPlane: segments itself on the host
+        if (!gp.isSegmented() && dynamic_cast<RansacPlane*>(&gp) == nullptr)  // e.g. SemanticPlane: segments itself
             gp.CalculateInliersPlane(*clouds[i], _parameters->ransac_plane_min_z, _parameters->ransac_plane_max_z);
         fill_plane(views[i], gp._modelCoeffs, gp._inliersIndex, gp.isSegmented(), gp.isSegmented() ? 0 : (int64_t)(*clouds[i])->points.size());
         cp[i] = &views[i].c;

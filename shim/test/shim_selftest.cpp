@@ -113,6 +113,21 @@ int main(int argc, char** argv) {
             if (total != F) return 9;
         }
 
+        // use_plane == 2: the production configuration (tracklets_depth/src/tracklet_depth_module.cpp:269-284) -- a SemanticPlane
+        // built from a label image (argv[7]: 376 x 1241 uint8, argv[8]: inlier threshold) is handed to CalculateDepth
+        if (std::atoi(argv[5]) == 2 && argc >= 9) {
+            auto lab = read_all<unsigned char>(argv[7]);
+            cv::Mat img(376, 1241, CV_8UC1, lab.data());
+            SemanticPlane::Camera cam;
+            cam.f = 718.856;
+            cam.cu = 607.1928;
+            cam.cv = 185.2157;
+            cam.transform_cam_lidar = T;
+            plane = std::make_shared<SemanticPlane>(img, cam, std::set<int>{6, 7, 8, 9}, std::atof(argv[8]));
+            est.CalculateDepth(ccloud, feats, depths, types, plane);  // setInputCloud segments the plane (DepthEstimator.cpp:281-283)
+            if (!plane->isSegmented()) return 13;
+        }
+
         std::ofstream(argv[3], std::ios::binary).write(reinterpret_cast<const char*>(depths.data()), (std::streamsize)(F * sizeof(double)));
         std::ofstream(argv[4], std::ios::binary).write(reinterpret_cast<const char*>(types.data()), (std::streamsize)(F * sizeof(int)));
         std::ofstream po(argv[6], std::ios::binary);

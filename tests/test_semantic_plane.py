@@ -33,11 +33,12 @@ F_, CU, CV = 718.856, 607.1928, 185.2157
 COEFF_TOL, MARGIN = 2e-3, 2e-3
 
 
-def _check_against(coeffs, inl, ref_coeffs, ref_inl, cloud, thr, what):
+def _check_against(coeffs, inl, ref_coeffs, ref_inl, first_model, cloud, thr, what):
+    """first_model: the first-pass plane, the one selectWithinDistance is evaluated with (RansacPlane.cpp:248)."""
     assert np.all(np.abs(np.asarray(coeffs) - ref_coeffs) < COEFF_TOL), (what, coeffs, ref_coeffs)
     diff = np.setxor1d(inl, ref_inl)
     xyz = cloud[diff, :3].astype(np.float64)
-    dist = np.abs(xyz @ ref_coeffs[:3].astype(np.float64) + float(ref_coeffs[3]))
+    dist = np.abs(xyz @ first_model[:3].astype(np.float64) + float(first_model[3]))
     assert np.all(np.abs(dist - thr) < MARGIN * (1.0 + np.linalg.norm(xyz, axis=1))), (what, len(diff), dist[:5])
     assert len(diff) <= 0.01 * max(len(ref_inl), 1), (what, len(diff), len(ref_inl))
 
@@ -85,9 +86,9 @@ def test_gpu_semantic_plane_matches_reference_outputs(case):
     plane = SemanticPlane(labels, SemanticPlane.Camera(F_, CU, CV, KT), gl, thr, est)
     plane.CalculateInliersPlane(cloud)
     assert plane.isSegmented()
-    _check_against(plane.getModelCoeffs(), plane.getInlinersIndex(), G[f"sem{case}_coeffs"], G[f"sem{case}_inliers"], cloud, thr, f"ref case {case}")
     c, inl, kept, first = SP.semantic_plane(cloud, labels, F_, CU, CV, KT, gl, thr)
-    _check_against(plane.getModelCoeffs(), plane.getInlinersIndex(), c, inl, cloud, thr, f"restatement case {case}")
+    _check_against(plane.getModelCoeffs(), plane.getInlinersIndex(), G[f"sem{case}_coeffs"], G[f"sem{case}_inliers"], first, cloud, thr, f"ref case {case}")
+    _check_against(plane.getModelCoeffs(), plane.getInlinersIndex(), c, inl, first, cloud, thr, f"restatement case {case}")
     # the plane plugs into the road path like any GroundPlane
     uv = synth.features_host(synth.default_config(), 3, case, 500)
     d, s = est.CalculateDepth(cloud, uv, plane)[:2]

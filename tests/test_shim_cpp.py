@@ -20,7 +20,7 @@ def test_shim_builds_against_stub_headers():
     out = subprocess.check_output(["nm", "-DC", str(ROOT / "shim" / "libmonolidar_fusion_b200.so")], text=True)
     for sym in ("Mono_Lidar::DepthEstimator::Initialize", "Mono_Lidar::DepthEstimator::InitConfig",
                 "Mono_Lidar::DepthEstimator::setInputCloud", "Mono_Lidar::DepthEstimator::CalculateDepth",
-                "Mono_Lidar::RansacPlane::CalculateInliersPlane"):
+                "Mono_Lidar::RansacPlane::CalculateInliersPlane", "Mono_Lidar::SemanticPlane::CalculateInliersPlane"):
         assert sym in out, sym
 
 
@@ -55,3 +55,40 @@ def test_shim_matches_oracle(tmp_path, use_plane):
         assert rc == 0 and np.array_equal(inl, inl_ref)
     d_ref, s_ref = orc.calculate_depth(uv, plane)
     PU.assert_depth_status_equal(d, s, d_ref, s_ref, f"shim plane={use_plane}")
+
+
+@pytest.mark.gpu
+def test_shim_semantic_plane_like_the_production_caller(tmp_path):
+    """tracklets_depth builds a SemanticPlane from the label image and hands it to CalculateDepth
+    (tracklet_depth_module.cpp:269-284, 318-330): same call sequence through the C++ shim, checked against the numpy
+    restatement (plane) and the oracle (depths with that plane)."""
+    import importlib.util
+    import sys
+
+    sys.path.insert(0, str(ROOT / "oracle"))
+    import semantic_plane_np as SP
+
+    spec = importlib.util.spec_from_file_location("make_ref_golden", ROOT / "tests" / "golden" / "make_ref_golden.py")
+    MK = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(MK)
+    subprocess.check_call(["make", "-C", str(ROOT / "shim")])
+    cloud, labels, gl, thr = MK.semantic_case(0)
+    uv = synth.features_host(synth.default_config(), 77, 0, 2000)
+    cloud.tofile(tmp_path / "pts.f32")
+    uv.tofile(tmp_path / "uv.f64")
+    labels.tofile(tmp_path / "labels.u8")
+    r = subprocess.run([str(ROOT / "shim" / "shim_selftest"), str(tmp_path / "pts.f32"), str(tmp_path / "uv.f64"),
+                        str(tmp_path / "d.f64"), str(tmp_path / "s.i32"), "2", str(tmp_path / "plane.bin"),
+                        str(tmp_path / "labels.u8"), repr(thr)], capture_output=True, text=True)
+    assert r.returncode == 0, (r.returncode, r.stdout, r.stderr)
+    raw = np.fromfile(tmp_path / "plane.bin", np.uint8)
+    coeffs, inl = raw[:16].view(np.float32), raw[16:].view(np.int32)
+    c_ref, inl_ref, kept, first = SP.semantic_plane(cloud, labels, 718.856, 607.1928, 185.2157, synth.KITTI_T_LIDAR_TO_CAM, gl, thr)
+    assert np.all(np.abs(coeffs - c_ref) < 2e-3) and len(np.setxor1d(inl, inl_ref)) <= 0.01 * len(inl_ref)
+    p = O.yaml_params()
+    orc = O.Oracle(p)
+    cam = synth.kitti_camera()
+    orc.initialize(1241, 376, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
+    orc.set_cloud(cloud)
+    d_ref, s_ref = orc.calculate_depth(uv, (coeffs, inl))
+    PU.assert_depth_status_equal(np.fromfile(tmp_path / "d.f64", np.float64), np.fromfile(tmp_path / "s.i32", np.int32), d_ref, s_ref, "shim semantic")
