@@ -9,7 +9,7 @@ A step is one pass of the hot path over this rank's block of the synthetic frame
 (BASELINE.json configs[1]: 10k KITTI-shaped frames, 120 000 points, 1241x376, 2000 features, yaml
 parameters with the ground plane disabled), inputs resident in HBM. Frames are independent, so N
 ranks each own a contiguous block (weak scaling, no data-path collective); the per-frame results are
-all-gathered over NCCL once per step. `e2e` is the same metric through the C ABI's host-buffer entry
+gathered on rank 0 over NCCL once per step. `e2e` is the same metric through the C ABI's host-buffer entry
 point (mld_process_frames_host): pinned host memory in, H2D + kernels + D2H inside the timed region.
 """
 from __future__ import annotations
@@ -324,9 +324,13 @@ def run_gpu(args, rank, local_rank, world):
     torch.cuda.synchronize()
 
     if world > 1:
+        # the per-frame results are gathered on rank 0 (one ncclGather of 12 F bytes per frame); an
+        # all-gather would move N times the bytes into every GPU's HBM for nothing
         per = -(-frames_total // world)
-        g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev)
-        g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev)
+        g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev) if rank == 0 else None
+        g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev) if rank == 0 else None
+        gl_depth = list(g_depth.split(per)) if rank == 0 else None
+        gl_status = list(g_status.split(per)) if rank == 0 else None
 
     pending = [[], []]
     step_no = [0]
@@ -340,8 +344,8 @@ def run_gpu(args, rank, local_rank, world):
         est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depths[b].data_ptr(), statuses[b].data_ptr(), nframes,
                                 road=use_road, seed=SEED + f0, d_plane_coeffs_out=coeffs.data_ptr() if use_road else 0, stream=stream)
         if world > 1:  # gather the per-frame results (the only inter-GPU traffic of the path), asynchronously
-            pending[b] = [dist.all_gather_into_tensor(g_depth, depths[b], async_op=True),
-                          dist.all_gather_into_tensor(g_status, statuses[b], async_op=True)]
+            pending[b] = [dist.gather(depths[b], gl_depth, dst=0, async_op=True),
+                          dist.gather(statuses[b], gl_status, dst=0, async_op=True)]
 
     def drain():
         for b in range(len(pending)):
@@ -513,7 +517,7 @@ def run_gpu(args, rank, local_rank, world):
                        "frames_per_gpu": frames_total // world, "points_per_frame": N_POINTS, "features_per_frame": N_FEATURES,
                        "image": [IMG_W, IMG_H], "chunk_frames_per_launch": chunk,
                        "l2": f"inputs of one step ({nframes * n * 16 / 1e9:.1f} GB of points per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"frames sharded in contiguous blocks over {world} GPU(s); NCCL all_gather of results per step" if world > 1 else "single GPU"},
+                       "parallelism": f"frames sharded in contiguous blocks over {world} GPU(s); NCCL gather of the results on rank 0 per step" if world > 1 else "single GPU"},
             "feature_depths_per_sec": value * N_FEATURES,
             "clocks": clk,
             "e2e": e2e,

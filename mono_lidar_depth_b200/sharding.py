@@ -23,11 +23,13 @@ def all_blocks(total_frames: int, world_size: int) -> List[Tuple[int, int]]:
     return [frame_block(total_frames, world_size, r) for r in range(world_size)]
 
 
-def gather_results(depth, status, total_frames: int, group=None):
-    """Gather the per-rank (frames_r, F) result tensors into (total_frames, F) on every rank.
+def gather_results(depth, status, total_frames: int, group=None, dst=None):
+    """Gather the per-rank (frames_r, F) result tensors into (total_frames, F): on every rank (dst=None, all_gather) or
+    only on rank `dst` (gather; the other ranks get (None, None) and receive nothing -- what bench.py uses, since the
+    consumer of a sequence's depths is one process).
 
     Works with any torch.distributed backend (NCCL on the GPUs, gloo in the CPU tests). Blocks are
-    padded to the common ceil(T/G) length for the all_gather and trimmed afterwards."""
+    padded to the common ceil(T/G) length for the collective and trimmed afterwards."""
     import torch
     import torch.distributed as dist
 
@@ -42,6 +44,15 @@ def gather_results(depth, status, total_frames: int, group=None):
         out[: t.shape[0]] = t
         return out
 
+    if dst is not None:
+        me = dist.get_rank(group)
+        d_all = [torch.empty((per, F), dtype=depth.dtype, device=depth.device) for _ in range(world)] if me == dst else None
+        s_all = [torch.empty((per, F), dtype=status.dtype, device=status.device) for _ in range(world)] if me == dst else None
+        dist.gather(padded(depth), d_all, dst=dst, group=group)
+        dist.gather(padded(status), s_all, dst=dst, group=group)
+        if me != dst:
+            return None, None
+        return torch.cat(d_all, 0)[:total_frames], torch.cat(s_all, 0)[:total_frames]
     d_all = [torch.empty((per, F), dtype=depth.dtype, device=depth.device) for _ in range(world)]
     s_all = [torch.empty((per, F), dtype=status.dtype, device=status.device) for _ in range(world)]
     dist.all_gather(d_all, padded(depth), group=group)

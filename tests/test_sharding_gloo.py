@@ -38,6 +38,12 @@ def _worker(rank, world, port, total, F, q):
     exp_frames = torch.arange(total, dtype=torch.float64)[:, None]
     ok = torch.equal(d, exp_frames + torch.arange(F, dtype=torch.float64)[None, :] / 1000.0) and torch.equal(
         s, (exp_frames.to(torch.int32) % 17).expand(total, F))
+    # gather on rank 0 only (what bench.py does over NCCL): the other rank receives nothing
+    d0, s0 = sharding.gather_results(depth, status, total, dst=0)
+    if rank == 0:
+        ok = ok and torch.equal(d0, d) and torch.equal(s0, s)
+    else:
+        ok = ok and d0 is None and s0 is None
     q.put((rank, bool(ok), tuple(d.shape)))
     dist.destroy_process_group()
 
