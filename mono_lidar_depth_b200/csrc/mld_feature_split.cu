@@ -30,6 +30,10 @@ namespace {
 #ifndef MLD_SBT_B
 #define MLD_SBT_B 128
 #endif
+#ifndef MLD_GATHER_ILP
+#define MLD_GATHER_ILP 2
+#endif
+constexpr int GILP = MLD_GATHER_ILP;  // (entry, survivor) pairs a gather thread keeps in flight
 constexpr int SCAP = MLD_SCAP;  // neighbours per feature in the normal window (more -> warp-kernel overflow list)
 constexpr int SBT_A = 128;  // threads per block, gather
 constexpr int SBT_B = MLD_SBT_B;  // threads per block, solve
@@ -156,19 +160,40 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
     // (dense warps whatever the spread of k), lanes of equal i store to consecutive slots.
     // map cell -> raw index -> point -> FP64 camera frame, stored [entry][xyz][slot]
     const int T = s_off[SCAP];
-    for (int p = tid; p < T; p += SBT_A) {
-        int i = 0;
+    // GILP pairs per thread and pass: the map loads of all of them are issued before the first point load, the point
+    // loads before the first FP64 transform, so a thread keeps GILP independent load chains in flight
+    for (int p0 = tid; p0 < T; p0 += GILP * SBT_A) {
+        long long dsti[GILP];
+        const unsigned int* cellp[GILP];
+        bool ok[GILP];
 #pragma unroll
-        for (int j = 1; j < SCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
-        const int rank = s_start[i + 1] + (p - s_off[i]);
-        const int owner = s_order[rank];
-        const unsigned int raw = map_cell_index(mc, __ldg(map + s_aux[i * SBT_A + owner]));
-        const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)raw * stride_f));
-        const D3 c = lidar_to_cam(P, q.x, q.y, q.z);
-        double* dst = surv_xyz + (long long)i * 3 * cap + ((long long)s_base + rank);
-        dst[0] = c.x;
-        dst[cap] = c.y;
-        dst[2 * cap] = c.z;
+        for (int u = 0; u < GILP; u++) {
+            const int p = p0 + u * SBT_A;
+            ok[u] = p < T;
+            int i = 0;
+#pragma unroll
+            for (int j = 1; j < SCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
+            const int rank = ok[u] ? s_start[i + 1] + (p - s_off[i]) : 0;
+            const int owner = s_order[rank];
+            cellp[u] = map + s_aux[i * SBT_A + owner];
+            dsti[u] = (long long)i * 3 * cap + ((long long)s_base + rank);
+        }
+        unsigned int raw[GILP];
+#pragma unroll
+        for (int u = 0; u < GILP; u++) raw[u] = ok[u] ? map_cell_index(mc, __ldg(cellp[u])) : 0u;
+        float4 q[GILP];
+#pragma unroll
+        for (int u = 0; u < GILP; u++)
+            q[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(fp + (long long)raw[u] * stride_f)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < GILP; u++) {
+            if (!ok[u]) continue;
+            const D3 c = lidar_to_cam(P, q[u].x, q[u].y, q[u].z);
+            double* dst = surv_xyz + dsti[u];
+            dst[0] = c.x;
+            dst[cap] = c.y;
+            dst[2 * cap] = c.z;
+        }
     }
 }
 

@@ -1,0 +1,12 @@
+run() { MLD_BENCH_CPU_SECONDS=1 MLD_BENCH_E2E_FRAMES=128 python bench.py --workload ${2:-kitti} --steps 4 --warmup 3 2>&1 | python -c "
+import sys,json
+for l in sys.stdin:
+    if l.startswith('{'):
+        d=json.loads(l); r=d['roofline']; print('$1 ${2:-kitti} fps',round(d['value']),{k:(round(v['avg_launch_ms']*1000,1) if isinstance(v,dict) and v['avg_launch_ms'] else None) for k,v in r['per_kernel'].items()}, d['parity']['status_exact'])
+    elif 'Error' in l or 'error' in l: print(l)
+"; }
+run gilp4; MLD_OVERLAP=1 run gilp4_serial
+for v in gilp1 gilp2 sbtb64 sbtb256; do
+  export MLD_CUDA_LIB=$PWD/build/variants/libmld_$v.so; run $v; MLD_OVERLAP=1 run ${v}_serial; unset MLD_CUDA_LIB
+done
+run gilp4 dense

@@ -10,7 +10,7 @@ ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))
 import torch  # noqa: E402
 
-from mono_lidar_depth_b200 import DepthEstimator, DepthEstimatorParameters, synth  # noqa: E402
+from mono_lidar_depth_b200 import DepthEstimator, DepthEstimatorParameters, SemanticPlane, synth  # noqa: E402
 
 
 def run(mode):
@@ -29,6 +29,13 @@ def run(mode):
     d, s, plane = est.CalculateDepth(cloud, uv, None)
     est.getPixelMap(); est.getNeighbors(600.0, 250.0); est.getVisible(); est.getPointsCloudCameraCs()
     est.getDepthCalcStats(s)
+    idx, img, dep_vis = est.getVisiblePoints()  # visible-order stream compaction
+    assert np.array_equal(idx, np.nonzero(est.getVisible())[0])
+    lab = np.zeros((376, 1241), np.uint8)
+    lab[200:, :] = 7
+    sp = SemanticPlane(lab, SemanticPlane.Camera(718.856, 607.1928, 185.2157, synth.KITTI_T_LIDAR_TO_CAM), (6, 7, 8, 9), 0.1, est)
+    sp.CalculateInliersPlane(cloud)  # semantic_label / semantic_select kernels
+    est.CalculateDepth(cloud, uv, sp)
     est.CalculateDepthPair(cloud, uv, None, cloud, uv, None)
     F, nframes = 500, 9
     pts = torch.empty((nframes, n, 4), dtype=torch.float32, device="cuda")
