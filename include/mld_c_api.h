@@ -178,6 +178,23 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
                               int stride_bytes, const double* d_uv, int F, double* d_depth, int32_t* d_status,
                               int64_t nframes, int road, uint64_t seed, float* d_plane_coeffs_out, void* stream);
 
+/* Same sequence with the ground plane of every frame fitted from a semantic label image on the device
+ * (SemanticPlane::CalculateInliersPlane, RansacPlane.cpp:195-274) before the road path runs: the per-frame work of
+ * TrackletDepthModule::process (tracklets_depth/src/tracklet_depth_module.cpp:269-330) in one call.
+ * d_labels: nframes images of label_h x label_w uint8. d_plane_rc_out (nullable): 0 or MLD_ERR_PCL_INVALID per frame
+ * (fewer than 3 ground-labelled points; such a frame gets no road depths). Requires a road estimator
+ * (do_use_ransac_plane != 0 in the parameters), else MLD_ERR_NO_ROAD_ESTIMATOR. */
+int mld_process_frames_device_semantic(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
+                                       int stride_bytes, const uint8_t* d_labels, int label_w, int label_h, double f, double cu,
+                                       double cv, const double* T_cam_lidar, const int32_t* ground_labels, int n_ground_labels,
+                                       double inlier_threshold, const double* d_uv, int F, double* d_depth, int32_t* d_status,
+                                       int64_t nframes, float* d_plane_coeffs_out, int32_t* d_plane_rc_out, void* stream);
+/* Same sequence with caller-provided, device-resident planes: nframes x 4 coefficients (lidar frame) and nframes inlier
+ * bitmasks over raw indices ((n_points + 31) / 32 words each) -- any GroundPlane computed elsewhere. */
+int mld_process_frames_device_planes(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
+                                     int stride_bytes, const float* d_plane_coeffs, const uint32_t* d_inlier_bits,
+                                     const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, void* stream);
+
 /* ---- batched, host-resident sequence: same as above with pinned (or pageable) host buffers;
  * H2D / kernels / D2H are pipelined over internal streams; returns after the results are in host
  * memory. plane_coeffs_out_host nullable. */

@@ -151,6 +151,16 @@ SYMBOLS = {
         [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
          C.c_uint64, C.c_void_p, C.c_void_p],
     ),
+    "mld_process_frames_device_semantic": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,
+         C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p],
+    ),
+    "mld_process_frames_device_planes": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64,
+         C.c_void_p],
+    ),
     "mld_process_frames_host": (
         C.c_int,
         [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

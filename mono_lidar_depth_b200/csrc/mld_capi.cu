@@ -276,10 +276,32 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
     return MLD_OK;
 }
 
+// where the ground plane of a batched frame comes from (road path): fitted by RANSAC on the device (the road flag of
+// mld_process_frames_*), fitted from a semantic label image on the device (SemanticPlane), or handed in by the caller
+struct PlaneSrc {
+    enum Kind { RANSAC = 0, SEMANTIC = 1, EXTERNAL = 2 } kind = RANSAC;
+    // SEMANTIC (pointers already offset to the chunk's first frame by the caller of enqueue_chunk)
+    const unsigned char* d_labels = nullptr;
+    int label_w = 0, label_h = 0;
+    double f = 0, cu = 0, cv = 0, T[12] = {0}, inlier_threshold = 0;
+    unsigned int ground[8] = {0};
+    int* d_rc_out = nullptr;
+    // EXTERNAL
+    const float* d_coeffs = nullptr;
+    const unsigned int* d_bits = nullptr;
+};
+
+void ground_label_set(const int32_t* labels, int n, unsigned int set8[8]) {
+    for (int i = 0; i < 8; i++) set8[i] = 0u;
+    for (int i = 0; i < n; i++)
+        if (labels[i] >= 0 && labels[i] <= 255) set8[labels[i] >> 5] |= 1u << (labels[i] & 31);
+}
+
+
 // one chunk of frames on one stream: [clear maps], K1, [K4], K2
 int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, long long n_points, long long pitch_pts,
                   int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
-                  long long frame0, float* d_coeffs_out, cudaStream_t st_k2 = nullptr) {
+                  long long frame0, float* d_coeffs_out, cudaStream_t st_k2 = nullptr, const PlaneSrc* src = nullptr) {
     // st: stream of the map clear + K1 (and of everything when st_k2 is null); st_k2: stream of K4 + K2
     const bool two = st_k2 != nullptr && st_k2 != st;
     cudaStream_t sb = two ? st_k2 : st;
@@ -319,12 +341,25 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     if (road && h->dp.road_mode != ROAD_NONE) {
         float* cdst = d_coeffs_out ? d_coeffs_out : s.d_coeffs;
         int nl = 0;
-        CK(mld_launch_ransac(ransac_config(h->params), d_pts, stride_f, n_points, pitch_pts, frames, seed, frame0, s.d_scratch,
-                             cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, sb, &nl));
+        if (src && src->kind == PlaneSrc::EXTERNAL) {
+            coeffs = src->d_coeffs;
+            bits = src->d_bits;
+        } else if (src && src->kind == PlaneSrc::SEMANTIC) {
+            // SemanticPlane::CalculateInliersPlane per frame (what TrackletDepthModule::process does before CalculateDepth)
+            CK(ensure(s.d_sem, s.sem_bytes, mld_semantic_state_bytes(frames)));
+            CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold,
+                                         d_pts, stride_f, n_points, pitch_pts, src->d_labels, frames, s.d_sem, cdst, s.d_bits, words,
+                                         s.d_small, src->d_rc_out ? src->d_rc_out : s.d_small + 2 * frames, sb, &nl));
+            coeffs = cdst;
+            bits = s.d_bits;
+        } else {
+            CK(mld_launch_ransac(ransac_config(h->params), d_pts, stride_f, n_points, pitch_pts, frames, seed, frame0, s.d_scratch,
+                                 cdst, s.d_bits, words, s.d_small, s.d_small + frames, s.d_small + 2 * frames, sb, &nl));
+            coeffs = cdst;
+            bits = s.d_bits;
+        }
         h->launches += nl;
         if (ev) h->prof_ransac_launches[h->prof_used] = nl;
-        coeffs = cdst;
-        bits = s.d_bits;
     }
     if (ev) CK(cudaEventRecord(ev[4], sb));
     int rcf = launch_features(h, s, mc, sb, d_pts, stride_f, pitch_pts, d_uv, F, d_depth, d_status, coeffs, bits, words, frames,
@@ -809,12 +844,6 @@ int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n,
     return run_ransac_single(h, s, n, stride_bytes / 4, seed, out_plane, iterations_out);
 }
 
-static void ground_label_set(const int32_t* labels, int n, unsigned int set8[8]) {
-    for (int i = 0; i < 8; i++) set8[i] = 0u;
-    for (int i = 0; i < n; i++)
-        if (labels[i] >= 0 && labels[i] <= 255) set8[labels[i] >> 5] |= 1u << (labels[i] & 31);
-}
-
 int mld_semantic_ground_plane_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
                                      int stride_bytes, const uint8_t* d_labels, int label_w, int label_h, double f, double cu,
                                      double cv, const double* T_cam_lidar, const int32_t* ground_labels, int n_ground_labels,
@@ -917,9 +946,9 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
     return MLD_OK;
 }
 
-int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
-                              const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
-                              uint64_t seed, float* d_plane_coeffs_out, void* stream) {
+static int process_frames_device_impl(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                                      const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
+                                      uint64_t seed, float* d_plane_coeffs_out, void* stream, const PlaneSrc* src) {
     if (!h) return MLD_ERR_INVALID_ARG;
     if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
     int rc = check_stride(h, stride_bytes);
@@ -932,7 +961,10 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
         return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device: points must be 16-byte aligned");
     if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
         return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
-    if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    if (road && n_points < 3 && !(src && src->kind == PlaneSrc::EXTERNAL))
+        return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
+    if (road && h->dp.road_mode == ROAD_NONE && src)
+        return fail(h, MLD_ERR_NO_ROAD_ESTIMATOR, "a ground plane was given but do_use_ransac_plane is off: no road depth estimator (DepthEstimator.cpp:84-103)");
     DeviceGuard g(h->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // short sequences are cut into at least `overlap_slots` chunks so that the streams still overlap
@@ -962,10 +994,18 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
     for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
         int c = (int)std::min<int64_t>(chunk, nframes - f0);
         Slot& s = h->slots[ci % nslots];
+        PlaneSrc cs;
+        if (src) {  // the chunk's view of the per-frame plane inputs
+            cs = *src;
+            if (cs.d_labels) cs.d_labels += f0 * (int64_t)cs.label_w * (int64_t)cs.label_h;
+            if (cs.d_rc_out) cs.d_rc_out += f0;
+            if (cs.d_coeffs) cs.d_coeffs += f0 * 4;
+            if (cs.d_bits) cs.d_bits += f0 * ((n_points + 31) / 32);
+        }
         rc = enqueue_chunk(h, s, prio ? h->st_lo : (nslots > 1 ? s.stream : st), pts + f0 * frame_pitch_points * stride_f, n_points,
                            frame_pitch_points, stride_f, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F,
                            d_status + f0 * (int64_t)F, c, use_road, seed, f0, d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : nullptr,
-                           prio ? h->st_hi : nullptr);
+                           prio ? h->st_hi : nullptr, src ? &cs : nullptr);
         if (rc) return rc;
     }
     if (prio) {
@@ -980,6 +1020,50 @@ int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_poi
     }
     h->have_cloud = false;  // slot 0's map now belongs to the batch
     return MLD_OK;
+}
+
+int mld_process_frames_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                              const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
+                              uint64_t seed, float* d_plane_coeffs_out, void* stream) {
+    return process_frames_device_impl(h, d_points, n_points, frame_pitch_points, stride_bytes, d_uv, F, d_depth, d_status, nframes, road, seed,
+                                      d_plane_coeffs_out, stream, nullptr);
+}
+
+int mld_process_frames_device_semantic(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                                       const uint8_t* d_labels, int label_w, int label_h, double f, double cu, double cv,
+                                       const double* T_cam_lidar, const int32_t* ground_labels, int n_ground_labels,
+                                       double inlier_threshold, const double* d_uv, int F, double* d_depth, int32_t* d_status,
+                                       int64_t nframes, float* d_plane_coeffs_out, int32_t* d_plane_rc_out, void* stream) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (!d_labels || label_w <= 0 || label_h <= 0 || !T_cam_lidar || (n_ground_labels > 0 && !ground_labels))
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device_semantic: bad label image / camera");
+    PlaneSrc src;
+    src.kind = PlaneSrc::SEMANTIC;
+    src.d_labels = d_labels;
+    src.label_w = label_w;
+    src.label_h = label_h;
+    src.f = f;
+    src.cu = cu;
+    src.cv = cv;
+    for (int i = 0; i < 12; i++) src.T[i] = T_cam_lidar[i];
+    src.inlier_threshold = inlier_threshold;
+    ground_label_set(ground_labels, n_ground_labels, src.ground);
+    src.d_rc_out = d_plane_rc_out;
+    return process_frames_device_impl(h, d_points, n_points, frame_pitch_points, stride_bytes, d_uv, F, d_depth, d_status, nframes, 1, 0,
+                                      d_plane_coeffs_out, stream, &src);
+}
+
+int mld_process_frames_device_planes(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
+                                     const float* d_plane_coeffs, const uint32_t* d_inlier_bits, const double* d_uv, int F,
+                                     double* d_depth, int32_t* d_status, int64_t nframes, void* stream) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    if (nframes > 0 && (!d_plane_coeffs || !d_inlier_bits)) return fail(h, MLD_ERR_INVALID_ARG, "mld_process_frames_device_planes: null plane buffers");
+    PlaneSrc src;
+    src.kind = PlaneSrc::EXTERNAL;
+    src.d_coeffs = d_plane_coeffs;
+    src.d_bits = d_inlier_bits;
+    return process_frames_device_impl(h, d_points, n_points, frame_pitch_points, stride_bytes, d_uv, F, d_depth, d_status, nframes, 1, 0,
+                                      nullptr, stream, &src);
 }
 
 int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,

@@ -13,7 +13,10 @@
 //
 // Two streaming passes over the cloud (16 B per point each, HBM bound) with the 3x3 fit done by the last block of
 // each pass (ticket counter), so a frame costs two launches and no host round trip. Thread i owns point i, hence
-// a warp's ballot IS word i/32 of the inlier bitmask: plain coalesced stores, no atomics, no clear.
+// a warp's ballot IS word i/32 of the inlier bitmask: plain coalesced stores, no atomics, no clear. In pass 1 a float
+// quotient on the rounded camera-frame coordinates removes the ~85 % of a sweep that cannot hit the image before the two
+// FP64 divisions; in a batch every block streams 8 tiles so that the ten-moment reduction is paid once per 8192 points
+// (first version, one tile per block and no pre-filter: 224 + 129 us per 128 sweeps; profiles/r1b_*).
 //
 // Arithmetic: the transform is evaluated in double and rounded to float per coordinate (PCL 1.8 computes
 // transform(i,0)*x + ... in the transform's scalar and casts), the projection in double with true division and
@@ -27,8 +30,14 @@
 
 namespace {
 
-constexpr int SP_THREADS = 256;
-constexpr int SP_PPT = 4;
+#ifndef MLD_SP_THREADS
+#define MLD_SP_THREADS 256
+#endif
+#ifndef MLD_SP_PPT
+#define MLD_SP_PPT 4
+#endif
+constexpr int SP_THREADS = MLD_SP_THREADS;
+constexpr int SP_PPT = MLD_SP_PPT;  // independent 16-byte loads a thread keeps in flight
 constexpr int SP_NSUM = 10;  // n, x, y, z, xx, xy, xz, yy, yz, zz
 
 __device__ __forceinline__ double sp_warp_sum(double v) {
@@ -93,7 +102,7 @@ struct SemCam {
 __global__ void __launch_bounds__(SP_THREADS)
 semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                       const unsigned char* __restrict__ labels, double* __restrict__ acc_all, float* __restrict__ coeff_all,
-                      unsigned int* __restrict__ ctl_all) {
+                      unsigned int* __restrict__ ctl_all, int iters) {
     const long long frame = blockIdx.y;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned char* lab = labels + frame * (long long)C.W * (long long)C.H;
@@ -101,38 +110,60 @@ semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int
     float* coeff = coeff_all + frame * 8;
     unsigned int* ctl = ctl_all + frame * 8;
     double v[SP_NSUM] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const int base = blockIdx.x * (SP_THREADS * SP_PPT) + threadIdx.x;
-    float4 p[SP_PPT];
+    const float ff = (float)C.f, fcu = (float)C.cu, fcv = (float)C.cv, fW = (float)C.W + 1.f, fH = (float)C.H + 1.f;
+    // a block streams `iters` tiles of SP_THREADS x SP_PPT points: the ten-moment block reduction at the end costs about as
+    // much as 12 points per thread, so batches give every thread 32 points (iters = 8) and a single sweep keeps 4 (iters = 1)
+    for (int it = 0; it < iters; it++) {
+        const int base = (blockIdx.x * iters + it) * (SP_THREADS * SP_PPT) + threadIdx.x;
+        if (base - (int)threadIdx.x >= n) break;  // uniform per block
+        float4 p[SP_PPT];
 #pragma unroll
-    for (int j = 0; j < SP_PPT; j++) {
-        const int i = base + j * SP_THREADS;
-        p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+        for (int j = 0; j < SP_PPT; j++) {
+            const int i = base + j * SP_THREADS;
+            p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        // phase A: pixel of every point (or -1); phase B: the label bytes, all loads in flight together; phase C: moments
+        int off[SP_PPT];
 #pragma unroll
-    for (int j = 0; j < SP_PPT; j++) {
-        const int i = base + j * SP_THREADS;
-        if (i >= n) break;
-        const double x = p[j].x, y = p[j].y, z = p[j].z;
-        // pcl::transformPointCloud: per coordinate in double, left to right, rounded to float
-        const float tx = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[0], x), __dmul_rn(C.T[1], y)), __dmul_rn(C.T[2], z)), C.T[3]);
-        const float ty = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[4], x), __dmul_rn(C.T[5], y)), __dmul_rn(C.T[6], z)), C.T[7]);
-        const float tz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[8], x), __dmul_rn(C.T[9], y)), __dmul_rn(C.T[10], z)), C.T[11]);
-        // project(): intrin * Vector3d{x,y,z}, p /= p[2], cv::Point(p[0], p[1]) (RansacPlane.cpp:174-177)
-        const double X = tx, Y = ty, Z = tz;
-        const double q0 = __dadd_rn(__dadd_rn(__dmul_rn(C.f, X), __dmul_rn(0.0, Y)), __dmul_rn(C.cu, Z));
-        const double q1 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, X), __dmul_rn(C.f, Y)), __dmul_rn(C.cv, Z));
-        const double q2 = __dadd_rn(__dadd_rn(__dmul_rn(0.0, X), __dmul_rn(0.0, Y)), __dmul_rn(1.0, Z));
-        const double u = __ddiv_rn(q0, q2), w = __ddiv_rn(q1, q2);
-        // double -> int like cvttsd2si: NaN and out-of-range values become INT_MIN, i.e. "x < 0" -> invalid
-        if (!(fabs(u) < 2147483648.0) || !(fabs(w) < 2147483648.0)) continue;
-        const int px = (int)u, py = (int)w;
-        if (px < 0 || px >= C.W || py < 0 || py >= C.H) continue;  // see the deviation note in the header
-        const unsigned int l = __ldg(lab + (long long)py * C.W + px);
-        if (!((C.ground[l >> 5] >> (l & 31)) & 1u)) continue;
-        // the fit runs on the ORIGINAL cloud (model_p is built on `cloud`, RansacPlane.cpp:236); PCL skips non-finite points
-        if (!(fabs(x) <= 3.4e38 && fabs(y) <= 3.4e38 && fabs(z) <= 3.4e38)) { v[0] += 0.0; continue; }
-        v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
-        v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
+        for (int j = 0; j < SP_PPT; j++) {
+            off[j] = -1;
+            const int i = base + j * SP_THREADS;
+            if (i >= n) continue;
+            const double x = p[j].x, y = p[j].y, z = p[j].z;
+            // pcl::transformPointCloud: per coordinate in double, left to right, rounded to float
+            const float tx = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[0], x), __dmul_rn(C.T[1], y)), __dmul_rn(C.T[2], z)), C.T[3]);
+            const float ty = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[4], x), __dmul_rn(C.T[5], y)), __dmul_rn(C.T[6], z)), C.T[7]);
+            const float tz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[8], x), __dmul_rn(C.T[9], y)), __dmul_rn(C.T[10], z)), C.T[11]);
+            // float pre-filter on the SAME rounded coordinates: the absolute error of uf, vf is < 0.01 pixel for any coordinate the
+            // exact path accepts (-1 < u < W), so such a point never falls outside (-2, W + 1); NaN fails the test and is invalid
+            // in the exact path too. About 85 % of a sweep leaves here without the two FP64 divisions.
+            const float uf = __fdividef(fmaf(ff, tx, fcu * tz), tz), vf = __fdividef(fmaf(ff, ty, fcv * tz), tz);
+            if (!(uf > -2.f && uf < fW && vf > -2.f && vf < fH)) continue;
+            // project(): intrin * Vector3d{x,y,z}, p /= p[2], cv::Point(p[0], p[1]) (RansacPlane.cpp:174-177); Eigen's 0*X, 0*Y
+            // terms are +-0 for the finite values that reach this point
+            const double X = tx, Y = ty, Z = tz;
+            const double q0 = __dadd_rn(__dmul_rn(C.f, X), __dmul_rn(C.cu, Z));
+            const double q1 = __dadd_rn(__dmul_rn(C.f, Y), __dmul_rn(C.cv, Z));
+            const double u = __ddiv_rn(q0, Z), w = __ddiv_rn(q1, Z);
+            // double -> int like cvttsd2si: NaN and out-of-range values become INT_MIN, i.e. "x < 0" -> invalid
+            if (!(fabs(u) < 2147483648.0) || !(fabs(w) < 2147483648.0)) continue;
+            const int px = (int)u, py = (int)w;
+            if (px < 0 || px >= C.W || py < 0 || py >= C.H) continue;  // see the deviation note in the header
+            // the fit runs on the ORIGINAL cloud (model_p is built on `cloud`, RansacPlane.cpp:236); PCL skips non-finite points
+            // (the coordinates are finite here: a non-finite one makes tx, ty or tz non-finite and fails the pre-filter)
+            off[j] = py * C.W + px;
+        }
+        unsigned int lbl[SP_PPT];
+#pragma unroll
+        for (int j = 0; j < SP_PPT; j++) lbl[j] = off[j] >= 0 ? (unsigned int)__ldg(lab + off[j]) : 256u;
+#pragma unroll
+        for (int j = 0; j < SP_PPT; j++) {
+            const unsigned int l = lbl[j];
+            if (l > 255u || !((C.ground[l >> 5] >> (l & 31)) & 1u)) continue;
+            const double x = p[j].x, y = p[j].y, z = p[j].z;
+            v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
+            v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
+        }
     }
     if (sp_commit(v, acc, ctl + 0, gridDim.x) && threadIdx.x == 0) {
         volatile double* va = acc;
@@ -152,7 +183,7 @@ __global__ void __launch_bounds__(SP_THREADS)
 semantic_select_kernel(const float* __restrict__ pts, int stride_f, int n, long long pitch_pts, double threshold,
                        double* __restrict__ acc_all, float* __restrict__ coeff_all, unsigned int* __restrict__ ctl_all,
                        unsigned int* __restrict__ bits_all, long long words_per_frame, float* __restrict__ coeffs_out,
-                       int* __restrict__ n_inliers_out, int* __restrict__ rc_out) {
+                       int* __restrict__ n_inliers_out, int* __restrict__ rc_out, int iters) {
     const long long frame = blockIdx.y;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     double* acc = acc_all + frame * 2 * SP_NSUM + SP_NSUM;
@@ -162,29 +193,32 @@ semantic_select_kernel(const float* __restrict__ pts, int stride_f, int n, long 
     const float a = coeff[0], b = coeff[1], c = coeff[2], d = coeff[3];
     const bool invalid = ctl[4] != 0u;
     double v[SP_NSUM] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    const int base = blockIdx.x * (SP_THREADS * SP_PPT) + threadIdx.x;
-    float4 p[SP_PPT];
+    for (int it = 0; it < iters; it++) {
+        const int base = (blockIdx.x * iters + it) * (SP_THREADS * SP_PPT) + threadIdx.x;
+        if (base - (int)threadIdx.x >= n) break;  // uniform per block
+        float4 p[SP_PPT];
 #pragma unroll
-    for (int j = 0; j < SP_PPT; j++) {
-        const int i = base + j * SP_THREADS;
-        p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-#pragma unroll
-    for (int j = 0; j < SP_PPT; j++) {
-        const int i = base + j * SP_THREADS;  // warp-uniform tail: i - lane is a multiple of 32
-        bool in = false;
-        if (i < n && !invalid) {
-            // pcl::SampleConsensusModelPlane::selectWithinDistance: fabs(dot((x,y,z,1), coeffs)) < threshold, float dot
-            const float dist = fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p[j].x), __fmul_rn(b, p[j].y)), __fmul_rn(c, p[j].z)), d));
-            in = (double)dist < threshold;
-            if (in) {
-                const double x = p[j].x, y = p[j].y, z = p[j].z;
-                v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
-                v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
-            }
+        for (int j = 0; j < SP_PPT; j++) {
+            const int i = base + j * SP_THREADS;
+            p[j] = (i < n) ? ld_stream_f4(fp + (long long)i * stride_f) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        const unsigned int m = __ballot_sync(MLD_FULL_MASK, in);
-        if ((threadIdx.x & 31) == 0 && (i - (int)(threadIdx.x & 31)) < n) bits[i >> 5] = m;
+#pragma unroll
+        for (int j = 0; j < SP_PPT; j++) {
+            const int i = base + j * SP_THREADS;  // warp-uniform tail: i - lane is a multiple of 32
+            bool in = false;
+            if (i < n && !invalid) {
+                // pcl::SampleConsensusModelPlane::selectWithinDistance: fabs(dot((x,y,z,1), coeffs)) < threshold, float dot
+                const float dist = fabsf(__fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, p[j].x), __fmul_rn(b, p[j].y)), __fmul_rn(c, p[j].z)), d));
+                in = (double)dist < threshold;
+                if (in) {
+                    const double x = p[j].x, y = p[j].y, z = p[j].z;
+                    v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
+                    v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
+                }
+            }
+            const unsigned int m = __ballot_sync(MLD_FULL_MASK, in);
+            if ((threadIdx.x & 31) == 0 && (i - (int)(threadIdx.x & 31)) < n) bits[i >> 5] = m;
+        }
     }
     if (sp_commit(v, acc, ctl + 1, gridDim.x) && threadIdx.x == 0) {
         volatile double* va = acc;
@@ -222,13 +256,17 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
     double* acc = reinterpret_cast<double*>(d_state);
     float* coeff = reinterpret_cast<float*>(acc + (size_t)nframes * 2 * SP_NSUM);
     unsigned int* ctl = reinterpret_cast<unsigned int*>(coeff + (size_t)nframes * 8);
-    const unsigned int gx = (unsigned int)std::max<long long>(1, (n_points + SP_THREADS * SP_PPT - 1) / (SP_THREADS * SP_PPT));
+    // tiles per block: a batch fills the machine with frames, so each block amortises its reduction over 8 tiles; one sweep
+    // alone needs all the blocks it can get
+    const int iters = nframes >= 8 ? 8 : 1;
+    const long long per_block = (long long)SP_THREADS * SP_PPT * iters;
+    const unsigned int gx = (unsigned int)std::max<long long>(1, (n_points + per_block - 1) / per_block);
     dim3 grid(gx, (unsigned)nframes);
-    semantic_label_kernel<<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl);
+    semantic_label_kernel<<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl, iters);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     semantic_select_kernel<<<grid, SP_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, inlier_threshold, acc, coeff, ctl,
-                                                           d_inlier_bits, words_per_frame, d_coeffs, d_n_inliers, d_rc);
+                                                           d_inlier_bits, words_per_frame, d_coeffs, d_n_inliers, d_rc, iters);
     if (launches) *launches += 2;
     return cudaGetLastError();
 }

@@ -418,6 +418,26 @@ class DepthEstimator:
                                                         d_depth, d_status, nframes, int(road), seed,
                                                         d_plane_coeffs_out or None, stream or None))
 
+    def processFramesDeviceSemantic(self, d_points: int, n_points: int, frame_pitch_points: int, stride_bytes: int, d_labels: int,
+                                    label_w: int, label_h: int, cam: "SemanticPlane.Camera", ground_labels, inlier_threshold: float,
+                                    d_uv: int, F: int, d_depth: int, d_status: int, nframes: int, d_plane_coeffs_out: int = 0,
+                                    d_plane_rc_out: int = 0, stream: int = 0) -> None:
+        """SemanticPlane fit per frame on the device + depth estimation with the road path: the per-frame work of
+        TrackletDepthModule::process (tracklet_depth_module.cpp:269-330) for a device-resident sequence."""
+        gl = np.ascontiguousarray(sorted(int(x) for x in set(ground_labels)), np.int32)
+        T = np.ascontiguousarray(cam.transform_cam_lidar, np.float64)
+        self._check(self._lib.mld_process_frames_device_semantic(self._h, d_points, n_points, frame_pitch_points, stride_bytes, d_labels,
+                                                                 label_w, label_h, cam.f, cam.cu, cam.cv, T.ctypes.data,
+                                                                 gl.ctypes.data if len(gl) else None, len(gl), float(inlier_threshold), d_uv, F,
+                                                                 d_depth, d_status, nframes, d_plane_coeffs_out or None,
+                                                                 d_plane_rc_out or None, stream or None))
+
+    def processFramesDevicePlanes(self, d_points: int, n_points: int, frame_pitch_points: int, stride_bytes: int, d_plane_coeffs: int,
+                                  d_inlier_bits: int, d_uv: int, F: int, d_depth: int, d_status: int, nframes: int, stream: int = 0) -> None:
+        """Device-resident sequence with caller-provided planes (nframes x 4 floats, nframes inlier bitmasks over raw indices)."""
+        self._check(self._lib.mld_process_frames_device_planes(self._h, d_points, n_points, frame_pitch_points, stride_bytes, d_plane_coeffs,
+                                                               d_inlier_bits, d_uv, F, d_depth, d_status, nframes, stream or None))
+
     def processFramesHost(self, points: np.ndarray, uv: np.ndarray, depth: np.ndarray, status: np.ndarray, road: bool = False,
                           seed: int = 0, plane_coeffs_out: Optional[np.ndarray] = None) -> None:
         """points (nframes, n, 4|8) float32, uv (nframes, F, 2) float64 -> depth (nframes, F) f64, status (nframes, F) i32."""

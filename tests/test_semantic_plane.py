@@ -126,3 +126,124 @@ def test_gpu_semantic_plane_ground_labelled_set_is_bit_exact():
     finite = np.nonzero(np.isfinite(cloud[:, :3]).all(axis=1))[0]
     assert np.array_equal(p.getInlinersIndex(), finite.astype(np.int32))
     assert len(kept) >= 3
+
+
+@pytest.mark.gpu
+def test_gpu_semantic_plane_batched_device_api_matches_single_frame_calls():
+    """mld_semantic_ground_plane_device: three sweeps and three label images resident on the device, one call; every frame
+    must reproduce the stand-alone host call bit for bit (same kernels), and the bitmask must plug into the batched road path."""
+    import ctypes as C
+
+    import torch
+
+    est = _estimator()
+    cases = [MK.semantic_case(c) for c in (0, 1, 2)]
+    thr = 0.1
+    gl = [6, 7, 8, 9]
+    n = len(cases[0][0])
+    pitch = n + 64  # frames further apart than n points: the pitch is honoured
+    pts = torch.zeros((3, pitch, 4), dtype=torch.float32, device="cuda")
+    labs = torch.zeros((3, 376, 1241), dtype=torch.uint8, device="cuda")
+    for i, (cloud, lab, _, _) in enumerate(cases):
+        pts[i, :n] = torch.from_numpy(cloud).cuda()
+        labs[i] = torch.from_numpy(lab).cuda()
+    words = (n + 31) // 32
+    coeffs = torch.zeros((3, 4), dtype=torch.float32, device="cuda")
+    bits = torch.zeros((3, words), dtype=torch.int32, device="cuda")
+    ninl = torch.zeros(3, dtype=torch.int32, device="cuda")
+    rc = torch.zeros(3, dtype=torch.int32, device="cuda")
+    T = np.ascontiguousarray(KT[:3, :4], np.float64)
+    g = np.ascontiguousarray(gl, np.int32)
+    est._check(est._lib.mld_semantic_ground_plane_device(est._h, pts.data_ptr(), n, pitch, 16, labs.data_ptr(), 1241, 376, F_, CU, CV,
+                                                         T.ctypes.data, g.ctypes.data, len(g), thr, 3, coeffs.data_ptr(), bits.data_ptr(),
+                                                         ninl.data_ptr(), rc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc.cpu().tolist() == [0, 0, 0]
+    hb = bits.cpu().numpy().view(np.uint32)
+    for i, (cloud, lab, _, _) in enumerate(cases):
+        single = SemanticPlane(lab, SemanticPlane.Camera(F_, CU, CV, KT), gl, thr, est)
+        single.CalculateInliersPlane(cloud)
+        idx = np.nonzero(np.unpackbits(hb[i].view(np.uint8), bitorder="little")[:n])[0].astype(np.int32)
+        assert np.array_equal(idx, single.getInlinersIndex()), i
+        assert int(ninl[i]) == len(idx)
+        assert np.allclose(coeffs[i].cpu().numpy(), single.getModelCoeffs(), rtol=0, atol=1e-6)  # double atomics: summation order varies
+    # a frame without ground pixels reports ExceptionPclInvalid through its return code only
+    labs[1].zero_()
+    est._check(est._lib.mld_semantic_ground_plane_device(est._h, pts.data_ptr(), n, pitch, 16, labs.data_ptr(), 1241, 376, F_, CU, CV,
+                                                         T.ctypes.data, g.ctypes.data, len(g), thr, 3, coeffs.data_ptr(), bits.data_ptr(),
+                                                         ninl.data_ptr(), rc.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    assert rc.cpu().tolist() == [0, -7, 0]  # MLD_ERR_PCL_INVALID
+    assert int(ninl[1]) == 0 and not bits[1].any()
+
+
+@pytest.mark.gpu
+def test_gpu_batched_semantic_road_path_matches_per_frame_calls():
+    """mld_process_frames_device_semantic (SemanticPlane fit + depth estimation per frame, one call) against
+    (a) the same sequence with the planes fitted first and handed in (mld_process_frames_device_planes) and
+    (b) the reference's per-frame call sequence through the single-frame API with the same plane, and the oracle."""
+    import torch
+
+    import oracle_lib as O
+
+    p = DepthEstimatorParameters.reference_yaml(1)
+    est = DepthEstimator()
+    est.InitConfig(p)
+    est.Initialize(synth.kitti_camera(), KT)
+    cases = [MK.semantic_case(c) for c in (0, 1, 2)] * 3  # 9 frames -> more than one chunk of the 3-slot pipeline
+    thr, gl = 0.1, [6, 7, 8, 9]
+    nf, n, F = len(cases), len(cases[0][0]), 700
+    cam = SemanticPlane.Camera(F_, CU, CV, KT)
+    rng = np.random.RandomState(4)
+    uv_h = np.stack([np.stack([rng.randint(0, 1241, F), rng.randint(150, 376, F)], 1).astype(np.float64) for _ in range(nf)])
+    pts = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
+    labs = torch.from_numpy(np.stack([c[1] for c in cases])).cuda()
+    uv = torch.from_numpy(uv_h).cuda()
+    dep = torch.empty((nf, F), dtype=torch.float64, device="cuda")
+    sta = torch.empty((nf, F), dtype=torch.int32, device="cuda")
+    coeffs = torch.zeros((nf, 4), dtype=torch.float32, device="cuda")
+    prc = torch.full((nf,), 99, dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    est.processFramesDeviceSemantic(pts.data_ptr(), n, n, 16, labs.data_ptr(), 1241, 376, cam, gl, thr, uv.data_ptr(), F, dep.data_ptr(),
+                                    sta.data_ptr(), nf, coeffs.data_ptr(), prc.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert prc.cpu().tolist() == [0] * nf
+    d_sem, s_sem = dep.cpu().numpy().copy(), sta.cpu().numpy().copy()
+    assert (s_sem == 16).sum() > 50  # SuccessRoad is exercised
+    # (a) planes fitted up front on the device, then handed in
+    words = (n + 31) // 32
+    c2 = torch.zeros((nf, 4), dtype=torch.float32, device="cuda")
+    bits = torch.zeros((nf, words), dtype=torch.int32, device="cuda")
+    ninl = torch.zeros(nf, dtype=torch.int32, device="cuda")
+    rc = torch.zeros(nf, dtype=torch.int32, device="cuda")
+    T = np.ascontiguousarray(KT[:3, :4], np.float64)
+    g = np.ascontiguousarray(gl, np.int32)
+    est._check(est._lib.mld_semantic_ground_plane_device(est._h, pts.data_ptr(), n, n, 16, labs.data_ptr(), 1241, 376, F_, CU, CV, T.ctypes.data,
+                                                         g.ctypes.data, len(g), thr, nf, c2.data_ptr(), bits.data_ptr(), ninl.data_ptr(),
+                                                         rc.data_ptr(), st))
+    est.processFramesDevicePlanes(pts.data_ptr(), n, n, 16, c2.data_ptr(), bits.data_ptr(), uv.data_ptr(), F, dep.data_ptr(), sta.data_ptr(), nf, st)
+    torch.cuda.synchronize()
+    assert np.array_equal(coeffs.cpu().numpy(), c2.cpu().numpy())
+    assert np.array_equal(sta.cpu().numpy(), s_sem) and np.array_equal(dep.cpu().numpy(), d_sem)
+    # (b) per frame through the reference-shaped API with the same plane, and the oracle
+    hb = bits.cpu().numpy().view(np.uint32)
+    orc = O.Oracle(O.yaml_params())
+    orc.initialize(1241, 376, 718.856, 607.1928, 185.2157, KT)
+    from mono_lidar_depth_b200 import GroundPlane
+    import parity_util as PU
+    for i in (0, 4, 8):
+        idx = np.nonzero(np.unpackbits(hb[i].view(np.uint8), bitorder="little")[:n])[0].astype(np.int32)
+        plane = GroundPlane(c2[i].cpu().numpy(), idx)
+        d1, s1 = est.CalculateDepth(cases[i][0], uv_h[i], plane)[:2]
+        assert np.array_equal(s1, s_sem[i]) and np.array_equal(d1, d_sem[i])
+        orc.set_cloud(cases[i][0])
+        d_o, s_o = orc.calculate_depth(uv_h[i], (c2[i].cpu().numpy(), idx))
+        PU.assert_depth_status_equal(d_sem[i], s_sem[i], d_o, s_o, f"semantic batch frame {i}")
+    # without a road estimator the call is refused like the reference's Initialize would leave _roadDepthEstimator null
+    e2 = DepthEstimator()
+    e2.InitConfig(DepthEstimatorParameters.reference_yaml(0))
+    e2.Initialize(synth.kitti_camera(), KT)
+    from mono_lidar_depth_b200 import MldError
+    with pytest.raises(MldError):
+        e2.processFramesDeviceSemantic(pts.data_ptr(), n, n, 16, labs.data_ptr(), 1241, 376, cam, gl, thr, uv.data_ptr(), F, dep.data_ptr(),
+                                       sta.data_ptr(), nf, 0, 0, st)
