@@ -158,6 +158,11 @@ int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n,
 int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
                               int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
                               const int32_t* ground_labels, int n_ground_labels, double inlier_threshold, mld_plane* out_plane);
+/* debug / parity view of the first stage: out_flags_host[i] = 1 when point i projects onto a ground-labelled pixel
+ * (the points kept by RansacPlane.cpp:201-222), 0 otherwise. */
+int mld_semantic_ground_labelled(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
+                                 int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
+                                 const int32_t* ground_labels, int n_ground_labels, uint8_t* out_flags_host);
 /* Device-resident, batched form: nframes clouds (frame_pitch_points apart) and nframes label images back to back.
  * Outputs per frame: 4 coefficients, an inlier bitmask over raw indices ((n_points + 31) / 32 words, the format the
  * road path consumes), the inlier count and a return code (0 or MLD_ERR_PCL_INVALID). Enqueued on `stream`. */

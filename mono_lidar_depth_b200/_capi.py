@@ -140,6 +140,11 @@ SYMBOLS = {
         [_H, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
          C.c_int, C.c_double, _PL],
     ),
+    "mld_semantic_ground_labelled": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p,
+         C.c_int, C.c_void_p],
+    ),
     "mld_semantic_ground_plane_device": (
         C.c_int,
         [_H, C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p,

@@ -903,6 +903,43 @@ int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n,
     return MLD_OK;
 }
 
+int mld_semantic_ground_labelled(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
+                                 int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
+                                 const int32_t* ground_labels, int n_ground_labels, uint8_t* out_flags_host) {
+    if (!h || !out_flags_host) return MLD_ERR_INVALID_ARG;
+    if (n < 0 || (n > 0 && !points_host) || !labels_host || label_w <= 0 || label_h <= 0 || !T_cam_lidar)
+        return fail(h, MLD_ERR_INVALID_ARG, "mld_semantic_ground_labelled: bad arguments");
+    int rc = check_stride(h, stride_bytes);
+    if (rc) return rc;
+    if (n == 0) return MLD_OK;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[1];
+    const long long words = (n + 31) / 32;
+    CK(ensure(s.d_pts, s.pts_bytes, (size_t)n * (size_t)stride_bytes));
+    CK(ensure(s.d_labels, s.labels_bytes, (size_t)label_w * (size_t)label_h));
+    CK(ensure(s.d_bits, s.bits_bytes, (size_t)words * sizeof(unsigned int)));
+    CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
+    CK(ensure(s.d_small, s.small_bytes, 3 * sizeof(int)));
+    CK(ensure(s.d_sem, s.sem_bytes, mld_semantic_state_bytes(1)));
+    unsigned char* d_flags = nullptr;
+    CK(cudaMalloc(&d_flags, (size_t)n));
+    unsigned int set8[8];
+    ground_label_set(ground_labels, n_ground_labels, set8);
+    int nl = 0;
+    cudaError_t e = cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_labels, labels_host, (size_t)label_w * (size_t)label_h, cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(d_flags, 0, (size_t)n, s.stream);
+    if (e == cudaSuccess)
+        e = mld_launch_semantic_plane(T_cam_lidar, f, cu, cv, label_w, label_h, set8, 0.0, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n,
+                                      n, s.d_labels, 1, s.d_sem, s.d_coeffs, s.d_bits, words, s.d_small, s.d_small + 2, s.stream, &nl, d_flags);
+    h->launches += nl;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_flags_host, d_flags, (size_t)n, cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_flags);
+    if (e != cudaSuccess) return fail_cuda(h, e, "mld_semantic_ground_labelled");
+    return MLD_OK;
+}
+
 int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* depth_host, int32_t* status_host,
                         const mld_plane* plane) {
     if (!h) return MLD_ERR_INVALID_ARG;

@@ -99,10 +99,11 @@ struct SemCam {
 
 // pass 1: label lookup -> moments of the labelled points; the last block fits the first model.
 // state per frame: acc1[10], acc2[10] doubles | coeffs1[4], coeffs2[4] floats | tickets[2], n_labelled, n_inliers, rc
+template <bool WITH_FLAGS>
 __global__ void __launch_bounds__(SP_THREADS)
 semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                       const unsigned char* __restrict__ labels, double* __restrict__ acc_all, float* __restrict__ coeff_all,
-                      unsigned int* __restrict__ ctl_all, int iters) {
+                      unsigned int* __restrict__ ctl_all, int iters, unsigned char* __restrict__ flags_out) {
     const long long frame = blockIdx.y;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned char* lab = labels + frame * (long long)C.W * (long long)C.H;
@@ -134,10 +135,11 @@ semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int
             const float tx = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[0], x), __dmul_rn(C.T[1], y)), __dmul_rn(C.T[2], z)), C.T[3]);
             const float ty = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[4], x), __dmul_rn(C.T[5], y)), __dmul_rn(C.T[6], z)), C.T[7]);
             const float tz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(C.T[8], x), __dmul_rn(C.T[9], y)), __dmul_rn(C.T[10], z)), C.T[11]);
-            // float pre-filter on the SAME rounded coordinates: the absolute error of uf, vf is < 0.01 pixel for any coordinate the
-            // exact path accepts (-1 < u < W), so such a point never falls outside (-2, W + 1); NaN fails the test and is invalid
-            // in the exact path too. About 85 % of a sweep leaves here without the two FP64 divisions.
-            const float uf = __fdividef(fmaf(ff, tx, fcu * tz), tz), vf = __fdividef(fmaf(ff, ty, fcv * tz), tz);
+            // float pre-filter on the SAME rounded coordinates the exact path uses, u = f * (tx / tz) + cu: the absolute error of
+            // uf, vf is < 0.01 pixel for any coordinate the exact path accepts (-1 < u < W), so such a point never falls outside
+            // (-2, W + 1); NaN fails the test and is invalid in the exact path too; for |tz| > 2^126 __fdividef returns 0 and the
+            // point simply goes on to the exact path (no product that could overflow is formed). About 85 % of a sweep leaves here.
+            const float uf = fmaf(ff, __fdividef(tx, tz), fcu), vf = fmaf(ff, __fdividef(ty, tz), fcv);
             if (!(uf > -2.f && uf < fW && vf > -2.f && vf < fH)) continue;
             // project(): intrin * Vector3d{x,y,z}, p /= p[2], cv::Point(p[0], p[1]) (RansacPlane.cpp:174-177); Eigen's 0*X, 0*Y
             // terms are +-0 for the finite values that reach this point
@@ -150,7 +152,7 @@ semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int
             const int px = (int)u, py = (int)w;
             if (px < 0 || px >= C.W || py < 0 || py >= C.H) continue;  // see the deviation note in the header
             // the fit runs on the ORIGINAL cloud (model_p is built on `cloud`, RansacPlane.cpp:236); PCL skips non-finite points
-            // (the coordinates are finite here: a non-finite one makes tx, ty or tz non-finite and fails the pre-filter)
+            // (the coordinates are finite here: a non-finite one makes tx, ty or tz non-finite and fails stage 2)
             off[j] = py * C.W + px;
         }
         unsigned int lbl[SP_PPT];
@@ -159,7 +161,9 @@ semantic_label_kernel(SemCam C, const float* __restrict__ pts, int stride_f, int
 #pragma unroll
         for (int j = 0; j < SP_PPT; j++) {
             const unsigned int l = lbl[j];
-            if (l > 255u || !((C.ground[l >> 5] >> (l & 31)) & 1u)) continue;
+            const bool ground = l <= 255u && ((C.ground[l >> 5] >> (l & 31)) & 1u);
+            if (WITH_FLAGS && base + j * SP_THREADS < n) flags_out[frame * (long long)n + base + j * SP_THREADS] = ground ? 1 : 0;  // parity view
+            if (!ground) continue;
             const double x = p[j].x, y = p[j].y, z = p[j].z;
             v[0] += 1.0; v[1] += x; v[2] += y; v[3] += z;
             v[4] += x * x; v[5] += x * y; v[6] += x * z; v[7] += y * y; v[8] += y * z; v[9] += z * z;
@@ -244,7 +248,7 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
                                       const unsigned int* ground_set8, double inlier_threshold, const float* d_pts, int stride_f,
                                       long long n_points, long long pitch_pts, const unsigned char* d_labels, int nframes,
                                       void* d_state, float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame,
-                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches) {
+                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches, unsigned char* d_flags_out) {
     if (nframes <= 0) return cudaSuccess;
     if (n_points > 0x7fffffffLL / 8) return cudaErrorInvalidValue;
     SemCam C;
@@ -262,7 +266,10 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
     const long long per_block = (long long)SP_THREADS * SP_PPT * iters;
     const unsigned int gx = (unsigned int)std::max<long long>(1, (n_points + per_block - 1) / per_block);
     dim3 grid(gx, (unsigned)nframes);
-    semantic_label_kernel<<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl, iters);
+    if (d_flags_out)
+        semantic_label_kernel<true><<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl, iters, d_flags_out);
+    else
+        semantic_label_kernel<false><<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl, iters, nullptr);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     semantic_select_kernel<<<grid, SP_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, inlier_threshold, acc, coeff, ctl,

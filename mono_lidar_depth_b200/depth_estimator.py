@@ -355,6 +355,18 @@ class DepthEstimator:
                                                         plane.inlier_threshold_, C.byref(pl_c)))
         plane._from_c(pl_c)
 
+    def semanticGroundLabelled(self, plane: SemanticPlane, cloud) -> np.ndarray:
+        """bool per point: projects onto a ground-labelled pixel (the set RansacPlane.cpp:201-222 keeps); parity view."""
+        a, n, stride = _cloud_buffer(cloud)
+        lab = plane.semantic_image_
+        gl = np.ascontiguousarray(plane.groundplane_label_, np.int32)
+        T = plane.cam_.transform_cam_lidar
+        out = np.zeros(max(n, 1), np.uint8)
+        self._check(self._lib.mld_semantic_ground_labelled(self._handle_for_plane(), a.ctypes.data if n else None, n, stride, lab.ctypes.data,
+                                                           lab.shape[1], lab.shape[0], plane.cam_.f, plane.cam_.cu, plane.cam_.cv, T.ctypes.data,
+                                                           gl.ctypes.data if len(gl) else None, len(gl), out.ctypes.data))
+        return out[:n].astype(bool)
+
     def _handle_for_plane(self):
         if not self._h:
             raise RuntimeError("Call 'InitConfig' before fitting a ground plane")

@@ -65,6 +65,27 @@ def semantic_case(case):
     return cloud, lab, gl, thr
 
 
+def semantic_boundary_cloud(m=60000):
+    """(cloud, label image): lidar points whose projection sits on every decision boundary of the SemanticPlane label test --
+    integer pixel coordinates +- 1e-7, the image frame, the camera plane, points behind the camera, huge / non-finite values.
+    Everything is ground except a lattice, so an off-by-one pixel changes the kept set."""
+    F_, CU, CV = KCAM[2], KCAM[3], KCAM[4]
+    rng = np.random.RandomState(12)
+    labels = np.full((376, 1241), 7, np.uint8)
+    labels[::2, ::3] = 1
+    u = np.concatenate([rng.randint(-3, 1245, m // 2) + rng.choice([0.0, 1e-7, -1e-7, 1e-4, -1e-4, 0.5], m // 2), rng.uniform(-5, 1246, m // 2)])
+    v = np.concatenate([rng.randint(-3, 380, m // 2) + rng.choice([0.0, 1e-7, -1e-7, 1e-4, -1e-4, 0.5], m // 2), rng.uniform(-5, 381, m // 2)])
+    z = rng.choice([0.26, 0.24, 0.01, 1e-4, 1.0, 7.3, 55.0, 400.0, -0.3, -2.0, -40.0], m) * rng.uniform(0.9, 1.1, m)
+    camp = np.stack([(u - CU) / F_ * z, (v - CV) / F_ * z, z], 1)
+    Tm = np.vstack([synth.KITTI_T_LIDAR_TO_CAM[:3], [0, 0, 0, 1]])
+    Ti = np.linalg.inv(Tm)
+    lid = (Ti[:3, :3] @ camp.T).T + Ti[:3, 3]
+    cloud = np.zeros((m + 8, 4), np.float32)
+    cloud[:m, :3] = lid.astype(np.float32)
+    cloud[m:, :3] = [[np.nan, 1, 1], [np.inf, 1, 1], [1, -np.inf, 2], [3e38, 0, 0], [1e6, 2e5, -3e4], [0, 0, 0], [1e-30, 0, 0], [5, np.nan, np.nan]]
+    return cloud, labels
+
+
 def main():
     assert R.available(), "build oracle/_ref first (make -C oracle in a container with /root/reference)"
     T = synth.KITTI_T_LIDAR_TO_CAM

@@ -424,3 +424,43 @@ def test_status_statistics_and_feature_point_packing():
     o = out.cpu().numpy()
     assert np.array_equal(o[:, 0], uv[:, 0].astype(np.float32)) and np.array_equal(o[:, 2], d.astype(np.float32))
     assert hist[1] == counts[1] and hist.sum() == len(s)
+
+
+def test_long_sequence_order_and_chunk_independence():
+    """Size-independent properties on a sequence long enough to span many chunks, slots and epochs (1500 KITTI-shaped
+    frames = 12 chunks of 128 over 3 slots): (1) reversing the frame order reverses the results bit for bit -- a frame's result
+    depends neither on its position in a chunk nor on what the slot's epoch-tagged map held before; (2) a second pass over the
+    same buffers reproduces the first (the first-point-wins scatter is deterministic under any schedule); (3) sampled frames
+    equal the oracle; (4) the status histogram kernel agrees with a host count of the whole block."""
+    import torch
+
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, orc = kitti_pair(p)
+    cfg = synth.default_config()
+    n = synth.points_per_frame(cfg)
+    F, nframes = 500, 1500
+    st = torch.cuda.current_stream().cuda_stream
+    pts = torch.empty((nframes, n, 4), dtype=torch.float32, device="cuda")
+    uv = torch.empty((nframes, F, 2), dtype=torch.float64, device="cuda")
+    synth.points_device(est, cfg, 314, 0, nframes, pts.data_ptr(), stream=st)
+    synth.features_device(est, cfg, 314, 0, nframes, F, uv.data_ptr(), stream=st)
+    out = []
+    for order in ("forward", "forward", "reversed"):
+        P, U = (pts, uv) if order == "forward" else (pts.flip(0).contiguous(), uv.flip(0).contiguous())
+        depth = torch.empty((nframes, F), dtype=torch.float64, device="cuda")
+        status = torch.empty((nframes, F), dtype=torch.int32, device="cuda")
+        est.processFramesDevice(P.data_ptr(), n, n, 16, U.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes, stream=st)
+        torch.cuda.synchronize()
+        out.append((depth.flip(0) if order == "reversed" else depth, status.flip(0) if order == "reversed" else status))
+        del P, U
+    (d0, s0), (d1, s1), (d2, s2) = out
+    assert torch.equal(s0, s1) and torch.equal(d0, d1), "second pass differs from the first"
+    assert torch.equal(s0, s2) and torch.equal(d0, d2), "reversed frame order changes a frame's result"
+    for i in (0, 127, 128, 777, 1499):
+        orc.set_cloud(synth.points_host(cfg, 314, i))
+        d_ref, s_ref = orc.calculate_depth(synth.features_host(cfg, 314, i, F))
+        PU.assert_depth_status_equal(d0[i].cpu().numpy(), s0[i].cpu().numpy(), d_ref, s_ref, f"long sequence frame {i}")
+    counts = np.bincount(s0.cpu().numpy().ravel(), minlength=21)
+    assert np.array_equal(est.statusHistogramDevice(s0.data_ptr(), nframes * F, st), counts)
+    assert int(counts.sum()) == nframes * F and counts[1] > 0 and counts[2] > 0

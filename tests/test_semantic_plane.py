@@ -63,12 +63,50 @@ def test_reference_throws_pcl_invalid_without_ground_pixels():
         SP.semantic_plane(cloud, np.zeros_like(labels), F_, CU, CV, KT, gl, thr)
 
 
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libmld_ref.so not built (no /root/reference here)")
+def test_restatement_label_test_matches_the_reference_on_boundary_points():
+    """The reference does not expose the set kept by its label test, so it is probed one point at a time: a cloud of three
+    fixed ground points plus the probe is fitted only when the probe is kept (optimizeModelCoefficients needs more than 3
+    points, else the dummy model (0,0,1,0) comes back, RansacPlane.cpp:236-242)."""
+    cloud, labels = MK.semantic_boundary_cloud(3000)
+    want = np.zeros(len(cloud), bool)
+    want[SP.ground_labelled(cloud, labels, F_, CU, CV, KT, [7])] = True
+    # three ground-labelled points in front of the camera, well inside the image, |z_lidar| far above the threshold
+    Tm = np.vstack([KT[:3], [0, 0, 0, 1]])
+    Ti = np.linalg.inv(Tm)
+    anchors_cam = np.array([[(100.5 - CU) / F_ * 9, (301.5 - CV) / F_ * 9, 9], [(900.5 - CU) / F_ * 14, (333.5 - CV) / F_ * 14, 14],
+                            [(500.5 - CU) / F_ * 6, (251.5 - CV) / F_ * 6, 6]])
+    anchors = ((Ti[:3, :3] @ anchors_cam.T).T + Ti[:3, 3]).astype(np.float32)
+    assert len(SP.ground_labelled(np.c_[anchors, np.zeros(3)], labels, F_, CU, CV, KT, [7])) == 3
+    probe4 = np.zeros((4, 4), np.float32)
+    probe4[:3, :3] = anchors
+    dummy = np.array([0, 0, 1, 0], np.float32)
+    idx = np.r_[np.arange(0, 3000, 2), np.arange(3000, 3008)]
+    got = np.zeros(len(cloud), bool)
+    for i in idx:
+        probe4[3, :3] = cloud[i, :3]
+        rc, c, inl = R.semantic_plane(labels, F_, CU, CV, KT, [7], 1e-6, probe4)
+        assert rc == 0
+        got[i] = not np.array_equal(c, dummy)
+    assert np.array_equal(got[idx], want[idx]), np.nonzero(got[idx] != want[idx])[0][:10]
+    assert 100 < want[idx].sum() < len(idx) - 100
+
+
 def test_restatement_reproduces_the_frozen_reference_outputs():
     for case in (0, 1, 2):
         cloud, labels, gl, thr = MK.semantic_case(case)
         c, inl, kept, first = SP.semantic_plane(cloud, labels, F_, CU, CV, KT, gl, thr)
         assert np.array_equal(inl, G[f"sem{case}_inliers"])
         assert np.allclose(c, G[f"sem{case}_coeffs"], rtol=0, atol=2e-6)
+
+
+def _debug_projection(pts):
+    """u, v, tz of a few points the way the restatement computes them (for assertion messages)."""
+    p = pts[:, :3].astype(np.float64)
+    T = KT[:3, :4]
+    t = np.stack([((T[i, 0] * p[:, 0] + T[i, 1] * p[:, 1]) + T[i, 2] * p[:, 2]) + T[i, 3] for i in range(3)], 1).astype(np.float32).astype(np.float64)
+    with np.errstate(all="ignore"):
+        return np.stack([(F_ * t[:, 0] + CU * t[:, 2]) / t[:, 2], (F_ * t[:, 1] + CV * t[:, 2]) / t[:, 2], t[:, 2]], 1)
 
 
 def _estimator():
@@ -115,17 +153,30 @@ def test_gpu_semantic_plane_32_byte_stride_and_pcl_invalid():
 
 @pytest.mark.gpu
 def test_gpu_semantic_plane_ground_labelled_set_is_bit_exact():
-    """inlier_threshold = +inf selects every finite point in pass 2, so n_inliers counts them; the labelled set itself is
-    checked through a one-label image: with threshold 0 nothing is selected, and the first-pass model must equal the fit of
-    exactly the restatement's labelled set (coefficients to 2e-3)."""
-    cloud, labels, gl, thr = MK.semantic_case(1)
+    """The set of points kept by the label test (RansacPlane.cpp:201-222) through the kernel's two float pre-filters and the
+    guarded quotient, against the numpy restatement (itself identical to the reference's code on these inputs): sweeps,
+    plus a cloud built to sit on every decision boundary -- pixel borders, the image frame, the camera plane, points behind
+    the camera, huge / non-finite coordinates."""
     est = _estimator()
-    kept = SP.ground_labelled(cloud, labels, F_, CU, CV, KT, gl)
-    p = SemanticPlane(labels, SemanticPlane.Camera(F_, CU, CV, KT), gl, 1e30, est)
-    p.CalculateInliersPlane(cloud)
-    finite = np.nonzero(np.isfinite(cloud[:, :3]).all(axis=1))[0]
-    assert np.array_equal(p.getInlinersIndex(), finite.astype(np.int32))
-    assert len(kept) >= 3
+    cam = SemanticPlane.Camera(F_, CU, CV, KT)
+    for case in (0, 1, 2):
+        cloud, labels, gl, thr = MK.semantic_case(case)
+        sp = SemanticPlane(labels, cam, gl, thr, est)
+        got = est.semanticGroundLabelled(sp, cloud)
+        want = np.zeros(len(cloud), bool)
+        want[SP.ground_labelled(cloud, labels, F_, CU, CV, KT, gl)] = True
+        assert np.array_equal(got, want), (case, int((got != want).sum()))
+        assert want.sum() > 1000
+    # boundary cloud: projections on / next to integer pixel coordinates, the frame, the camera plane (see make_ref_golden)
+    cloud, labels = MK.semantic_boundary_cloud()
+    m = len(cloud) - 8
+    sp = SemanticPlane(labels, cam, [7], 0.1, est)
+    got = est.semanticGroundLabelled(sp, cloud)
+    want = np.zeros(len(cloud), bool)
+    want[SP.ground_labelled(cloud, labels, F_, CU, CV, KT, [7])] = True
+    bad = np.nonzero(got != want)[0]
+    assert len(bad) == 0, (len(bad), bad[:5], cloud[bad[:5]], got[bad[:5]], _debug_projection(cloud[bad[:5]]))
+    assert 5000 < want.sum() < m
 
 
 @pytest.mark.gpu
