@@ -42,6 +42,18 @@ typedef enum mld_error {
     MLD_ERR_IO = -12               /* settings file cannot be read (reference: throw "Cant find settings file") */
 } mld_error;
 
+/* Status codes written to the status outputs: Mono_Lidar::DepthResultType (eDepthResultType.h:9-31), one list for the
+ * C ABI, the kernels, mld_status_name() and the C++ shim's enum. X(name, value). */
+#define MLD_DEPTH_RESULT_TYPES(X)                                                                                              \
+    X(Unspecified, 0) X(Success, 1) X(RadiusSearchInsufficientPoints, 2) X(HistogramNoLocalMax, 3)                             \
+    X(TresholdDepthGlobalGreaterMax, 4) X(TresholdDepthGlobalSmallerMin, 5) X(TresholdDepthLocalGreaterMax, 6)                 \
+    X(TresholdDepthLocalSmallerMin, 7) X(TriangleNotPlanar, 8) X(TriangleNotPlanarInsufficientPoints, 9)                       \
+    X(CornerBehindCamera, 10) X(PlaneViewrayNotOrthogonal, 11) X(PcaIsPoint, 12) X(PcaIsLine, 13) X(PcaIsCubic, 14)            \
+    X(InsufficientRoadPoints, 15) X(SuccessRoad, 16) X(RegionGrowingNearestSeedNotAvailable, 17)                               \
+    X(RegionGrowingSeedsOutOfRange, 18) X(RegionGrowingInsufficientPoints, 19) X(SuccessRegionGrowing, 20)
+#define MLD_STATUS_ENUM_ENTRY(name, value) MLD_STATUS_##name = value,
+typedef enum mld_status { MLD_DEPTH_RESULT_TYPES(MLD_STATUS_ENUM_ENTRY) MLD_STATUS_COUNT = 21 } mld_status;
+
 /* Mono_Lidar::DepthEstimatorParameters (DepthEstimatorParameters.h:12-172): same field names,
  * bools as int32 (the reference's loader reads them as (int), DepthEstimatorParameters.cpp:27 ff.).
  * Only the fields the hot path reads are present. */

@@ -520,27 +520,10 @@ int mld_params_from_yaml(const char* path, mld_params* p) {
 
 const char* mld_status_name(int status) {
     switch (status) {
-        case 0: return "Unspecified";
-        case 1: return "Success";
-        case 2: return "RadiusSearchInsufficientPoints";
-        case 3: return "HistogramNoLocalMax";
-        case 4: return "TresholdDepthGlobalGreaterMax";
-        case 5: return "TresholdDepthGlobalSmallerMin";
-        case 6: return "TresholdDepthLocalGreaterMax";
-        case 7: return "TresholdDepthLocalSmallerMin";
-        case 8: return "TriangleNotPlanar";
-        case 9: return "TriangleNotPlanarInsufficientPoints";
-        case 10: return "CornerBehindCamera";
-        case 11: return "PlaneViewrayNotOrthogonal";
-        case 12: return "PcaIsPoint";
-        case 13: return "PcaIsLine";
-        case 14: return "PcaIsCubic";
-        case 15: return "InsufficientRoadPoints";
-        case 16: return "SuccessRoad";
-        case 17: return "RegionGrowingNearestSeedNotAvailable";
-        case 18: return "RegionGrowingSeedsOutOfRange";
-        case 19: return "RegionGrowingInsufficientPoints";
-        case 20: return "SuccessRegionGrowing";
+#define MLD_STATUS_NAME_CASE(name, value) \
+    case value: return #name;
+        MLD_DEPTH_RESULT_TYPES(MLD_STATUS_NAME_CASE)
+#undef MLD_STATUS_NAME_CASE
         default: return "unknown";
     }
 }

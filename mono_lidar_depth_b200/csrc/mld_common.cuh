@@ -14,26 +14,10 @@
 #define MLD_FULL_MASK 0xffffffffu
 #define MLD_EMPTY 0xffffffffu  // pixel-map cell without a point; reads as int32 -1 (POINT_NOT_DEFINED)
 
-// Mono_Lidar::DepthResultType, monolidar_fusion/include/monolidar_fusion/eDepthResultType.h:9-31
-enum MldStatus : int {
-    ST_Unspecified = 0,
-    ST_Success = 1,
-    ST_RadiusSearchInsufficientPoints = 2,
-    ST_HistogramNoLocalMax = 3,
-    ST_TresholdDepthGlobalGreaterMax = 4,
-    ST_TresholdDepthGlobalSmallerMin = 5,
-    ST_TresholdDepthLocalGreaterMax = 6,
-    ST_TresholdDepthLocalSmallerMin = 7,
-    ST_TriangleNotPlanar = 8,
-    ST_TriangleNotPlanarInsufficientPoints = 9,
-    ST_CornerBehindCamera = 10,
-    ST_PlaneViewrayNotOrthogonal = 11,
-    ST_PcaIsPoint = 12,
-    ST_PcaIsLine = 13,
-    ST_PcaIsCubic = 14,
-    ST_InsufficientRoadPoints = 15,
-    ST_SuccessRoad = 16
-};
+// Mono_Lidar::DepthResultType (eDepthResultType.h:9-31) as ST_<name>, from the C ABI's list
+#define MLD_ST_ENTRY(name, value) ST_##name = value,
+enum MldStatus : int { MLD_DEPTH_RESULT_TYPES(MLD_ST_ENTRY) };
+#undef MLD_ST_ENTRY
 
 enum MldRoadMode : int { ROAD_NONE = 0, ROAD_TRIANGLE = 1, ROAD_LEASTSQUARES = 2, ROAD_MESTIMATOR = 3 };
 

@@ -1,31 +1,13 @@
-// Status codes of the depth estimation, value-compatible with the reference's
-// Mono_Lidar::DepthResultType (monolidar_fusion/include/monolidar_fusion/eDepthResultType.h:9-31).
+// Mono_Lidar::DepthResultType for callers of the shim: generated from the C ABI's status list
+// (MLD_DEPTH_RESULT_TYPES in include/mld_c_api.h), which is value-compatible with the reference's enum
+// (monolidar_fusion/include/monolidar_fusion/eDepthResultType.h:9-31).
 #pragma once
+#include "mld_c_api.h"
 
 namespace Mono_Lidar {
 
-enum DepthResultType {
-    Unspecified = 0,
-    Success = 1,
-    RadiusSearchInsufficientPoints = 2,
-    HistogramNoLocalMax = 3,
-    TresholdDepthGlobalGreaterMax = 4,
-    TresholdDepthGlobalSmallerMin = 5,
-    TresholdDepthLocalGreaterMax = 6,
-    TresholdDepthLocalSmallerMin = 7,
-    TriangleNotPlanar = 8,
-    TriangleNotPlanarInsufficientPoints = 9,
-    CornerBehindCamera = 10,
-    PlaneViewrayNotOrthogonal = 11,
-    PcaIsPoint = 12,
-    PcaIsLine = 13,
-    PcaIsCubic = 14,
-    InsufficientRoadPoints = 15,
-    SuccessRoad = 16,
-    RegionGrowingNearestSeedNotAvailable = 17,
-    RegionGrowingSeedsOutOfRange = 18,
-    RegionGrowingInsufficientPoints = 19,
-    SuccessRegionGrowing = 20
-};
+#define MLD_SHIM_RESULT_TYPE(name, value) name = value,
+enum DepthResultType { MLD_DEPTH_RESULT_TYPES(MLD_SHIM_RESULT_TYPE) };
+#undef MLD_SHIM_RESULT_TYPE
 
 }  // namespace Mono_Lidar
