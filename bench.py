@@ -500,7 +500,7 @@ def run_gpu(args, rank, local_rank, world):
                              "achieved": ALGO_BYTES_PER_FRAME * (value / world) / 1e9, "frac": ALGO_BYTES_PER_FRAME * (value / world) / 1e9 / peak,
                              "note": "whole hot path per GPU: B * frames/s against the same peak"}}
         traffic_file = ROOT / "profiles" / "traffic.json"
-        if roof and traffic_file.exists():
+        if roof and traffic_file.exists() and WORKLOAD == "kitti":  # the committed ncu launch list is of the headline workload
             try:
                 tr = json.loads(traffic_file.read_text())
                 roof["traffic"] = tr.get(dom, {}).get("dram_bytes_per_launch")
