@@ -367,7 +367,7 @@ def run_gpu(args, rank, local_rank, world):
     clocks.start()
     time.sleep(0.3)
     launches0 = est.kernelLaunchCount()
-    est.profileEnable(True)
+    est.profileEnable(not os.environ.get("MLD_BENCH_NO_PROF"))  # event brackets per launch group (a few % of the step)
     est.profileRead()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -467,16 +467,23 @@ def run_gpu(args, rank, local_rank, world):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        chunk = est.chunkFrames()
+        # device-resident non-road sequences run K1 of chunk j and the gather of chunk j-1 as ONE launch
+        fused = est.fusedChunkFrames() if not use_road else 0
+        chunk = fused or est.chunkFrames()
         per_class = {}
         for name, (ms, ln) in prof.items():
             per_class[name] = {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None}
         # dominant kernel of the step and its algorithmic bytes per launch (DESIGN.md "roofline")
         # single kernels only: feature_depth is the sum of feature_gather + feature_solve + feature_rest (road kernels and the
         # overflow pass), listed for the share of the step but not a kernel of its own
-        kernels = {k: v for k, v in per_class.items() if k in ("project_scatter", "feature_gather", "feature_solve") and v["launches"]}
-        per_class["note"] = ("durations are bracketed by CUDA events on each chunk's stream inside the timed region; chunks run on "
-                             "3 overlapping streams, so a kernel's duration includes time shared with the other chunks' kernels")
+        if fused:
+            per_class["fused_project_gather"] = per_class.pop("project_scatter")
+            per_class.pop("feature_gather", None)
+        kernels = {k: v for k, v in per_class.items()
+                   if k in ("project_scatter", "fused_project_gather", "feature_gather", "feature_solve") and v["launches"] and v["ms_total"] > 0}
+        per_class["note"] = ("durations are bracketed by CUDA events on the launching streams inside the timed region; launches of different "
+                             "chunks overlap (front stream: fused K1 + gather launches; slot streams: solve + overflow pass), so a kernel's "
+                             "duration includes time shared with other kernels; in the fused pipeline every 4th launch group is sampled")
         dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
         roof = None
         if dom:
@@ -484,10 +491,12 @@ def run_gpu(args, rank, local_rank, world):
             # K1 owns the point stream and the pixel map (written once per frame in the reference's accounting; the
             # epoch-tagged map makes the actual clear traffic ~0), K2 the feature reads and the result writes
             per_frame_bytes = {"project_scatter": 16 * N_POINTS + 4 * IMG_W * IMG_H, "feature_gather": 16 * N_FEATURES,
+                               "fused_project_gather": 16 * N_POINTS + 4 * IMG_W * IMG_H + 16 * N_FEATURES,
                                "feature_solve": 12 * N_FEATURES}[dom]
             avg_s = per_class[dom]["avg_launch_ms"] * 1e-3
             achieved = per_frame_bytes * frames_per_launch / avg_s / 1e9
-            sampled_ms = sum(v["ms_total"] for k, v in per_class.items() if isinstance(v, dict) and k in ("map_clear", "project_scatter", "ransac", "feature_depth"))
+            sampled_ms = sum(v["ms_total"] for k, v in per_class.items()
+                             if isinstance(v, dict) and k in ("map_clear", "project_scatter", "fused_project_gather", "ransac", "feature_depth"))
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,
@@ -495,7 +504,8 @@ def run_gpu(args, rank, local_rank, world):
                     "per_kernel": per_class,
                     "algorithmic_bytes_split": "SURVEY.md 8(d): B = 16 N + 4 W H + 28 F per frame; project_scatter owns 16 N + 4 W H (point stream + "
                                                "one write per map cell; the epoch-tagged map replaces the physical clear, so its DRAM traffic is "
-                                               "below this figure), feature_gather 16 F (feature reads), feature_solve 12 F (result writes)",
+                                               "below this figure), feature_gather 16 F (feature reads), feature_solve 12 F (result writes); "
+                                               "fused_project_gather = project_scatter of one chunk + feature_gather of the previous one in one launch",
                     "path": {"algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
                              "achieved": ALGO_BYTES_PER_FRAME * (value / world) / 1e9, "frac": ALGO_BYTES_PER_FRAME * (value / world) / 1e9 / peak,
                              "note": "whole hot path per GPU: B * frames/s against the same peak"}}

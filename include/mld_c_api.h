@@ -252,6 +252,9 @@ int mld_profile_enable(mld_handle* h, int on);
 int mld_profile_read(mld_handle* h, double* ms7, int64_t* launches7, int64_t* frames_sampled);
 /* frames processed per kernel launch in the batched paths (env MLD_CHUNK_FRAMES, default 16) */
 int mld_chunk_frames(const mld_handle* h);
+/* frames per fused K1 + gather launch of device-resident non-road sequences (env MLD_FUSE_CHUNK, default 512), or 0 when
+ * the fused pipeline is off (MLD_FUSE=0 or another K2 mode): such sequences then use mld_chunk_frames() like the rest */
+int mld_fused_chunk_frames(const mld_handle* h);
 /* largest neighbour count per feature the kernels were built for */
 int mld_neighbor_capacity(void);
 

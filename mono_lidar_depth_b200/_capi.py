@@ -183,6 +183,7 @@ SYMBOLS = {
     "mld_neighbor_capacity": (C.c_int, []),
     "mld_profile_enable": (C.c_int, [_H, C.c_int]),
     "mld_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "mld_fused_chunk_frames": (C.c_int, [_H]),
     "mld_chunk_frames": (C.c_int, [_H]),
     "mld_get_pixel_map": (C.c_int, [_H, C.c_void_p]),
     "mld_get_neighbors": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),

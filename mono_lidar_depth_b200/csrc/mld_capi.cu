@@ -83,6 +83,8 @@ struct mld_handle {
     int feature_mode = 2;
     int overflow_blocks = 296;
     bool use_tagged_maps = true;
+    bool fuse_k1_gather = true;     // K1 of chunk j and the gather of chunk j-1 in one heterogeneous launch (MLD_FUSE=0: off)
+    int fuse_chunk = 512;           // frames per fused launch (MLD_FUSE_CHUNK)
     int k1_persist_per_sm = 0;
     int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
     int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
@@ -298,6 +300,24 @@ void ground_label_set(const int32_t* labels, int n, unsigned int set8[8]) {
 }
 
 
+// profiling: the event set of the next sampled chunk (nullptr when profiling is off or the pool is exhausted)
+int prof_acquire(mld_handle* h, int frames, cudaEvent_t** out) {
+    *out = nullptr;
+    if (!h->prof_on || h->prof_used >= MLD_PROF_MAX_CHUNKS) return MLD_OK;
+    if (h->prof_events.size() < (h->prof_used + 1) * MLD_PROF_EVENTS) {
+        for (int q = 0; q < MLD_PROF_EVENTS; q++) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->prof_events.push_back(e);
+        }
+        h->prof_frames.push_back(0);
+        h->prof_ransac_launches.push_back(0);
+    }
+    *out = &h->prof_events[h->prof_used * MLD_PROF_EVENTS];
+    h->prof_frames[h->prof_used] = frames;
+    h->prof_ransac_launches[h->prof_used] = 0;
+    return MLD_OK;
+}
 // one chunk of frames on one stream: [clear maps], K1, [K4], K2
 int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, long long n_points, long long pitch_pts,
                   int stride_f, const double* d_uv, int F, double* d_depth, int* d_status, int frames, int road, uint64_t seed,
@@ -306,20 +326,8 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     const bool two = st_k2 != nullptr && st_k2 != st;
     cudaStream_t sb = two ? st_k2 : st;
     cudaEvent_t* ev = nullptr;
-    if (h->prof_on && h->prof_used < MLD_PROF_MAX_CHUNKS) {
-        if (h->prof_events.size() < (h->prof_used + 1) * MLD_PROF_EVENTS) {
-            for (int q = 0; q < MLD_PROF_EVENTS; q++) {
-                cudaEvent_t e;
-                CK(cudaEventCreate(&e));
-                h->prof_events.push_back(e);
-            }
-            h->prof_frames.push_back(0);
-            h->prof_ransac_launches.push_back(0);
-        }
-        ev = &h->prof_events[h->prof_used * MLD_PROF_EVENTS];
-        h->prof_frames[h->prof_used] = frames;
-        h->prof_ransac_launches[h->prof_used] = 0;
-    }
+    int rcp = prof_acquire(h, frames, &ev);
+    if (rcp) return rcp;
     if (two) CK(cudaStreamWaitEvent(st, s.ev_k2, 0));  // the slot's maps are free once its previous chunk's K2 has finished
     if (ev) CK(cudaEventRecord(ev[0], st));
     MapCode mc;
@@ -563,6 +571,10 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "split") == 0) h->feature_mode = 2;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
+    env = getenv("MLD_FUSE");          // "0": separate K1 / gather launches for device-resident non-road sequences too
+    if (env) h->fuse_k1_gather = atoi(env) != 0;
+    env = getenv("MLD_FUSE_CHUNK");
+    if (env && atoi(env) > 0) h->fuse_chunk = atoi(env);
     env = getenv("MLD_K1_PERSIST");    // blocks per SM of the persistent K1 grid (0 = one block per tile)
     if (env && atoi(env) >= 0) h->k1_persist_per_sm = atoi(env);
     env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
@@ -710,6 +722,7 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
 
 int mld_neighbor_capacity(void) { return 1024; }
 int mld_chunk_frames(const mld_handle* h) { return h ? h->chunk_frames : 0; }
+int mld_fused_chunk_frames(const mld_handle* h) { return (h && h->fuse_k1_gather && h->feature_mode == 2 && h->overlap_slots >= 2) ? h->fuse_chunk : 0; }
 
 int mld_profile_enable(mld_handle* h, int on) {
     if (!h) return MLD_ERR_INVALID_ARG;
@@ -966,6 +979,90 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
     return MLD_OK;
 }
 
+// Device-resident non-road sequence with K1 of chunk j and the gather of chunk j-1 in ONE launch on the front stream
+// (slot 0's ev_k1/ev_k2 streams are not involved): front stream = clears + fused launches in chunk order; the solve and the
+// overflow pass of a chunk run on its slot's stream under the next fused launch. A slot (maps, occupancy, survivor lists)
+// is reused by chunk j once chunk j - nslots has finished its overflow pass (which still reads the maps).
+static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t n_points, int64_t frame_pitch_points, int stride_f,
+                                       const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int chunk,
+                                       cudaStream_t st) {
+    const int nslots = h->overlap_slots < 2 ? 2 : h->overlap_slots;
+    const int64_t nchunks = (nframes + chunk - 1) / chunk;
+    cudaStream_t front = h->st_lo;
+    CK(cudaEventRecord(h->ev_fork, st));
+    CK(cudaStreamWaitEvent(front, h->ev_fork, 0));
+    for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
+    for (int i = 0; i < nslots; i++) CK(ensure(h->slots[i].d_split, h->slots[i].split_bytes, mld_split_scratch_bytes((long long)chunk * F, 0)));
+    for (int64_t j = 0; j <= nchunks; j++) {
+        const bool have_k1 = j < nchunks, have_g = j >= 1;
+        Slot* sk = have_k1 ? &h->slots[j % nslots] : nullptr;
+        Slot* sg = have_g ? &h->slots[(j - 1) % nslots] : nullptr;
+        const int64_t f0k = j * chunk, f0g = (j - 1) * chunk;
+        const int ck = have_k1 ? (int)std::min<int64_t>(chunk, nframes - f0k) : 0;
+        const int cg = have_g ? (int)std::min<int64_t>(chunk, nframes - f0g) : 0;
+        MapCode mck{0u, 0u};
+        // profiling brackets of this launch group: [0,1] clears, [1,2] the fused launch (reported as the K1 class), [6,7] the
+        // solve, [7,5] the overflow pass; the gather has no bracket of its own ([4,6] is empty)
+        // (every 4th full launch group is sampled: the timing events cost ~4 % of the step when every group carries them)
+        cudaEvent_t* ev = nullptr;
+        if (have_k1 && have_g && (j & 3) == 1) {
+            int rcp = prof_acquire(h, ck, &ev);
+            if (rcp) return rcp;
+        }
+        if (have_k1 && j >= nslots) CK(cudaStreamWaitEvent(front, sk->done, 0));  // chunk j - nslots has left the slot
+        if (ev) CK(cudaEventRecord(ev[0], front));
+        if (have_k1) {
+            int rcm = begin_maps(h, *sk, ck, n_points, front, mck);
+            if (rcm) return rcm;
+            sk->mc = mck;
+        }
+        if (have_g) CK(cudaMemsetAsync(sg->d_ovf, 0, sizeof(int), front));
+        if (ev) CK(cudaEventRecord(ev[1], front));
+        int nl = 0;
+        CK(mld_launch_fused_project_gather(h->dp, stride_f, mck, have_k1 ? pts + f0k * frame_pitch_points * stride_f : nullptr, n_points,
+                                           frame_pitch_points, have_k1 ? sk->d_maps : nullptr, have_k1 ? sk->d_occ : nullptr, ck,
+                                           have_g ? sg->mc : mck, have_g ? pts + f0g * frame_pitch_points * stride_f : nullptr,
+                                           have_g ? sg->d_maps : nullptr, have_g ? sg->d_occ : nullptr,
+                                           have_g ? d_uv + f0g * (int64_t)F * 2 : nullptr, F, have_g ? d_depth + f0g * (int64_t)F : nullptr,
+                                           have_g ? d_status + f0g * (int64_t)F : nullptr, cg, have_g ? sg->d_ovf + 1 : nullptr,
+                                           have_g ? sg->d_ovf : nullptr, have_g ? sg->d_split : nullptr, front, &nl));
+        h->launches += nl;
+        if (ev) CK(cudaEventRecord(ev[2], front));
+        cudaStream_t s2 = have_g ? sg->stream : front;
+        if (have_g) {
+            CK(cudaEventRecord(sg->ev_k1, front));
+            CK(cudaStreamWaitEvent(sg->stream, sg->ev_k1, 0));
+        }
+        if (ev) {
+            CK(cudaEventRecord(ev[3], s2));
+            CK(cudaEventRecord(ev[4], s2));
+            CK(cudaEventRecord(ev[6], s2));
+        }
+        if (have_g) {
+            int nl2 = 0;
+            CK(mld_launch_feature_solve(h->dp, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F, cg,
+                                        sg->d_split, sg->stream, &nl2));
+            if (ev) CK(cudaEventRecord(ev[7], sg->stream));
+            CK(mld_launch_feature_depth(h->dp, sg->mc, h->kcap, pts + f0g * frame_pitch_points * stride_f, stride_f, frame_pitch_points,
+                                        sg->d_maps, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F,
+                                        nullptr, nullptr, (n_points + 31) / 32, cg, sg->d_ovf + 1, sg->d_ovf, overflow_grid(h, *sg), sg->stream));
+            CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, sg->stream));
+            if (ev) CK(cudaEventRecord(ev[5], sg->stream));
+            CK(cudaEventRecord(sg->done, sg->stream));
+            h->launches += nl2 + 1;
+        } else if (ev) {
+            CK(cudaEventRecord(ev[7], s2));
+            CK(cudaEventRecord(ev[5], s2));
+        }
+        if (ev) h->prof_used++;
+    }
+    for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(st, h->slots[i].done, 0));
+    CK(cudaEventRecord(h->ev_join, front));
+    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
+    h->have_cloud = false;
+    return MLD_OK;
+}
+
 static int process_frames_device_impl(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
                                       const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
                                       uint64_t seed, float* d_plane_coeffs_out, void* stream, const PlaneSrc* src) {
@@ -988,8 +1085,10 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     DeviceGuard g(h->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // short sequences are cut into at least `overlap_slots` chunks so that the streams still overlap
-    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(h->chunk_frames, std::max<int64_t>(8, (nframes + h->overlap_slots - 1) / h->overlap_slots)));
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
+    const bool fused_ok = h->fuse_k1_gather && !use_road && !src && h->feature_mode == 2 && h->overlap_slots >= 2 && F > 0 && n_points > 0;
+    const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(fused_ok ? h->fuse_chunk : h->chunk_frames,
+                                                                  std::max<int64_t>(8, (nframes + h->overlap_slots - 1) / h->overlap_slots)));
     const int64_t nchunks = (nframes + chunk - 1) / chunk;
     // K1 is issue/DRAM bound, K2 latency bound: chunks alternate over `nslots` slots (own maps + stream) so
     // that K1 of one chunk runs under K2 of the previous one. Fork from / join into the caller's stream.
@@ -1000,6 +1099,8 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
+    if (fused_ok && nchunks >= 2 && nslots >= 2)
+        return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st);
     const bool prio = nslots > 1 && h->overlap_mode == 1;
     if (nslots > 1) {
         CK(cudaEventRecord(h->ev_fork, st));

@@ -21,6 +21,7 @@
 #include "mld_geometry.cuh"
 #include "mld_kernels.h"
 #include "mld_thread_helpers.cuh"
+#include "mld_project.cuh"
 
 namespace {
 
@@ -44,21 +45,22 @@ constexpr int SBT_C = 64;   // threads per block, road
 __device__ __forceinline__ unsigned int pack_rec(int k, long long o) { return ((unsigned int)k << 27) | (unsigned int)o; }
 
 // ---- K2a ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SBT_A)
-feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
-                      const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
-                      const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
-                      int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
-                      double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap) {
+// one block of SBT_A features of `frame` (bx = block index inside the frame)
+__device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& mc, const float* __restrict__ pts, int stride_f,
+                                             long long pitch_pts, const unsigned int* __restrict__ maps,
+                                             const unsigned int* __restrict__ occs, const double* __restrict__ uv, int F,
+                                             double* __restrict__ depth, int* __restrict__ status, int* __restrict__ overflow_list,
+                                             int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
+                                             double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap, int bx,
+                                             long long frame) {
     __shared__ int s_aux[SCAP * SBT_A];
     __shared__ int s_hist[SCAP + 1], s_start[SCAP + 2], s_off[SCAP + 1];
     __shared__ unsigned char s_order[SBT_A];
     __shared__ int s_base;
     static_assert(SBT_A <= 256, "s_order holds thread ids in a byte");
     const int tid = threadIdx.x;
-    const int fi = blockIdx.x * SBT_A + tid;
+    const int fi = bx * SBT_A + tid;
     const bool valid = fi < F;
-    const long long frame = blockIdx.y;
     const long long o = frame * (long long)F + fi;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
@@ -195,6 +197,65 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
             dst[2 * cap] = c.z;
         }
     }
+}
+
+__global__ void __launch_bounds__(SBT_A)
+feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, long long pitch_pts,
+                      const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
+                      const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
+                      int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
+                      double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap) {
+    gather_block(P, mc, pts, stride_f, pitch_pts, maps, occs, uv, F, depth, status, overflow_list, overflow_count, surv_rec, surv_xyz,
+                 surv_count, cap, (int)blockIdx.x, (long long)blockIdx.y);
+}
+
+// ---- K1 of one chunk and K2a of the previous chunk in ONE launch ------------------------------------------------
+// Both are latency bound and independent of each other (different map slots); on separate streams the hardware runs
+// them mostly back to back because K1's grid fills every SM. Here every `period`-th block is a gather block, so the two
+// kinds are co-resident in a fixed ratio for the whole launch and cover each other's memory stalls.
+struct FusedK1 {
+    MapCode mc;
+    const float* pts;
+    int n;
+    long long pitch_pts;
+    unsigned int* maps;
+    unsigned int* occ;
+    int tiles_per_frame;
+};
+struct FusedGather {
+    MapCode mc;
+    const float* pts;
+    long long pitch_pts;
+    const unsigned int* maps;
+    const unsigned int* occs;
+    const double* uv;
+    int F;
+    double* depth;
+    int* status;
+    int* overflow_list;
+    int* overflow_count;
+    unsigned int* surv_rec;
+    double* surv_xyz;
+    int* surv_count;
+    long long cap;
+    int blocks_per_frame;
+};
+static_assert(SBT_A == K1_THREADS, "the fused launch uses one block size for both roles");
+
+__global__ void __launch_bounds__(SBT_A)
+fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g, int k1_blocks, int g_blocks, int period) {
+    const int b = (int)blockIdx.x;
+    const int gi = b / period;
+    if (b % period == period - 1 && gi < g_blocks) {  // uniform per block
+        const int frame = gi / g.blocks_per_frame;
+        gather_block(P, g.mc, g.pts, stride_f, g.pitch_pts, g.maps, g.occs, g.uv, g.F, g.depth, g.status, g.overflow_list, g.overflow_count,
+                     g.surv_rec, g.surv_xyz, g.surv_count, g.cap, gi - frame * g.blocks_per_frame, (long long)frame);
+        return;
+    }
+    const int ki = b - min(g_blocks, gi);  // gather blocks with a smaller block index: min(g_blocks, b / period)
+    if (ki >= k1_blocks) return;
+    const int frame = ki / a.tiles_per_frame;
+    k1_tile(P, a.mc, a.pts, stride_f, a.n, a.pitch_pts, a.maps, a.occ, (unsigned int)frame, ki - frame * a.tiles_per_frame);
 }
 
 // ---- K2b ------------------------------------------------------------------------------------------
@@ -455,6 +516,79 @@ size_t mld_split_scratch_bytes(long long features, int road) {
     // reuses the arrays for its own (rarer, up to RCAP-entry) survivors
     const int entries = road ? (SCAP > RCAP ? SCAP : RCAP) : SCAP;
     return 64 + (size_t)features * (sizeof(unsigned int) + sizeof(int)) + (size_t)features * entries * 3 * sizeof(double) + 256;
+}
+
+namespace {
+struct SplitLayout {
+    int *surv_count, *road_count, *rs_count, *road_list;
+    unsigned int* surv_rec;
+    double* surv_xyz;
+};
+SplitLayout split_layout(void* d_scratch, long long features) {
+    unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
+    SplitLayout L;
+    L.surv_count = reinterpret_cast<int*>(base);
+    L.road_count = L.surv_count + 1;
+    L.rs_count = L.surv_count + 2;
+    L.surv_rec = reinterpret_cast<unsigned int*>(base + 64);
+    L.road_list = reinterpret_cast<int*>(L.surv_rec + features);
+    size_t off = 64 + (size_t)features * 8;
+    off = (off + 255) & ~(size_t)255;
+    L.surv_xyz = reinterpret_cast<double*>(base + off);
+    return L;
+}
+}  // namespace
+
+// K1 of (frames_k1 frames at d_pts_k1 into maps_k1 / occ_k1) together with the gather of a previous chunk (frames_g frames
+// whose maps are complete). Either part may be empty (frames_* == 0): the first launch of a sequence has no gather, the
+// last no K1. The gather's counters are zeroed here. Non-road path only.
+cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, const MapCode& mc_k1, const float* d_pts_k1, long long n_points,
+                                            long long pitch_pts, unsigned int* d_maps_k1, unsigned int* d_occ_k1, int frames_k1,
+                                            const MapCode& mc_g, const float* d_pts_g, const unsigned int* d_maps_g,
+                                            const unsigned int* d_occ_g, const double* d_uv_g, int F, double* d_depth_g, int* d_status_g,
+                                            int frames_g, int* d_overflow_list, int* d_overflow_count, void* d_scratch_g,
+                                            cudaStream_t stream, int* launches) {
+    const long long tiles = (n_points + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT);
+    const long long k1_blocks = (frames_k1 > 0 && n_points > 0) ? tiles * frames_k1 : 0;
+    const long long gbpf = (F + SBT_A - 1) / SBT_A;
+    const long long g_blocks = (frames_g > 0 && F > 0) ? gbpf * frames_g : 0;
+    if (k1_blocks + g_blocks == 0) return cudaSuccess;
+    if (k1_blocks + g_blocks > 0x7fffffffLL || n_points > 0x7fffffffLL / 8) return cudaErrorInvalidValue;
+    const long long features = (long long)frames_g * F;
+    if (features >= (1ll << 27)) return cudaErrorInvalidValue;
+    FusedK1 a{mc_k1, d_pts_k1, (int)n_points, pitch_pts, d_maps_k1, d_occ_k1, (int)std::max<long long>(tiles, 1)};
+    FusedGather g{};
+    g.blocks_per_frame = (int)std::max<long long>(gbpf, 1);
+    if (g_blocks > 0) {
+        const SplitLayout L = split_layout(d_scratch_g, features);
+        cudaError_t e = cudaMemsetAsync(L.surv_count, 0, 3 * sizeof(int), stream);
+        if (e != cudaSuccess) return e;
+        g = FusedGather{mc_g, d_pts_g, pitch_pts, d_maps_g, d_occ_g, d_uv_g, F, d_depth_g, d_status_g, d_overflow_list, d_overflow_count,
+                        L.surv_rec, L.surv_xyz, L.surv_count, features, (int)gbpf};
+    }
+    // one gather block after every (period - 1) K1 blocks; when there are fewer K1 blocks than that the gather blocks simply
+    // come every second block and the K1 blocks run out first
+    int period = k1_blocks == 0 ? 1 : 2;
+    if (g_blocks > 0 && k1_blocks / g_blocks >= 1) period = (int)std::min<long long>(k1_blocks / g_blocks + 1, 1 << 20);
+    // every block index must map to a role: gather blocks sit at b = period*gi + period-1, so the grid must reach the last one
+    const long long need = std::max(k1_blocks + g_blocks, g_blocks > 0 ? (long long)period * g_blocks : 0);
+    if (need > 0x7fffffffLL) return cudaErrorInvalidValue;
+    fused_project_gather_kernel<<<(unsigned)need, SBT_A, 0, stream>>>(P, stride_f, a, g, (int)k1_blocks, (int)g_blocks, period);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
+}
+
+// K2b alone on the survivors a gather (fused or not) left in d_scratch; non-road path
+cudaError_t mld_launch_feature_solve(const DevParams& P, const double* d_uv, int F, double* d_depth, int* d_status, int nframes,
+                                     void* d_scratch, cudaStream_t stream, int* launches) {
+    if (F <= 0 || nframes <= 0) return cudaSuccess;
+    const long long features = (long long)nframes * F;
+    const SplitLayout L = split_layout(d_scratch, features);
+    const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
+    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, L.surv_rec, L.surv_xyz, L.surv_count, features, 0, L.road_list,
+                                                  L.road_count);
+    if (launches) (*launches)++;
+    return cudaGetLastError();
 }
 
 cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,

@@ -18,118 +18,14 @@
 // two FP64 divisions whose truncated results index the map.
 #include "mld_common.cuh"
 #include "mld_kernels.h"
+#include "mld_project.cuh"
 
 namespace {
-
-#ifndef MLD_K1_THREADS
-#define MLD_K1_THREADS 128
-#endif
-#ifndef MLD_K1_PPT
-#define MLD_K1_PPT 8
-#endif
-#ifndef MLD_K1_MINBLOCKS
-#define MLD_K1_MINBLOCKS 1
-#endif
-constexpr int K1_THREADS = MLD_K1_THREADS;
-constexpr int K1_PPT = MLD_K1_PPT;  // points per thread: independent 16-byte loads in flight
-
-// exact projection of one point; returns false when the point is culled, else its image coordinates and camera-frame point
-__device__ __forceinline__ bool project_uv(const DevParams& P, float x, float y, float z, bool need_front, double& u, double& v, D3& c);
-
-// exact projection of one point; returns false when the point does not enter the map, else its pixel
-__device__ __forceinline__ bool project_pixel(const DevParams& P, float x, float y, float z, bool need_front, int& px, int& py) {
-    double u, v;
-    D3 c;
-    if (!project_uv(P, x, y, z, need_front, u, v, c)) return false;
-    px = (int)u;  // int x_img = u; int y_img = v (NeighborFinderPixel.cpp:41-42)
-    py = (int)v;
-    return true;
-}
-
-__device__ __forceinline__ bool project_uv(const DevParams& P, float x, float y, float z, bool need_front, double& u, double& v, D3& c) {
-    c = lidar_to_cam(P, x, y, z);
-    // the map only accepts points in front of the camera (NeighborFinderPixel.cpp:51)
-    if (need_front && !(c.z > 0.0)) return false;
-    // K * p with K = [f 0 cx; 0 f cy; 0 0 1] (camera_pinhole.h:88), then colwise().hnormalized() = division by the third
-    // row (:90). Eigen's product also adds the terms 0*X, 0*Y: they are +-0 for finite coordinates and change no value
-    // (at most the sign of a zero numerator, which fails u > 0 / v > 0 either way); for non-finite coordinates they make
-    // the quotient NaN, and so does the division below (inf/inf) or the point fails the bounds as +-inf. Left out.
-    const double q0 = __dadd_rn(__dmul_rn(P.f, c.x), __dmul_rn(P.cx, c.z));
-    const double q1 = __dadd_rn(__dmul_rn(P.f, c.y), __dmul_rn(P.cy, c.z));
-    u = __ddiv_rn(q0, c.z);
-    v = __ddiv_rn(q1, c.z);
-    bool in_range = (u >= 0.) && (u <= P.Wd) && (v >= 0.) && (v <= P.Hd);  // camera_pinhole.h:93-96
-    bool visible = (u > 0.) && (u < P.Wd) && (v > 0.) && (v < P.Hd);       // DepthEstimator.cpp:186-187
-    return in_range && visible;
-}
-
-// FP32 pre-filter: true when the point certainly fails one of  z_cam > 0, u > 0, u < W, v > 0, v < H
-// (or is not finite, which fails all of them in the exact path as well).
-__device__ __forceinline__ float pf_form(const DevParams& P, int k, float x, float y, float z) {
-    return fmaf(P.pf_g[k][0], x, fmaf(P.pf_g[k][1], y, fmaf(P.pf_g[k][2], z, P.pf_h[k])));
-}
-__device__ __forceinline__ bool surely_outside(const DevParams& P, float x, float y, float z) {
-    const float S = fabsf(x) + fabsf(y) + fabsf(z);
-    // tests ordered by how much of a 360-degree sweep they remove; a sweep is azimuth ordered, so the early exits are
-    // nearly warp uniform. Each test is written so that a NaN (dropout) is rejected by the first one; an infinite
-    // coordinate is rejected here or, failing that, by the exact path -- a rejection is only ever a shortcut.
-    if (!(pf_form(P, 0, x, y, z) + fmaf(P.pf_G[0], S, P.pf_H[0]) >= 0.f)) return true;  // z_cam < 0
-    if (!(pf_form(P, 1, x, y, z) + fmaf(P.pf_G[1], S, P.pf_H[1]) >= 0.f)) return true;  // f*X + cx*Z < 0      <=> u < 0
-    if (!(pf_form(P, 2, x, y, z) - fmaf(P.pf_G[2], S, P.pf_H[2]) <= 0.f)) return true;  // f*X + (cx-W)*Z > 0  <=> u > W
-    if (!(pf_form(P, 3, x, y, z) + fmaf(P.pf_G[3], S, P.pf_H[3]) >= 0.f)) return true;  // f*Y + cy*Z < 0      <=> v < 0
-    if (!(pf_form(P, 4, x, y, z) - fmaf(P.pf_G[4], S, P.pf_H[4]) <= 0.f)) return true;  // f*Y + (cy-H)*Z > 0  <=> v > H
-    return false;
-}
-
-// pre-filter, exact projection and scatter of the K1_PPT points a thread holds in registers
-__device__ __forceinline__ void scatter_points(const DevParams& P, const float4 (&p)[K1_PPT], int base, int n, unsigned int hi,
-                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch) {
-#pragma unroll
-    for (int j = 0; j < K1_PPT; j++) {
-        const int i = base + j * K1_THREADS;
-        if (i >= n) break;
-        if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
-#ifdef MLD_DIAG_NOFP64
-        if (p[j].x == 123456.f) map[0] = 1;  // diagnostic build: keep the loads alive, skip the exact path
-        continue;
-#endif
-        int x, y;
-        if (!project_pixel(P, p[j].x, p[j].y, p[j].z, true, x, y)) continue;
-#ifdef MLD_DIAG_NOATOM
-        if (x == -5) map[0] = 1;  // diagnostic build: no scatter
-        continue;
-#endif
-        atomicMin(&map[y * P.W + x], hi | (unsigned int)i);
-        if (ob) {
-            unsigned int* orow = ob + y * occ_pitch;
-            const int wj = x >> 4, b = x & 15;
-            atomicOr(orow + wj, 1u << b);
-            if (wj > 0) atomicOr(orow + wj - 1, 1u << (16 + b));
-        }
-    }
-}
 
 __global__ void __launch_bounds__(K1_THREADS, MLD_K1_MINBLOCKS)
 project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                        unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
-    const unsigned int frame = blockIdx.y;
-    const int occ_pitch = occ_words_per_row(P.W);
-    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
-    const int base = blockIdx.x * (K1_THREADS * K1_PPT) + threadIdx.x;
-    const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
-    const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
-    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
-
-    float4 p[K1_PPT];
-#pragma unroll
-    for (int j = 0; j < K1_PPT; j++) {
-        if (base + j * K1_THREADS < n)
-            p[j] = ld_stream_f4(src + j * step);
-        else
-            p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    scatter_points(P, p, base, n, hi, map, ob, occ_pitch);
+    k1_tile(P, mc, pts, stride_f, n, pitch_pts, maps, occ, blockIdx.y, (int)blockIdx.x);
 }
 
 // Persistent variant: gridDim.x blocks loop over the (frame, tile) pairs of the chunk with the next tile's loads

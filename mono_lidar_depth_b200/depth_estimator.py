@@ -476,6 +476,10 @@ class DepthEstimator:
         names = ("map_clear", "project_scatter", "ransac", "feature_depth", "feature_gather", "feature_solve", "feature_rest")
         return {n: (ms[i], ln[i]) for i, n in enumerate(names)}, fr.value
 
+    def fusedChunkFrames(self) -> int:
+        """Frames per fused K1 + gather launch of device-resident non-road sequences, 0 when that pipeline is off."""
+        return int(self._lib.mld_fused_chunk_frames(self._h))
+
     def chunkFrames(self) -> int:
         return int(self._lib.mld_chunk_frames(self._h))
 

@@ -464,3 +464,36 @@ def test_long_sequence_order_and_chunk_independence():
     counts = np.bincount(s0.cpu().numpy().ravel(), minlength=21)
     assert np.array_equal(est.statusHistogramDevice(s0.data_ptr(), nframes * F, st), counts)
     assert int(counts.sum()) == nframes * F and counts[1] > 0 and counts[2] > 0
+
+
+def test_fused_and_separate_launch_pipelines_agree(monkeypatch):
+    """Device-resident non-road sequences run K1 of chunk j and the gather of chunk j-1 as one heterogeneous launch (default);
+    MLD_FUSE=0 keeps separate launches on per-chunk streams. Same results bit for bit, for chunk counts that exercise the
+    first (K1 only) and last (gather only) launch, slot reuse, a ragged last chunk and a features-heavy block ratio."""
+    import torch
+
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    cfg = synth.default_config()
+    n = synth.points_per_frame(cfg)
+    st = torch.cuda.current_stream().cuda_stream
+    for F, nframes, chunk in ((700, 50, 8), (2000, 29, 512), (9000, 31, 8)):
+        outs = []
+        for fuse in ("1", "0"):
+            monkeypatch.setenv("MLD_FUSE", fuse)
+            monkeypatch.setenv("MLD_FUSE_CHUNK", str(chunk))
+            monkeypatch.setenv("MLD_CHUNK_FRAMES", str(chunk))
+            est, _ = kitti_pair(p)
+            assert (est.fusedChunkFrames() > 0) == (fuse == "1")
+            pts = torch.empty((nframes, n, 4), dtype=torch.float32, device="cuda")
+            uv = torch.empty((nframes, F, 2), dtype=torch.float64, device="cuda")
+            depth = torch.full((nframes, F), -7.0, dtype=torch.float64, device="cuda")
+            status = torch.full((nframes, F), -7, dtype=torch.int32, device="cuda")
+            synth.points_device(est, cfg, 77, 0, nframes, pts.data_ptr(), stream=st)
+            synth.features_device(est, cfg, 77, 0, nframes, F, uv.data_ptr(), stream=st)
+            for _ in range(2):  # twice: the second pass reuses slots whose maps carry the first pass's epochs
+                est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes, stream=st)
+            torch.cuda.synchronize()
+            outs.append((depth.cpu().numpy(), status.cpu().numpy()))
+        assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0]), (F, nframes, chunk)
+        assert outs[0][1].min() >= 1  # every feature got a status
