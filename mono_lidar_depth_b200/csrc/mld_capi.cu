@@ -85,6 +85,7 @@ struct mld_handle {
     bool use_tagged_maps = true;
     bool fuse_k1_gather = true;     // K1 of chunk j and the gather of chunk j-1 in one heterogeneous launch (MLD_FUSE=0: off)
     int fuse_chunk = 512;           // frames per fused launch (MLD_FUSE_CHUNK)
+    bool fuse_serial = false;       // MLD_FUSE_SERIAL=1: solve + overflow pass on the front stream too (no concurrency at all)
     int k1_persist_per_sm = 0;
     int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
     int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
@@ -573,6 +574,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
     env = getenv("MLD_FUSE");          // "0": separate K1 / gather launches for device-resident non-road sequences too
     if (env) h->fuse_k1_gather = atoi(env) != 0;
+    env = getenv("MLD_FUSE_SERIAL");
+    if (env) h->fuse_serial = atoi(env) != 0;
     env = getenv("MLD_FUSE_CHUNK");
     if (env && atoi(env) > 0) h->fuse_chunk = atoi(env);
     env = getenv("MLD_K1_PERSIST");    // blocks per SM of the persistent K1 grid (0 = one block per tile)
@@ -1028,8 +1031,8 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
                                            have_g ? sg->d_ovf : nullptr, have_g ? sg->d_split : nullptr, front, &nl));
         h->launches += nl;
         if (ev) CK(cudaEventRecord(ev[2], front));
-        cudaStream_t s2 = have_g ? sg->stream : front;
-        if (have_g) {
+        cudaStream_t s2 = (have_g && !h->fuse_serial) ? sg->stream : front;
+        if (have_g && !h->fuse_serial) {
             CK(cudaEventRecord(sg->ev_k1, front));
             CK(cudaStreamWaitEvent(sg->stream, sg->ev_k1, 0));
         }
@@ -1041,14 +1044,14 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
         if (have_g) {
             int nl2 = 0;
             CK(mld_launch_feature_solve(h->dp, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F, cg,
-                                        sg->d_split, sg->stream, &nl2));
-            if (ev) CK(cudaEventRecord(ev[7], sg->stream));
+                                        sg->d_split, s2, &nl2));
+            if (ev) CK(cudaEventRecord(ev[7], s2));
             CK(mld_launch_feature_depth(h->dp, sg->mc, h->kcap, pts + f0g * frame_pitch_points * stride_f, stride_f, frame_pitch_points,
                                         sg->d_maps, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F,
-                                        nullptr, nullptr, (n_points + 31) / 32, cg, sg->d_ovf + 1, sg->d_ovf, overflow_grid(h, *sg), sg->stream));
-            CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, sg->stream));
-            if (ev) CK(cudaEventRecord(ev[5], sg->stream));
-            CK(cudaEventRecord(sg->done, sg->stream));
+                                        nullptr, nullptr, (n_points + 31) / 32, cg, sg->d_ovf + 1, sg->d_ovf, overflow_grid(h, *sg), s2));
+            CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s2));
+            if (ev) CK(cudaEventRecord(ev[5], s2));
+            CK(cudaEventRecord(sg->done, s2));
             h->launches += nl2 + 1;
         } else if (ev) {
             CK(cudaEventRecord(ev[7], s2));

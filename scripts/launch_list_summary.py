@@ -24,8 +24,21 @@ def main():
         m = re.search(r"([A-Za-z_0-9]+)(<[^(]*>)?\(", r[ix["Kernel Name"]])
         per[r[ix["ID"]]]["name"] = m.group(1) if m else r[ix["Kernel Name"]]
         per[r[ix["ID"]]]["grid"] = r[ix["Grid Size"]]
+    # a sequence starts with a K1-only and ends with a gather-only fused launch, and its last chunk may be ragged: per kernel
+    # only the launches with the kernel's largest grid (full launch groups) enter the per-launch figures
+    def blocks(g):
+        n = 1
+        for t in re.findall(r"\d+", g):
+            n *= int(t)
+        return n
+
+    biggest = defaultdict(int)
+    for d in per.values():
+        biggest[d["name"]] = max(biggest[d["name"]], blocks(d["grid"]))
     agg = defaultdict(lambda: {"n": 0, "us": 0.0, "bytes": 0.0})
     for d in per.values():
+        if blocks(d["grid"]) != biggest[d["name"]]:
+            continue
         a = agg[d["name"]]
         a["n"] += 1
         a["us"] += d.get("gpu__time_duration.sum", 0.0)
