@@ -467,8 +467,8 @@ def run_gpu(args, rank, local_rank, world):
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # device-resident non-road sequences run K1 of chunk j and the gather of chunk j-1 as ONE launch
-        fused = est.fusedChunkFrames() if not use_road else 0
+        # device-resident sequences run K1 of chunk j and the gather of chunk j-1 as ONE launch
+        fused = est.fusedChunkFrames()
         chunk = fused or est.chunkFrames()
         per_class = {}
         for name, (ms, ln) in prof.items():

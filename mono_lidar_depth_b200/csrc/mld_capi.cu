@@ -85,6 +85,7 @@ struct mld_handle {
     bool use_tagged_maps = true;
     bool fuse_k1_gather = true;     // K1 of chunk j and the gather of chunk j-1 in one heterogeneous launch (MLD_FUSE=0: off)
     int fuse_chunk = 512;           // frames per fused launch (MLD_FUSE_CHUNK)
+    bool fuse_road = true;          // the road / SemanticPlane / external-plane sequences use the fused pipeline too (MLD_FUSE=2: no)
     bool fuse_serial = false;       // MLD_FUSE_SERIAL=1: solve + overflow pass on the front stream too (no concurrency at all)
     int k1_persist_per_sm = 0;
     int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
@@ -574,6 +575,7 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
     env = getenv("MLD_FUSE");          // "0": separate K1 / gather launches for device-resident non-road sequences too
     if (env) h->fuse_k1_gather = atoi(env) != 0;
+    if (env) h->fuse_road = atoi(env) == 1;
     env = getenv("MLD_FUSE_SERIAL");
     if (env) h->fuse_serial = atoi(env) != 0;
     env = getenv("MLD_FUSE_CHUNK");
@@ -988,14 +990,16 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
 // is reused by chunk j once chunk j - nslots has finished its overflow pass (which still reads the maps).
 static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t n_points, int64_t frame_pitch_points, int stride_f,
                                        const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int chunk,
-                                       cudaStream_t st) {
+                                       cudaStream_t st, bool use_road, uint64_t seed, float* d_plane_coeffs_out, const PlaneSrc* src) {
     const int nslots = h->overlap_slots < 2 ? 2 : h->overlap_slots;
     const int64_t nchunks = (nframes + chunk - 1) / chunk;
     cudaStream_t front = h->st_lo;
     CK(cudaEventRecord(h->ev_fork, st));
     CK(cudaStreamWaitEvent(front, h->ev_fork, 0));
     for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
-    for (int i = 0; i < nslots; i++) CK(ensure(h->slots[i].d_split, h->slots[i].split_bytes, mld_split_scratch_bytes((long long)chunk * F, 0)));
+    for (int i = 0; i < nslots; i++)
+        CK(ensure(h->slots[i].d_split, h->slots[i].split_bytes, mld_split_scratch_bytes((long long)chunk * F, use_road ? 1 : 0)));
+    const long long words = (n_points + 31) / 32;
     for (int64_t j = 0; j <= nchunks; j++) {
         const bool have_k1 = j < nchunks, have_g = j >= 1;
         Slot* sk = have_k1 ? &h->slots[j % nslots] : nullptr;
@@ -1021,6 +1025,24 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
         }
         if (have_g) CK(cudaMemsetAsync(sg->d_ovf, 0, sizeof(int), front));
         if (ev) CK(cudaEventRecord(ev[1], front));
+        if (have_k1 && use_road && !(src && src->kind == PlaneSrc::EXTERNAL)) {
+            // the ground plane of chunk j only needs the points: fitted on the slot's stream (behind chunk j - nslots, whose road
+            // kernels were the last readers of the slot's plane buffers) while the fused launches go on
+            float* cdst = d_plane_coeffs_out ? d_plane_coeffs_out + f0k * 4 : sk->d_coeffs;
+            const float* cp = pts + f0k * frame_pitch_points * stride_f;
+            int nlp = 0;
+            if (src && src->kind == PlaneSrc::SEMANTIC) {
+                CK(ensure(sk->d_sem, sk->sem_bytes, mld_semantic_state_bytes(ck)));
+                CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
+                                             stride_f, n_points, frame_pitch_points, src->d_labels + f0k * (int64_t)src->label_w * src->label_h, ck,
+                                             sk->d_sem, cdst, sk->d_bits, words, sk->d_small,
+                                             src->d_rc_out ? src->d_rc_out + f0k : sk->d_small + 2 * ck, sk->stream, &nlp));
+            } else {
+                CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, ck, seed, f0k, sk->d_scratch, cdst,
+                                     sk->d_bits, words, sk->d_small, sk->d_small + ck, sk->d_small + 2 * ck, sk->stream, &nlp));
+            }
+            h->launches += nlp;
+        }
         int nl = 0;
         CK(mld_launch_fused_project_gather(h->dp, stride_f, mck, have_k1 ? pts + f0k * frame_pitch_points * stride_f : nullptr, n_points,
                                            frame_pitch_points, have_k1 ? sk->d_maps : nullptr, have_k1 ? sk->d_occ : nullptr, ck,
@@ -1043,12 +1065,24 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
         }
         if (have_g) {
             int nl2 = 0;
-            CK(mld_launch_feature_solve(h->dp, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F, cg,
-                                        sg->d_split, s2, &nl2));
-            if (ev) CK(cudaEventRecord(ev[7], s2));
-            CK(mld_launch_feature_depth(h->dp, sg->mc, h->kcap, pts + f0g * frame_pitch_points * stride_f, stride_f, frame_pitch_points,
-                                        sg->d_maps, d_uv + f0g * (int64_t)F * 2, F, d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F,
-                                        nullptr, nullptr, (n_points + 31) / 32, cg, sg->d_ovf + 1, sg->d_ovf, overflow_grid(h, *sg), s2));
+            const float* gp = pts + f0g * frame_pitch_points * stride_f;
+            const float* coeffs = nullptr;
+            const unsigned int* bits = nullptr;
+            if (use_road) {
+                if (src && src->kind == PlaneSrc::EXTERNAL) {
+                    coeffs = src->d_coeffs + f0g * 4;
+                    bits = src->d_bits + f0g * words;
+                } else {
+                    coeffs = d_plane_coeffs_out ? d_plane_coeffs_out + f0g * 4 : sg->d_coeffs;
+                    bits = sg->d_bits;
+                }
+            }
+            CK(mld_launch_feature_solve(h->dp, sg->mc, gp, stride_f, frame_pitch_points, sg->d_maps, sg->d_occ, d_uv + f0g * (int64_t)F * 2, F,
+                                        d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F, coeffs, bits, words, cg, sg->d_ovf + 1,
+                                        sg->d_ovf, sg->d_split, s2, &nl2, ev ? &ev[7] : nullptr));
+            CK(mld_launch_feature_depth(h->dp, sg->mc, h->kcap, gp, stride_f, frame_pitch_points, sg->d_maps, d_uv + f0g * (int64_t)F * 2, F,
+                                        d_depth + f0g * (int64_t)F, d_status + f0g * (int64_t)F, coeffs, bits, words, cg, sg->d_ovf + 1,
+                                        sg->d_ovf, overflow_grid(h, *sg), s2));
             CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s2));
             if (ev) CK(cudaEventRecord(ev[5], s2));
             CK(cudaEventRecord(sg->done, s2));
@@ -1089,7 +1123,9 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // short sequences are cut into at least `overlap_slots` chunks so that the streams still overlap
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
-    const bool fused_ok = h->fuse_k1_gather && !use_road && !src && h->feature_mode == 2 && h->overlap_slots >= 2 && F > 0 && n_points > 0;
+    // MLD_FUSE=2 restricts the fused pipeline to the non-road path
+    const bool fused_ok = h->fuse_k1_gather && (!(use_road || src) || h->fuse_road) && h->feature_mode == 2 && h->overlap_slots >= 2 && F > 0 &&
+                          n_points > 0 && !(h->fuse_serial && use_road);
     const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(fused_ok ? h->fuse_chunk : h->chunk_frames,
                                                                   std::max<int64_t>(8, (nframes + h->overlap_slots - 1) / h->overlap_slots)));
     const int64_t nchunks = (nframes + chunk - 1) / chunk;
@@ -1103,7 +1139,8 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
     if (fused_ok && nchunks >= 2 && nslots >= 2)
-        return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st);
+        return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st,
+                                           use_road, seed, d_plane_coeffs_out, src);
     const bool prio = nslots > 1 && h->overlap_mode == 1;
     if (nslots > 1) {
         CK(cudaEventRecord(h->ev_fork, st));

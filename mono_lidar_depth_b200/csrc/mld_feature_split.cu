@@ -541,7 +541,7 @@ SplitLayout split_layout(void* d_scratch, long long features) {
 
 // K1 of (frames_k1 frames at d_pts_k1 into maps_k1 / occ_k1) together with the gather of a previous chunk (frames_g frames
 // whose maps are complete). Either part may be empty (frames_* == 0): the first launch of a sequence has no gather, the
-// last no K1. The gather's counters are zeroed here. Non-road path only.
+// last no K1. The gather's counters are zeroed here.
 cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, const MapCode& mc_k1, const float* d_pts_k1, long long n_points,
                                             long long pitch_pts, unsigned int* d_maps_k1, unsigned int* d_occ_k1, int frames_k1,
                                             const MapCode& mc_g, const float* d_pts_g, const unsigned int* d_maps_g,
@@ -578,17 +578,41 @@ cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, co
     return cudaGetLastError();
 }
 
-// K2b alone on the survivors a gather (fused or not) left in d_scratch; non-road path
-cudaError_t mld_launch_feature_solve(const DevParams& P, const double* d_uv, int F, double* d_depth, int* d_status, int nframes,
-                                     void* d_scratch, cudaStream_t stream, int* launches) {
-    if (F <= 0 || nframes <= 0) return cudaSuccess;
+// K2b on the survivors a gather (fused or not) left in d_scratch, followed by the road kernels when a plane is given
+// (d_plane_coeffs != nullptr and a road estimator is configured)
+cudaError_t mld_launch_feature_solve(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long pitch_pts,
+                                     const unsigned int* d_maps, const unsigned int* d_occ, const double* d_uv, int F, double* d_depth,
+                                     int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, int* d_overflow_list, int* d_overflow_count, void* d_scratch,
+                                     cudaStream_t stream, int* launches, cudaEvent_t* ev_after_solve) {
+    if (F <= 0 || nframes <= 0) {
+        if (ev_after_solve) return cudaEventRecord(*ev_after_solve, stream);
+        return cudaSuccess;
+    }
     const long long features = (long long)nframes * F;
     const SplitLayout L = split_layout(d_scratch, features);
+    const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
+    cudaError_t e;
     const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
-    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, L.surv_rec, L.surv_xyz, L.surv_count, features, 0, L.road_list,
-                                                  L.road_count);
+    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, L.surv_rec, L.surv_xyz, L.surv_count, features, road ? 1 : 0,
+                                                  L.road_list, L.road_count);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (ev_after_solve && (e = cudaEventRecord(*ev_after_solve, stream)) != cudaSuccess) return e;  // profiling: end of the solve
     if (launches) (*launches)++;
-    return cudaGetLastError();
+    if (road) {
+        // the survivor arrays are free again once K2b has finished: the road pass reuses them
+        const unsigned gc = (unsigned)((features + SBT_A - 1) / SBT_A);
+        feature_road_gather_kernel<<<gc, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
+                                                            d_plane_coeffs, d_inlier_bits, words_per_frame, L.road_list, L.road_count,
+                                                            d_overflow_list, d_overflow_count, L.surv_rec, L.surv_xyz, L.rs_count, features);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        const unsigned gd = (unsigned)((features + SBT_C - 1) / SBT_C);
+        feature_road_solve_kernel<<<gd, SBT_C, 0, stream>>>(P, d_uv, F, d_depth, d_status, d_plane_coeffs, L.surv_rec, L.surv_xyz, L.rs_count,
+                                                           features);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) *launches += 2;
+    }
+    return cudaSuccess;
 }
 
 cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
@@ -600,41 +624,16 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
     if (F <= 0 || nframes <= 0) return cudaSuccess;
     const long long features = (long long)nframes * F;
     if (features >= (1ll << 27)) return cudaErrorInvalidValue;  // survivor records hold 27-bit feature ids
-    unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
-    int* surv_count = reinterpret_cast<int*>(base);
-    int* road_count = surv_count + 1;
-    int* rs_count = surv_count + 2;
-    unsigned int* surv_rec = reinterpret_cast<unsigned int*>(base + 64);
-    int* road_list = reinterpret_cast<int*>(surv_rec + features);
-    size_t off = 64 + (size_t)features * 8;
-    off = (off + 255) & ~(size_t)255;
-    double* surv_xyz = reinterpret_cast<double*>(base + off);
-    const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
-    cudaError_t e = cudaMemsetAsync(surv_count, 0, 3 * sizeof(int), stream);
+    const SplitLayout L = split_layout(d_scratch, features);
+    cudaError_t e = cudaMemsetAsync(L.surv_count, 0, 3 * sizeof(int), stream);
     if (e != cudaSuccess) return e;
     dim3 ga((unsigned)((F + SBT_A - 1) / SBT_A), (unsigned)nframes);
     feature_gather_kernel<<<ga, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
-                                                   d_overflow_list, d_overflow_count, surv_rec, surv_xyz, surv_count, features);
+                                                   d_overflow_list, d_overflow_count, L.surv_rec, L.surv_xyz, L.surv_count, features);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (launches) (*launches)++;
     if (ev_mid && (e = cudaEventRecord(ev_mid[0], stream)) != cudaSuccess) return e;  // profiling: end of the gather
-    const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
-    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, surv_rec, surv_xyz, surv_count, features, road ? 1 : 0,
-                                                  road_list, road_count);
-    if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    if (ev_mid && (e = cudaEventRecord(ev_mid[1], stream)) != cudaSuccess) return e;  // profiling: end of the solve
-    if (launches) *launches += 2;
-    if (road) {
-        // the survivor arrays are free again once K2b has finished: the road pass reuses them
-        const unsigned gc = (unsigned)((features + SBT_A - 1) / SBT_A);
-        feature_road_gather_kernel<<<gc, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
-                                                            d_plane_coeffs, d_inlier_bits, words_per_frame, road_list, road_count,
-                                                            d_overflow_list, d_overflow_count, surv_rec, surv_xyz, rs_count, features);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        const unsigned gd = (unsigned)((features + SBT_C - 1) / SBT_C);
-        feature_road_solve_kernel<<<gd, SBT_C, 0, stream>>>(P, d_uv, F, d_depth, d_status, d_plane_coeffs, surv_rec, surv_xyz, rs_count,
-                                                           features);
-        if ((e = cudaGetLastError()) != cudaSuccess) return e;
-        if (launches) *launches += 2;
-    }
-    return cudaSuccess;
+    return mld_launch_feature_solve(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status, d_plane_coeffs, d_inlier_bits,
+                                    words_per_frame, nframes, d_overflow_list, d_overflow_count, d_scratch, stream, launches,
+                                    ev_mid ? ev_mid + 1 : nullptr);
 }

@@ -55,15 +55,18 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
                                            int* d_overflow_list, int* d_overflow_count, void* d_scratch, cudaStream_t stream,
                                            int* launches, cudaEvent_t* ev_mid = nullptr);
 
-// K1 of one chunk + K2a (gather) of the previous chunk as one heterogeneous launch, and K2b alone (non-road path)
+// K1 of one chunk + K2a (gather) of the previous chunk as one heterogeneous launch, and K2b (+ road kernels) alone
 cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, const MapCode& mc_k1, const float* d_pts_k1, long long n_points,
                                             long long pitch_pts, unsigned int* d_maps_k1, unsigned int* d_occ_k1, int frames_k1,
                                             const MapCode& mc_g, const float* d_pts_g, const unsigned int* d_maps_g,
                                             const unsigned int* d_occ_g, const double* d_uv_g, int F, double* d_depth_g, int* d_status_g,
                                             int frames_g, int* d_overflow_list, int* d_overflow_count, void* d_scratch_g,
                                             cudaStream_t stream, int* launches);
-cudaError_t mld_launch_feature_solve(const DevParams& P, const double* d_uv, int F, double* d_depth, int* d_status, int nframes,
-                                     void* d_scratch, cudaStream_t stream, int* launches);
+cudaError_t mld_launch_feature_solve(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long pitch_pts,
+                                     const unsigned int* d_maps, const unsigned int* d_occ, const double* d_uv, int F, double* d_depth,
+                                     int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
+                                     long long words_per_frame, int nframes, int* d_overflow_list, int* d_overflow_count, void* d_scratch,
+                                     cudaStream_t stream, int* launches, cudaEvent_t* ev_after_solve = nullptr);
 
 // K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
 struct RansacConfig {
