@@ -190,7 +190,7 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
     CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int), &maps_changed));
     if (maps_changed) s.epoch = 0;  // fresh memory holds no valid tags
     CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)frames * (size_t)std::max(F, 1) + 1) * sizeof(int)));
-    CK(ensure(s.d_occ, s.occ_bytes, (size_t)frames * (size_t)occ_words_per_row(h->dp.W) * (size_t)h->dp.H * sizeof(unsigned int)));
+    CK(ensure(s.d_occ, s.occ_bytes, (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int)));
     if (road) {
         const size_t words = (size_t)((n_points + 31) / 32);
         CK(ensure(s.d_bits, s.bits_bytes, (size_t)frames * words * sizeof(unsigned int)));
@@ -221,7 +221,7 @@ int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStrea
     }
     s.mc = mc;
     if (h->feature_mode >= 1)
-        CK(cudaMemsetAsync(s.d_occ, 0, (size_t)frames * (size_t)occ_words_per_row(h->dp.W) * (size_t)h->dp.H * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(s.d_occ, 0, (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int), st));
     return MLD_OK;
 }
 

@@ -76,12 +76,17 @@ __host__ __device__ __forceinline__ unsigned int map_cell_index(const MapCode& m
     return mc.tagged ? (cell & MLD_TAG_IDX_MASK) : cell;
 }
 
-// Occupancy bitmap of the pixel map (one per in-flight frame, cleared per chunk): word j of a row
-// covers pixels [16 j, 16 j + 32), i.e. consecutive words overlap by 16 pixels, so every window row of
-// up to 17 pixels is one 32-bit load (word x0 >> 4); wider rows walk words j, j+2, ... K1 sets the
-// (at most two) bits of every pixel it writes; K2 reads window rows from here instead of loading
-// every pixel cell of the 4-byte map.
-__host__ __device__ __forceinline__ int occ_words_per_row(int W) { return ((W + 15) >> 4) + 1; }
+// Occupancy bitmap of the pixel map (one per in-flight frame, cleared per chunk), tiled: a 16 x 16 pixel tile is one
+// 32-byte sector (8 words; word w holds rows 2w and 2w+1 of the tile, 16 bits each). A search window (7 x 10 pixels
+// by default) touches 1-4 tiles = 1-4 sectors instead of one sector per window row, and K1 sets ONE bit per pixel it
+// writes. K2 reads window rows from here instead of loading every pixel cell of the 4-byte map.
+__host__ __device__ __forceinline__ int occ_tiles_x(int W) { return (W + 15) >> 4; }
+__host__ __device__ __forceinline__ long long occ_words_per_frame(int W, int H) { return (long long)occ_tiles_x(W) * ((H + 15) >> 4) * 8; }
+// word holding pixel (x, y) and the bit inside it
+__host__ __device__ __forceinline__ long long occ_word_of(int tiles_x, int x, int y) {
+    return ((long long)(y >> 4) * tiles_x + (x >> 4)) * 8 + ((y & 15) >> 1);
+}
+__host__ __device__ __forceinline__ unsigned int occ_bit_of(int x, int y) { return 1u << (((y & 1) << 4) | (x & 15)); }
 
 struct D3 {
     double x, y, z;

@@ -64,7 +64,7 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
     const long long o = frame * (long long)F + fi;
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
-    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+    const unsigned int* occ = occs + frame * occ_words_per_frame(P.W, P.H);
     int* aux = s_aux + tid;
 
     if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
@@ -84,34 +84,10 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             const int x0 = (int)fmax(u - P.hx1, 0.), x1 = (int)fmin(u + P.hx1, (double)(P.W - 1));
             const int y0 = (int)fmax(v - P.hy1, 0.), y1 = (int)fmin(v + P.hy1, (double)(P.H - 1));
             if (x1 >= x0 && y1 >= y0) {
-                const int pitch = occ_words_per_row(P.W);
-                const int wj0 = x0 >> 4;
-                for (int yb = y0; yb <= y1; yb += T_ROWS) {
-                    unsigned int w[T_ROWS];
-#pragma unroll
-                    for (int r = 0; r < T_ROWS; r++) {
-                        const int y = yb + r;
-                        w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
-                    }
-#pragma unroll
-                    for (int r = 0; r < T_ROWS; r++) {
-                        const int y = yb + r;
-                        if (y > y1) break;
-                        unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
-                        int wj = wj0;
-                        while (true) {
-                            while (m) {
-                                const int b = __ffs(m) - 1;
-                                m &= m - 1;
-                                if (k < SCAP) aux[k * SBT_A] = y * P.W + (wj << 4) + b;
-                                k++;
-                            }
-                            wj += 2;
-                            if ((wj << 4) > x1) break;
-                            m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
-                        }
-                    }
-                }
+                occ_scan_window(occ, P.W, x0, x1, y0, y1, [&](int off) {
+                    if (k < SCAP) aux[k * SBT_A] = off;
+                    k++;
+                });
             }
         }
     }
@@ -242,7 +218,7 @@ struct FusedGather {
 };
 static_assert(SBT_A == K1_THREADS, "the fused launch uses one block size for both roles");
 
-__global__ void __launch_bounds__(SBT_A)
+__global__ void __launch_bounds__(SBT_A, 8)
 fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g, int k1_blocks, int g_blocks, int period) {
     const int b = (int)blockIdx.x;
     const int gi = b / period;
@@ -390,7 +366,7 @@ feature_road_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pt
         const long long frame = o / F;
         fp = pts + frame * pitch_pts * (long long)stride_f;
         map = maps + frame * (long long)P.W * (long long)P.H;
-        const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+        const unsigned int* occ = occs + frame * occ_words_per_frame(P.W, P.H);
         const float* pc = plane_coeffs + frame * 4;
         const unsigned int* bits = inlier_bits + frame * inlier_words_per_frame;
         const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
@@ -401,34 +377,10 @@ feature_road_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pt
             const int x0 = (int)fmax(u - P.hx2, 0.), x1 = (int)fmin(u + P.hx2, (double)(P.W - 1));
             const int y0 = (int)fmax(v - P.hy2, 0.), y1 = (int)fmin(v + P.hy2, (double)(P.H - 1));
             if (x1 >= x0 && y1 >= y0) {
-                const int pitch = occ_words_per_row(P.W);
-                const int wj0 = x0 >> 4;
-                for (int yb = y0; yb <= y1; yb += T_ROWS) {
-                    unsigned int w[T_ROWS];
-#pragma unroll
-                    for (int r = 0; r < T_ROWS; r++) {
-                        const int y = yb + r;
-                        w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
-                    }
-#pragma unroll
-                    for (int r = 0; r < T_ROWS; r++) {
-                        const int y = yb + r;
-                        if (y > y1) break;
-                        unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
-                        int wj = wj0;
-                        while (true) {
-                            while (m) {
-                                const int b = __ffs(m) - 1;
-                                m &= m - 1;
-                                if (k2 < RCAP) aux[k2 * SBT_A] = y * P.W + (wj << 4) + b;
-                                k2++;
-                            }
-                            wj += 2;
-                            if ((wj << 4) > x1) break;
-                            m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
-                        }
-                    }
-                }
+                occ_scan_window(occ, P.W, x0, x1, y0, y1, [&](int off) {
+                    if (k2 < RCAP) aux[k2 * SBT_A] = off;
+                    k2++;
+                });
             }
         }
         if (k2 > RCAP) {

@@ -50,7 +50,7 @@ feature_depth_thread_kernel(DevParams P, MapCode mc, const float* __restrict__ p
     const long long obase = frame * (long long)F + (long long)blockIdx.x * TBT;  // global id of this block's feature 0
     const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
-    const unsigned int* occ = occs + frame * (long long)occ_words_per_row(P.W) * (long long)P.H;
+    const unsigned int* occ = occs + frame * occ_words_per_frame(P.W, P.H);
     const float* pc = plane_coeffs ? plane_coeffs + frame * 4 : nullptr;
     const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
     const bool road = pc != nullptr && P.road_mode != ROAD_NONE;

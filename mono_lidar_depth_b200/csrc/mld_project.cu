@@ -35,7 +35,7 @@ project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, i
 __global__ void __launch_bounds__(K1_THREADS)
 project_scatter_persistent_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                                   unsigned int* __restrict__ maps, unsigned int* __restrict__ occ, int tiles_per_frame, int total_tiles) {
-    const int occ_pitch = occ_words_per_row(P.W);
+    const int occ_pitch = occ_tiles_x(P.W);
     const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
     const int step = K1_THREADS * stride_f;
     auto load_tile = [&](int t, float4 (&q)[K1_PPT]) {
@@ -59,8 +59,8 @@ project_scatter_persistent_kernel(DevParams P, MapCode mc, const float* __restri
         if (tn < total_tiles) load_tile(tn, nxt);
         const int frame = t / tiles_per_frame, tile = t - frame * tiles_per_frame;
         unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-        unsigned int* ob = occ ? occ + (size_t)frame * (size_t)(occ_pitch * P.H) : nullptr;
-        scatter_points(P, cur, tile * (K1_THREADS * K1_PPT) + threadIdx.x, n, hi, map, ob, occ_pitch);
+        unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
+        scatter_points<false>(P, cur, tile * (K1_THREADS * K1_PPT) + threadIdx.x, n, hi, map, ob, occ_pitch);
         if (tn >= total_tiles) break;
 #pragma unroll
         for (int j = 0; j < K1_PPT; j++) cur[j] = nxt[j];

@@ -34,7 +34,7 @@ struct TSlabT {
 // Three phases, each a batch of independent loads: (1) one occupancy word per window row (rows of up
 // to 17 pixels; wider rows walk further words), set bits -> pixel offsets in scan order; (2) the map
 // cells of the occupied pixels -> raw point indices; (3) the points themselves -> FP64 camera frame.
-constexpr int T_ROWS = 16;  // window rows whose occupancy words are fetched up front
+constexpr int T_PAIRS = 8;  // row pairs (= occupancy words per tile column) fetched up front: windows of up to 15-16 rows in one batch
 
 __device__ __forceinline__ unsigned int row_mask(unsigned int w, int base_px, int x0, int x1) {
     // keep the bits of word `w` (covering pixels base_px .. base_px+31) that lie in [x0, x1]
@@ -43,6 +43,52 @@ __device__ __forceinline__ unsigned int row_mask(unsigned int w, int base_px, in
     if (hi > 31) hi = 31;
     if (hi < lo) return 0u;
     return w & (0xFFFFFFFFu << lo) & (0xFFFFFFFFu >> (31 - hi));
+}
+
+// Occupied pixels of the window [x0, x1] x [y0, y1] in the reference's scan order (rows outer, columns inner,
+// NeighborFinderPixel.cpp:78-92): emit(pixel offset) per occupied pixel. The occupancy words of the first two tile
+// columns are fetched for all row pairs of a batch before any is used (independent loads); wider windows walk on.
+template <typename Emit>
+__device__ __forceinline__ void occ_scan_window(const unsigned int* __restrict__ occ, int W, int x0, int x1, int y0, int y1, Emit emit) {
+    const int tiles_x = occ_tiles_x(W);
+    const int tx0 = x0 >> 4, tx1 = x1 >> 4;
+    const int yp_last = y1 >> 1;
+    for (int ypb = y0 >> 1; ypb <= yp_last; ypb += T_PAIRS) {
+        unsigned int w0[T_PAIRS], w1[T_PAIRS];
+#pragma unroll
+        for (int r = 0; r < T_PAIRS; r++) {
+            const int yp = ypb + r;  // rows 2 yp and 2 yp + 1: tile row yp >> 3, word yp & 7 of the tile
+            const bool on = yp <= yp_last;
+            const long long base = ((long long)(yp >> 3) * tiles_x + tx0) * 8 + (yp & 7);
+            w0[r] = on ? __ldg(occ + base) : 0u;
+            w1[r] = (on && tx1 > tx0) ? __ldg(occ + base + 8) : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < T_PAIRS; r++) {
+            const int yp = ypb + r;
+            if (yp > yp_last) break;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const int y = 2 * yp + h;
+                if (y < y0 || y > y1) continue;
+                const int sh = h << 4;
+                unsigned int m = row_mask(((w0[r] >> sh) & 0xFFFFu) | (((w1[r] >> sh) & 0xFFFFu) << 16), tx0 << 4, x0, x1);
+                int tx = tx0;
+                while (true) {
+                    while (m) {
+                        const int b = __ffs(m) - 1;
+                        m &= m - 1;
+                        emit(y * W + (tx << 4) + b);
+                    }
+                    tx += 2;  // next 32-pixel span of a wide row
+                    if ((tx << 4) > x1) break;
+                    const long long base = ((long long)(yp >> 3) * tiles_x + tx) * 8 + (yp & 7);
+                    const unsigned int a = __ldg(occ + base), c = (tx + 1 <= tx1) ? __ldg(occ + base + 8) : 0u;
+                    m = row_mask(((a >> sh) & 0xFFFFu) | (((c >> sh) & 0xFFFFu) << 16), tx << 4, x0, x1);
+                }
+            }
+        }
+    }
 }
 
 template <typename TSlab>
@@ -58,36 +104,12 @@ __device__ int t_gather_window(const DevParams& P, const MapCode& mc, const unsi
     double bottomEdgeY = fmin(v + hy, (double)(P.H - 1));
     const int x0 = (int)leftEdgeX, x1 = (int)rightEdgeX, y0 = (int)topEdgeY, y1 = (int)bottomEdgeY;
     if (x1 < x0 || y1 < y0) return 0;
-    const int pitch = occ_words_per_row(P.W);
-    const int wj0 = x0 >> 4;
     int k = 0;
-    // ---- phase 1: occupancy words -> pixel offsets (row-major order) ----
-    for (int yb = y0; yb <= y1; yb += T_ROWS) {
-        unsigned int w[T_ROWS];
-#pragma unroll
-        for (int r = 0; r < T_ROWS; r++) {
-            const int y = yb + r;
-            w[r] = (y <= y1) ? __ldg(occ + (long long)y * pitch + wj0) : 0u;
-        }
-#pragma unroll
-        for (int r = 0; r < T_ROWS; r++) {
-            const int y = yb + r;
-            if (y > y1) break;
-            unsigned int m = row_mask(w[r], wj0 << 4, x0, x1);
-            int wj = wj0;
-            while (true) {
-                while (m) {
-                    const int b = __ffs(m) - 1;
-                    m &= m - 1;
-                    if (k < TSlab::TCAP) s.A(k) = y * P.W + (wj << 4) + b;
-                    k++;
-                }
-                wj += 2;  // next non-overlapping 32-pixel span of a wide row
-                if ((wj << 4) > x1) break;
-                m = row_mask(__ldg(occ + (long long)y * pitch + wj), wj << 4, x0, x1);
-            }
-        }
-    }
+    // ---- phase 1: occupancy tiles -> pixel offsets (row-major order) ----
+    occ_scan_window(occ, P.W, x0, x1, y0, y1, [&](int off) {
+        if (k < TSlab::TCAP) s.A(k) = off;
+        k++;
+    });
     if (k > TSlab::TCAP) return -1;
     // ---- phase 2: map cells -> raw indices ----
 #pragma unroll 4
