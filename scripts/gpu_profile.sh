@@ -1,4 +1,4 @@
-TAG=r1d
+TAG=r1e
 python -m pytest tests -m gpu -q --no-header -rf --timeout 900 > gpurun_out/test_$TAG.log 2>&1; tail -3 gpurun_out/test_$TAG.log
 export MLD_BENCH_FRAMES=2048 MLD_BENCH_E2E_FRAMES=32 MLD_BENCH_CPU_SECONDS=1
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 20 -c 45 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 > gpurun_out/ncu_launch_$TAG.log 2>&1
