@@ -25,8 +25,15 @@
 
 namespace {
 
+// 8 entries: the solve kernel's per-thread slab is 8 x 28 bytes of shared memory -> 31 KB per block, 6-7 blocks per SM
+// instead of 4 with 12 entries (1.22 -> 1.31 M frames/s; 10 entries: 1.23 M). A 7 x 10 window over an HDL-64 sweep holds
+// 2 rings x 3-4 returns; fuller windows take the warp-per-feature overflow pass.
 #ifndef MLD_SCAP
-#define MLD_SCAP 12
+#define MLD_SCAP 8
+#endif
+// 7 resident blocks asked for: 72 registers instead of 81 (a few spilled bytes in the cold tail), +2 % on the path
+#ifndef MLD_SOLVE_MINBLOCKS
+#define MLD_SOLVE_MINBLOCKS 7
 #endif
 #ifndef MLD_SBT_B
 #define MLD_SBT_B 128
@@ -235,7 +242,7 @@ fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g,
 }
 
 // ---- K2b ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SBT_B)
+__global__ void __launch_bounds__(SBT_B, MLD_SOLVE_MINBLOCKS)
 feature_solve_kernel(DevParams P, const double* __restrict__ uv, double* __restrict__ depth, int* __restrict__ status,
                      const unsigned int* __restrict__ surv_rec, const double* __restrict__ surv_xyz,
                      const int* __restrict__ surv_count, long long cap, int road, int* __restrict__ road_list,
