@@ -144,3 +144,65 @@ def variant_params(variant) -> MldParams:
         p.do_check_triangleplanar_condition = 0
         p.viewray_plane_orthoganality_treshold = 0.0
     return p
+
+
+def random_configuration(seed):
+    """(params, (W, H, f, cx, cy), T[3x4], cloud, features, plane or None): a random camera, extrinsic, window size, set of
+    thresholds and module switches on a random scene -- shared by the oracle-vs-reference and the GPU-vs-oracle tests."""
+    from mono_lidar_depth_b200 import synth
+
+    KITTI_T = synth.KITTI_T_LIDAR_TO_CAM
+    rng = np.random.RandomState(1000 + seed)
+    W, H = int(rng.randint(48, 420)), int(rng.randint(40, 300))
+    f = float(rng.uniform(0.6, 2.5) * W)
+    cx, cy = float(W * rng.uniform(0.3, 0.7)), float(H * rng.uniform(0.3, 0.7))
+    # a random rigid transform: the KITTI axes permutation times a random rotation of up to ~20 degrees, random offset
+    a = rng.normal(0, 0.2, 3)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    Rr = np.eye(3) + K + K @ K / 2
+    U, _, Vt = np.linalg.svd(Rr)
+    Rr = U @ Vt
+    T = np.zeros((3, 4))
+    T[:, :3] = Rr @ np.asarray(KITTI_T, np.float64)[:, :3]
+    T[:, 3] = rng.uniform(-0.5, 0.5, 3)
+    p = O.yaml_params()
+    p.do_use_ransac_plane = int(rng.rand() < 0.5)
+    p.pixelarea_search_witdh = int(rng.randint(1, 21))
+    p.pixelarea_search_height = int(rng.randint(1, 21))
+    p.radiusSearch_count_min = int(rng.randint(0, 5))
+    p.do_use_histogram_segmentation = int(rng.rand() < 0.8)
+    p.histogram_segmentation_bin_witdh = float(rng.choice([0.05, 0.1, 0.3, 0.7, 1.5]))
+    p.histogram_segmentation_min_pointcount = int(rng.randint(0, 5))
+    p.treshold_depth_enabled = int(rng.rand() < 0.8)
+    p.treshold_depth_mode = int(rng.randint(0, 2))
+    p.treshold_depth_min = int(rng.randint(0, 6))
+    p.treshold_depth_max = int(rng.randint(10, 120))
+    p.treshold_depth_local_enabled = int(rng.rand() < 0.8)
+    p.treshold_depth_local_mode = int(rng.randint(0, 2))
+    p.treshold_depth_local_valuetype = int(rng.randint(0, 2))
+    p.treshold_depth_local_value = float(rng.choice([0.0, 0.05, 0.5, 2.0]))
+    p.do_use_triangle_size_maximation = int(rng.rand() < 0.8)
+    p.do_check_triangleplanar_condition = int(rng.rand() < 0.8)
+    p.triangleplanar_crossnorm_treshold = float(rng.choice([0.0, 0.05, 0.1, 0.4]))
+    p.viewray_plane_orthoganality_treshold = float(rng.choice([0.0, 0.03, 0.2, 0.6]))
+    p.do_use_cut_behind_camera = int(rng.rand() < 0.7)
+    road_mode = rng.randint(0, 2)
+    p.plane_estimator_use_mestimator = int(road_mode == 0)
+    p.plane_estimator_use_triangle_maximation = int(road_mode == 1)
+    p.plane_estimator_z_x_min_relation = float(rng.choice([0.0, 0.2, 1.0]))
+    p.ransac_plane_point_distance_treshold = float(rng.choice([0.05, 0.2, 1.0]))
+    cloud = random_scene_cloud(rng, 4000, W, H, f, cx, cy, T, zmin=1.0, zmax=40.0, dense_patches=int(rng.randint(5, 40)))
+    cloud[rng.randint(0, len(cloud), 40), rng.randint(0, 3, 40)] = np.nan
+    uv = np.stack([rng.uniform(-8, W + 8, 700), rng.uniform(-8, H + 8, 700)], 1)
+    uv[:200] = np.floor(uv[:200])
+    plane = None
+    if p.do_use_ransac_plane:
+        # a plane through part of the cloud, in the lidar frame, with a random subset of the near points as inliers
+        n3 = rng.normal(0, 1, 3)
+        n3 /= np.linalg.norm(n3)
+        fin = np.nonzero(np.isfinite(cloud[:, :3]).all(axis=1))[0]
+        d0 = -float(np.median(cloud[fin, :3] @ n3))
+        dist = np.abs(cloud[fin, :3].astype(np.float64) @ n3 + d0)
+        near = fin[dist < np.percentile(dist, 40)]
+        plane = (np.array([n3[0], n3[1], n3[2], d0], np.float32), np.sort(rng.choice(near, max(3, len(near) // 2), replace=False)).astype(np.int32))
+    return p, (W, H, f, cx, cy), T, cloud, uv, plane

@@ -497,3 +497,12 @@ def test_fused_and_separate_launch_pipelines_agree(monkeypatch):
             outs.append((depth.cpu().numpy(), status.cpu().numpy()))
         assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0]), (F, nframes, chunk)
         assert outs[0][1].min() >= 1  # every feature got a status
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configurations(seed):
+    """The random configurations of tests/test_ref_pin.py (where the oracle is checked against the reference's code) on the
+    GPU: pixel map, neighbour lists and statuses bit-exact, depths within 1e-4 relative."""
+    p, cam, T, cloud, uv, plane = PU.random_configuration(seed)
+    est, orc = PU.make_pair(p, CameraPinhole(*cam), T)
+    PU.compare_frame(est, orc, cloud, uv, plane=plane, what=f"random config {seed}", neighbor_samples=24)

@@ -302,3 +302,13 @@ def test_full_pipeline_with_the_references_own_ransac_plane():
     assert np.array_equal(s_o, s_r)
     assert np.all(np.abs(d_o - d_r) <= 1e-9 * np.abs(d_r))
     assert (s_r == 16).sum() > 20  # the inlier set is a 6000-point subsample, so few windows hold 3 inliers
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_randomised_configurations(seed):
+    """Random cameras, extrinsics, window sizes, thresholds and module switches on random scenes: the oracle must follow
+    the reference's code bit for bit through whatever combination of branches a configuration opens."""
+    p, cam, T, cloud, uv, plane = PU.random_configuration(seed)
+    o, r = pair(p, cam, T)
+    d, s = compare(o, r, cloud, uv, plane=plane, what=f"random config {seed}", depth_rtol=1e-9 if plane is not None else 0.0, neighbor_samples=24)
+    assert len(set(s.tolist())) >= 2
