@@ -92,6 +92,38 @@ def test_restatement_label_test_matches_the_reference_on_boundary_points():
     assert 100 < want[idx].sum() < len(idx) - 100
 
 
+@pytest.mark.skipif(not R.available(), reason="oracle/_ref/libmld_ref.so not built (no /root/reference here)")
+@pytest.mark.parametrize("seed", range(8))
+def test_restatement_matches_the_reference_on_random_cameras_and_label_images(seed):
+    """Random image size, intrinsics, extrinsic, label layout, ground-label set and threshold: inlier set identical, coefficients
+    to float rounding; PclInvalid when the reference throws."""
+    rng = np.random.RandomState(500 + seed)
+    W, H = int(rng.randint(60, 500)), int(rng.randint(40, 300))
+    f, cu, cv = float(rng.uniform(0.5, 2.0) * W), float(W * rng.uniform(0.3, 0.7)), float(H * rng.uniform(0.3, 0.7))
+    a = rng.normal(0, 0.15, 3)
+    K = np.array([[0, -a[2], a[1]], [a[2], 0, -a[0]], [-a[1], a[0], 0]])
+    U, _, Vt = np.linalg.svd(np.eye(3) + K)
+    T = np.zeros((3, 4))
+    T[:, :3] = (U @ Vt) @ KT[:, :3]
+    T[:, 3] = rng.uniform(-0.4, 0.4, 3)
+    labels = rng.randint(0, 12, (H, W)).astype(np.uint8) if seed % 2 else np.zeros((H, W), np.uint8)
+    labels[int(H * rng.uniform(0.4, 0.7)):, :] = rng.choice([6, 7, 8, 9])
+    gl = sorted(set(rng.choice([3, 6, 7, 8, 9, 11, 200, 300, -4], rng.randint(1, 5)).tolist()))
+    thr = float(rng.choice([0.02, 0.1, 0.5, 5.0]))
+    cfg = synth.default_config()
+    cfg.azimuth_steps = 300
+    cloud = synth.points_host(cfg, 900 + seed, seed)
+    rc, c_ref, inl_ref = R.semantic_plane(labels, f, cu, cv, T, gl, thr, cloud)
+    if rc != 0:
+        assert rc == -4
+        with pytest.raises(SP.PclInvalid):
+            SP.semantic_plane(cloud, labels, f, cu, cv, T, gl, thr)
+        return
+    c, inl, kept, first = SP.semantic_plane(cloud, labels, f, cu, cv, T, gl, thr)
+    assert np.array_equal(inl, inl_ref), (len(inl), len(inl_ref))
+    assert np.allclose(c, c_ref, rtol=0, atol=5e-6)
+
+
 def test_restatement_reproduces_the_frozen_reference_outputs():
     for case in (0, 1, 2):
         cloud, labels, gl, thr = MK.semantic_case(case)
