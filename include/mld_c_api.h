@@ -22,6 +22,8 @@
 
 #include <stdint.h>
 
+#include "mld_synth.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -279,29 +281,9 @@ int mld_get_visible_points(mld_handle* h, int32_t* point_index_out, double* imag
 /* camera-frame coordinates of raw point i (3 doubles each), _points_cs_camera */
 int mld_get_points_camera(mld_handle* h, double* out_host);
 
-/* ---- synthetic KITTI-shaped input (bench / tests; deterministic, host and device agree bit for bit) ---- */
-typedef struct mld_synth_config {
-    int32_t rings;            /* 64 (HDL-64) or 128 */
-    int32_t azimuth_steps;    /* 1875 -> 120000 points */
-    float elev_top_deg;       /* +2.0 */
-    float elev_bottom_deg;    /* -24.8 */
-    float sensor_height;      /* 1.73 m above ground */
-    float max_range;          /* 120 m */
-    float range_noise_sigma;  /* 0.02 m */
-    float dropout_prob;       /* 0.02 -> NaN points */
-    int32_t n_boxes;          /* <= 64 obstacles per frame */
-    int32_t image_width, image_height;
-    float band_top_frac;      /* features: fraction of image height where the lidar band starts */
-    float band_feature_frac;  /* fraction of features placed inside the band (0.7) */
-    int32_t reserved0;
-} mld_synth_config;
-
-void mld_synth_default_config(mld_synth_config* c, int dense);   /* dense=0: KITTI shape, 1: 128-beam shape */
-int64_t mld_synth_points_per_frame(const mld_synth_config* c);
-/* host generators (no GPU needed): points as float4 (x,y,z,intensity), features as 2 x F doubles */
-int mld_synth_points_host(const mld_synth_config* c, uint64_t seed, int64_t frame, float* out_xyzi);
-int mld_synth_features_host(const mld_synth_config* c, uint64_t seed, int64_t frame, int F, double* out_uv);
-/* device generators: frames [frame0, frame0 + nframes) written frame_pitch_points apart */
+/* ---- synthetic KITTI-shaped input, device generators (bench / tests; include/mld_synth.h has the configuration and the
+ * host generators of libmld_synth.so, which agree with these bit for bit) ----
+ * frames [frame0, frame0 + nframes) written frame_pitch_points apart */
 int mld_synth_points_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,
                             int64_t frame_pitch_points, float* d_out_xyzi, void* stream);
 int mld_synth_features_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,

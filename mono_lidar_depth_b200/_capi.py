@@ -100,6 +100,8 @@ class MldPlane(C.Structure):
 
 
 class MldSynthConfig(C.Structure):
+    """mld_synth_config (include/mld_synth.h)."""
+
     _fields_ = [
         ("rings", C.c_int32),
         ("azimuth_steps", C.c_int32),
@@ -113,8 +115,14 @@ class MldSynthConfig(C.Structure):
         ("image_width", C.c_int32),
         ("image_height", C.c_int32),
         ("band_top_frac", C.c_float),
-        ("band_feature_frac", C.c_float),
-        ("reserved0", C.c_int32),
+        ("above_band_frac", C.c_float),
+        ("object_frac", C.c_float),
+        ("road_frac", C.c_float),
+        ("cam_f", C.c_float),
+        ("cam_cx", C.c_float),
+        ("cam_cy", C.c_float),
+        ("cam_T", C.c_float * 12),
+        ("two_block_rings", C.c_int32),
     ]
 
 
@@ -189,15 +197,40 @@ SYMBOLS = {
     "mld_get_neighbors": (C.c_int, [_H, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "mld_get_visible": (C.c_int, [_H, C.c_void_p, C.POINTER(C.c_int64)]),
     "mld_get_points_camera": (C.c_int, [_H, C.c_void_p]),
-    "mld_synth_default_config": (None, [_SC, C.c_int]),
-    "mld_synth_points_per_frame": (C.c_int64, [_SC]),
-    "mld_synth_points_host": (C.c_int, [_SC, C.c_uint64, C.c_int64, C.c_void_p]),
-    "mld_synth_features_host": (C.c_int, [_SC, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
     "mld_synth_points_device": (C.c_int, [_H, _SC, C.c_uint64, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p]),
     "mld_synth_features_device": (C.c_int, [_H, _SC, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_void_p, C.c_void_p]),
 }
 
+# libmld_synth.so (include/mld_synth.h): host generators of the synthetic input, plain C++ without CUDA
+SYNTH_LIB_PATH = _PKG / "libmld_synth.so"
+SYNTH_SYMBOLS = {
+    "mld_synth_default_config": (None, [_SC, C.c_int]),
+    "mld_synth_config_for": (None, [_SC, C.c_int, C.c_int]),
+    "mld_synth_points_per_frame": (C.c_int64, [_SC]),
+    "mld_synth_points_host": (C.c_int, [_SC, C.c_uint64, C.c_int64, C.c_void_p]),
+    "mld_synth_points_host_xyzi32": (C.c_int, [_SC, C.c_uint64, C.c_int64, C.c_void_p]),
+    "mld_synth_features_host": (C.c_int, [_SC, C.c_uint64, C.c_int64, C.c_int, C.c_void_p]),
+}
+
 _lib = None
+_synth_lib = None
+
+
+def load_synth() -> C.CDLL:
+    """Load libmld_synth.so (no CUDA involved: usable by the CPU arm of bench.py and the CPU tests)."""
+    global _synth_lib
+    if _synth_lib is not None:
+        return _synth_lib
+    path = Path(os.environ.get("MLD_SYNTH_LIB", str(SYNTH_LIB_PATH)))
+    if not path.exists():
+        raise ImportError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(str(path))
+    for name, (res, args) in SYNTH_SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _synth_lib = lib
+    return lib
 
 
 def load() -> C.CDLL:

@@ -1539,69 +1539,43 @@ int mld_get_points_camera(mld_handle* h, double* out_host) {
     return debug_views(h, nullptr, nullptr, out_host);
 }
 
-// ---- synthetic input ----
-void mld_synth_default_config(mld_synth_config* c, int dense) {
-    memset(c, 0, sizeof(*c));
-    c->rings = dense ? 128 : 64;
-    c->azimuth_steps = dense ? 2032 : 1875;
-    c->elev_top_deg = 2.0f;
-    c->elev_bottom_deg = -24.8f;
-    c->sensor_height = 1.73f;
-    c->max_range = 120.0f;
-    c->range_noise_sigma = 0.02f;
-    c->dropout_prob = 0.02f;
-    c->n_boxes = 40;
-    c->image_width = dense ? 2048 : 1241;
-    c->image_height = dense ? 1024 : 376;
-    c->band_top_frac = 0.4f;
-    c->band_feature_frac = 0.7f;
-}
-int64_t mld_synth_points_per_frame(const mld_synth_config* c) { return (int64_t)c->rings * c->azimuth_steps; }
-
-static bool synth_cfg_ok(const mld_synth_config* c) {
-    return c && c->rings > 0 && c->azimuth_steps >= 6 && c->n_boxes >= 0 && c->n_boxes <= 64 && c->image_width > 0 && c->image_height > 1;
-}
-
-int mld_synth_points_host(const mld_synth_config* c, uint64_t seed, int64_t frame, float* out_xyzi) {
-    if (!synth_cfg_ok(c) || !out_xyzi) return MLD_ERR_INVALID_ARG;
-    std::vector<float> tables((size_t)(2 * c->rings + 2 * c->azimuth_steps));
+// ---- synthetic input (device generators; the host generators live in libmld_synth.so) ----
+static int synth_tables(mld_handle* h, const mld_synth_config* c, cudaStream_t st) {
+    const size_t tn = mld_synth_table_floats(*c);
+    if (h->synth_tables_valid && memcmp(&h->synth_cfg_cached, c, sizeof(*c)) == 0) return MLD_OK;
+    std::vector<float> tables(tn);
     mld_synth_build_tables(*c, tables.data());
-    mld_synth_points_host_impl(*c, seed, frame, tables.data(), out_xyzi);
-    return MLD_OK;
-}
-int mld_synth_features_host(const mld_synth_config* c, uint64_t seed, int64_t frame, int F, double* out_uv) {
-    if (!synth_cfg_ok(c) || !out_uv || F < 0) return MLD_ERR_INVALID_ARG;
-    mld_synth_features_host_impl(*c, seed, frame, F, out_uv);
+    CK(cudaStreamSynchronize(st));
+    if (h->d_synth_tables) CK(cudaFree(h->d_synth_tables));
+    h->d_synth_tables = nullptr;
+    h->synth_tables_valid = false;
+    CK(cudaMalloc(&h->d_synth_tables, tn * sizeof(float)));
+    CK(cudaMemcpy(h->d_synth_tables, tables.data(), tn * sizeof(float), cudaMemcpyHostToDevice));
+    h->synth_cfg_cached = *c;
+    h->synth_tables_valid = true;
     return MLD_OK;
 }
 
 int mld_synth_points_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes,
                             int64_t frame_pitch_points, float* d_out_xyzi, void* stream) {
-    if (!h || !synth_cfg_ok(c) || !d_out_xyzi) return MLD_ERR_INVALID_ARG;
-    if (frame_pitch_points < mld_synth_points_per_frame(c)) return fail(h, MLD_ERR_INVALID_ARG, "frame pitch smaller than the cloud");
+    if (!h || !mld_synth_config_ok(c) || !d_out_xyzi) return MLD_ERR_INVALID_ARG;
+    if (frame_pitch_points < (int64_t)c->rings * c->azimuth_steps) return fail(h, MLD_ERR_INVALID_ARG, "frame pitch smaller than the cloud");
     DeviceGuard g(h->device);
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-    const size_t tn = (size_t)(2 * c->rings + 2 * c->azimuth_steps);
-    if (!h->synth_tables_valid || memcmp(&h->synth_cfg_cached, c, sizeof(*c)) != 0) {
-        std::vector<float> tables(tn);
-        mld_synth_build_tables(*c, tables.data());
-        CK(cudaStreamSynchronize(st));
-        if (h->d_synth_tables) CK(cudaFree(h->d_synth_tables));
-        h->d_synth_tables = nullptr;
-        CK(cudaMalloc(&h->d_synth_tables, tn * sizeof(float)));
-        CK(cudaMemcpy(h->d_synth_tables, tables.data(), tn * sizeof(float), cudaMemcpyHostToDevice));
-        h->synth_cfg_cached = *c;
-        h->synth_tables_valid = true;
-    }
+    int rc = synth_tables(h, c, st);
+    if (rc) return rc;
     CK(mld_launch_synth_points(*c, seed, frame0, nframes, frame_pitch_points, h->d_synth_tables, d_out_xyzi, st));
     return MLD_OK;
 }
 
 int mld_synth_features_device(mld_handle* h, const mld_synth_config* c, uint64_t seed, int64_t frame0, int64_t nframes, int F,
                               double* d_out_uv, void* stream) {
-    if (!h || !synth_cfg_ok(c) || !d_out_uv || F < 0) return MLD_ERR_INVALID_ARG;
+    if (!h || !mld_synth_config_ok(c) || !d_out_uv || F < 0) return MLD_ERR_INVALID_ARG;
     DeviceGuard g(h->device);
-    CK(mld_launch_synth_features(*c, seed, frame0, nframes, F, d_out_uv, reinterpret_cast<cudaStream_t>(stream)));
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    int rc = synth_tables(h, c, st);
+    if (rc) return rc;
+    CK(mld_launch_synth_features(*c, seed, frame0, nframes, F, h->d_synth_tables, d_out_uv, st));
     return MLD_OK;
 }
 

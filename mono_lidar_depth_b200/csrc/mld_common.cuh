@@ -10,6 +10,7 @@
 #include <stdint.h>
 
 #include "mld_c_api.h"
+#include "mld_hash.h"
 
 #define MLD_FULL_MASK 0xffffffffu
 #define MLD_EMPTY 0xffffffffu  // pixel-map cell without a point; reads as int32 -1 (POINT_NOT_DEFINED)
@@ -161,17 +162,6 @@ __device__ __forceinline__ int warp_min_i(int v) {
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) v = min(v, __shfl_xor_sync(MLD_FULL_MASK, v, m));
     return v;
-}
-
-// counter-based RNG (splitmix64 finaliser) shared by the RANSAC kernels and the synthetic generator
-__host__ __device__ __forceinline__ uint64_t mld_mix64(uint64_t z) {
-    z += 0x9E3779B97F4A7C15ull;
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return z ^ (z >> 31);
-}
-__host__ __device__ __forceinline__ uint64_t mld_hash3(uint64_t seed, uint64_t a, uint64_t b, uint64_t c) {
-    return mld_mix64(mld_mix64(mld_mix64(mld_mix64(seed) ^ a) ^ b) ^ c);
 }
 
 // Jacobi eigen-decomposition of a symmetric 3x3 held in registers. a = (a00,a01,a02,a11,a12,a22).

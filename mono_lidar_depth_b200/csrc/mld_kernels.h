@@ -102,12 +102,11 @@ cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int s
 cudaError_t mld_launch_status_histogram(const int* d_status, long long n, unsigned long long* d_hist21, cudaStream_t stream);
 cudaError_t mld_launch_pack_feature_points(const double* d_uv, const double* d_depth, long long n, float* d_out, cudaStream_t stream);
 
-// synthetic data (mld_synth.cu)
+// synthetic data (mld_synth.cu; scene model in mld_synth_model.h, host generators in libmld_synth.so)
 cudaError_t mld_launch_synth_points(const mld_synth_config& c, uint64_t seed, long long frame0, long long nframes,
                                     long long pitch_pts, const float* d_tables, float* d_out, cudaStream_t stream);
 cudaError_t mld_launch_synth_features(const mld_synth_config& c, uint64_t seed, long long frame0, long long nframes, int F,
-                                      double* d_out, cudaStream_t stream);
-// host side of the same generator
-void mld_synth_build_tables(const mld_synth_config& c, float* tables /* 2*rings + 2*azimuth_steps */);
-void mld_synth_points_host_impl(const mld_synth_config& c, uint64_t seed, long long frame, const float* tables, float* out);
-void mld_synth_features_host_impl(const mld_synth_config& c, uint64_t seed, long long frame, int F, double* out);
+                                      const float* d_tables, double* d_out, cudaStream_t stream);
+void mld_synth_build_tables(const mld_synth_config& c, float* tables);
+size_t mld_synth_table_floats(const mld_synth_config& c);
+bool mld_synth_config_ok(const mld_synth_config* c);

@@ -13,8 +13,8 @@ from mono_lidar_depth_b200 import DepthEstimator, DepthEstimatorParameters, MldE
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _declared_functions():
-    text = (ROOT / "include" / "mld_c_api.h").read_text()
+def _declared_functions(header="mld_c_api.h"):
+    text = (ROOT / "include" / header).read_text()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(mld_[a-z0-9_]+)\s*\(", text)))
 
@@ -27,6 +27,20 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"libmld_cuda.so does not export {n}"
         assert n in _capi.SYMBOLS, f"{n} declared in mld_c_api.h but not bound in _capi.py"
     assert set(_capi.SYMBOLS) == set(names)
+
+
+def test_synth_library_exports_every_declared_symbol_and_needs_no_cuda():
+    """include/mld_synth.h -> libmld_synth.so: the host generators (CPU arm of bench.py) never map the product library."""
+    lib = _capi.load_synth()
+    names = _declared_functions("mld_synth.h")
+    assert len(names) >= 5
+    for n in names:
+        assert hasattr(lib, n), f"libmld_synth.so does not export {n}"
+    assert set(_capi.SYNTH_SYMBOLS) == set(names)
+    import subprocess
+
+    deps = subprocess.run(["ldd", str(_capi.SYNTH_LIB_PATH)], capture_output=True, text=True).stdout
+    assert "cuda" not in deps.lower() and "mld_cuda" not in deps
 
 
 def test_params_layout_matches_oracle_and_header():
