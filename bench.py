@@ -148,7 +148,7 @@ def cpu_reference_throughput(budget_s: float, frames_host=None, uv_host=None):
     p = O.yaml_params()
     p.do_use_ransac_plane = 1 if wl["road"] else 0
     cam = synth.dense_camera() if wl["dense"] else synth.kitti_camera()
-    cfg = synth.default_config(wl["dense"])
+    cfg = synth.default_config(wl["dense"], road=bool(wl["road"]))
 
     def make():
         o = O.Oracle(p)
@@ -300,7 +300,7 @@ def run_gpu(args, rank, local_rank, world):
     wl = WORKLOADS[WORKLOAD]
     frames_total = env_int("MLD_BENCH_FRAMES", wl["frames"]) * world  # weak scaling: the same block per GPU
     f0, nframes = sharding.frame_block(frames_total, world, rank)
-    cfg = synth.default_config(wl["dense"])
+    cfg = synth.default_config(wl["dense"], road=bool(wl["road"]))
     n = synth.points_per_frame(cfg)
     F = N_FEATURES
     assert n == N_POINTS
@@ -468,19 +468,22 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
         # device-resident sequences run K1 of chunk j and the gather of chunk j-1 as ONE launch
-        fused = est.fusedChunkFrames()
-        chunk = fused or est.chunkFrames()
+        pipelined = est.pipelineFrames()
+        fused = 0 if pipelined else est.fusedChunkFrames()
+        chunk = nframes if pipelined else (fused or est.chunkFrames())
         per_class = {}
         for name, (ms, ln) in prof.items():
             per_class[name] = {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None}
         # dominant kernel of the step and its algorithmic bytes per launch (DESIGN.md "roofline")
         # single kernels only: feature_depth is the sum of feature_gather + feature_solve + feature_rest (road kernels and the
         # overflow pass), listed for the share of the step but not a kernel of its own
-        if fused:
+        if pipelined:  # one persistent launch per sequence does all of it (mld_pipeline.cu)
+            per_class = {"depth_pipeline": per_class["project_scatter"], "ransac": per_class.get("ransac")}
+        elif fused:
             per_class["fused_project_gather"] = per_class.pop("project_scatter")
             per_class.pop("feature_gather", None)
         kernels = {k: v for k, v in per_class.items()
-                   if k in ("project_scatter", "fused_project_gather", "feature_gather", "feature_solve") and v["launches"] and v["ms_total"] > 0}
+                   if k in ("depth_pipeline", "project_scatter", "fused_project_gather", "feature_gather", "feature_solve") and v and v["launches"] and v["ms_total"] > 0}
         per_class["note"] = ("durations are bracketed by CUDA events on the launching streams inside the timed region; launches of different "
                              "chunks overlap (front stream: fused K1 + gather launches; slot streams: solve + overflow pass), so a kernel's "
                              "duration includes time shared with other kernels; in the fused pipeline every 4th launch group is sampled")
@@ -489,7 +492,7 @@ def run_gpu(args, rank, local_rank, world):
         # list of this same command when it is committed (profiles/traffic.json, headline workload), else from the brackets.
         traffic_file = ROOT / "profiles" / "traffic.json"
         tr = {}
-        if traffic_file.exists() and WORKLOAD == "kitti":
+        if traffic_file.exists() and WORKLOAD == "kitti" and not pipelined:
             try:
                 tr = json.loads(traffic_file.read_text())
             except Exception:
@@ -507,12 +510,12 @@ def run_gpu(args, rank, local_rank, world):
             # bytes the kernel has to move given the algorithm as built: the point stream once, the feature reads, the result
             # writes. SURVEY.md 8(d)'s 4 W H map term is NOT charged to a kernel: the epoch-tagged map is never rewritten
             # as a whole (only the cells of visible points are touched), so charging it would report more than the DRAM moved.
-            per_frame_bytes = {"project_scatter": 16 * N_POINTS, "feature_gather": 16 * N_FEATURES,
+            per_frame_bytes = {"depth_pipeline": 16 * N_POINTS + 28 * N_FEATURES, "project_scatter": 16 * N_POINTS, "feature_gather": 16 * N_FEATURES,
                                "fused_project_gather": 16 * N_POINTS + 16 * N_FEATURES, "feature_solve": 12 * N_FEATURES}[dom]
             avg_s = per_class[dom]["avg_launch_ms"] * 1e-3
             achieved = per_frame_bytes * frames_per_launch / avg_s / 1e9
             sampled_ms = sum(v["ms_total"] for k, v in per_class.items()
-                             if isinstance(v, dict) and k in ("map_clear", "project_scatter", "fused_project_gather", "ransac", "feature_depth"))
+                             if isinstance(v, dict) and k in ("map_clear", "depth_pipeline", "project_scatter", "fused_project_gather", "ransac", "feature_depth"))
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,

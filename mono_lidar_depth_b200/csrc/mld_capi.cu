@@ -99,6 +99,22 @@ struct mld_handle {
     long long cur_n = 0;
     int cur_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
+    // persistent pipeline (mld_pipeline.cu): one launch per device-resident sequence; ring of map / occupancy slots
+    bool use_pipeline = true;       // MLD_PIPE=0: chunked launches (fused K1 + gather, solve, overflow pass) as in round 1
+    int pipe_delay = 64;            // K1 may run this many frames ahead of the feature queue (MLD_PIPE_DELAY; <= ring slots)
+    int pipe_hint = 1;              // evict_first L2 policy on the point stream (MLD_PIPE_HINT)
+    int pipe_bps = 0;               // resident blocks per SM of the persistent grid (MLD_PIPE_BPS; 0 = what fits)
+    int pipe_ring = 0;              // ring slots (MLD_PIPE_RING; 0 = mld_pipeline_ring_slots())
+    int pipe_k1_group = 8;          // consecutive K1 tiles per work item, streamed through two staging buffers (MLD_PIPE_K1_GROUP)
+    int pipe_timing = 0;            // MLD_PIPE_TIMING=1: clock64() accumulators per role / phase (mld_pipeline_counters)
+    int pipe_road_chunk = 512;      // frames per launch when a ground plane is fitted per frame (plane buffers are per chunk)
+    int sm_count = 148;
+    unsigned int* d_ring_maps = nullptr; size_t ring_maps_bytes = 0;
+    unsigned int* d_ring_occ = nullptr;  size_t ring_occ_bytes = 0;
+    int* d_ring_sync = nullptr;          size_t ring_sync_bytes = 0;
+    unsigned ring_epoch = 0;        // epochs consumed by every slot of the ring since its last clear (0 = never cleared)
+    int* h_pipe_flags = nullptr;    // pinned: [0] error flag of the last pipeline launch (read back asynchronously)
+    int* h_pipe_counters = nullptr; // pinned: the 16 sync words of the last launch (ticket, error, profiling accumulators)
     int* d_dbg = nullptr;           // neighbour debug buffer
     float* d_synth_tables = nullptr;
     mld_synth_config synth_cfg_cached;
@@ -580,6 +596,22 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env) h->fuse_serial = atoi(env) != 0;
     env = getenv("MLD_FUSE_CHUNK");
     if (env && atoi(env) > 0) h->fuse_chunk = atoi(env);
+    env = getenv("MLD_PIPE");          // "0": chunked launches instead of the persistent pipeline
+    if (env) h->use_pipeline = atoi(env) != 0;
+    env = getenv("MLD_PIPE_DELAY");
+    if (env && atoi(env) > 0) h->pipe_delay = atoi(env);
+    env = getenv("MLD_PIPE_HINT");
+    if (env) h->pipe_hint = atoi(env) != 0;
+    env = getenv("MLD_PIPE_BPS");
+    if (env && atoi(env) > 0) h->pipe_bps = atoi(env);
+    env = getenv("MLD_PIPE_RING");
+    if (env && atoi(env) >= 4) h->pipe_ring = atoi(env);
+    env = getenv("MLD_PIPE_K1_GROUP");
+    if (env && atoi(env) > 0) h->pipe_k1_group = atoi(env);
+    env = getenv("MLD_PIPE_TIMING");
+    if (env) h->pipe_timing = atoi(env) != 0;
+    env = getenv("MLD_PIPE_ROAD_CHUNK");
+    if (env && atoi(env) > 0) h->pipe_road_chunk = atoi(env);
     env = getenv("MLD_K1_PERSIST");    // blocks per SM of the persistent K1 grid (0 = one block per tile)
     if (env && atoi(env) >= 0) h->k1_persist_per_sm = atoi(env);
     env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
@@ -604,10 +636,13 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
         }
     }
     e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_pipe_flags), 36 * sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         delete h;
         return fail_cuda(nullptr, e, "event creation");
     }
+    memset(h->h_pipe_flags, 0, 36 * sizeof(int));
+    h->h_pipe_counters = h->h_pipe_flags + 4;
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
         e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
@@ -639,6 +674,8 @@ int mld_destroy(mld_handle* h) {
     }
     cudaFree(h->d_dbg);
     cudaFree(h->d_synth_tables);
+    cudaFree(h->d_ring_maps); cudaFree(h->d_ring_occ); cudaFree(h->d_ring_sync);
+    if (h->h_pipe_flags) cudaFreeHost(h->h_pipe_flags);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -718,8 +755,10 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) {
         h->overflow_blocks = 2 * sms;
         h->k1_persistent_blocks = h->k1_persist_per_sm * sms;
+        h->sm_count = sms;
     }
     for (auto& sl : h->slots) sl.epoch = 0;  // image size may have changed
+    h->ring_epoch = 0;
     h->initialized = true;
     h->have_cloud = false;
     return MLD_OK;
@@ -761,6 +800,15 @@ int mld_profile_read(mld_handle* h, double* ms7, int64_t* launches7, int64_t* fr
     return MLD_OK;
 }
 int64_t mld_kernel_launch_count(const mld_handle* h) { return h ? h->launches : 0; }
+int mld_pipeline_frames(const mld_handle* h) { return (h && h->use_pipeline && h->feature_mode == 2 && h->use_tagged_maps) ? 1 : 0; }
+int mld_pipeline_counters(const mld_handle* h, int64_t* out8) {
+    if (!h || !out8 || !h->h_pipe_counters) return MLD_ERR_INVALID_ARG;
+    const unsigned long long* c = reinterpret_cast<const unsigned long long*>(h->h_pipe_counters + 8);
+    for (int i = 0; i < 7; i++) out8[i] = (int64_t)c[i];
+    out8[7] = (int64_t)h->h_pipe_counters[24];  // features that took the warp path
+    return MLD_OK;
+}
+int mld_pipeline_aborted(const mld_handle* h) { return (h && h->h_pipe_flags) ? *reinterpret_cast<volatile int*>(h->h_pipe_flags) : 0; }
 
 static int check_stride(mld_handle* h, int stride_bytes) {
     if (stride_bytes < 16 || stride_bytes % 16 != 0)
@@ -1100,6 +1148,96 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
     return MLD_OK;
 }
 
+// Device-resident sequence through the persistent pipeline (mld_pipeline.cu): ONE launch for the whole sequence when no plane
+// has to be fitted; with a per-frame ground plane (RANSAC / SemanticPlane) the sequence is cut into chunks whose planes are fitted
+// on a slot stream while the previous chunk's launch runs. Profiling brackets: [1,2] = the pipeline launch (class 1).
+static int process_frames_device_pipeline(mld_handle* h, const float* pts, int64_t n_points, int64_t frame_pitch_points, int stride_f,
+                                          const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, cudaStream_t st,
+                                          bool use_road, uint64_t seed, float* d_plane_coeffs_out, const PlaneSrc* src) {
+    const int R = h->pipe_ring > 0 ? h->pipe_ring : mld_pipeline_ring_slots();
+    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
+    const size_t OW = (size_t)occ_words_per_frame(h->dp.W, h->dp.H);
+    bool fresh = false;
+    CK(ensure(h->d_ring_maps, h->ring_maps_bytes, (size_t)R * WH * sizeof(unsigned int), &fresh));
+    CK(ensure(h->d_ring_occ, h->ring_occ_bytes, (size_t)R * OW * sizeof(unsigned int)));
+    CK(ensure(h->d_ring_sync, h->ring_sync_bytes, mld_pipeline_sync_bytes(R)));
+    if (fresh) h->ring_epoch = 0;
+    const int bps = h->pipe_bps > 0 ? h->pipe_bps : mld_pipeline_blocks_per_sm();
+    const int grid = bps * h->sm_count;
+    const long long words = (n_points + 31) / 32;
+    const bool fit_planes = use_road && !(src && src->kind == PlaneSrc::EXTERNAL);
+    const int64_t chunk = fit_planes ? std::min<int64_t>(h->pipe_road_chunk, nframes) : std::min<int64_t>(nframes, 1 << 20);
+    const int64_t nchunks = (nframes + chunk - 1) / chunk;
+    if (fit_planes) {
+        for (int i = 0; i < 2; i++) {
+            int rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_f * 4, F, (int)chunk, false, true);
+            if (rc) return rc;
+        }
+        CK(cudaEventRecord(h->ev_fork, st));
+        for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
+    }
+    for (int64_t j = 0; j < nchunks; j++) {
+        const int64_t f0 = j * chunk;
+        const int64_t c = std::min<int64_t>(chunk, nframes - f0);
+        const float* cp = pts + f0 * frame_pitch_points * stride_f;
+        const float* coeffs = nullptr;
+        const unsigned int* bits = nullptr;
+        if (use_road && !fit_planes) {
+            coeffs = src->d_coeffs + f0 * 4;
+            bits = src->d_bits + f0 * words;
+        } else if (fit_planes) {
+            Slot& sp = h->slots[j & 1];
+            // the slot's plane buffers are free once the launch of chunk j - 2 has finished reading them
+            if (j >= 2) CK(cudaStreamWaitEvent(sp.stream, sp.done, 0));
+            float* cdst = d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : sp.d_coeffs;
+            int nlp = 0;
+            if (src && src->kind == PlaneSrc::SEMANTIC) {
+                CK(ensure(sp.d_sem, sp.sem_bytes, mld_semantic_state_bytes((int)c)));
+                CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
+                                             stride_f, n_points, frame_pitch_points, src->d_labels + f0 * (int64_t)src->label_w * src->label_h, (int)c,
+                                             sp.d_sem, cdst, sp.d_bits, words, sp.d_small, src->d_rc_out ? src->d_rc_out + f0 : sp.d_small + 2 * c,
+                                             sp.stream, &nlp));
+            } else {
+                CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, (int)c, seed, f0, sp.d_scratch, cdst,
+                                     sp.d_bits, words, sp.d_small, sp.d_small + c, sp.d_small + 2 * c, sp.stream, &nlp));
+            }
+            h->launches += nlp;
+            CK(cudaEventRecord(sp.ev_k1, sp.stream));
+            CK(cudaStreamWaitEvent(st, sp.ev_k1, 0));
+            coeffs = cdst;
+            bits = sp.d_bits;
+        }
+        const unsigned uses = (unsigned)((c + R - 1) / R);
+        if (h->ring_epoch == 0 || h->ring_epoch + uses > MLD_TAG_MAX_EPOCH) {
+            CK(cudaMemsetAsync(h->d_ring_maps, 0xFF, h->ring_maps_bytes, st));
+            h->ring_epoch = 0;
+        }
+        cudaEvent_t* ev = nullptr;
+        int rcp = prof_acquire(h, (int)c, &ev);
+        if (rcp) return rcp;
+        if (ev) {
+            CK(cudaEventRecord(ev[0], st));
+            CK(cudaEventRecord(ev[1], st));
+        }
+        int nl = 0;
+        CK(mld_launch_depth_pipeline(h->dp, cp, stride_f, n_points, frame_pitch_points, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F,
+                                     d_status + f0 * (int64_t)F, c, h->d_ring_maps, h->d_ring_occ, R, h->ring_epoch, h->d_ring_sync, coeffs, bits,
+                                     words, h->kcap, h->pipe_delay, h->pipe_hint, h->pipe_timing, h->pipe_k1_group, grid, st, &nl));
+        h->ring_epoch += uses;
+        h->launches += nl;
+        if (ev) {
+            for (int q = 2; q < MLD_PROF_EVENTS; q++) CK(cudaEventRecord(ev[q], st));
+            h->prof_used++;
+        }
+        if (fit_planes) CK(cudaEventRecord(h->slots[j & 1].done, st));
+    }
+    // error flag of the (last) launch: read back asynchronously, reported by mld_pipeline_aborted() once the stream is idle
+    CK(cudaMemcpyAsync(h->h_pipe_flags, h->d_ring_sync + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (h->pipe_timing) CK(cudaMemcpyAsync(h->h_pipe_counters, h->d_ring_sync, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    h->have_cloud = false;
+    return MLD_OK;
+}
+
 static int process_frames_device_impl(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
                                       const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
                                       uint64_t seed, float* d_plane_coeffs_out, void* stream, const PlaneSrc* src) {
@@ -1138,6 +1276,10 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
+    if (h->use_pipeline && h->feature_mode == 2 && F > 0 && n_points > 0 && nframes > 0 && n_points <= (long long)(MLD_TAG_IDX_MASK + 1u) &&
+        h->use_tagged_maps)
+        return process_frames_device_pipeline(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, st, use_road,
+                                              seed, d_plane_coeffs_out, src);
     if (fused_ok && nchunks >= 2 && nslots >= 2)
         return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st,
                                            use_road, seed, d_plane_coeffs_out, src);

@@ -135,6 +135,20 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     return v;
 }
 
+// the same load with an L2 eviction-priority policy (createpolicy) attached
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ float4 ld_stream_f4_hint(const float* p, unsigned long long policy) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p), "l"(policy));
+    return v;
+}
+
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(MLD_FULL_MASK, v, m); }
 
 __device__ __forceinline__ double warp_sum_d(double v) {
@@ -179,7 +193,7 @@ __device__ __forceinline__ int warp_min_i(int v) {
         (vp) = nvp; (vq) = nvq;                                                           \
     }
 
-__host__ __device__ inline void eig3_sym_regs(double a00, double a01, double a02, double a11, double a12, double a22,
+static __device__ __noinline__ void eig3_sym_regs(double a00, double a01, double a02, double a11, double a12, double a22,
                                               double w[3], D3 v[3]) {
     // v[c] is eigenvector c (columns of the rotation product)
     D3 v0 = D3{1, 0, 0}, v1 = D3{0, 1, 0}, v2 = D3{0, 0, 1};

@@ -29,7 +29,7 @@ namespace {
 // instead of 4 with 12 entries (1.22 -> 1.31 M frames/s; 10 entries: 1.23 M). A 7 x 10 window over an HDL-64 sweep holds
 // 2 rings x 3-4 returns; fuller windows take the warp-per-feature overflow pass.
 #ifndef MLD_SCAP
-#define MLD_SCAP 8
+#define MLD_SCAP 9  // 3 rings x 3 returns fit (round 2 scene: HDL-64E ring layout); 8 sent 3.5 % of the features to the overflow pass
 #endif
 // 7 resident blocks asked for: 72 registers instead of 81 (a few spilled bytes in the cold tail), +2 % on the path
 #ifndef MLD_SOLVE_MINBLOCKS

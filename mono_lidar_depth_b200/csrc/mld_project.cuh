@@ -67,10 +67,13 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
 }
 
 // pre-filter, exact projection and scatter of the K1_PPT points a thread holds in registers.
-// The first test (z_cam < 0, which removes half of a sweep) runs over all K1_PPT points before anything else: its six
-// constants stay in registers, there is no branch per point, and a thread whose points all fail -- the common case, a
-// thread's points span a few degrees of azimuth -- leaves at once. (One test after the other per point costs ~14
-// instructions per point and test, 4 of them constant loads: ncu r1c, 604 warp instructions per 8 points.)
+// Stage 1: the five pre-filter tests, one test at a time over all K1_PPT points (branch-free inside a test: the test's six
+// constants stay in registers), leaving as soon as no point of the thread is alive -- the common case, since a thread's points
+// span a few degrees of azimuth: half of a sweep leaves after the first test (z_cam < 0), the front-left / front-right sectors
+// outside the image after the second / third. (One test after the other per point cost ~14 instructions per point and test,
+// 4 of them constant loads: ncu r1c, 604 warp instructions per 8 points.)
+// Stage 2: ONE copy of the exact FP64 path, looped over the surviving points (a set bit per point): eight unrolled copies
+// cost 5.6 k instructions of I-cache and ~30 registers of hoisted FP64 constants (spills once the kernel carries a second role).
 template <bool FULL_TILE>
 __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 (&p)[K1_PPT], int base, int n, unsigned int hi,
                                                unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch) {
@@ -87,56 +90,92 @@ __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 
     }
     if (!alive) return;
 #pragma unroll
-    for (int j = 0; j < K1_PPT; j++) {
-        if (!((alive >> j) & 1u)) continue;
-        const int i = base + j * K1_THREADS;
-        if (surely_outside(P, p[j].x, p[j].y, p[j].z)) continue;
+    for (int t = 1; t < 5; t++) {
+        // t = 1: f*X + cx*Z < 0 <=> u < 0;  2: f*X + (cx-W)*Z > 0 <=> u > W;  3: f*Y + cy*Z < 0 <=> v < 0;  4: f*Y + (cy-H)*Z > 0 <=> v > H
+        const float g0 = P.pf_g[t][0], g1 = P.pf_g[t][1], g2 = P.pf_g[t][2], h0 = P.pf_h[t], G0 = P.pf_G[t], H0 = P.pf_H[t];
+        unsigned int keep = 0u;
+#pragma unroll
+        for (int j = 0; j < K1_PPT; j++) {
+            const float S = fabsf(p[j].x) + fabsf(p[j].y) + fabsf(p[j].z);
+            const float f = fmaf(g0, p[j].x, fmaf(g1, p[j].y, fmaf(g2, p[j].z, h0)));
+            const float e = fmaf(G0, S, H0);
+            // a rejection is only ever a shortcut: an infinite coordinate that slips through fails the exact tests below
+            const bool in = (t & 1) ? (f + e >= 0.f) : (f - e <= 0.f);
+            if (in) keep |= 1u << j;
+        }
+        alive &= keep;
+        if (!alive) return;
+    }
 #ifdef MLD_DIAG_NOFP64
-        if (p[j].x == 123456.f) map[0] = 1;  // diagnostic build: keep the loads alive, skip the exact path
-        continue;
+    if (p[0].x == 123456.f) map[0] = alive;  // diagnostic build: keep the loads alive, skip the exact path
+    return;
 #endif
-        int x, y;
-        if (!project_pixel(P, p[j].x, p[j].y, p[j].z, true, x, y)) continue;
+#pragma unroll 1
+    while (alive) {
+        const int j = __ffs((int)alive) - 1;
+        alive &= alive - 1u;
+        float x = p[0].x, y = p[0].y, z = p[0].z;
+#pragma unroll
+        for (int q = 1; q < K1_PPT; q++) {
+            if (j == q) {
+                x = p[q].x;
+                y = p[q].y;
+                z = p[q].z;
+            }
+        }
+        int px, py;
+        if (!project_pixel(P, x, y, z, true, px, py)) continue;
 #ifdef MLD_DIAG_NOATOM
-        if (x == -5) map[0] = 1;  // diagnostic build: no scatter
+        if (px == -5) map[0] = 1;  // diagnostic build: no scatter
         continue;
 #endif
-        atomicMin(&map[y * P.W + x], hi | (unsigned int)i);
-        if (ob) atomicOr(ob + occ_word_of(occ_pitch, x, y), occ_bit_of(x, y));  // occ_pitch = tiles per image row
+        atomicMin(&map[py * P.W + px], hi | (unsigned int)(base + j * K1_THREADS));
+        if (ob) atomicOr(ob + occ_word_of(occ_pitch, px, py), occ_bit_of(px, py));  // occ_pitch = tiles per image row
     }
 }
 
-// one K1 tile: K1_THREADS x K1_PPT consecutive points of `frame`, starting at point tile * K1_THREADS * K1_PPT.
-// STRIDE_F = 4 (float4) or 8 (pcl::PointXYZI) makes the eight load offsets immediates; a tile that lies completely inside
-// the frame (all but the last) loads without per-point bounds predicates.
-template <int STRIDE_F>
-__device__ __forceinline__ void k1_tile_s(const DevParams& P, const MapCode& mc, const float* __restrict__ pts, int stride_rt, int n,
-                                          long long pitch_pts, unsigned int* __restrict__ maps, unsigned int* __restrict__ occ,
-                                          unsigned int frame, int tile) {
+// one K1 tile: K1_THREADS x K1_PPT consecutive points of one frame, starting at point tile * K1_THREADS * K1_PPT of the cloud at
+// `cloud` (n points), scattered into `map` / `ob` (the frame's pixel map and occupancy bitmap). STRIDE_F = 4 (float4) or 8
+// (pcl::PointXYZI) makes the eight load offsets immediates; a tile that lies completely inside the frame (all but the last)
+// loads without per-point bounds predicates. HINT: the loads carry an L2 eviction-priority policy (evict_first: the stream is
+// read once, the pixel maps it is scattered into should stay resident -- the persistent pipeline, mld_pipeline.cu).
+template <int STRIDE_F, bool HINT>
+__device__ __forceinline__ void k1_tile_at(const DevParams& P, unsigned int hi, const float* __restrict__ cloud, int stride_rt, int n,
+                                           unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int tile,
+                                           unsigned long long policy) {
     const int stride_f = STRIDE_F > 0 ? STRIDE_F : stride_rt;
     const int occ_pitch = occ_tiles_x(P.W);
-    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
     const int base = tile * (K1_THREADS * K1_PPT) + threadIdx.x;
-    const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
+    const float* src = cloud + (size_t)base * (size_t)stride_f;
     const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
-    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
 
     float4 p[K1_PPT];
     if ((tile + 1) * (K1_THREADS * K1_PPT) <= n) {  // uniform per block
 #pragma unroll
-        for (int j = 0; j < K1_PPT; j++) p[j] = ld_stream_f4(src + j * step);
+        for (int j = 0; j < K1_PPT; j++) p[j] = HINT ? ld_stream_f4_hint(src + j * step, policy) : ld_stream_f4(src + j * step);
         scatter_points<true>(P, p, base, n, hi, map, ob, occ_pitch);
     } else {
 #pragma unroll
         for (int j = 0; j < K1_PPT; j++) {
             if (base + j * K1_THREADS < n)
-                p[j] = ld_stream_f4(src + j * step);
+                p[j] = HINT ? ld_stream_f4_hint(src + j * step, policy) : ld_stream_f4(src + j * step);
             else
                 p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         scatter_points<false>(P, p, base, n, hi, map, ob, occ_pitch);
     }
+}
+
+template <int STRIDE_F>
+__device__ __forceinline__ void k1_tile_s(const DevParams& P, const MapCode& mc, const float* __restrict__ pts, int stride_rt, int n,
+                                          long long pitch_pts, unsigned int* __restrict__ maps, unsigned int* __restrict__ occ,
+                                          unsigned int frame, int tile) {
+    const int stride_f = STRIDE_F > 0 ? STRIDE_F : stride_rt;
+    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
+    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
+    const float* cloud = pts + (size_t)frame * (size_t)pitch_pts * (size_t)stride_f;
+    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
+    k1_tile_at<STRIDE_F, false>(P, hi, cloud, stride_rt, n, map, ob, tile, 0ull);
 }
 
 __device__ __forceinline__ void k1_tile(const DevParams& P, const MapCode& mc, const float* __restrict__ pts, int stride_f, int n,

@@ -22,11 +22,12 @@ void mld_synth_config_for(mld_synth_config* c, int dense, int road) {
     c->image_width = dense ? 2048 : 1241;
     c->image_height = dense ? 1024 : 376;
     c->band_top_frac = 0.4f;
-    // feature mix: calibrated so that the status histogram under monolidar_fusion/parameters.yaml resembles the reference's own log
-    // (monolidar_fusion/Logs/log_depth_calc_stats.txt: 22.5 % success, 72.9 % insufficient points, 4.7 % no local maximum):
-    // ~40 % Success, ~47 % RadiusSearchInsufficientPoints, < 10 % HistogramNoLocalMax (measured with the oracle)
-    c->above_band_frac = road ? 0.2f : 0.45f;
-    c->object_frac = road ? 0.25f : 0.47f;
+    // feature mix: calibrated with the oracle so that the status histogram under monolidar_fusion/parameters.yaml matches the
+    // reference's own logs -- monolidar_fusion/Logs/log_depths.txt: 586 of 2009 features (29 %) got a depth;
+    // Logs/log_depth_calc_stats.txt: 22.5 % success, 72.9 % insufficient points, 4.7 % no local maximum -- i.e. ~29 % Success,
+    // ~60 % RadiusSearchInsufficientPoints, < 10 % HistogramNoLocalMax
+    c->above_band_frac = road ? 0.2f : 0.58f;
+    c->object_frac = road ? 0.25f : 0.31f;
     c->road_frac = road ? 0.5f : 0.0f;
     // KITTI raw 2011_09_26 calib_velo_to_cam (public calibration values) and the matching pinhole cameras
     c->cam_f = dense ? 1400.0f : 718.856f;
