@@ -257,8 +257,8 @@ int mld_chunk_frames(const mld_handle* h);
 /* frames per fused K1 + gather launch of device-resident non-road sequences (env MLD_FUSE_CHUNK, default 512), or 0 when
  * the fused pipeline is off (MLD_FUSE=0 or another K2 mode): such sequences then use mld_chunk_frames() like the rest */
 int mld_fused_chunk_frames(const mld_handle* h);
-/* 1 when device-resident sequences run through the persistent pipeline (one launch per sequence: projection and feature
- * estimation as two roles of one grid; env MLD_PIPE=0 selects the chunked launches instead) */
+/* 1 when device-resident sequences run through the persistent pipeline (env MLD_PIPE=1: one launch per sequence, projection
+ * and feature estimation as two roles of one grid) instead of the default chunked launches */
 int mld_pipeline_frames(const mld_handle* h);
 /* error flag of the last persistent-pipeline launch (valid once its stream is idle): non-zero when a dependency wait timed
  * out and the launch was abandoned -- the results of that call are then incomplete */

@@ -46,6 +46,7 @@ struct Slot {
     void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
     int* h_ovf_seen = nullptr;  // pinned: overflow count of this slot's previous chunk (sizes the next overflow launch)
     unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
+    size_t occ_clean_bytes = 0; // leading bytes of d_occ known to be zero once the slot's `done` event has fired (fused pipeline)
     MapCode mc = {0u, 0u};      // encoding of the maps currently held by this slot
 };
 
@@ -100,7 +101,8 @@ struct mld_handle {
     int cur_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
     // persistent pipeline (mld_pipeline.cu): one launch per device-resident sequence; ring of map / occupancy slots
-    bool use_pipeline = true;       // MLD_PIPE=0: chunked launches (fused K1 + gather, solve, overflow pass) as in round 1
+    bool use_pipeline = false;      // MLD_PIPE=1: one persistent launch per sequence (mld_pipeline.cu) instead of the chunked launches
+                                    // (fused K1 + gather, solve, overflow pass); measured 2.3x slower on B200, kept as an option
     int pipe_delay = 64;            // K1 may run this many frames ahead of the feature queue (MLD_PIPE_DELAY; <= ring slots)
     int pipe_hint = 1;              // evict_first L2 policy on the point stream (MLD_PIPE_HINT)
     int pipe_bps = 0;               // resident blocks per SM of the persistent grid (MLD_PIPE_BPS; 0 = what fits)
@@ -206,7 +208,9 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
     CK(ensure(s.d_maps, s.maps_bytes, (size_t)frames * WH * sizeof(unsigned int), &maps_changed));
     if (maps_changed) s.epoch = 0;  // fresh memory holds no valid tags
     CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)frames * (size_t)std::max(F, 1) + 1) * sizeof(int)));
-    CK(ensure(s.d_occ, s.occ_bytes, (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int)));
+    bool occ_changed = false;
+    CK(ensure(s.d_occ, s.occ_bytes, (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int), &occ_changed));
+    if (occ_changed) s.occ_clean_bytes = 0;
     if (road) {
         const size_t words = (size_t)((n_points + 31) / 32);
         CK(ensure(s.d_bits, s.bits_bytes, (size_t)frames * words * sizeof(unsigned int)));
@@ -219,7 +223,7 @@ int slot_reserve(mld_handle* h, Slot& s, long long n_points, int stride_bytes, i
 
 // Prepare the slot's maps for `frames` new frames: tagged mode bumps the epoch (and clears only when the
 // 14-bit epoch space is exhausted or the memory is fresh), plain mode clears every time.
-int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStream_t st, MapCode& mc) {
+int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStream_t st, MapCode& mc, bool occ_may_be_clean = false) {
     const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
     const bool tagged = h->use_tagged_maps && n_points <= (long long)(MLD_TAG_IDX_MASK + 1u);
     if (!tagged) {
@@ -236,8 +240,13 @@ int begin_maps(mld_handle* h, Slot& s, int frames, long long n_points, cudaStrea
         mc = MapCode{1u, MLD_TAG_MAX_EPOCH - s.epoch};
     }
     s.mc = mc;
-    if (h->feature_mode >= 1)
-        CK(cudaMemsetAsync(s.d_occ, 0, (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int), st));
+    if (h->feature_mode >= 1) {
+        // the fused pipeline clears a slot's occupancy bitmaps on the slot's own stream behind its last reader (off the front
+        // stream's critical path); every other path clears here, right before use
+        const size_t need = (size_t)frames * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int);
+        if (!(occ_may_be_clean && s.occ_clean_bytes >= need)) CK(cudaMemsetAsync(s.d_occ, 0, need, st));
+        s.occ_clean_bytes = 0;  // about to be written
+    }
     return MLD_OK;
 }
 
@@ -643,8 +652,12 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     }
     memset(h->h_pipe_flags, 0, 36 * sizeof(int));
     h->h_pipe_counters = h->h_pipe_flags + 4;
+    env = getenv("MLD_SOLVE_PRIO");    // "1": slot streams (solve + overflow pass of the fused pipeline) at the highest priority
+    const bool slot_prio = env && atoi(env) != 0;
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
-        e = cudaStreamCreateWithFlags(&h->slots[i].stream, cudaStreamNonBlocking);
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&h->slots[i].stream, cudaStreamNonBlocking, slot_prio ? hi : lo);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k1, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k2, cudaEventDisableTiming);
@@ -1067,7 +1080,7 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
         if (have_k1 && j >= nslots) CK(cudaStreamWaitEvent(front, sk->done, 0));  // chunk j - nslots has left the slot
         if (ev) CK(cudaEventRecord(ev[0], front));
         if (have_k1) {
-            int rcm = begin_maps(h, *sk, ck, n_points, front, mck);
+            int rcm = begin_maps(h, *sk, ck, n_points, front, mck, true);
             if (rcm) return rcm;
             sk->mc = mck;
         }
@@ -1133,6 +1146,11 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
                                         sg->d_ovf, overflow_grid(h, *sg), s2));
             CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s2));
             if (ev) CK(cudaEventRecord(ev[5], s2));
+            if (!h->fuse_serial) {  // the overflow pass was the slot's last reader: clear its occupancy bitmaps for the next chunk here
+                const size_t ob = (size_t)chunk * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int);
+                CK(cudaMemsetAsync(sg->d_occ, 0, std::min(ob, sg->occ_bytes), s2));
+                sg->occ_clean_bytes = std::min(ob, sg->occ_bytes);
+            }
             CK(cudaEventRecord(sg->done, s2));
             h->launches += nl2 + 1;
         } else if (ev) {

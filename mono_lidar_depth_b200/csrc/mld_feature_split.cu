@@ -25,15 +25,15 @@
 
 namespace {
 
-// 8 entries: the solve kernel's per-thread slab is 8 x 28 bytes of shared memory -> 31 KB per block, 6-7 blocks per SM
-// instead of 4 with 12 entries (1.22 -> 1.31 M frames/s; 10 entries: 1.23 M). A 7 x 10 window over an HDL-64 sweep holds
-// 2 rings x 3-4 returns; fuller windows take the warp-per-feature overflow pass.
+// Entries of the solve kernel's per-thread slab (28 bytes of shared memory each). Round 1 (uniform ring spacing: 2 rings x 3-4
+// returns per 7 x 10 window): 8 entries, 31 KB per block, 6-7 blocks per SM (12 entries: 4 blocks, 1.22 instead of 1.31 M frames/s).
+// Round 2 (HDL-64E ring layout: the upper block's rings are 4 pixels apart, 3 rings x 3 returns fit a window): 9 entries, 35 KB,
+// 6 blocks per SM; with 8 entries 3.5 % of the features took the warp-per-feature overflow pass (0.56 ms per 512 frames).
 #ifndef MLD_SCAP
 #define MLD_SCAP 9  // 3 rings x 3 returns fit (round 2 scene: HDL-64E ring layout); 8 sent 3.5 % of the features to the overflow pass
 #endif
-// 7 resident blocks asked for: 72 registers instead of 81 (a few spilled bytes in the cold tail), +2 % on the path
 #ifndef MLD_SOLVE_MINBLOCKS
-#define MLD_SOLVE_MINBLOCKS 7
+#define MLD_SOLVE_MINBLOCKS 6  // 9-entry slabs: 35 KB of shared memory per block -> 6 blocks per SM; 80 registers, no spills
 #endif
 #ifndef MLD_SBT_B
 #define MLD_SBT_B 128

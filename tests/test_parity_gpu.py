@@ -580,7 +580,7 @@ def test_persistent_pipeline_against_oracle():
         orc.set_cloud(pts[i].cpu().numpy())
         d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy())
         PU.assert_depth_status_equal(d[i], s[i], d_ref, s_ref, f"pipeline frame {i}")
-    assert (s == 1).mean() > 0.3  # the calibrated workload: the geometry tail is exercised
+    assert (s == 1).mean() > 0.2  # the calibrated workload (~30 % Success): the geometry tail is exercised
 
 
 @pytest.mark.gpu
