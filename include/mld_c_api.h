@@ -133,6 +133,8 @@ int mld_sizeof_params(void);
 void mld_default_params(mld_params* p);                       /* C++ member defaults */
 int mld_params_from_yaml(const char* path, mld_params* p);    /* DepthEstimatorParameters::fromFile (DepthEstimatorParameters.cpp:16-114):
                                                                  flat "key: value # comment" OpenCV-YAML; absent keys read as 0 */
+/* one integer key of the same flat yaml (DepthEstimatorParameters' debug switches that are not part of mld_params); absent -> 0 */
+int mld_yaml_int(const char* path, const char* key, int32_t* out, int32_t* found);
 const char* mld_status_name(int status);                      /* DepthResultTypeMap (DepthEstimator.h:45-60) */
 const char* mld_last_error(const mld_handle* h);              /* h may be NULL: error of the last failed mld_create on this thread */
 
@@ -233,7 +235,12 @@ int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev
                              int64_t n_cur, const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur,
                              mld_plane* plane_cur, int stride_bytes, uint64_t ransac_seed);
 
-/* ---- DepthCalculationStatistics (DepthEstimator.cpp:1039-1090): counters per DepthResultType (0..20) ---- */
+/* ---- DepthCalculationStatistics (DepthEstimator.cpp:1039-1090): counters per DepthResultType (0..20) ----
+ * mld_set_statistics(on): every mld_calculate_depth call also reduces its status array (still on the device) to the 21
+ * counters (the reference's per-feature LogDepthCalcStats, DepthEstimator.cpp:470-479); mld_last_status_histogram returns the
+ * counters of the last call (zeros before the first). */
+int mld_set_statistics(mld_handle* h, int on);
+int mld_last_status_histogram(mld_handle* h, int64_t* hist21_out);
 int mld_status_histogram_host(mld_handle* h, const int32_t* status_host, int64_t n, int64_t* hist21_out);
 int mld_status_histogram_device(mld_handle* h, const int32_t* d_status, int64_t n, int64_t* hist21_out_host, void* stream);
 
@@ -290,6 +297,13 @@ int mld_get_visible_points(mld_handle* h, int32_t* point_index_out, double* imag
                            int64_t capacity, int64_t* n_visible_out);
 /* camera-frame coordinates of raw point i (3 doubles each), _points_cs_camera */
 int mld_get_points_camera(mld_handle* h, double* out_host);
+/* the same for selected raw indices (getCloudRansacPlane: the ground plane's inliers, DepthEstimator.cpp:294-308); an index
+ * outside the cloud yields NaN */
+int mld_get_points_camera_indexed(mld_handle* h, const int32_t* idx_host, int64_t n_idx, double* out_host);
+/* the three triangle corners CalculateDepthSegmented picked for each feature of the current cloud (camera frame, 9 doubles per
+ * feature; getCloudTriangleCorners / _points_triangle_corners, DepthEstimator.cpp:915-926); valid_out[i] = 0 and NaN corners when
+ * the feature never reached a corner selection (empty window, no histogram maximum, no triangle) */
+int mld_get_triangle_corners(mld_handle* h, const double* uv_host, int F, double* corners_out_host, uint8_t* valid_out_host);
 
 /* ---- synthetic KITTI-shaped input, device generators (bench / tests; include/mld_synth.h has the configuration and the
  * host generators of libmld_synth.so, which agree with these bit for bit) ----

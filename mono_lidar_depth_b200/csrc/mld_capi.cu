@@ -117,6 +117,11 @@ struct mld_handle {
     unsigned ring_epoch = 0;        // epochs consumed by every slot of the ring since its last clear (0 = never cleared)
     int* h_pipe_flags = nullptr;    // pinned: [0] error flag of the last pipeline launch (read back asynchronously)
     int* h_pipe_counters = nullptr; // pinned: the 16 sync words of the last launch (ticket, error, profiling accumulators)
+    bool stats_on = false;          // mld_set_statistics: status histogram of every mld_calculate_depth call
+    unsigned long long* d_hist = nullptr;  // 21 counters on the device
+    unsigned long long* h_hist = nullptr;  // pinned copy
+    int64_t last_hist[21] = {0};
+    bool last_hist_valid = false;
     int* d_dbg = nullptr;           // neighbour debug buffer
     float* d_synth_tables = nullptr;
     mld_synth_config synth_cfg_cached;
@@ -553,6 +558,15 @@ int mld_params_from_yaml(const char* path, mld_params* p) {
     return MLD_OK;
 }
 
+int mld_yaml_int(const char* path, const char* key, int32_t* out, int32_t* found) {
+    if (!path || !key || !out) return MLD_ERR_INVALID_ARG;
+    std::map<std::string, std::string> kv;
+    if (!parse_yaml(path, kv)) return fail(nullptr, MLD_ERR_IO, std::string("Cant find settings file: ") + path);
+    if (found) *found = kv.count(key) ? 1 : 0;
+    *out = yaml_int(kv, key);  // absent keys read as 0, like cv::FileStorage
+    return MLD_OK;
+}
+
 const char* mld_status_name(int status) {
     switch (status) {
 #define MLD_STATUS_NAME_CASE(name, value) \
@@ -686,6 +700,8 @@ int mld_destroy(mld_handle* h) {
         if (s.stream) cudaStreamDestroy(s.stream);
     }
     cudaFree(h->d_dbg);
+    cudaFree(h->d_hist);
+    if (h->h_hist) cudaFreeHost(h->h_hist);
     cudaFree(h->d_synth_tables);
     cudaFree(h->d_ring_maps); cudaFree(h->d_ring_occ); cudaFree(h->d_ring_sync);
     if (h->h_pipe_flags) cudaFreeHost(h->h_pipe_flags);
@@ -1041,7 +1057,56 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
     if (rc) return rc;
     CK(cudaMemcpyAsync(depth_host, s.d_depth, (size_t)F * sizeof(double), cudaMemcpyDeviceToHost, s.stream));
     CK(cudaMemcpyAsync(status_host, s.d_status, (size_t)F * sizeof(int), cudaMemcpyDeviceToHost, s.stream));
+    if (h->stats_on) {  // DepthCalculationStatistics: counters of this call, from the status array that is still on the device
+        if (!h->d_hist) CK(cudaMalloc(&h->d_hist, 21 * sizeof(unsigned long long)));
+        if (!h->h_hist) CK(cudaHostAlloc(reinterpret_cast<void**>(&h->h_hist), 21 * sizeof(unsigned long long), cudaHostAllocDefault));
+        CK(mld_launch_status_histogram(s.d_status, F, h->d_hist, s.stream));
+        h->launches++;
+        CK(cudaMemcpyAsync(h->h_hist, h->d_hist, 21 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
+    }
     CK(cudaStreamSynchronize(s.stream));
+    if (h->stats_on) {
+        for (int i = 0; i < 21; i++) h->last_hist[i] = (int64_t)h->h_hist[i];
+        h->last_hist_valid = true;
+    }
+    return MLD_OK;
+}
+
+int mld_set_statistics(mld_handle* h, int on) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    h->stats_on = on != 0;
+    return MLD_OK;
+}
+
+int mld_last_status_histogram(mld_handle* h, int64_t* hist21_out) {
+    if (!h || !hist21_out) return MLD_ERR_INVALID_ARG;
+    for (int i = 0; i < 21; i++) hist21_out[i] = h->last_hist_valid ? h->last_hist[i] : 0;
+    return MLD_OK;
+}
+
+// debug view: the max-spanning-triangle corners CalculateDepthSegmented used per feature (DepthEstimator.cpp:915-926), camera frame
+int mld_get_triangle_corners(mld_handle* h, const double* uv_host, int F, double* corners_out_host, uint8_t* valid_out_host) {
+    if (!h || F < 0 || (F > 0 && (!uv_host || !corners_out_host || !valid_out_host))) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "call of 'CalculateDepth' without 'SetInputCloud'");
+    if (F == 0) return MLD_OK;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    CK(ensure(s.d_uv, s.uv_bytes, (size_t)F * 2 * sizeof(double)));
+    CK(ensure(s.d_depth, s.depth_bytes, (size_t)F * sizeof(double)));
+    CK(ensure(s.d_status, s.status_bytes, (size_t)F * sizeof(int)));
+    double* d_corners = nullptr;
+    CK(cudaMalloc(&d_corners, (size_t)F * 9 * sizeof(double)));
+    cudaError_t e = cudaMemsetAsync(d_corners, 0xFF, (size_t)F * 9 * sizeof(double), s.stream);  // all-ones = NaN: "no triangle"
+    if (e == cudaSuccess) e = cudaMemcpyAsync(s.d_uv, uv_host, (size_t)F * 2 * sizeof(double), cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess)
+        e = mld_launch_feature_depth(h->dp, s.mc, h->kcap, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, h->cur_n, s.d_maps, s.d_uv, F,
+                                     s.d_depth, s.d_status, nullptr, nullptr, 0, 1, nullptr, nullptr, 0, s.stream, d_corners);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(corners_out_host, d_corners, (size_t)F * 9 * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_corners);
+    if (e != cudaSuccess) return fail_cuda(h, e, "mld_get_triangle_corners");
+    for (int i = 0; i < F; i++) valid_out_host[i] = (corners_out_host[(size_t)i * 9] == corners_out_host[(size_t)i * 9]) ? 1 : 0;
     return MLD_OK;
 }
 
@@ -1692,6 +1757,27 @@ int mld_get_visible_points(mld_handle* h, int32_t* point_index_out, double* imag
     cudaFree(d_buf);
     if (e != cudaSuccess) return fail_cuda(h, e, "mld_get_visible_points");
     if (n_visible_out) *n_visible_out = (int64_t)nvis;
+    return MLD_OK;
+}
+int mld_get_points_camera_indexed(mld_handle* h, const int32_t* idx_host, int64_t n_idx, double* out_host) {
+    if (!h || n_idx < 0 || (n_idx > 0 && (!idx_host || !out_host))) return MLD_ERR_INVALID_ARG;
+    if (!h->have_cloud) return fail(h, MLD_ERR_NO_CLOUD, "no cloud set");
+    if (n_idx == 0) return MLD_OK;
+    DeviceGuard g(h->device);
+    Slot& s = h->slots[0];
+    int* d_idx = nullptr;
+    double* d_out = nullptr;
+    CK(cudaMalloc(&d_idx, (size_t)n_idx * sizeof(int)));
+    cudaError_t e = cudaMalloc(&d_out, (size_t)n_idx * 3 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, idx_host, (size_t)n_idx * sizeof(int), cudaMemcpyHostToDevice, s.stream);
+    if (e == cudaSuccess)
+        e = mld_launch_points_camera_indexed(h->dp, reinterpret_cast<const float*>(s.d_pts), h->cur_stride_f, h->cur_n, d_idx, n_idx, d_out, s.stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_host, d_out, (size_t)n_idx * 3 * sizeof(double), cudaMemcpyDeviceToHost, s.stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s.stream);
+    cudaFree(d_idx);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail_cuda(h, e, "mld_get_points_camera_indexed");
     return MLD_OK;
 }
 int mld_get_points_camera(mld_handle* h, double* out_host) {

@@ -40,7 +40,7 @@ feature_depth_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int
                      const unsigned int* __restrict__ maps, const double* __restrict__ uv, int F,
                      double* __restrict__ depth, int* __restrict__ status, const float* __restrict__ plane_coeffs,
                      const unsigned int* __restrict__ inlier_bits, long long inlier_words_per_frame,
-                     const int* __restrict__ list, const int* __restrict__ list_count) {
+                     const int* __restrict__ list, const int* __restrict__ list_count, double* __restrict__ corners) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double* sx = reinterpret_cast<double*>(smem_raw) + (size_t)warp * 3 * KCAP;
@@ -78,7 +78,7 @@ feature_depth_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int
         const unsigned int* bits = inlier_bits ? inlier_bits + frame * inlier_words_per_frame : nullptr;
         int st;
         double dp;
-        feature_depth(P, mc, map, fp, stride_f, u, v, pc, bits, lane, s, KCAP, st, dp);
+        feature_depth(P, mc, map, fp, stride_f, u, v, pc, bits, lane, s, KCAP, st, dp, corners ? corners + o * 9 : nullptr);
         if (lane == 0) {
             status[o] = st;
             depth[o] = (st == ST_Success || st == ST_SuccessRoad) ? dp : -1.0;
@@ -125,12 +125,12 @@ template <int KCAP, int K2_WARPS>
 cudaError_t launch_feature(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long pitch_pts,
                            const unsigned int* d_maps, const double* d_uv, int F, double* d_depth, int* d_status,
                            const float* d_plane_coeffs, const unsigned int* d_inlier_bits, long long words_per_frame,
-                           int nframes, const int* d_list, const int* d_list_count, int list_blocks, cudaStream_t stream) {
+                           int nframes, const int* d_list, const int* d_list_count, int list_blocks, cudaStream_t stream, double* d_corners) {
     constexpr size_t smem = (size_t)K2_WARPS * KCAP * (3 * sizeof(double) + sizeof(int));
     dim3 grid = d_list ? dim3((unsigned)list_blocks, 1) : dim3((unsigned)((F + K2_WARPS - 1) / K2_WARPS), (unsigned)nframes);
     feature_depth_kernel<KCAP, K2_WARPS><<<grid, K2_WARPS * 32, smem, stream>>>(
         P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs, d_inlier_bits, words_per_frame,
-        d_list, d_list_count);
+        d_list, d_list_count, d_corners);
     return cudaGetLastError();
 }
 
@@ -153,18 +153,18 @@ cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int 
                                      long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F, double* d_depth,
                                      int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
                                      long long words_per_frame, int nframes, const int* d_list, const int* d_list_count,
-                                     int list_blocks, cudaStream_t stream) {
+                                     int list_blocks, cudaStream_t stream, double* d_corners) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
     switch (kcap) {
         case 96:
             return launch_feature<96, 8>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                         d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
+                                         d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream, d_corners);
         case 256:
             return launch_feature<256, 8>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                          d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
+                                          d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream, d_corners);
         case 1024:
             return launch_feature<1024, 4>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
-                                           d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream);
+                                           d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, list_blocks, stream, d_corners);
         default:
             return cudaErrorInvalidValue;
     }

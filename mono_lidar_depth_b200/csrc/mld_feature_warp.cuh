@@ -281,7 +281,9 @@ __device__ void slab_weighted_scatter(int n, int lane, const WarpSlab& s, bool w
 }
 
 // ---- A12: CalculateDepthSegmented ----------------------------------------------------------------
-__device__ int depth_segmented(const DevParams& P, double u, double v, int n, int lane, const WarpSlab& s, double& depth_out) {
+// corners9 (debug view, normally nullptr): the three triangle corners of a feature whose corner selection succeeded, camera frame
+__device__ int depth_segmented(const DevParams& P, double u, double v, int n, int lane, const WarpSlab& s, double& depth_out,
+                               double* corners9 = nullptr) {
     depth_out = -1;
     D3 c1{}, c2{}, c3{};
     if (!P.use_pca && P.use_tri_max) {
@@ -291,6 +293,11 @@ __device__ int depth_segmented(const DevParams& P, double u, double v, int n, in
     } else {
         if (n < 3) return ST_HistogramNoLocalMax;  // DepthEstimator.cpp:920-921
         c1 = slab_pt(s, 0); c2 = slab_pt(s, 1); c3 = slab_pt(s, 2);
+    }
+    if (corners9 != nullptr && lane == 0) {  // _points_triangle_corners (PlaneEstimationCalcMaxSpanningTriangle.cpp:27-33)
+        corners9[0] = c1.x; corners9[1] = c1.y; corners9[2] = c1.z;
+        corners9[3] = c2.x; corners9[4] = c2.y; corners9[5] = c2.z;
+        corners9[6] = c3.x; corners9[7] = c3.y; corners9[8] = c3.z;
     }
     if (!P.use_pca && P.check_planar)
         if (!check_planar(c1, c2, c3, P.crossnorm_thr)) return ST_TriangleNotPlanar;
@@ -412,7 +419,7 @@ __device__ int road_depth(const DevParams& P, double u, double v, int k2, int la
 __device__ __noinline__ void feature_depth(const DevParams& P, const MapCode& mc, const unsigned int* __restrict__ map,
                                            const float* __restrict__ pts, int stride_f, double u, double v, const float* plane_coeffs,
                                            const unsigned int* __restrict__ inlier_bits, int lane, const WarpSlab& s, const int KCAP,
-                                           int& status_out, double& depth_out) {
+                                           int& status_out, double& depth_out, double* corners9 = nullptr) {
     depth_out = -1;
     int k = gather_window(P, mc, map, pts, stride_f, u, v, P.hx1, P.hy1, lane, s, KCAP);
     if ((unsigned)k < (unsigned)P.count_min) {  // neighbors.size() < (uint)radiusSearch_count_min (:680)
@@ -427,7 +434,7 @@ __device__ __noinline__ void feature_depth(const DevParams& P, const MapCode& mc
     }
     if (status != ST_HistogramNoLocalMax) {
         double depth;
-        status = depth_segmented(P, u, v, n, lane, s, depth);
+        status = depth_segmented(P, u, v, n, lane, s, depth, corners9);
         if (status == ST_Success) {
             status_out = status;
             depth_out = depth;

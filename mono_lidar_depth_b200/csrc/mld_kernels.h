@@ -20,6 +20,8 @@ size_t mld_visible_scratch_bytes(long long n);
 cudaError_t mld_launch_visible_compact(const DevParams& P, const float* d_pts, int stride_f, long long n, void* d_scratch, long long capacity,
                                        int* d_point_index, double* d_image_points, double* d_depth_cam, const unsigned int** d_count_out,
                                        cudaStream_t stream, int* launches);
+cudaError_t mld_launch_points_camera_indexed(const DevParams& P, const float* d_pts, int stride_f, long long n, const int* d_idx, long long n_idx,
+                                             double* d_out, cudaStream_t stream);
 cudaError_t mld_launch_visible_debug(const DevParams& P, const float* d_pts, int stride_f, long long n,
                                      unsigned char* d_visible, double* d_cam, cudaStream_t stream);
 
@@ -31,7 +33,7 @@ cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int 
                                      long long pitch_pts, const unsigned int* d_maps, const double* d_uv, int F, double* d_depth,
                                      int* d_status, const float* d_plane_coeffs, const unsigned int* d_inlier_bits,
                                      long long words_per_frame, int nframes, const int* d_list, const int* d_list_count,
-                                     int list_blocks, cudaStream_t stream);
+                                     int list_blocks, cudaStream_t stream, double* d_corners = nullptr /* debug: 9 doubles per feature */);
 cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, const unsigned int* d_map, double u, double v,
                                        double hx, double hy, int* d_out, int cap, int* d_k, cudaStream_t stream);
 

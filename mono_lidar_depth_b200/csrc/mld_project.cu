@@ -85,6 +85,19 @@ __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts,
     }
 }
 
+// camera-frame coordinates of selected raw points (getCloudRansacPlane: the plane's inliers, DepthEstimator.cpp:294-308)
+__global__ void points_camera_indexed_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n, const int* __restrict__ idx,
+                                             long long n_idx, double* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_idx) return;
+    const long long r = idx[i];
+    D3 c = D3{__longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll), __longlong_as_double(0x7ff8000000000000ll)};
+    if (r >= 0 && r < n) c = lidar_to_cam(P, pts[r * stride_f], pts[r * stride_f + 1], pts[r * stride_f + 2]);
+    out[i * 3] = c.x;
+    out[i * 3 + 1] = c.y;
+    out[i * 3 + 2] = c.z;
+}
+
 // ---- visible-order views: _pointIndex, _points_cs_image_visible, getPointDepthCamVisible ----
 // Transform_Cloud_LidarToCamera compacts the visible points in cloud order (DepthEstimator.cpp:189-207). On the GPU
 // that is an order-preserving stream compaction: per-block counts, an exclusive scan of the counts, and a second
@@ -262,6 +275,13 @@ cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, co
     }
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
     project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps, d_occ);
+    return cudaGetLastError();
+}
+
+cudaError_t mld_launch_points_camera_indexed(const DevParams& P, const float* d_pts, int stride_f, long long n, const int* d_idx, long long n_idx,
+                                             double* d_out, cudaStream_t stream) {
+    if (n_idx <= 0) return cudaSuccess;
+    points_camera_indexed_kernel<<<(unsigned)((n_idx + 255) / 256), 256, 0, stream>>>(P, d_pts, stride_f, n, d_idx, n_idx, d_out);
     return cudaGetLastError();
 }
 

@@ -219,7 +219,12 @@ class DepthEstimator:
             if groundPlane is None:  # DepthEstimator.cpp:275-278
                 groundPlane = RansacPlane(self._parameters, self.ransac_seed)
             if not groundPlane.isSegmented():
-                pl_c = groundPlane._as_c(capacity=max(n, 1))
+                if isinstance(groundPlane, RansacPlane):
+                    pl_c = groundPlane._as_c(capacity=max(n, 1))  # fitted on the GPU, sharing the cloud's H2D copy
+                else:
+                    # any other GroundPlane segments itself (virtual CalculateInliersPlane, DepthEstimator.cpp:281-283),
+                    # e.g. SemanticPlane -- what tracklets_depth hands in
+                    groundPlane.CalculateInliersPlane(cloud, self._parameters.ransac_plane_min_z, self._parameters.ransac_plane_max_z)
         seed = getattr(groundPlane, "seed", self.ransac_seed) if groundPlane is not None else 0
         self._check(self._lib.mld_set_cloud(self._h, a.ctypes.data if n else None, n, stride,
                                             C.byref(pl_c) if pl_c is not None else None, seed))
@@ -229,30 +234,44 @@ class DepthEstimator:
         return groundPlane
 
     # -- DepthEstimator::CalculateDepth (DepthEstimator.cpp:404-488) -----------------------------
-    def CalculateDepth(self, *args):
+    def CalculateDepth(self, *args, layout: Optional[str] = None):
         """CalculateDepth(points_image_cs, ransacPlane=None) -> (depths, resultType)
         CalculateDepth(pointCloud, points_image_cs, ransacPlane=None) -> (depths, resultType, ransacPlane)
 
-        points_image_cs: 2xF (reference layout) or Fx2 array of pixel coordinates."""
+        points_image_cs: 2xF (reference layout, rows u and v) or Fx2 array of pixel coordinates. A 2x2 array is ambiguous:
+        pass layout="2xF" or layout="Fx2" (without it a 2x2 array raises)."""
         if len(args) >= 2 and np.ndim(args[0]) == 2 and np.ndim(args[1]) == 2:
             cloud, feats = args[0], args[1]
             plane = args[2] if len(args) > 2 else None
             plane = self.setInputCloud(cloud, plane)
-            d, s = self._calculate(feats, plane)
+            d, s = self._calculate(feats, plane, layout)
             return d, s, plane
         feats = args[0]
         plane = args[1] if len(args) > 1 else None
-        return self._calculate(feats, plane)
+        return self._calculate(feats, plane, layout)
 
-    def _calculate(self, feats, plane):
-        if not self._isInitializedPointCloud:
-            raise RuntimeError("call of 'CalculateDepth' without 'SetInputCloud'")
+    @staticmethod
+    def _features(feats, layout: Optional[str] = None) -> np.ndarray:
+        """(F, 2) C-contiguous doubles == the memory of a column-major Eigen::Matrix2Xd (u0, v0, u1, v1, ...)."""
         f = np.asarray(feats, np.float64)
         if f.ndim != 2 or 2 not in f.shape:
             raise ValueError("features must be 2xF or Fx2")
-        if f.shape[0] == 2 and f.shape[1] != 2:
-            f = f.T  # Eigen::Matrix2Xd is column-major: memory order u0,v0,u1,v1,... == (F,2) C-order
-        f = np.ascontiguousarray(f)
+        if layout not in (None, "2xF", "Fx2"):
+            raise ValueError("layout must be '2xF' or 'Fx2'")
+        if layout is None and f.shape == (2, 2):
+            raise ValueError("a 2x2 feature array is ambiguous: pass layout='2xF' (reference layout) or layout='Fx2'")
+        if layout == "2xF" or (layout is None and f.shape[0] == 2):
+            if f.shape[0] != 2:
+                raise ValueError("layout '2xF' needs two rows")
+            f = f.T
+        elif f.shape[1] != 2:
+            raise ValueError("layout 'Fx2' needs two columns")
+        return np.ascontiguousarray(f)
+
+    def _calculate(self, feats, plane, layout: Optional[str] = None):
+        if not self._isInitializedPointCloud:
+            raise RuntimeError("call of 'CalculateDepth' without 'SetInputCloud'")
+        f = self._features(feats, layout)
         F = f.shape[0]
         depths = np.empty(F, np.float64)
         status = np.empty(F, np.int32)
@@ -262,7 +281,7 @@ class DepthEstimator:
         return depths, status
 
     # -- tracklets_depth batch adaptor (TrackletDepthModule::process, tracklet_depth_module.cpp:318,330) ---------
-    def CalculateDepthPair(self, cloud_last, feats_last, plane_last, cloud_cur, feats_cur, plane_cur):
+    def CalculateDepthPair(self, cloud_last, feats_last, plane_last, cloud_cur, feats_cur, plane_cur, layout: Optional[str] = None):
         """Previous and current cloud with their own feature sets in one call (both clouds are on the device
         concurrently). cloud_last may be None (first frame): its depths are -1. Planes follow setInputCloud:
         with do_use_ransac_plane a None / un-segmented plane is fitted on the GPU and returned.
@@ -272,9 +291,7 @@ class DepthEstimator:
 
         def prep(feats):
             f = np.asarray(feats, np.float64)
-            if f.ndim == 2 and f.shape[0] == 2 and f.shape[1] != 2:
-                f = f.T
-            return np.ascontiguousarray(f.reshape(-1, 2))
+            return np.empty((0, 2), np.float64) if f.size == 0 else self._features(f, layout)
 
         fl, fc = prep(feats_last), prep(feats_cur)
         dl, dc = np.empty(len(fl), np.float64), np.empty(len(fc), np.float64)
@@ -294,6 +311,9 @@ class DepthEstimator:
                     continue
                 if planes[i] is None:
                     planes[i] = RansacPlane(self._parameters, self.ransac_seed)
+                if not planes[i].isSegmented() and not isinstance(planes[i], RansacPlane):  # e.g. SemanticPlane: segments itself
+                    planes[i].CalculateInliersPlane(cloud_last if i == 0 else cloud_cur, self._parameters.ransac_plane_min_z,
+                                                    self._parameters.ransac_plane_max_z)
                 cplanes[i] = planes[i]._as_c(capacity=max(sizes[i], 1) if not planes[i].isSegmented() else 0)
         self._check(self._lib.mld_calculate_depth_pair(
             self._h, a_last.ctypes.data if a_last is not None else None, n_last,

@@ -11,12 +11,14 @@
 #include <memory>
 #include <string>
 #include <utility>
+#include <vector>
 
 #include <Eigen/Eigen>
 #include <Eigen/Geometry>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 
+#include "DepthCalculationStatistics.h"
 #include "DepthEstimatorParameters.h"
 #include "RansacPlane.h"
 #include "camera_pinhole.h"
@@ -66,12 +68,26 @@ public:
                             GroundPlane::Ptr& planeLast, const Cloud::ConstPtr& pointCloudCur, const Eigen::Matrix2Xd& featuresCur,
                             Eigen::VectorXd& depthsCur, GroundPlane::Ptr& planeCur);
 
-    // DepthCalculationStatistics counters (one per DepthResultType value) of a result vector
+    // ---- statistics and debug views (DepthEstimator.h:116-164), served from device buffers on demand ----
+    // counters of the last CalculateDepth call (kept when the parameters' do_depth_calc_statistics is set, as upstream)
+    const DepthCalculationStatistics& getDepthCalcStats() { return _depthCalcStats; }
+    // the same counters for any result vector (not in the reference)
     void getDepthCalcStats(const Eigen::VectorXi& resultType, long long counters[21]);
-
-    // debug views served from device buffers on demand
+    // camera-frame depth of visible point `index` (_points_cs_camera(2, _pointIndex[index]))
+    double getPointDepthCamVisible(int index);
+    // _points_cs_image_visible: image coordinates of the visible points in cloud order (device stream compaction)
     void getPointsCloudImageCs(Eigen::Matrix2Xd& visiblePointsImageCs);
+    // the whole cloud in the camera frame (intensity 1, like upstream)
     void getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs);
+    // the ground plane's inliers in the camera frame, optionally cut at |x| <= ransac_plane_treshold_camx (:294-308)
+    void getCloudRansacPlane(Cloud::Ptr& pointCloud_plane_ransac);
+    // the triangle corners CalculateDepthSegmented used for the features of the last CalculateDepth call (three per feature
+    // that reached a corner selection, in feature order; upstream the order is whatever the OpenMP threads produced)
+    void getCloudTriangleCorners(Cloud::Ptr& pointCloud_triangle_corner);
+    // Upstream never fills these lists any more (the push_backs are commented out, DepthEstimator.cpp:663, :1032): empty clouds
+    void getCloudInterpolated(Cloud::Ptr& pointCloud_interpolated);
+    void getCloudInterpolatedPlane(Cloud::Ptr& pointCloud_interpolated_plane);
+    void getCloudNeighbors(Cloud::Ptr& pointCloud_neighbors);
 
     void setRansacSeed(unsigned long long seed) { _ransacSeed = seed; }
 
@@ -87,6 +103,11 @@ private:
     bool _isInitializedPointCloud{false};
     long long _pointCount{0};
     unsigned long long _ransacSeed{0};
+    DepthCalculationStatistics _depthCalcStats;
+    std::vector<int> _groundInliers;         // inlier indices of the plane seen by the last setInputCloud (getCloudRansacPlane)
+    std::vector<double> _lastFeatures;       // 2 x F features of the last CalculateDepth call (getCloudTriangleCorners)
+    std::vector<double> _depthCamVisible;    // lazily fetched per cloud (getPointDepthCamVisible)
+    bool _depthCamVisibleValid{false};
 };
 
 }  // namespace Mono_Lidar

@@ -7,6 +7,8 @@
 //   RansacPlane::CalculateInliersPlane  monolidar_fusion/src/RansacPlane.cpp:41-140
 #include "monolidar_fusion/DepthEstimator.h"
 
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 #include <iostream>
 #include <stdexcept>
@@ -159,6 +161,7 @@ bool DepthEstimator::InitConfig(std::shared_ptr<DepthEstimatorParameters> parame
     _handle = nullptr;
     int rc = mld_create(_parameters.get(), -1, &_handle);
     if (rc != MLD_OK) throw std::runtime_error(std::string("mld: ") + mld_last_error(nullptr));
+    mld_set_statistics(_handle, _parameters->do_depth_calc_statistics ? 1 : 0);
     _isInitializedConfig = true;
     _isInitialized = false;
     _isInitializedPointCloud = false;
@@ -202,6 +205,8 @@ void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Pt
                 groundPlane->is_segmented_ = true;
                 _pointCount = n;
                 _isInitializedPointCloud = true;
+                _groundInliers = groundPlane->_inliersIndex;
+                _depthCamVisibleValid = false;
                 return;
             }
             // any other GroundPlane segments itself (SemanticPlane: on the GPU through mld_semantic_ground_plane)
@@ -212,6 +217,9 @@ void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Pt
     if (rc != MLD_OK) rethrow(rc);
     _pointCount = n;
     _isInitializedPointCloud = true;
+    _depthCamVisibleValid = false;
+    _groundInliers.clear();  // _points_groundplane is rebuilt per cloud, from the plane's inliers (DepthEstimator.cpp:234, :294-308)
+    if (_parameters->do_use_ransac_plane && groundPlane != nullptr) _groundInliers = groundPlane->_inliersIndex;
 }
 
 void DepthEstimator::CalculateDepth(const Cloud::ConstPtr& pointCloud, const Eigen::Matrix2Xd& points_image_cs,
@@ -248,6 +256,15 @@ void DepthEstimator::CalculateDepth(const Eigen::Matrix2Xd& featurePoints_image_
     int rc = mld_calculate_depth(_handle, featurePoints_image_cs.data(), imgPointCount, points_depths.data(),
                                  reinterpret_cast<int32_t*>(resultType.data()), pl);
     if (rc != MLD_OK) rethrow(rc);
+    _lastFeatures.assign(featurePoints_image_cs.data(), featurePoints_image_cs.data() + 2 * (size_t)imgPointCount);
+    if (_parameters->do_depth_calc_statistics) {  // DepthEstimator.cpp:445-446, :482-485
+        int64_t hist[21];
+        long long h2[21];
+        rc = mld_last_status_histogram(_handle, hist);
+        if (rc != MLD_OK) rethrow(rc);
+        for (int i = 0; i < 21; i++) h2[i] = (long long)hist[i];
+        _depthCalcStats.SetFromHistogram(h2, imgPointCount);
+    }
 }
 
 std::pair<DepthResultType, double> DepthEstimator::CalculateDepth(const Eigen::Vector2d& featurePoint_image_cs,
@@ -298,6 +315,10 @@ void DepthEstimator::CalculateDepthPair(const Cloud::ConstPtr& cloudLast, const 
     }
     _pointCount = (long long)cloudCur->points.size();
     _isInitializedPointCloud = true;
+    _depthCamVisibleValid = false;
+    _groundInliers.clear();
+    if (road && planeCur != nullptr) _groundInliers = planeCur->_inliersIndex;
+    _lastFeatures.assign(featuresCur.data(), featuresCur.data() + 2 * (size_t)featuresCur.cols());
 }
 
 void DepthEstimator::getDepthCalcStats(const Eigen::VectorXi& resultType, long long counters[21]) {
@@ -326,25 +347,83 @@ void DepthEstimator::getCloudCameraCs(Cloud::Ptr& pointCloud_cam_cs) {
 }
 
 void DepthEstimator::getPointsCloudImageCs(Eigen::Matrix2Xd& visiblePointsImageCs) {
-    // _points_cs_image_visible: the visible points' image coordinates in cloud order; flags and
-    // camera-frame coordinates come from the device, the per-point division is the debug view's only host work
-    std::vector<uint8_t> vis((size_t)std::max<long long>(_pointCount, 1));
-    std::vector<double> cam((size_t)std::max<long long>(_pointCount, 1) * 3);
+    // _points_cs_image_visible: compacted in cloud order on the device (mld_get_visible_points)
     int64_t nvis = 0;
-    int rc = mld_get_visible(_handle, vis.data(), &nvis);
-    if (rc != MLD_OK) rethrow(rc);
-    rc = mld_get_points_camera(_handle, cam.data());
+    int rc = mld_get_visible_points(_handle, nullptr, nullptr, nullptr, 0, &nvis);
     if (rc != MLD_OK) rethrow(rc);
     visiblePointsImageCs.resize(2, (int)nvis);
-    const double f = _camera->focalLength(), cx = _camera->principalPointX(), cy = _camera->principalPointY();
-    int k = 0;
-    for (long long i = 0; i < _pointCount; i++) {
-        if (!vis[(size_t)i]) continue;
-        const double X = cam[(size_t)i * 3], Y = cam[(size_t)i * 3 + 1], Z = cam[(size_t)i * 3 + 2];
-        visiblePointsImageCs(0, k) = ((f * X + 0.0 * Y) + cx * Z) / Z;
-        visiblePointsImageCs(1, k) = ((0.0 * X + f * Y) + cy * Z) / Z;
-        k++;
-    }
+    if (nvis == 0) return;
+    rc = mld_get_visible_points(_handle, nullptr, visiblePointsImageCs.data(), nullptr, nvis, &nvis);
+    if (rc != MLD_OK) rethrow(rc);
 }
+
+double DepthEstimator::getPointDepthCamVisible(int index) {
+    if (!_depthCamVisibleValid) {
+        int64_t nvis = 0;
+        int rc = mld_get_visible_points(_handle, nullptr, nullptr, nullptr, 0, &nvis);
+        if (rc != MLD_OK) rethrow(rc);
+        _depthCamVisible.assign((size_t)std::max<int64_t>(nvis, 1), 0.0);
+        if (nvis > 0) {
+            rc = mld_get_visible_points(_handle, nullptr, nullptr, _depthCamVisible.data(), nvis, &nvis);
+            if (rc != MLD_OK) rethrow(rc);
+        }
+        _depthCamVisible.resize((size_t)nvis);
+        _depthCamVisibleValid = true;
+    }
+    return _depthCamVisible.at((size_t)index);
+}
+
+namespace {
+// DepthEstimator::FillCloud (DepthEstimator.cpp:354-374): xyz triples -> PointXYZI with intensity 1
+void fill_cloud(const double* xyz, size_t n, const std::vector<unsigned char>* keep, DepthEstimator::Cloud::Ptr& cloud) {
+    cloud->clear();
+    for (size_t i = 0; i < n; i++) {
+        if (keep && !(*keep)[i]) continue;
+        pcl::PointXYZI point;
+        point.x = (float)xyz[i * 3];
+        point.y = (float)xyz[i * 3 + 1];
+        point.z = (float)xyz[i * 3 + 2];
+        point.intensity = 1;
+        cloud->points.push_back(point);
+    }
+    cloud->width = (uint32_t)cloud->points.size();
+    cloud->height = 1;
+    cloud->is_dense = false;
+}
+}  // namespace
+
+void DepthEstimator::getCloudRansacPlane(Cloud::Ptr& pointCloud_plane_ransac) {
+    std::vector<int32_t> idx(_groundInliers.begin(), _groundInliers.end());
+    std::vector<double> cam(std::max<size_t>(idx.size(), 1) * 3);
+    if (!idx.empty()) {
+        int rc = mld_get_points_camera_indexed(_handle, idx.data(), (int64_t)idx.size(), cam.data());
+        if (rc != MLD_OK) rethrow(rc);
+    }
+    std::vector<unsigned char> keep(idx.size(), 1);
+    if (_parameters->ransac_plane_use_camx_treshold) {  // DepthEstimator.cpp:300-305
+        const double treshold = _parameters->ransac_plane_treshold_camx;
+        for (size_t i = 0; i < idx.size(); i++) keep[i] = std::fabs(cam[i * 3]) <= treshold ? 1 : 0;
+    }
+    fill_cloud(cam.data(), idx.size(), &keep, pointCloud_plane_ransac);
+}
+
+void DepthEstimator::getCloudTriangleCorners(Cloud::Ptr& pointCloud_triangle_corner) {
+    const int F = (int)(_lastFeatures.size() / 2);
+    std::vector<double> corners((size_t)std::max(F, 1) * 9);
+    std::vector<uint8_t> valid((size_t)std::max(F, 1), 0);
+    if (F > 0 && _isInitializedPointCloud) {
+        int rc = mld_get_triangle_corners(_handle, _lastFeatures.data(), F, corners.data(), valid.data());
+        if (rc != MLD_OK) rethrow(rc);
+    }
+    std::vector<unsigned char> keep((size_t)F * 3, 0);
+    for (int i = 0; i < F; i++) keep[(size_t)i * 3] = keep[(size_t)i * 3 + 1] = keep[(size_t)i * 3 + 2] = valid[(size_t)i];
+    fill_cloud(corners.data(), (size_t)F * 3, &keep, pointCloud_triangle_corner);
+}
+
+void DepthEstimator::getCloudInterpolated(Cloud::Ptr& pointCloud_interpolated) { fill_cloud(nullptr, 0, nullptr, pointCloud_interpolated); }
+void DepthEstimator::getCloudInterpolatedPlane(Cloud::Ptr& pointCloud_interpolated_plane) {
+    fill_cloud(nullptr, 0, nullptr, pointCloud_interpolated_plane);
+}
+void DepthEstimator::getCloudNeighbors(Cloud::Ptr& pointCloud_neighbors) { fill_cloud(nullptr, 0, nullptr, pointCloud_neighbors); }
 
 }  // namespace Mono_Lidar

@@ -84,6 +84,48 @@ int main(int argc, char** argv) {
         if (use_plane && (plane == nullptr || !plane->isSegmented())) return 4;
         if (!use_plane && plane != nullptr) return 5;
 
+        // statistics and debug views of DepthEstimator.h:116-164
+        {
+            auto stats = est.getDepthCalcStats();
+            int n_success = 0, n_reached = 0;
+            for (int i = 0; i < F; i++) {
+                n_success += types(i) == Success ? 1 : 0;
+                // statuses that are decided after the corner selection
+                n_reached += (types(i) == Success || types(i) == TriangleNotPlanar || types(i) == PlaneViewrayNotOrthogonal ||
+                              (types(i) >= TresholdDepthGlobalGreaterMax && types(i) <= TresholdDepthLocalSmallerMin) || types(i) == CornerBehindCamera)
+                                 ? 1 : 0;
+            }
+            if (stats.getPointCount() != F || stats.getSuccess() != n_success) return 20;
+            int total = 0;
+            for (int t = 0; t < DepthCalculationStatistics::kTypes; t++) total += stats.count((DepthResultType)t);
+            if (total != F) return 21;
+            Eigen::Matrix2Xd vis;
+            est.getPointsCloudImageCs(vis);
+            auto camc = std::make_shared<DepthEstimator::Cloud>();
+            DepthEstimator::Cloud::Ptr camp = camc;
+            est.getCloudCameraCs(camp);
+            if (camp->points.size() != cloud->points.size() || vis.cols() < 100) return 22;
+            // visible point 0: its camera-frame depth re-projects its image coordinates' scale (z > 0 is not required upstream)
+            const double z0 = est.getPointDepthCamVisible(0), zl = est.getPointDepthCamVisible(vis.cols() - 1);
+            if (!(z0 == z0) || !(zl == zl)) return 23;
+            auto tri = std::make_shared<DepthEstimator::Cloud>();
+            DepthEstimator::Cloud::Ptr trip = tri;
+            est.getCloudTriangleCorners(trip);
+            if (trip->points.size() % 3 != 0 || (int)trip->points.size() < 3 * n_success) return 24;
+            if (!use_plane && (int)trip->points.size() != 3 * n_reached) return 25;  // road-path triangles are not part of this view
+            auto gpc = std::make_shared<DepthEstimator::Cloud>();
+            DepthEstimator::Cloud::Ptr gpp = gpc;
+            est.getCloudRansacPlane(gpp);
+            if (use_plane && gpp->points.size() != plane->getInlinersIndex().size()) return 26;
+            if (!use_plane && !gpp->points.empty()) return 27;
+            auto e1 = std::make_shared<DepthEstimator::Cloud>();
+            DepthEstimator::Cloud::Ptr e1p = e1;
+            est.getCloudInterpolated(e1p);
+            est.getCloudInterpolatedPlane(e1p);
+            est.getCloudNeighbors(e1p);
+            if (!e1p->points.empty()) return 28;
+        }
+
         // the 4-argument overload the real caller uses discards the status vector
         Eigen::VectorXd depths2;
         est.CalculateDepth(feats, depths2, plane);

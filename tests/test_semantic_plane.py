@@ -330,3 +330,42 @@ def test_gpu_batched_semantic_road_path_matches_per_frame_calls():
     with pytest.raises(MldError):
         e2.processFramesDeviceSemantic(pts.data_ptr(), n, n, 16, labs.data_ptr(), 1241, 376, cam, gl, thr, uv.data_ptr(), F, dep.data_ptr(),
                                        sta.data_ptr(), nf, 0, 0, st)
+
+
+@pytest.mark.gpu
+def test_unsegmented_semantic_plane_through_setinputcloud_segments_itself():
+    """DepthEstimator::setInputCloud dispatches virtually to groundPlane->CalculateInliersPlane (DepthEstimator.cpp:281-283): an
+    un-segmented SemanticPlane handed to CalculateDepth(cloud, features, plane) must be fitted from its label image, not by the GPU
+    RANSAC (what the Python mirror did before round 2) -- same result as segmenting it explicitly first."""
+    p = DepthEstimatorParameters.reference_yaml(1)
+    est = DepthEstimator()
+    est.InitConfig(p)
+    est.Initialize(synth.kitti_camera(), KT)
+    cloud, labels, gl, thr = MK.semantic_case(1)
+    cam = SemanticPlane.Camera(F_, CU, CV, KT)
+    uv = synth.features_host(synth.default_config(road=True), 5, 0, 1500)
+    explicit = SemanticPlane(labels, cam, gl, thr, estimator=est)
+    explicit.CalculateInliersPlane(cloud)
+    d_ref, s_ref, _ = est.CalculateDepth(cloud, uv, explicit)
+    lazy = SemanticPlane(labels, cam, gl, thr, estimator=est)
+    assert not lazy.isSegmented()
+    d, s, plane = est.CalculateDepth(cloud, uv, lazy)
+    assert plane is lazy and lazy.isSegmented()
+    assert np.array_equal(lazy.getModelCoeffs(), explicit.getModelCoeffs())
+    assert np.array_equal(lazy.getInlinersIndex(), explicit.getInlinersIndex())
+    assert np.array_equal(s, s_ref) and np.array_equal(d, d_ref)
+    assert (s == 16).sum() > 20
+    # the pair adaptor follows the same rule
+    lazy2 = SemanticPlane(labels, cam, gl, thr, estimator=est)
+    dl, dc, pl_last, pl_cur = est.CalculateDepthPair(None, np.empty((0, 2)), None, cloud, uv, lazy2)
+    assert pl_cur is lazy2 and lazy2.isSegmented() and np.array_equal(dc, d_ref)
+
+
+def test_feature_layout_is_explicit_for_2x2():
+    f = DepthEstimator._features
+    a = np.arange(10, dtype=np.float64).reshape(2, 5)
+    assert np.array_equal(f(a), a.T) and np.array_equal(f(a.T), a.T)
+    b = np.array([[1.0, 2.0], [3.0, 4.0]])
+    with pytest.raises(ValueError):
+        f(b)
+    assert np.array_equal(f(b, "2xF"), b.T) and np.array_equal(f(b, "Fx2"), b)
