@@ -41,6 +41,8 @@ WORKLOADS = {
                  desc="BASELINE.json configs[2]: RANSAC ground plane fitted per frame on the GPU + road-depth path"),
     "dense": dict(dense=True, road=False, frames=2000, features=20000,
                   desc="BASELINE.json configs[3]: 128-beam sweep (260096 pts), 2048x1024 image, 20000 features"),
+    "seq100k": dict(dense=False, road=False, frames=10000, features=2000,
+                    desc="BASELINE.json configs[4]: 100k-frame sequence sharded across the GPUs (strong scaling)"),
 }
 
 
@@ -278,244 +280,386 @@ def run_reference(args, rank, world):
         "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample", "reference_sources_frames_per_s")},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        # the CPU arm generates its inputs with libmld_synth.so and never maps the product library
+        "product_library_mapped": any("libmld_cuda" in ln for ln in open("/proc/self/maps")),
     }
     line["cpu_baseline"]["value"] = v
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+SEMANTIC_ROAD_ROW = 230  # rows >= this carry the road label in the synthetic label image of the "semantic" pass
+
+
+class Sequence:
+    """A device-resident synthetic sequence of one workload on one rank: estimator, inputs, result buffers."""
+
+    def __init__(self, name, frames, f0, local_rank, results=1, semantic=False):
+        import torch
+
+        from mono_lidar_depth_b200 import DepthEstimator, DepthEstimatorParameters, synth
+
+        self.torch, self.synth = torch, synth
+        self.name, self.wl, self.f0, self.nframes = name, WORKLOADS[name], f0, frames
+        self.dense, self.road, self.semantic = bool(self.wl["dense"]), bool(self.wl["road"]), semantic
+        self.dev = torch.device("cuda", local_rank)
+        self.cfg = synth.default_config(self.dense, road=self.road)
+        self.n = synth.points_per_frame(self.cfg)
+        self.F = self.wl["features"]
+        self.W, self.H = (2048, 1024) if self.dense else (1241, 376)
+        self.cam = synth.dense_camera() if self.dense else synth.kitti_camera()
+        self.est = DepthEstimator(device=local_rank)
+        self.est.InitConfig(DepthEstimatorParameters.reference_yaml(do_use_ransac_plane=1 if self.road else 0))
+        self.est.Initialize(self.cam, synth.KITTI_T_LIDAR_TO_CAM)
+        self.stream = torch.cuda.current_stream().cuda_stream
+        self.pts = torch.empty((frames, self.n, 4), dtype=torch.float32, device=self.dev)
+        self.uv = torch.empty((frames, self.F, 2), dtype=torch.float64, device=self.dev)
+        self.depths = [torch.empty((frames, self.F), dtype=torch.float64, device=self.dev) for _ in range(results)]
+        self.statuses = [torch.empty((frames, self.F), dtype=torch.int32, device=self.dev) for _ in range(results)]
+        self.coeffs = torch.zeros((frames, 4), dtype=torch.float32, device=self.dev)
+        self.labels = None
+        if semantic:
+            lab = torch.zeros((self.H, self.W), dtype=torch.uint8, device=self.dev)
+            lab[SEMANTIC_ROAD_ROW:, :] = 7
+            self.labels = lab.unsqueeze(0).repeat(frames, 1, 1).contiguous()
+        self.generate(f0)
+
+    def generate(self, f0, count=None):
+        """(Re)generates frames [f0, f0 + count) of the sequence into the resident buffers (seed = frame index)."""
+        count = self.nframes if count is None else count
+        self.synth.points_device(self.est, self.cfg, SEED, f0, count, self.pts.data_ptr(), stream=self.stream)
+        self.synth.features_device(self.est, self.cfg, SEED, f0, count, self.F, self.uv.data_ptr(), stream=self.stream)
+        self.f0 = f0
+        self.torch.cuda.synchronize()
+
+    def step(self, b=0, count=None):
+        count = self.nframes if count is None else count
+        if self.semantic:
+            from mono_lidar_depth_b200 import SemanticPlane
+
+            cam = SemanticPlane.Camera(self.cam.focal_length_, self.cam.principal_point_x_, self.cam.principal_point_y_, self.synth.KITTI_T_LIDAR_TO_CAM)
+            self.est.processFramesDeviceSemantic(self.pts.data_ptr(), self.n, self.n, 16, self.labels.data_ptr(), self.W, self.H, cam, [6, 7, 8, 9],
+                                                 0.2, self.uv.data_ptr(), self.F, self.depths[b].data_ptr(), self.statuses[b].data_ptr(), count,
+                                                 self.coeffs.data_ptr(), 0, self.stream)
+        else:
+            self.est.processFramesDevice(self.pts.data_ptr(), self.n, self.n, 16, self.uv.data_ptr(), self.F, self.depths[b].data_ptr(),
+                                         self.statuses[b].data_ptr(), count, road=self.road, seed=SEED + self.f0,
+                                         d_plane_coeffs_out=self.coeffs.data_ptr() if self.road else 0, stream=self.stream)
+
+    def algorithmic_bytes_per_frame(self, with_map=True):
+        return 16 * self.n + (4 * self.W * self.H if with_map else 0) + 28 * self.F
+
+    def parity(self, frames, b=0):
+        """Spot check against the oracle (status exact, depth within DEPTH_RTOL) + the status mix of the whole block."""
+        import numpy as np
+
+        sys.path.insert(0, str(ROOT / "tests"))
+        import oracle_lib as O
+        import parity_util as PU
+
+        p = O.yaml_params()
+        p.do_use_ransac_plane = 1 if self.road else 0
+        orc = O.Oracle(p)
+        orc.initialize(self.W, self.H, self.cam.focal_length_, self.cam.principal_point_x_, self.cam.principal_point_y_, self.synth.KITTI_T_LIDAR_TO_CAM)
+        depth, status = self.depths[b], self.statuses[b]
+        checked = 0
+        for i in frames:
+            cloud_i = self.pts[i].cpu().numpy()
+            orc.set_cloud(cloud_i)
+            plane_i = None
+            if self.semantic:  # the plane the GPU fitted from the label image (single-frame API), handed to the oracle
+                from mono_lidar_depth_b200 import SemanticPlane
+
+                cam = SemanticPlane.Camera(self.cam.focal_length_, self.cam.principal_point_x_, self.cam.principal_point_y_, self.synth.KITTI_T_LIDAR_TO_CAM)
+                sp = SemanticPlane(self.labels[i].cpu().numpy(), cam, [6, 7, 8, 9], 0.2, estimator=self.est)
+                sp.CalculateInliersPlane(cloud_i)
+                plane_i = (sp.getModelCoeffs(), sp.getInlinersIndex())
+            elif self.road:  # the oracle's RANSAC with the same per-frame seed gives the inlier set; coefficients from the GPU
+                rc_i, c_ref, inl_i, _ = O.ransac_plane(p, cloud_i, SEED + self.f0 + i)
+                c_gpu = self.coeffs[i].cpu().numpy()
+                assert rc_i == 0 and np.allclose(c_gpu, c_ref, rtol=1e-5, atol=1e-6), (c_gpu, c_ref)
+                plane_i = (c_gpu, inl_i)
+            d_ref, s_ref = orc.calculate_depth(self.uv[i].cpu().numpy(), plane_i)
+            PU.assert_depth_status_equal(depth[i].cpu().numpy(), status[i].cpu().numpy(), d_ref, s_ref, f"bench {self.name} frame {i}")
+            checked += 1
+        s_all = status.cpu().numpy()
+        hist = np.bincount(s_all.ravel(), minlength=21)
+        return {"frames_checked_vs_oracle": checked, "status_exact": True, "depth_rtol": PU.DEPTH_RTOL,
+                "success_fraction": float(hist[1] / s_all.size), "success_road_fraction": float(hist[16] / s_all.size),
+                "insufficient_points_fraction": float(hist[2] / s_all.size), "no_local_max_fraction": float(hist[3] / s_all.size)}
+
+
+def timed_steps(seq, steps, warm, barrier, after=None):
+    """W untimed + K timed steps of one sequence; device time by CUDA events on the launching stream. `after` (optional) runs
+    once after the last step INSIDE the timed region (the end-of-run gather of the results)."""
+    torch = seq.torch
+    for i in range(warm):
+        seq.step(i % len(seq.depths))
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        seq.step(i % len(seq.depths))
+    if after is not None:
+        after((steps - 1) % len(seq.depths))
+    e1.record()
+    barrier()
+    return e0.elapsed_time(e1)
+
+
+def kernel_profile(est, pipelined, fused):
+    """Event-bracket classes of the timed region (mld_profile_read) -> per-kernel dict."""
+    prof, prof_frames = est.profileRead()
+    per = {name: {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None} for name, (ms, ln) in prof.items()}
+    if pipelined:
+        per = {"depth_pipeline": per["project_scatter"], "ransac": per.get("ransac")}
+    elif fused:
+        per["fused_project_gather"] = per.pop("project_scatter")
+        per.pop("feature_gather", None)
+    return per, prof_frames
+
+
 def run_gpu(args, rank, local_rank, world):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from mono_lidar_depth_b200 import DepthEstimator, DepthEstimatorParameters, sharding, synth
+    from mono_lidar_depth_b200 import sharding
+    from mono_lidar_depth_b200.buildinfo import source_hash
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    wl = WORKLOADS[WORKLOAD]
-    frames_total = env_int("MLD_BENCH_FRAMES", wl["frames"]) * world  # weak scaling: the same block per GPU
-    f0, nframes = sharding.frame_block(frames_total, world, rank)
-    cfg = synth.default_config(wl["dense"], road=bool(wl["road"]))
-    n = synth.points_per_frame(cfg)
-    F = N_FEATURES
-    assert n == N_POINTS
-    use_road = bool(wl["road"])
-    cam = synth.dense_camera() if wl["dense"] else synth.kitti_camera()
-
-    est = DepthEstimator(device=local_rank)
-    est.InitConfig(DepthEstimatorParameters.reference_yaml(do_use_ransac_plane=1 if use_road else 0))
-    est.Initialize(cam, synth.KITTI_T_LIDAR_TO_CAM)
-
-    pts = torch.empty((nframes, n, 4), dtype=torch.float32, device=dev)
-    uv = torch.empty((nframes, F, 2), dtype=torch.float64, device=dev)
-    # two result sets: with N > 1 the NCCL gather of step i overlaps the kernels of step i+1
-    depths = [torch.empty((nframes, F), dtype=torch.float64, device=dev) for _ in range(2 if world > 1 else 1)]
-    statuses = [torch.empty((nframes, F), dtype=torch.int32, device=dev) for _ in range(2 if world > 1 else 1)]
-    depth, status = depths[0], statuses[0]
-    coeffs = torch.zeros((nframes, 4), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream().cuda_stream
-    synth.points_device(est, cfg, SEED, f0, nframes, pts.data_ptr(), stream=stream)
-    synth.features_device(est, cfg, SEED, f0, nframes, F, uv.data_ptr(), stream=stream)
-    torch.cuda.synchronize()
-
-    if world > 1:
-        # the per-frame results are gathered on rank 0 (one ncclGather of 12 F bytes per frame); an
-        # all-gather would move N times the bytes into every GPU's HBM for nothing
-        per = -(-frames_total // world)
-        g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev) if rank == 0 else None
-        g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev) if rank == 0 else None
-        gl_depth = list(g_depth.split(per)) if rank == 0 else None
-        gl_status = list(g_status.split(per)) if rank == 0 else None
-
-    pending = [[], []]
-    step_no = [0]
-
-    def step():
-        b = step_no[0] % len(depths)
-        step_no[0] += 1
-        for w in pending[b]:  # the gather that last read this result set must be done before it is overwritten
-            w.wait()
-        pending[b] = []
-        est.processFramesDevice(pts.data_ptr(), n, n, 16, uv.data_ptr(), F, depths[b].data_ptr(), statuses[b].data_ptr(), nframes,
-                                road=use_road, seed=SEED + f0, d_plane_coeffs_out=coeffs.data_ptr() if use_road else 0, stream=stream)
-        if world > 1:  # gather the per-frame results (the only inter-GPU traffic of the path), asynchronously
-            pending[b] = [dist.gather(depths[b], gl_depth, dst=0, async_op=True),
-                          dist.gather(statuses[b], gl_status, dst=0, async_op=True)]
-
-    def drain():
-        for b in range(len(pending)):
-            for w in pending[b]:
-                w.wait()
-            pending[b] = []
+    cores = os.cpu_count() or 1
+    # host threads that pack PointXYZI records in the end-to-end pipeline: the box's cores are shared by the ranks
+    os.environ.setdefault("MLD_PACK_THREADS", str(max(1, min(14, cores // world - (1 if world > 1 else 2)))))
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wl = WORKLOADS[WORKLOAD]
+    seq100k = WORKLOAD == "seq100k"
+    frames_per_gpu = env_int("MLD_BENCH_FRAMES", wl["frames"])
+    if seq100k:  # strong scaling: a fixed 100k-frame sequence cut into contiguous blocks; each block streams through a resident window
+        frames_total = env_int("MLD_BENCH_SEQ_FRAMES", 100000)
+        f0, block = sharding.frame_block(frames_total, world, rank)
+        window = min(block, frames_per_gpu)
+        seq = Sequence(WORKLOAD, window, f0, local_rank)
+    else:  # weak scaling: the same block per GPU
+        frames_total = frames_per_gpu * world
+        f0, block = sharding.frame_block(frames_total, world, rank)
+        seq = Sequence(WORKLOAD, block, f0, local_rank)
+    est, n, F, nframes = seq.est, seq.n, seq.F, seq.nframes
+
+    # SURVEY.md 8e: the per-frame results are gathered on rank 0 ONCE, at the end of the run (ncclSend/Recv under dist.gather),
+    # inside the timed region. (Round 1 gathered every step: rank 0 ingested 1.7 GB per step while it computed and became the
+    # straggler of the max-over-ranks time.)
+    gather = None
+    if world > 1 and not seq100k:
+        per = -(-frames_total // world)
+        g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev) if rank == 0 else None
+        g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev) if rank == 0 else None
+
+        def gather(b):
+            dist.gather(seq.depths[b], list(g_depth.split(per)) if rank == 0 else None, dst=0)
+            dist.gather(seq.statuses[b], list(g_status.split(per)) if rank == 0 else None, dst=0)
+
     steps, warm = max(1, args.steps), max(3, args.warmup)
-    for _ in range(warm):
-        step()
-    drain()
-    barrier()
     clocks = ClockSampler(local_rank)
-    clocks.start()
-    time.sleep(0.3)
-    launches0 = est.kernelLaunchCount()
-    est.profileEnable(not os.environ.get("MLD_BENCH_NO_PROF"))  # event brackets per launch group (a few % of the step)
-    est.profileRead()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    tw0 = time.perf_counter()
-    e0.record()
-    for _ in range(steps):
-        step()
-    drain()  # every gather has completed inside the timed region
-    e1.record()
-    barrier()
-    tw1 = time.perf_counter()
-    depth, status = depths[(step_no[0] - 1) % len(depths)], statuses[(step_no[0] - 1) % len(depths)]
+    if seq100k:
+        # untimed: regenerate the window; timed: the hot path over it. The times of the windows add up to the block's time.
+        for _ in range(warm):
+            seq.step()
+        barrier()
+        clocks.start()
+        time.sleep(0.3)
+        launches0 = est.kernelLaunchCount()
+        est.profileEnable(not os.environ.get("MLD_BENCH_NO_PROF"))
+        est.profileRead()
+        tw0 = time.perf_counter()
+        ms_block = 0.0
+        windows = 0
+        for _ in range(steps):
+            done = 0
+            while done < block:
+                cnt = min(nframes, block - done)
+                if not (done == 0 and block <= nframes):
+                    seq.generate(f0 + done, cnt)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                seq.step(0, cnt)
+                e1.record()
+                torch.cuda.synchronize()
+                ms_block += e0.elapsed_time(e1)
+                done += cnt
+                windows += 1
+        barrier()
+        tw1 = time.perf_counter()
+        ms_total = max_over_ranks(ms_block)
+    else:
+        for i in range(warm):
+            seq.step()
+        barrier()
+        clocks.start()
+        time.sleep(0.3)
+        launches0 = est.kernelLaunchCount()
+        est.profileEnable(not os.environ.get("MLD_BENCH_NO_PROF"))  # event brackets per launch group (a few % of the step)
+        est.profileRead()
+        tw0 = time.perf_counter()
+        ms_rank = timed_steps(seq, steps, 0, barrier, gather)
+        tw1 = time.perf_counter()
+        ms_total = max_over_ranks(ms_rank)
     est.profileEnable(False)
-    prof, prof_frames = est.profileRead()
+    pipelined = est.pipelineFrames()
+    fused = 0 if pipelined else est.fusedChunkFrames()
+    per_class, prof_frames = kernel_profile(est, pipelined, fused)
     launches = est.kernelLaunchCount() - launches0
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     clocks.stop()
     clk = clocks.summary(tw0, tw1)
     ms_per_step = ms_total / steps
     value = frames_total / (ms_per_step * 1e-3)
+    per_rank_ms = None
+    if world > 1 and not seq100k:
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = ms_rank / steps
+        dist.all_reduce(t)
+        per_rank_ms = [round(float(x), 4) for x in t.cpu()]
 
     # ---- in-run parity spot check against the oracle (rank 0) ----
     parity = None
-    cpu_base = None
-    e2e = None
     if rank == 0 and not os.environ.get("MLD_BENCH_NO_PARITY"):  # (diagnostic kernel builds only)
-        sys.path.insert(0, str(ROOT / "tests"))
-        import oracle_lib as O
-        import parity_util as PU
+        last = min(nframes, block) - 1
+        parity = seq.parity(sorted({0, last // 2, last}), b=(steps - 1) % len(seq.depths) if not seq100k else 0)
 
-        p = O.yaml_params()
-        p.do_use_ransac_plane = 1 if use_road else 0
-        orc = O.Oracle(p)
-        orc.initialize(IMG_W, IMG_H, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, synth.KITTI_T_LIDAR_TO_CAM)
-        checked = 0
-        for i in sorted({0, nframes // 2, nframes - 1}):
-            cloud_i = pts[i].cpu().numpy()
-            orc.set_cloud(cloud_i)
-            plane_i = None
-            if use_road:  # the oracle's RANSAC with the same per-frame seed gives the inlier set; coefficients from the GPU
-                rc_i, c_ref, inl_i, _ = O.ransac_plane(p, cloud_i, SEED + f0 + i)
-                c_gpu = coeffs[i].cpu().numpy()
-                assert rc_i == 0 and np.allclose(c_gpu, c_ref, rtol=1e-5, atol=1e-6), (c_gpu, c_ref)
-                plane_i = (c_gpu, inl_i)
-            d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy(), plane_i)
-            PU.assert_depth_status_equal(depth[i].cpu().numpy(), status[i].cpu().numpy(), d_ref, s_ref, f"bench frame {i}")
-            checked += 1
-        s_all = status.cpu().numpy()
-        parity = {"frames_checked_vs_oracle": checked, "status_exact": True, "depth_rtol": PU.DEPTH_RTOL,
-                  "success_fraction": float((s_all == 1).mean()), "success_road_fraction": float((s_all == 16).mean())}
-
-    # ---- e2e: host buffers through mld_process_frames_host ----
+    # ---- e2e: host buffers through mld_process_frames_host, pcl::PointXYZI records (the drop-in caller's layout) ----
     ne = min(nframes, env_int("MLD_BENCH_E2E_FRAMES", 256 if wl["dense"] else 1024))
-    h_pts = torch.empty((ne, n, 4), dtype=torch.float32).pin_memory()
+    h_pts = torch.zeros((ne, n, 8), dtype=torch.float32).pin_memory()  # x y z 1 | intensity pad pad pad
+    h_pts[:, :, :3].copy_(seq.pts[:ne, :, :3])
+    h_pts[:, :, 3] = 1.0
+    h_pts[:, :, 4].copy_(seq.pts[:ne, :, 3])
     h_uv = torch.empty((ne, F, 2), dtype=torch.float64).pin_memory()
     h_depth = torch.empty((ne, F), dtype=torch.float64).pin_memory()
     h_status = torch.empty((ne, F), dtype=torch.int32).pin_memory()
-    h_pts.copy_(pts[:ne])
-    h_uv.copy_(uv[:ne])
+    h_uv.copy_(seq.uv[:ne])
     torch.cuda.synchronize()
 
-    def e2e_step():
-        est.processFramesHostPtr(h_pts.data_ptr(), n, n, 16, h_uv.data_ptr(), F, h_depth.data_ptr(), h_status.data_ptr(), ne,
-                                 road=use_road, seed=SEED + f0)
+    def e2e_run(ptr, stride, reps):
+        for _ in range(2):
+            est.processFramesHostPtr(ptr, n, n, stride, h_uv.data_ptr(), F, h_depth.data_ptr(), h_status.data_ptr(), ne, road=seq.road, seed=SEED + seq.f0)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            est.processFramesHostPtr(ptr, n, n, stride, h_uv.data_ptr(), F, h_depth.data_ptr(), h_status.data_ptr(), ne, road=seq.road, seed=SEED + seq.f0)
+        torch.cuda.synchronize()
+        return max_over_ranks(time.perf_counter() - t0)
 
-    for _ in range(2):
-        e2e_step()
-    barrier()
-    te0 = time.perf_counter()
     e2e_steps = max(2, min(steps, 5))
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    te = time.perf_counter() - te0
-    tt = torch.tensor([te], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    te = float(tt.item())
-    if not os.environ.get("MLD_BENCH_NO_PARITY"):
-        assert torch.equal(h_status, status[:ne].cpu()) and torch.equal(h_depth, depth[:ne].cpu()), "host pipeline != device path"
-    e2e_value = world * ne * e2e_steps / te
-    scale = nframes / ne  # bytes per full step of this rank's block
-    e2e = {"value": e2e_value, "unit": "frames/s",
-           "h2d_bytes_per_step": int((h_pts.numel() * 4 + h_uv.numel() * 8) * scale) * world,
-           "d2h_bytes_per_step": int((h_depth.numel() * 8 + h_status.numel() * 4) * scale) * world,
-           "frames_timed_per_rank": ne * e2e_steps, "api": "mld_process_frames_host (pinned host buffers, 3-slot H2D/compute/D2H pipeline)"}
+    hs0 = est.hostPipelineStats()
+    te = e2e_run(h_pts.data_ptr(), 32, e2e_steps)
+    hs1 = est.hostPipelineStats()
+    hs = {k: hs1[k] - hs0[k] for k in hs0}
+    frames_moved = max(1, hs["frames_packed"] + hs["frames_direct"])  # warm-up passes included
+    if not os.environ.get("MLD_BENCH_NO_PARITY") and not seq100k:
+        b = (steps - 1) % len(seq.depths)
+        assert torch.equal(h_status, seq.statuses[b][:ne].cpu()) and torch.equal(h_depth, seq.depths[b][:ne].cpu()), "host pipeline != device path"
+    step_frames = min(nframes, block) * world  # frames of one full step of the job
+    e2e = {"value": world * ne * e2e_steps / te, "unit": "frames/s",
+           # counted by the library from the copies it issued (mld_host_pipeline_stats), scaled to one step of the job
+           "h2d_bytes_per_step": int(hs["h2d_bytes"] / frames_moved * step_frames),
+           "d2h_bytes_per_step": int(hs["d2h_bytes"] / frames_moved * step_frames),
+           "frames_timed_per_rank": ne * e2e_steps,
+           "frames_packed_fraction": hs["frames_packed"] / frames_moved,
+           "input": "pinned host memory, pcl::PointXYZI records (32 bytes per point, the drop-in caller's cloud layout)",
+           "api": (f"mld_process_frames_host: 3-slot H2D / kernels / D2H pipeline; {os.environ['MLD_PACK_THREADS']} host threads strip the records to "
+                   "12-byte xyz in pinned staging buffers while the copy engine has work queued, chunks go out as whole records when it would idle")}
+    if rank == 0 or world > 1:
+        # the round-1 figure for comparison: 16-byte float4 points copied as they are
+        h4 = torch.empty((ne, n, 4), dtype=torch.float32).pin_memory()
+        h4.copy_(seq.pts[:ne])
+        t4 = e2e_run(h4.data_ptr(), 16, 2)
+        e2e["float4_input_frames_per_s"] = world * ne * 2 / t4
+        del h4
+    del h_pts
 
-    if rank == 0 and world == 1:
+    cpu_base = None
+    if rank == 0 and world == 1 and not seq100k:
         budget = float(os.environ.get("MLD_BENCH_CPU_SECONDS", "20"))
-        hp = [pts[i].cpu().numpy() for i in range(min(32, nframes))]
-        hu = [uv[i].cpu().numpy() for i in range(min(32, nframes))]
+        hp = [seq.pts[i].cpu().numpy() for i in range(min(32, nframes))]
+        hu = [seq.uv[i].cpu().numpy() for i in range(min(32, nframes))]
         cpu_base = cpu_reference_throughput(budget, hp, hu)
+
+    # ---- the other BASELINE configs, short passes on rank 0 at N = 1 (configs[2] road, configs[3] dense, production SemanticPlane) ----
+    others = None
+    if rank == 0 and world == 1 and WORKLOAD == "kitti" and not os.environ.get("MLD_BENCH_NO_OTHERS"):
+        peak, _ = measured_peak_gbs()
+        others = {}
+        for name, frames_o, semantic in (("road", env_int("MLD_BENCH_OTHER_FRAMES", 2048), False), ("dense", env_int("MLD_BENCH_OTHER_FRAMES", 2048) // 4, False),
+                                         ("road", env_int("MLD_BENCH_OTHER_FRAMES", 2048), True)):
+            del seq.pts, seq.uv  # free the headline's 20 GB first time round (harmless afterwards)
+            seq.pts = seq.uv = None
+            torch.cuda.empty_cache()
+            so = Sequence(name, frames_o, 0, local_rank, semantic=semantic)
+            ms = timed_steps(so, 3, 3, barrier) / 3
+            v = frames_o / (ms * 1e-3)
+            key = "semantic" if semantic else name
+            others[key] = {"config": ("production caller: SemanticPlane fitted per frame from a label image on the GPU + road path (tracklet_depth_module.cpp:269-330), "
+                                      "road / non-road feature mix" if semantic else WORKLOADS[name]["desc"]),
+                           "frames": frames_o, "points_per_frame": so.n, "features_per_frame": so.F, "image": [so.W, so.H],
+                           "value": v, "unit": "frames/s", "ms_per_step": ms, "feature_depths_per_sec": v * so.F,
+                           "roofline_path": {"algorithmic_bytes_per_frame": so.algorithmic_bytes_per_frame(),
+                                             "frac": so.algorithmic_bytes_per_frame() * v / 1e9 / peak,
+                                             "frac_without_map_term": so.algorithmic_bytes_per_frame(False) * v / 1e9 / peak},
+                           "parity": so.parity([0, frames_o - 1])}
+            del so
+            torch.cuda.empty_cache()
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
-        # device-resident sequences run K1 of chunk j and the gather of chunk j-1 as ONE launch
-        pipelined = est.pipelineFrames()
-        fused = 0 if pipelined else est.fusedChunkFrames()
         chunk = nframes if pipelined else (fused or est.chunkFrames())
-        per_class = {}
-        for name, (ms, ln) in prof.items():
-            per_class[name] = {"ms_total": ms, "launches": ln, "avg_launch_ms": (ms / ln) if ln else None}
-        # dominant kernel of the step and its algorithmic bytes per launch (DESIGN.md "roofline")
-        # single kernels only: feature_depth is the sum of feature_gather + feature_solve + feature_rest (road kernels and the
-        # overflow pass), listed for the share of the step but not a kernel of its own
-        if pipelined:  # one persistent launch per sequence does all of it (mld_pipeline.cu)
-            per_class = {"depth_pipeline": per_class["project_scatter"], "ransac": per_class.get("ransac")}
-        elif fused:
-            per_class["fused_project_gather"] = per_class.pop("project_scatter")
-            per_class.pop("feature_gather", None)
         kernels = {k: v for k, v in per_class.items()
                    if k in ("depth_pipeline", "project_scatter", "fused_project_gather", "feature_gather", "feature_solve") and v and v["launches"] and v["ms_total"] > 0}
         per_class["note"] = ("durations are bracketed by CUDA events on the launching streams inside the timed region; launches of different "
                              "chunks overlap (front stream: fused K1 + gather launches; slot streams: solve + overflow pass), so a kernel's "
                              "duration includes time shared with other kernels; in the fused pipeline every 4th launch group is sampled")
-        # Which single kernel dominates the step: the event brackets of kernels that run concurrently overlap (the solve of one
-        # chunk is stretched by the fused launch of the next and vice versa), so the ranking comes from the serialised ncu launch
-        # list of this same command when it is committed (profiles/traffic.json, headline workload), else from the brackets.
-        traffic_file = ROOT / "profiles" / "traffic.json"
+        # Which single kernel dominates the step: the event brackets of concurrent kernels overlap, so the ranking and the DRAM traffic
+        # come from the serialised ncu launch list of this same command (profiles/traffic.json) -- only when that file was taken from
+        # the sources that are running now (source_hash), else from the brackets and traffic stays null.
         tr = {}
-        if traffic_file.exists() and WORKLOAD == "kitti" and not pipelined:
+        traffic_file = ROOT / "profiles" / "traffic.json"
+        if traffic_file.exists() and WORKLOAD == "kitti":
             try:
                 tr = json.loads(traffic_file.read_text())
+                if tr.get("source_hash") != source_hash():
+                    tr = {"stale": f"profiles/traffic.json was taken from sources {tr.get('source_hash')}, running {source_hash()}"}
             except Exception:
                 tr = {}
         shares = {k: v for k, v in tr.get("share_of_step_ncu", {}).items() if k in kernels}
-        if shares:
-            dom = max(shares, key=shares.get)
-        else:
-            dom = max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None
+        dom = max(shares, key=shares.get) if shares else (max(kernels, key=lambda k: kernels[k]["ms_total"]) if kernels else None)
         roof = None
         if dom:
             frames_per_launch = prof_frames / per_class[dom]["launches"]
-            # K1 owns the point stream and the pixel map (written once per frame in the reference's accounting; the
-            # epoch-tagged map makes the actual clear traffic ~0), K2 the feature reads and the result writes
-            # bytes the kernel has to move given the algorithm as built: the point stream once, the feature reads, the result
-            # writes. SURVEY.md 8(d)'s 4 W H map term is NOT charged to a kernel: the epoch-tagged map is never rewritten
-            # as a whole (only the cells of visible points are touched), so charging it would report more than the DRAM moved.
-            per_frame_bytes = {"depth_pipeline": 16 * N_POINTS + 28 * N_FEATURES, "project_scatter": 16 * N_POINTS, "feature_gather": 16 * N_FEATURES,
-                               "fused_project_gather": 16 * N_POINTS + 16 * N_FEATURES, "feature_solve": 12 * N_FEATURES}[dom]
+            # bytes the kernel has to move given the algorithm as built: the point stream once, the feature reads, the result writes.
+            # SURVEY.md 8(d)'s 4 W H map term is NOT charged to a kernel: the epoch-tagged map is never rewritten as a whole.
+            per_frame_bytes = {"depth_pipeline": 16 * n + 28 * F, "project_scatter": 16 * n, "feature_gather": 16 * F,
+                               "fused_project_gather": 16 * n + 16 * F, "feature_solve": 12 * F}[dom]
             avg_s = per_class[dom]["avg_launch_ms"] * 1e-3
             achieved = per_frame_bytes * frames_per_launch / avg_s / 1e9
             sampled_ms = sum(v["ms_total"] for k, v in per_class.items()
                              if isinstance(v, dict) and k in ("map_clear", "depth_pipeline", "project_scatter", "fused_project_gather", "ransac", "feature_depth"))
+            per_gpu = value / world
             roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,
@@ -526,35 +670,49 @@ def run_gpu(args, rank, local_rank, world):
                                                "12 F (result writes); fused_project_gather = project_scatter of one chunk + feature_gather of the "
                                                "previous one in one launch = 16 N + 16 F. SURVEY.md 8(d)'s 4 W H map term is not charged to a kernel "
                                                "(the epoch-tagged map is never rewritten as a whole); `path` reports both accountings",
-                    "path": {"algorithmic_bytes_per_frame": ALGO_BYTES_PER_FRAME,
-                             "achieved": ALGO_BYTES_PER_FRAME * (value / world) / 1e9, "frac": ALGO_BYTES_PER_FRAME * (value / world) / 1e9 / peak,
-                             "frac_without_map_term": (16 * N_POINTS + 28 * N_FEATURES) * (value / world) / 1e9 / peak,
+                    "path": {"algorithmic_bytes_per_frame": seq.algorithmic_bytes_per_frame(),
+                             "achieved": seq.algorithmic_bytes_per_frame() * per_gpu / 1e9, "frac": seq.algorithmic_bytes_per_frame() * per_gpu / 1e9 / peak,
+                             "frac_without_map_term": seq.algorithmic_bytes_per_frame(False) * per_gpu / 1e9 / peak,
                              "note": "whole hot path per GPU: B * frames/s against the same peak, B = 16 N + 4 W H + 28 F (SURVEY.md 8(d)); "
                                      "frac_without_map_term leaves out the 4 W H map write that the epoch-tagged map performs without moving the bytes"}}
-        if roof and tr:
-            roof["traffic"] = tr.get(dom, {}).get("dram_bytes_per_launch")
-            roof["traffic_source"] = tr.get("source")
-            fpl = tr.get("frames_per_launch")
-            if roof["traffic"] and fpl and abs(fpl - frames_per_launch) > 1:  # the capture used another launch size: scale per frame
-                roof["traffic"] = int(roof["traffic"] / fpl * frames_per_launch)
+            if tr.get("stale"):
+                roof["traffic_note"] = tr["stale"]
+            elif tr:
+                roof["traffic"] = tr.get(dom, {}).get("dram_bytes_per_launch")
+                roof["traffic_source"] = tr.get("source")
+                roof["all_kernels_ncu"] = {k: tr[k] for k in tr.get("share_of_step_ncu", {}) if k in tr}
+                fpl = tr.get("frames_per_launch")
+                if roof["traffic"] and fpl and abs(fpl - frames_per_launch) > 1:  # the capture used another launch size: scale per frame
+                    roof["traffic"] = int(roof["traffic"] / fpl * frames_per_launch)
+        if seq100k:
+            workload = (f"seq100k: BASELINE.json configs[4], ONE sequence of {frames_total} synthetic KITTI-shaped frames cut into contiguous blocks over "
+                        f"{world} GPU(s) ({block} frames on rank 0); a block streams through a resident window of {nframes} frames that is regenerated on "
+                        f"the device between passes (100k frames = 192 GB of points do not fit one GPU); the timed region is the hot path over every "
+                        f"window ({windows // steps} per step on rank 0), the regeneration is not timed")
+        else:
+            workload = (f"{WORKLOAD}: sequence of {frames_total // world} synthetic frames per GPU, batched; {wl['desc']}; "
+                        f"{n} pts, {seq.W}x{seq.H}, {F} features, monolidar_fusion/parameters.yaml with do_use_depth_segmentation 0; feature mix "
+                        "calibrated to the reference's status log (include/mld_synth.h)")
         line = {
             "metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": steps, "warmup": warm,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if seq100k else "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: sequence of {frames_total // world} synthetic frames per GPU, batched; {wl['desc']}; "
-                                   f"{N_POINTS} pts, {IMG_W}x{IMG_H}, {N_FEATURES} features, monolidar_fusion/parameters.yaml "
-                                   "with do_use_depth_segmentation 0",
-                       "frames_per_gpu": frames_total // world, "points_per_frame": N_POINTS, "features_per_frame": N_FEATURES,
-                       "image": [IMG_W, IMG_H], "chunk_frames_per_launch": chunk,
+            "config": {"workload": workload,
+                       "frames_per_gpu": block, "points_per_frame": n, "features_per_frame": F,
+                       "image": [seq.W, seq.H], "chunk_frames_per_launch": chunk,
                        "l2": f"inputs of one step ({nframes * n * 16 / 1e9:.1f} GB of points per GPU) are far larger than the 126 MB L2; no flush needed",
-                       "parallelism": f"frames sharded in contiguous blocks over {world} GPU(s); NCCL gather of the results on rank 0 per step" if world > 1 else "single GPU"},
-            "feature_depths_per_sec": value * N_FEATURES,
+                       "parallelism": (f"frames sharded in contiguous blocks over {world} GPU(s), no collective on the data path; one gather of the per-frame "
+                                       "results on rank 0 at the end of the run (ncclSend/Recv under dist.gather), inside the timed region"
+                                       if world > 1 and not seq100k else ("contiguous blocks, no collective" if world > 1 else "single GPU"))},
+            "feature_depths_per_sec": value * F,
             "clocks": clk,
             "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": roof,
             "cpu_baseline": cpu_base,
             "parity": parity,
+            "per_rank_ms_per_step": per_rank_ms,
+            "other_workloads": others,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

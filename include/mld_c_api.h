@@ -223,6 +223,12 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
                             int stride_bytes, const double* uv_host, int F, double* depth_host, int32_t* status_host,
                             int64_t nframes, int road, uint64_t seed, float* plane_coeffs_out_host);
 
+/* counters of mld_process_frames_host since mld_create: [0] bytes copied host -> device, [1] device -> host, [2] frames whose
+ * points were packed to 12-byte xyz by the host threads, [3] frames copied as whole records. Records wider than 16 bytes
+ * (pcl::PointXYZI) are packed whenever the copy engine still has work queued and copied as they are when it would idle; env
+ * MLD_HOST_PACK=1 / 0 forces packing on / off, MLD_PACK_THREADS sets the worker count. */
+int mld_host_pipeline_stats(const mld_handle* h, int64_t* out4);
+
 /* ---- tracklets_depth batch adaptor ----
  * TrackletDepthModule::process calls CalculateDepth twice per frame, for the previous and the current cloud
  * with different feature sets (tracklets_depth/src/tracklet_depth_module.cpp:318, :330). Both clouds go through
@@ -234,6 +240,16 @@ int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev
                              double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur,
                              int64_t n_cur, const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur,
                              mld_plane* plane_cur, int stride_bytes, uint64_t ransac_seed);
+
+/* The same per-frame work when the caller walks a sequence (TrackletDepthModule keeps _cloud_last_frame = the cloud of its previous
+ * callback, tracklet_depth_module.cpp:318-354): the previous cloud is the one that was `cur` in the last call of either pair entry
+ * point (or the handle's current cloud after mld_set_cloud) and is STILL ON THE DEVICE with its pixel map -- only the new cloud
+ * crosses PCIe, one upload and one projection per frame instead of two. Without a resident cloud (first frame, or a batched call
+ * in between) the previous side yields depth -1 like a NULL cloud. mld_has_resident_cloud tells which case the next call is. */
+int mld_calculate_depth_pair_resident(mld_handle* h, const double* uv_prev, int F_prev, double* depth_prev, int32_t* status_prev,
+                                      mld_plane* plane_prev, const void* pts_cur, int64_t n_cur, const double* uv_cur, int F_cur,
+                                      double* depth_cur, int32_t* status_cur, mld_plane* plane_cur, int stride_bytes, uint64_t ransac_seed);
+int mld_has_resident_cloud(const mld_handle* h);
 
 /* ---- DepthCalculationStatistics (DepthEstimator.cpp:1039-1090): counters per DepthResultType (0..20) ----
  * mld_set_statistics(on): every mld_calculate_depth call also reduces its status array (still on the device) to the 21

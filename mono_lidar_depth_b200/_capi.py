@@ -189,11 +189,18 @@ SYMBOLS = {
     "mld_get_points_camera_indexed": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "mld_get_triangle_corners": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "mld_yaml_int": (C.c_int, [C.c_char_p, C.c_char_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "mld_calculate_depth_pair_resident": (
+        C.c_int,
+        [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _PL, C.c_void_p, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, _PL,
+         C.c_int, C.c_uint64],
+    ),
+    "mld_has_resident_cloud": (C.c_int, [_H]),
     "mld_status_histogram_host": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     "mld_status_histogram_device": (C.c_int, [_H, C.c_void_p, C.c_int64, C.POINTER(C.c_int64), C.c_void_p]),
     "mld_pack_feature_points_device": (C.c_int, [_H, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "mld_kernel_launch_count": (C.c_int64, [_H]),
     "mld_neighbor_capacity": (C.c_int, []),
+    "mld_host_pipeline_stats": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "mld_pipeline_frames": (C.c_int, [_H]),
     "mld_pipeline_aborted": (C.c_int, [_H]),
     "mld_pipeline_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),

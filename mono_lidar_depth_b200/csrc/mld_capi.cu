@@ -2,13 +2,20 @@
 // device buffers, stream pipelines and kernel launches. No arithmetic of the hot path lives here and
 // there is no CPU fallback: without a CUDA device every compute entry point fails with MLD_ERR_CUDA.
 #include <cuda_runtime.h>
+#include <immintrin.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <fstream>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <map>
 #include <sstream>
 #include <string>
@@ -24,6 +31,7 @@ thread_local std::string g_create_error;
 
 constexpr int MLD_PIPE_SLOTS = 6;   // slots (streams + buffers) a handle owns
 constexpr int MLD_HOST_SLOTS = 3;   // of which the host-buffer pipeline uses
+constexpr int MLD_PREV_SLOT = 5;    // holds the previous cloud of mld_calculate_depth_pair_resident (batched paths use slots 0..2)
 
 // everything one in-flight chunk of frames needs on the device
 struct Slot {
@@ -44,6 +52,10 @@ struct Slot {
     unsigned char* d_sem = nullptr; size_t sem_bytes = 0;       // SemanticPlane scratch
     unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
     void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
+    unsigned char* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging of the packed (12-byte xyz) host pipeline
+    float* d_pack = nullptr;    size_t d_pack_bytes = 0;          // its device copy, expanded to float4 in d_pts
+    cudaEvent_t ev_stage = nullptr;                                // the H2D copy out of h_stage has finished
+    bool stage_busy = false;                                       // ev_stage has been recorded in the current call
     int* h_ovf_seen = nullptr;  // pinned: overflow count of this slot's previous chunk (sizes the next overflow launch)
     unsigned epoch = 0;         // uses of d_maps since its last clear (tagged mode), 0 = never cleared
     size_t occ_clean_bytes = 0; // leading bytes of d_occ known to be zero once the slot's `done` event has fired (fused pipeline)
@@ -70,6 +82,84 @@ cudaError_t ensure(T*& p, size_t& cap, size_t need, bool* changed = nullptr) {
 }
 
 }  // namespace
+
+// Host worker threads that strip pcl::PointXYZI records (32 bytes: x y z pad | intensity pad pad pad) down to 12-byte xyz in
+// pinned staging buffers: the host-buffer pipeline is PCIe bound, and only 12 of the 32 bytes are ever used
+// (DepthEstimator.cpp:169 casts topRows<3>). run() blocks until every item is done; the calling thread works too.
+class HostPool {
+public:
+    explicit HostPool(int workers) {
+        for (int i = 0; i < workers; i++) threads_.emplace_back([this] { loop(); });
+    }
+    ~HostPool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void run(int items, const std::function<void(int)>& fn) {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            fn_ = &fn;
+            items_ = items;
+            next_.store(0);
+            done_.store(0);
+            generation_++;
+        }
+        cv_.notify_all();
+        work();
+        std::unique_lock<std::mutex> lk(m_);
+        // every item is done AND no worker is still inside work() with this job's function pointer
+        cv_done_.wait(lk, [this] { return done_.load() >= items_ && active_ == 0; });
+        fn_ = nullptr;
+    }
+    int workers() const { return (int)threads_.size(); }
+
+private:
+    void work() {
+        const std::function<void(int)>* fn = fn_;
+        const int items = items_;
+        while (fn) {
+            const int i = next_.fetch_add(1);
+            if (i >= items) break;
+            (*fn)(i);
+            if (done_.fetch_add(1) + 1 >= items) {
+                std::lock_guard<std::mutex> lk(m_);
+                cv_done_.notify_all();
+            }
+        }
+    }
+    void loop() {
+        unsigned long long seen = 0;
+        while (true) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                if (!fn_) continue;  // the job finished before this worker woke up
+                active_++;
+            }
+            work();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                active_--;
+            }
+            cv_done_.notify_all();
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, cv_done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int items_ = 0;
+    std::atomic<int> next_{0}, done_{0};
+    unsigned long long generation_ = 0;
+    int active_ = 0;
+    bool stop_ = false;
+};
 
 struct mld_handle {
     mld_params params;
@@ -99,6 +189,9 @@ struct mld_handle {
     cudaEvent_t ev_join = nullptr;
     long long cur_n = 0;
     int cur_stride_f = 4;
+    bool have_prev = false;         // slots[MLD_PREV_SLOT] holds the previous cloud of mld_calculate_depth_pair_resident
+    long long prev_n = 0;
+    int prev_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
     // persistent pipeline (mld_pipeline.cu): one launch per device-resident sequence; ring of map / occupancy slots
     bool use_pipeline = false;      // MLD_PIPE=1: one persistent launch per sequence (mld_pipeline.cu) instead of the chunked launches
@@ -122,6 +215,12 @@ struct mld_handle {
     unsigned long long* h_hist = nullptr;  // pinned copy
     int64_t last_hist[21] = {0};
     bool last_hist_valid = false;
+    // host-buffer pipeline: pack xyz on host threads (always for strides > 16 bytes; MLD_HOST_PACK=1/0 forces it on / off)
+    int host_pack = -1;
+    int host_pack_threads = 0;      // MLD_PACK_THREADS (0 = hardware concurrency - 2, at most 14)
+    HostPool* pool = nullptr;
+    double pcie_gbs = 50.0;         // link rate the pack / copy choice is modelled with (MLD_PCIE_GBS)
+    int64_t host_stats[4] = {0, 0, 0, 0};  // since creation: H2D bytes, D2H bytes, frames packed, frames copied as they are
     int* d_dbg = nullptr;           // neighbour debug buffer
     float* d_synth_tables = nullptr;
     mld_synth_config synth_cfg_cached;
@@ -666,6 +765,12 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     }
     memset(h->h_pipe_flags, 0, 36 * sizeof(int));
     h->h_pipe_counters = h->h_pipe_flags + 4;
+    env = getenv("MLD_HOST_PACK");
+    if (env) h->host_pack = atoi(env) != 0 ? 1 : 0;
+    env = getenv("MLD_PCIE_GBS");
+    if (env && atof(env) > 0) h->pcie_gbs = atof(env);
+    env = getenv("MLD_PACK_THREADS");
+    if (env && atoi(env) > 0) h->host_pack_threads = atoi(env);
     env = getenv("MLD_SOLVE_PRIO");    // "1": slot streams (solve + overflow pass of the fused pipeline) at the highest priority
     const bool slot_prio = env && atoi(env) != 0;
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
@@ -697,8 +802,12 @@ int mld_destroy(mld_handle* h) {
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_k2) cudaEventDestroy(s.ev_k2);
         if (s.h_ovf_seen) cudaFreeHost(s.h_ovf_seen);
+        if (s.h_stage) cudaFreeHost(s.h_stage);
+        cudaFree(s.d_pack);
+        if (s.ev_stage) cudaEventDestroy(s.ev_stage);
         if (s.stream) cudaStreamDestroy(s.stream);
     }
+    delete h->pool;
     cudaFree(h->d_dbg);
     cudaFree(h->d_hist);
     if (h->h_hist) cudaFreeHost(h->h_hist);
@@ -790,6 +899,7 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     h->ring_epoch = 0;
     h->initialized = true;
     h->have_cloud = false;
+    h->have_prev = false;
     return MLD_OK;
 }
 
@@ -829,6 +939,11 @@ int mld_profile_read(mld_handle* h, double* ms7, int64_t* launches7, int64_t* fr
     return MLD_OK;
 }
 int64_t mld_kernel_launch_count(const mld_handle* h) { return h ? h->launches : 0; }
+int mld_host_pipeline_stats(const mld_handle* h, int64_t* out4) {
+    if (!h || !out4) return MLD_ERR_INVALID_ARG;
+    for (int i = 0; i < 4; i++) out4[i] = h->host_stats[i];
+    return MLD_OK;
+}
 int mld_pipeline_frames(const mld_handle* h) { return (h && h->use_pipeline && h->feature_mode == 2 && h->use_tagged_maps) ? 1 : 0; }
 int mld_pipeline_counters(const mld_handle* h, int64_t* out8) {
     if (!h || !out8 || !h->h_pipe_counters) return MLD_ERR_INVALID_ARG;
@@ -1478,20 +1593,111 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
         rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_bytes, std::max(F, 1), chunk, true, use_road);
         if (rc) return rc;
     }
+    // Only x, y, z of a point are used (12 of the 16 / 32 bytes of a record) and the pipeline is PCIe bound: host threads pack
+    // the chunk's points to 12-byte xyz in a pinned staging buffer, one contiguous copy moves them, a kernel expands them to the
+    // float4 layout the projection kernel streams. (A strided 2-D DMA copy that skips the padding runs at 11 GB/s and a kernel
+    // reading mapped pinned memory transfers every byte of the 32-byte sectors anyway: measured, scripts/pcie_probe.cu.)
+    const bool pack = n_points > 0 && (h->host_pack == 1 || (h->host_pack != 0 && stride_bytes > 16));
+    if (pack && !h->pool) {
+        int t = h->host_pack_threads;
+        if (t <= 0) t = std::max(1, std::min(14, (int)std::thread::hardware_concurrency() - 2));
+        h->pool = new HostPool(t - 1);  // the calling thread is the t-th worker
+    }
+    if (pack) {
+        for (int i = 0; i < MLD_HOST_SLOTS; i++) {
+            Slot& s = h->slots[i];
+            const size_t need = (size_t)chunk * (size_t)n_points * 12;
+            if (need > s.h_stage_bytes) {
+                CK(cudaStreamSynchronize(s.stream));
+                if (s.h_stage) CK(cudaFreeHost(s.h_stage));
+                s.h_stage = nullptr;
+                s.h_stage_bytes = 0;
+                CK(cudaHostAlloc(reinterpret_cast<void**>(&s.h_stage), need, cudaHostAllocDefault));
+                s.h_stage_bytes = need;
+            }
+            CK(ensure(s.d_pack, s.d_pack_bytes, need));
+            CK(ensure(s.d_pts, s.pts_bytes, (size_t)chunk * (size_t)n_points * 16));
+            if (!s.ev_stage) CK(cudaEventCreateWithFlags(&s.ev_stage, cudaEventDisableTiming));
+        }
+    }
     int64_t ci = 0;
+    cudaEvent_t last_h2d = nullptr;  // the most recently queued H2D copy of the cloud
+    const auto t_origin = std::chrono::steady_clock::now();
+    double link_free_at = 0.0;       // modelled time (s since t_origin) at which the queued H2D copies will have left the host
+    double pack_s_per_frame = 0.0;   // measured, smoothed
+    const double link_bytes_per_s = h->pcie_gbs * 1e9;
+    auto queue_copy = [&](double bytes) {
+        const double now = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_origin).count();
+        link_free_at = std::max(link_free_at, now) + bytes / link_bytes_per_s;
+    };
+    for (int i = 0; i < MLD_HOST_SLOTS; i++) h->slots[i].stage_busy = false;
     for (int64_t f0 = 0; f0 < nframes; f0 += chunk, ci++) {
         Slot& s = h->slots[ci % MLD_HOST_SLOTS];
         int c = (int)std::min<int64_t>(chunk, nframes - f0);
         // stream order makes the slot's buffers safe to reuse: the previous chunk on this stream is complete
         // (its D2H copies included) before these copies start
-        if (n_points > 0)
+        // Packing costs host time, copying whole records costs PCIe time (measured on a 16-core host: 14.2 k frames/s copying 32-byte
+        // records, 20.3 k packing everything with 14 threads). A chunk is packed when the copies already queued keep the link busy until
+        // the packed data is ready, and goes out as whole records when the link would otherwise idle: both resources stay busy.
+        // The link's backlog is modelled on the host (bytes queued / link rate); it only steers the choice, never correctness.
+        bool pack_this = pack;
+        if (pack && h->host_pack != 1) {
+            const double now = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_origin).count();
+            if (last_h2d != nullptr && cudaEventQuery(last_h2d) == cudaSuccess) link_free_at = std::min(link_free_at, now);  // backlog drained
+            if (now + pack_s_per_frame * c > link_free_at) pack_this = false;
+        }
+        if (pack_this) {
+            if (s.stage_busy) CK(cudaEventSynchronize(s.ev_stage));  // the staging buffer's previous copy has left the host
+            const int pieces = 8;                                          // per frame: load balance over the workers
+            const long long per = (n_points + pieces - 1) / pieces;
+            unsigned char* stage = s.h_stage;
+            const std::function<void(int)> job = [&](int item) {
+                const int fr = item / pieces, pc = item % pieces;
+                const long long lo = (long long)pc * per, hi = std::min<long long>(n_points, lo + per);
+                const unsigned char* p = src + ((size_t)(f0 + fr) * (size_t)frame_pitch_points + (size_t)lo) * (size_t)stride_bytes;
+                float* q = reinterpret_cast<float*>(stage + ((size_t)fr * (size_t)n_points + (size_t)lo) * 12);
+                // a core's streaming bandwidth is bounded by its outstanding cache misses: prefetch ~1 KB ahead and store past the
+                // cache (no read-for-ownership of the staging lines)
+                for (long long i = lo; i < hi; i++, p += stride_bytes, q += 3) {
+                    const int* f = reinterpret_cast<const int*>(p);
+                    _mm_prefetch(reinterpret_cast<const char*>(p) + 1024, _MM_HINT_NTA);
+                    _mm_stream_si32(reinterpret_cast<int*>(q), f[0]);
+                    _mm_stream_si32(reinterpret_cast<int*>(q) + 1, f[1]);
+                    _mm_stream_si32(reinterpret_cast<int*>(q) + 2, f[2]);
+                }
+                _mm_sfence();
+            };
+            const auto tp0 = std::chrono::steady_clock::now();
+            h->pool->run(c * pieces, job);
+            const double took = std::chrono::duration<double>(std::chrono::steady_clock::now() - tp0).count() / c;
+            pack_s_per_frame = pack_s_per_frame > 0 ? 0.7 * pack_s_per_frame + 0.3 * took : took;
+            CK(cudaMemcpyAsync(s.d_pack, s.h_stage, (size_t)c * (size_t)n_points * 12, cudaMemcpyHostToDevice, s.stream));
+            CK(cudaEventRecord(s.ev_stage, s.stream));
+            s.stage_busy = true;
+            last_h2d = s.ev_stage;
+            h->host_stats[0] += (int64_t)c * n_points * 12;
+            h->host_stats[2] += c;
+            queue_copy((double)c * (double)n_points * 12.0);
+            CK(mld_launch_unpack_xyz(s.d_pack, reinterpret_cast<float*>(s.d_pts), (long long)c * n_points, s.stream));
+            h->launches++;
+        } else if (n_points > 0) {
             CK(cudaMemcpy2DAsync(s.d_pts, frame_bytes, src + (size_t)f0 * (size_t)frame_pitch_points * (size_t)stride_bytes,
                                  (size_t)frame_pitch_points * (size_t)stride_bytes, frame_bytes, (size_t)c, cudaMemcpyHostToDevice,
                                  s.stream));
+            if (pack) {
+                CK(cudaEventRecord(s.ev_k1, s.stream));
+                last_h2d = s.ev_k1;
+            }
+            h->host_stats[0] += (int64_t)c * (int64_t)frame_bytes;
+            h->host_stats[3] += c;
+            queue_copy((double)c * (double)frame_bytes);
+        }
+        h->host_stats[0] += (int64_t)c * F * 16;
+        h->host_stats[1] += (int64_t)c * F * 12;
         if (F > 0)
             CK(cudaMemcpyAsync(s.d_uv, uv_host + f0 * (int64_t)F * 2, (size_t)c * (size_t)F * 2 * sizeof(double),
                                cudaMemcpyHostToDevice, s.stream));
-        rc = enqueue_chunk(h, s, s.stream, reinterpret_cast<const float*>(s.d_pts), n_points, n_points, stride_f, s.d_uv, F, s.d_depth,
+        rc = enqueue_chunk(h, s, s.stream, reinterpret_cast<const float*>(s.d_pts), n_points, n_points, pack_this ? 4 : stride_f, s.d_uv, F, s.d_depth,
                            s.d_status, c, use_road, seed, f0, nullptr);
         if (rc) return rc;
         if (F > 0) {
@@ -1510,19 +1716,36 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
 }
 
 // ---- tracklets_depth batch adaptor: previous + current cloud in one call ----
+// resident: the slot already holds this cloud (points, pixel map, occupancy) from the call in which it was the current cloud; only
+// the features (and the plane) go to the device
 static int pair_side_begin(mld_handle* h, Slot& s, const void* pts, int64_t n, int stride_bytes, const double* uv, int F,
-                           const mld_plane* plane, bool want_ransac, uint64_t seed, std::vector<unsigned int>& hb) {
-    int rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, std::max(F, 1), 1, true, want_ransac || plane != nullptr);
-    if (rc) return rc;
+                           const mld_plane* plane, bool want_ransac, uint64_t seed, std::vector<unsigned int>& hb, bool resident = false) {
+    int rc = MLD_OK;
     const int stride_f = stride_bytes / 4;
-    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, pts, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    MapCode mc = s.mc;
+    if (!resident) {
+        rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, std::max(F, 1), 1, true, want_ransac || plane != nullptr);
+        if (rc) return rc;
+        if (n > 0) CK(cudaMemcpyAsync(s.d_pts, pts, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+        rc = begin_maps(h, s, 1, n, s.stream, mc);
+        if (rc) return rc;
+        CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, s.d_maps,
+                                      h->feature_mode >= 1 ? s.d_occ : nullptr, 1, s.stream));
+        if (n > 0) h->launches++;
+    } else {
+        CK(ensure(s.d_uv, s.uv_bytes, (size_t)std::max(F, 1) * 2 * sizeof(double)));
+        CK(ensure(s.d_depth, s.depth_bytes, (size_t)std::max(F, 1) * sizeof(double)));
+        CK(ensure(s.d_status, s.status_bytes, (size_t)std::max(F, 1) * sizeof(int)));
+        CK(ensure(s.d_ovf, s.ovf_bytes, ((size_t)std::max(F, 1) + 1) * sizeof(int)));
+        if (want_ransac || plane != nullptr) {
+            const size_t words = (size_t)((n + 31) / 32);
+            CK(ensure(s.d_bits, s.bits_bytes, std::max<size_t>(words, 1) * sizeof(unsigned int)));
+            CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
+            CK(ensure(s.d_scratch, s.scratch_bytes, mld_ransac_scratch_bytes(std::max<int64_t>(n, 1), 1)));
+            CK(ensure(s.d_small, s.small_bytes, 3 * sizeof(int)));
+        }
+    }
     if (F > 0) CK(cudaMemcpyAsync(s.d_uv, uv, (size_t)F * 2 * sizeof(double), cudaMemcpyHostToDevice, s.stream));
-    MapCode mc;
-    rc = begin_maps(h, s, 1, n, s.stream, mc);
-    if (rc) return rc;
-    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, s.d_maps,
-                                  h->feature_mode >= 1 ? s.d_occ : nullptr, 1, s.stream));
-    if (n > 0) h->launches++;
     const long long words = (n + 31) / 32;
     const float* coeffs = nullptr;
     const unsigned int* bits = nullptr;
@@ -1552,32 +1775,48 @@ static int pair_side_begin(mld_handle* h, Slot& s, const void* pts, int64_t n, i
     return MLD_OK;
 }
 
-int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev, const double* uv_prev, int F_prev,
-                             double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur, int64_t n_cur,
-                             const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur, mld_plane* plane_cur,
-                             int stride_bytes, uint64_t ransac_seed) {
+static int calculate_depth_pair_impl(mld_handle* h, const void* pts_prev, int64_t n_prev, const double* uv_prev, int F_prev,
+                                     double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur, int64_t n_cur,
+                                     const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur, mld_plane* plane_cur,
+                                     int stride_bytes, uint64_t ransac_seed, bool prev_resident) {
     if (!h) return MLD_ERR_INVALID_ARG;
     if (!h->initialized) return fail(h, MLD_ERR_NOT_INITIALIZED, "call of 'setInputCloud' without 'initialize'");
     int rc = check_stride(h, stride_bytes);
     if (rc) return rc;
-    if (n_prev < 0 || n_cur < 0 || F_prev < 0 || F_cur < 0 || !pts_cur || (F_prev > 0 && (!uv_prev || !depth_prev)) ||
+    if ((!prev_resident && n_prev < 0) || n_cur < 0 || F_prev < 0 || F_cur < 0 || !pts_cur || (F_prev > 0 && (!uv_prev || !depth_prev)) ||
         (F_cur > 0 && (!uv_cur || !depth_cur)))
         return fail(h, MLD_ERR_INVALID_ARG, "mld_calculate_depth_pair: bad arguments");
     if (h->params.do_use_depth_segmentation && !h->params.set_all_depths_to_zero)
         return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
     DeviceGuard g(h->device);
-    const bool have_prev = pts_prev != nullptr;
+    int prev_stride_bytes = stride_bytes;
+    if (prev_resident) {
+        // the cloud that was current in the previous call becomes the previous cloud: its slot (points, pixel map, occupancy)
+        // moves aside as it is, and only the new cloud crosses PCIe
+        if (h->have_cloud) {
+            std::swap(h->slots[0], h->slots[MLD_PREV_SLOT]);
+            h->prev_n = h->cur_n;
+            h->prev_stride_f = h->cur_stride_f;
+            h->have_prev = true;
+            h->have_cloud = false;
+        } else {
+            h->have_prev = false;
+        }
+        n_prev = h->have_prev ? h->prev_n : 0;
+        prev_stride_bytes = h->prev_stride_f * 4;
+    }
+    const bool have_prev = prev_resident ? h->have_prev : pts_prev != nullptr;
     const bool road = h->params.do_use_ransac_plane != 0;
     const bool ransac_prev = have_prev && road && plane_prev && !plane_prev->segmented;
     const bool ransac_cur = road && plane_cur && !plane_cur->segmented;
     if ((ransac_prev && n_prev < 3) || (ransac_cur && n_cur < 3)) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     Slot& sc = h->slots[0];  // current cloud stays the handle's cloud
-    Slot& sp = h->slots[1];
+    Slot& sp = h->slots[prev_resident ? MLD_PREV_SLOT : 1];
     std::vector<unsigned int> hb_prev, hb_cur;
     std::vector<int32_t> st_prev_tmp, st_cur_tmp;
     if (have_prev) {
-        rc = pair_side_begin(h, sp, pts_prev, n_prev, stride_bytes, uv_prev, F_prev, (road && plane_prev && !ransac_prev) ? plane_prev : nullptr,
-                             ransac_prev, ransac_seed, hb_prev);
+        rc = pair_side_begin(h, sp, pts_prev, n_prev, prev_stride_bytes, uv_prev, F_prev, (road && plane_prev && !ransac_prev) ? plane_prev : nullptr,
+                             ransac_prev, ransac_seed, hb_prev, prev_resident);
         if (rc) return rc;
     } else {
         for (int i = 0; i < F_prev; i++) {  // depths.setConstant(-1) (tracklet_depth_module.cpp:97-100)
@@ -1620,6 +1859,23 @@ int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev
     h->have_cloud = true;
     return MLD_OK;
 }
+
+int mld_calculate_depth_pair(mld_handle* h, const void* pts_prev, int64_t n_prev, const double* uv_prev, int F_prev,
+                             double* depth_prev, int32_t* status_prev, mld_plane* plane_prev, const void* pts_cur, int64_t n_cur,
+                             const double* uv_cur, int F_cur, double* depth_cur, int32_t* status_cur, mld_plane* plane_cur,
+                             int stride_bytes, uint64_t ransac_seed) {
+    return calculate_depth_pair_impl(h, pts_prev, n_prev, uv_prev, F_prev, depth_prev, status_prev, plane_prev, pts_cur, n_cur, uv_cur, F_cur,
+                                     depth_cur, status_cur, plane_cur, stride_bytes, ransac_seed, false);
+}
+
+int mld_calculate_depth_pair_resident(mld_handle* h, const double* uv_prev, int F_prev, double* depth_prev, int32_t* status_prev,
+                                      mld_plane* plane_prev, const void* pts_cur, int64_t n_cur, const double* uv_cur, int F_cur,
+                                      double* depth_cur, int32_t* status_cur, mld_plane* plane_cur, int stride_bytes, uint64_t ransac_seed) {
+    return calculate_depth_pair_impl(h, nullptr, 0, uv_prev, F_prev, depth_prev, status_prev, plane_prev, pts_cur, n_cur, uv_cur, F_cur, depth_cur,
+                                     status_cur, plane_cur, stride_bytes, ransac_seed, true);
+}
+
+int mld_has_resident_cloud(const mld_handle* h) { return (h && h->have_cloud) ? 1 : 0; }
 
 // ---- DepthCalculationStatistics / FeaturePoint packing ----
 int mld_status_histogram_device(mld_handle* h, const int32_t* d_status, int64_t n, int64_t* hist21_out_host, void* stream) {

@@ -44,6 +44,17 @@ cudaError_t mld_launch_status_histogram(const int* d_status, long long n, unsign
     return cudaGetLastError();
 }
 
+// 12-byte xyz records (host-packed, mld_process_frames_host) -> the float4 layout K1 streams
+__global__ void unpack_xyz_kernel(const float* __restrict__ src, float4* __restrict__ dst, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = make_float4(src[3 * i], src[3 * i + 1], src[3 * i + 2], 0.f);
+}
+cudaError_t mld_launch_unpack_xyz(const float* d_xyz, float* d_out4, long long n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    unpack_xyz_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_xyz, reinterpret_cast<float4*>(d_out4), n);
+    return cudaGetLastError();
+}
+
 cudaError_t mld_launch_pack_feature_points(const double* d_uv, const double* d_depth, long long n, float* d_out, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
     pack_feature_points_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(d_uv, d_depth, n, d_out);

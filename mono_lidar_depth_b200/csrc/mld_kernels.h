@@ -113,6 +113,7 @@ cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int s
                               int* d_iterations, int* d_rc, cudaStream_t stream, int* launches);
 // extras (mld_extras.cu)
 cudaError_t mld_launch_status_histogram(const int* d_status, long long n, unsigned long long* d_hist21, cudaStream_t stream);
+cudaError_t mld_launch_unpack_xyz(const float* d_xyz, float* d_out4, long long n, cudaStream_t stream);
 cudaError_t mld_launch_pack_feature_points(const double* d_uv, const double* d_depth, long long n, float* d_out, cudaStream_t stream);
 
 // synthetic data (mld_synth.cu; scene model in mld_synth_model.h, host generators in libmld_synth.so)

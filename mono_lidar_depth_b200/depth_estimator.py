@@ -281,10 +281,14 @@ class DepthEstimator:
         return depths, status
 
     # -- tracklets_depth batch adaptor (TrackletDepthModule::process, tracklet_depth_module.cpp:318,330) ---------
-    def CalculateDepthPair(self, cloud_last, feats_last, plane_last, cloud_cur, feats_cur, plane_cur, layout: Optional[str] = None):
+    def CalculateDepthPair(self, cloud_last, feats_last, plane_last, cloud_cur, feats_cur, plane_cur, layout: Optional[str] = None,
+                           resident: bool = False):
         """Previous and current cloud with their own feature sets in one call (both clouds are on the device
         concurrently). cloud_last may be None (first frame): its depths are -1. Planes follow setInputCloud:
         with do_use_ransac_plane a None / un-segmented plane is fitted on the GPU and returned.
+
+        resident=True (cloud_last is then ignored): the previous cloud is the one that was current in the last call and is still
+        on the device with its pixel map -- one upload and one projection per frame (mld_calculate_depth_pair_resident).
         Returns (depths_last, depths_cur, plane_last, plane_cur)."""
         if not self._isInitialized:
             raise RuntimeError("call of 'setInputCloud' without 'initialize'")
@@ -297,7 +301,10 @@ class DepthEstimator:
         dl, dc = np.empty(len(fl), np.float64), np.empty(len(fc), np.float64)
         use_plane = bool(self._parameters.do_use_ransac_plane)
         a_cur, n_cur, stride = _cloud_buffer(cloud_cur)
-        if cloud_last is not None:
+        have_last = bool(self._lib.mld_has_resident_cloud(self._h)) if resident else cloud_last is not None
+        if resident:
+            a_last, n_last = None, (self._n if have_last else 0)
+        elif cloud_last is not None:
             a_last, n_last, stride_l = _cloud_buffer(cloud_last)
             if stride_l != stride:
                 raise ValueError("both clouds must use the same point layout")
@@ -307,20 +314,24 @@ class DepthEstimator:
         sizes = [n_last, n_cur]
         if use_plane:
             for i in range(2):
-                if i == 0 and cloud_last is None:
+                if i == 0 and not have_last:
                     continue
                 if planes[i] is None:
                     planes[i] = RansacPlane(self._parameters, self.ransac_seed)
                 if not planes[i].isSegmented() and not isinstance(planes[i], RansacPlane):  # e.g. SemanticPlane: segments itself
+                    if i == 0 and resident:
+                        raise ValueError("an un-segmented non-RANSAC plane for the resident previous cloud needs the cloud: segment it first")
                     planes[i].CalculateInliersPlane(cloud_last if i == 0 else cloud_cur, self._parameters.ransac_plane_min_z,
                                                     self._parameters.ransac_plane_max_z)
                 cplanes[i] = planes[i]._as_c(capacity=max(sizes[i], 1) if not planes[i].isSegmented() else 0)
-        self._check(self._lib.mld_calculate_depth_pair(
-            self._h, a_last.ctypes.data if a_last is not None else None, n_last,
-            fl.ctypes.data if len(fl) else None, len(fl), dl.ctypes.data if len(fl) else None, None,
-            C.byref(cplanes[0]) if cplanes[0] is not None else None,
-            a_cur.ctypes.data, n_cur, fc.ctypes.data if len(fc) else None, len(fc), dc.ctypes.data if len(fc) else None, None,
-            C.byref(cplanes[1]) if cplanes[1] is not None else None, stride, self.ransac_seed))
+        common = (a_cur.ctypes.data, n_cur, fc.ctypes.data if len(fc) else None, len(fc), dc.ctypes.data if len(fc) else None, None,
+                  C.byref(cplanes[1]) if cplanes[1] is not None else None, stride, self.ransac_seed)
+        prev = (fl.ctypes.data if len(fl) else None, len(fl), dl.ctypes.data if len(fl) else None, None,
+                C.byref(cplanes[0]) if cplanes[0] is not None else None)
+        if resident:
+            self._check(self._lib.mld_calculate_depth_pair_resident(self._h, *prev, *common))
+        else:
+            self._check(self._lib.mld_calculate_depth_pair(self._h, a_last.ctypes.data if a_last is not None else None, n_last, *prev, *common))
         for i in range(2):
             if cplanes[i] is not None:
                 planes[i]._from_c(cplanes[i])
@@ -499,6 +510,12 @@ class DepthEstimator:
     def fusedChunkFrames(self) -> int:
         """Frames per fused K1 + gather launch of device-resident non-road sequences, 0 when that pipeline is off."""
         return int(self._lib.mld_fused_chunk_frames(self._h))
+
+    def hostPipelineStats(self) -> dict:
+        """Counters of processFramesHost since creation (mld_host_pipeline_stats)."""
+        out = (C.c_int64 * 4)()
+        self._check(self._lib.mld_host_pipeline_stats(self._h, out))
+        return dict(zip(("h2d_bytes", "d2h_bytes", "frames_packed", "frames_direct"), [int(x) for x in out]))
 
     def pipelineFrames(self) -> bool:
         """True when device-resident sequences run through the persistent pipeline (one launch per sequence)."""

@@ -7,6 +7,10 @@ import json
 import re
 import sys
 from collections import defaultdict
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+from mono_lidar_depth_b200.buildinfo import source_hash  # noqa: E402
 
 
 def main():
@@ -44,7 +48,7 @@ def main():
         a["us"] += d.get("gpu__time_duration.sum", 0.0)
         a["bytes"] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
     total = sum(a["us"] for a in agg.values())
-    out = {"source": how, "frames_per_launch": fpl, "share_of_step_ncu": {}}
+    out = {"source": how, "source_hash": source_hash(), "frames_per_launch": fpl, "share_of_step_ncu": {}}
     for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
         key = name.replace("_kernel", "")
         out[key] = {"launches": a["n"], "dram_bytes_per_launch": round(a["bytes"] / a["n"]), "avg_launch_us_ncu_serialised": round(a["us"] / a["n"], 2)}

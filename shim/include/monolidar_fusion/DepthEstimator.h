@@ -63,7 +63,8 @@ public:
 
     // tracklets_depth batch adaptor: previous + current cloud of one frame in a single call
     // (TrackletDepthModule::process issues them back to back, tracklet_depth_module.cpp:318, :330). A null
-    // pointCloudLast (first frame) sets depthsLast to -1 like CalculateFeatureDepthsLastFrame (:97-100).
+    // pointCloudLast (first frame) sets depthsLast to -1 like CalculateFeatureDepthsLastFrame (:97-100). When pointCloudLast is the
+    // very cloud the previous call (or setInputCloud) put on the device, it is not uploaded or projected again.
     void CalculateDepthPair(const Cloud::ConstPtr& pointCloudLast, const Eigen::Matrix2Xd& featuresLast, Eigen::VectorXd& depthsLast,
                             GroundPlane::Ptr& planeLast, const Cloud::ConstPtr& pointCloudCur, const Eigen::Matrix2Xd& featuresCur,
                             Eigen::VectorXd& depthsCur, GroundPlane::Ptr& planeCur);
@@ -108,6 +109,7 @@ private:
     std::vector<double> _lastFeatures;       // 2 x F features of the last CalculateDepth call (getCloudTriangleCorners)
     std::vector<double> _depthCamVisible;    // lazily fetched per cloud (getPointDepthCamVisible)
     bool _depthCamVisibleValid{false};
+    Cloud::ConstPtr _residentCloud;          // the cloud whose projection is on the device (CalculateDepthPair reuses it as 'previous')
 };
 
 }  // namespace Mono_Lidar

@@ -207,6 +207,7 @@ void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Pt
                 _isInitializedPointCloud = true;
                 _groundInliers = groundPlane->_inliersIndex;
                 _depthCamVisibleValid = false;
+                _residentCloud = cloud;
                 return;
             }
             // any other GroundPlane segments itself (SemanticPlane: on the GPU through mld_semantic_ground_plane)
@@ -218,6 +219,7 @@ void DepthEstimator::setInputCloud(const Cloud::ConstPtr& cloud, GroundPlane::Pt
     _pointCount = n;
     _isInitializedPointCloud = true;
     _depthCamVisibleValid = false;
+    _residentCloud = cloud;
     _groundInliers.clear();  // _points_groundplane is rebuilt per cloud, from the plane's inliers (DepthEstimator.cpp:234, :294-308)
     if (_parameters->do_use_ransac_plane && groundPlane != nullptr) _groundInliers = groundPlane->_inliersIndex;
 }
@@ -299,11 +301,21 @@ void DepthEstimator::CalculateDepthPair(const Cloud::ConstPtr& cloudLast, const 
         cp[i] = &views[i].c;
     }
     const bool have_last = cloudLast != nullptr;
-    int rc = mld_calculate_depth_pair(_handle, have_last ? cloudLast->points.data() : nullptr, have_last ? (int64_t)cloudLast->points.size() : 0,
+    int rc;
+    if (have_last && cloudLast == _residentCloud && mld_has_resident_cloud(_handle)) {
+        // walking a sequence: the previous cloud is the one uploaded as current by the last call and is still on the device with its
+        // pixel map (the shim holds the shared_ptr, so the identity test cannot be fooled by a recycled address)
+        rc = mld_calculate_depth_pair_resident(_handle, featuresLast.data(), featuresLast.cols(), depthsLast.data(), nullptr, cp[0],
+                                               cloudCur->points.data(), (int64_t)cloudCur->points.size(), featuresCur.data(), featuresCur.cols(),
+                                               depthsCur.data(), nullptr, cp[1], (int)sizeof(Point), _ransacSeed);
+    } else {
+        rc = mld_calculate_depth_pair(_handle, have_last ? cloudLast->points.data() : nullptr, have_last ? (int64_t)cloudLast->points.size() : 0,
                                       featuresLast.data(), featuresLast.cols(), depthsLast.data(), nullptr, cp[0], cloudCur->points.data(),
                                       (int64_t)cloudCur->points.size(), featuresCur.data(), featuresCur.cols(), depthsCur.data(), nullptr, cp[1],
                                       (int)sizeof(Point), _ransacSeed);
+    }
     if (rc != MLD_OK) rethrow(rc);
+    _residentCloud = cloudCur;
     for (int i = 0; i < 2; i++) {
         if (!cp[i] || (*planes[i])->isSegmented()) continue;
         GroundPlane& gp = **planes[i];

@@ -13,7 +13,7 @@ BASE_KEYS = {"metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_ste
 
 
 def _latest_kitti_line():
-    files = sorted((ROOT / "profiles").glob("r1*_bench_kitti.json"))
+    files = sorted((ROOT / "profiles").glob("r*_bench_kitti.json"))
     assert files, "no committed bench line under profiles/"
     return json.loads(files[-1].read_text())
 
@@ -49,3 +49,4 @@ def test_reference_arm_prints_the_contract_line():
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["cpu_baseline"]["value"] == d["value"] and d["cpu_baseline"]["kind"] == "port" and d["gpu_launches"] == 0
     assert d["metric"] == "frames_per_sec" and d["value"] > 0
+    assert d["product_library_mapped"] is False  # the CPU arm's inputs come from libmld_synth.so, never from libmld_cuda.so

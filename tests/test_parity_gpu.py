@@ -611,3 +611,34 @@ def test_randomised_configurations(seed):
     p, cam, T, cloud, uv, plane = PU.random_configuration(seed)
     est, orc = PU.make_pair(p, CameraPinhole(*cam), T)
     PU.compare_frame(est, orc, cloud, uv, plane=plane, what=f"random config {seed}", neighbor_samples=24)
+
+
+def test_pair_adaptor_keeps_the_previous_cloud_on_the_device():
+    """Walking a sequence the way TrackletDepthModule does (previous + current cloud per frame, tracklet_depth_module.cpp:318-354):
+    with resident=True frame t's cloud and pixel map stay on the device as frame t+1's previous cloud -- same depths as uploading
+    both clouds every frame, with and without the road path."""
+    cfg = synth.default_config(road=True)
+    for road in (0, 1):
+        p = O.yaml_params()
+        p.do_use_ransac_plane = road
+        est_a, _ = kitti_pair(p)
+        est_b, _ = kitti_pair(p)
+        clouds = [synth.points_host(cfg, 31, f) for f in range(4)]
+        feats = [synth.features_host(cfg, 31, f, 800) for f in range(4)]
+        prev_cloud, plane_a, plane_b = None, None, None
+        for t in range(4):
+            f_last = feats[t][:300] + 1.0  # features of the previous frame (where the new tracklets were one frame ago)
+            dl_a, dc_a, pl_a, pc_a = est_a.CalculateDepthPair(prev_cloud, f_last, plane_a, clouds[t], feats[t], None)
+            dl_b, dc_b, pl_b, pc_b = est_b.CalculateDepthPair(None, f_last, plane_b, clouds[t], feats[t], None, resident=True)
+            assert np.array_equal(dc_a, dc_b) and np.array_equal(dl_a, dl_b), (road, t)
+            if t == 0:
+                assert np.all(dl_b == -1)
+            else:
+                assert (dl_b >= 0).sum() > 20
+            prev_cloud, plane_a, plane_b = clouds[t], pc_a, pc_b  # the current plane becomes the previous one (groundPlaneLast_)
+            if road:
+                assert np.array_equal(pc_a.getInlinersIndex(), pc_b.getInlinersIndex())
+        # a batched call in between drops the resident cloud: the next resident call has no previous cloud
+        est_b.processFramesHost(np.stack(clouds[:2]), np.stack(feats[:2]), np.empty((2, 800)), np.empty((2, 800), np.int32))
+        dl_b, _, _, _ = est_b.CalculateDepthPair(None, feats[0][:10], None, clouds[0], feats[0], None, resident=True)
+        assert np.all(dl_b == -1)
