@@ -174,6 +174,13 @@ int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n,
 int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,
                               int label_w, int label_h, double f, double cu, double cv, const double* T_cam_lidar,
                               const int32_t* ground_labels, int n_ground_labels, double inlier_threshold, mld_plane* out_plane);
+/* Fit mode of every SemanticPlane entry point of this handle. 0 (default): the moments of the labelled points / inliers are
+ * accumulated in double by a parallel reduction -- the better-conditioned fit; coefficients agree with the reference's to ~2e-3,
+ * inlier sets differ only for points within that margin of the threshold. 1: PCL's own order -- nine sequential FLOAT
+ * accumulators over the points in index order (computeMeanAndCovarianceMatrix), which loses 4-5 digits over 1e4 points but is what
+ * the reference computes: coefficients and inlier set bit-identical to it (about 0.2 ms per sweep and pass instead of 15 us).
+ * Env MLD_SEMANTIC_EXACT=1 sets it at mld_create. */
+int mld_set_semantic_exact(mld_handle* h, int on);
 /* debug / parity view of the first stage: out_flags_host[i] = 1 when point i projects onto a ground-labelled pixel
  * (the points kept by RansacPlane.cpp:201-222), 0 otherwise. */
 int mld_semantic_ground_labelled(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, const uint8_t* labels_host,

@@ -185,6 +185,7 @@ SYMBOLS = {
          C.c_void_p, C.c_void_p, _PL, C.c_int, C.c_uint64],
     ),
     "mld_set_statistics": (C.c_int, [_H, C.c_int]),
+    "mld_set_semantic_exact": (C.c_int, [_H, C.c_int]),
     "mld_last_status_histogram": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "mld_get_points_camera_indexed": (C.c_int, [_H, C.c_void_p, C.c_int64, C.c_void_p]),
     "mld_get_triangle_corners": (C.c_int, [_H, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),

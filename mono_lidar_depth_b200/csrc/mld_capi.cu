@@ -50,6 +50,7 @@ struct Slot {
     int* d_ovf = nullptr;       size_t ovf_bytes = 0;    // [0] overflow count, [1..] global feature ids
     unsigned char* d_labels = nullptr; size_t labels_bytes = 0; // semantic label image (mld_semantic_ground_plane)
     unsigned char* d_sem = nullptr; size_t sem_bytes = 0;       // SemanticPlane scratch
+    unsigned char* d_flags = nullptr; size_t flags_bytes = 0;   // ground-labelled flag per point (SemanticPlane exact mode)
     unsigned int* d_occ = nullptr; size_t occ_bytes = 0; // occupancy bitmaps of the maps
     void* d_split = nullptr;    size_t split_bytes = 0;  // survivor / road lists of the split K2 kernels
     unsigned char* h_stage = nullptr; size_t h_stage_bytes = 0;  // pinned staging of the packed (12-byte xyz) host pipeline
@@ -210,6 +211,7 @@ struct mld_handle {
     unsigned ring_epoch = 0;        // epochs consumed by every slot of the ring since its last clear (0 = never cleared)
     int* h_pipe_flags = nullptr;    // pinned: [0] error flag of the last pipeline launch (read back asynchronously)
     int* h_pipe_counters = nullptr; // pinned: the 16 sync words of the last launch (ticket, error, profiling accumulators)
+    bool semantic_exact = false;    // mld_set_semantic_exact / MLD_SEMANTIC_EXACT=1: PCL's sequential float accumulation order
     bool stats_on = false;          // mld_set_statistics: status histogram of every mld_calculate_depth call
     unsigned long long* d_hist = nullptr;  // 21 counters on the device
     unsigned long long* h_hist = nullptr;  // pinned copy
@@ -424,6 +426,15 @@ struct PlaneSrc {
     const unsigned int* d_bits = nullptr;
 };
 
+// exact mode of the SemanticPlane fit: the labelled flags of `frames` clouds live in the slot
+int sem_flags(mld_handle* h, Slot& s, long long n_points, long long frames, unsigned char** out) {
+    *out = nullptr;
+    if (!h->semantic_exact) return MLD_OK;
+    CK(ensure(s.d_flags, s.flags_bytes, (size_t)std::max<long long>(n_points * frames, 1)));
+    *out = s.d_flags;
+    return MLD_OK;
+}
+
 void ground_label_set(const int32_t* labels, int n, unsigned int set8[8]) {
     for (int i = 0; i < 8; i++) set8[i] = 0u;
     for (int i = 0; i < n; i++)
@@ -486,9 +497,12 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
         } else if (src && src->kind == PlaneSrc::SEMANTIC) {
             // SemanticPlane::CalculateInliersPlane per frame (what TrackletDepthModule::process does before CalculateDepth)
             CK(ensure(s.d_sem, s.sem_bytes, mld_semantic_state_bytes(frames)));
+            unsigned char* fl = nullptr;
+            int rcs = sem_flags(h, s, n_points, frames, &fl);
+            if (rcs) return rcs;
             CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold,
                                          d_pts, stride_f, n_points, pitch_pts, src->d_labels, frames, s.d_sem, cdst, s.d_bits, words,
-                                         s.d_small, src->d_rc_out ? src->d_rc_out : s.d_small + 2 * frames, sb, &nl));
+                                         s.d_small, src->d_rc_out ? src->d_rc_out : s.d_small + 2 * frames, sb, &nl, fl, fl ? 1 : 0));
             coeffs = cdst;
             bits = s.d_bits;
         } else {
@@ -765,6 +779,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     }
     memset(h->h_pipe_flags, 0, 36 * sizeof(int));
     h->h_pipe_counters = h->h_pipe_flags + 4;
+    env = getenv("MLD_SEMANTIC_EXACT");
+    if (env) h->semantic_exact = atoi(env) != 0;
     env = getenv("MLD_HOST_PACK");
     if (env) h->host_pack = atoi(env) != 0 ? 1 : 0;
     env = getenv("MLD_PCIE_GBS");
@@ -797,7 +813,7 @@ int mld_destroy(mld_handle* h) {
     for (auto& s : h->slots) {
         if (s.stream) cudaStreamSynchronize(s.stream);
         cudaFree(s.d_pts); cudaFree(s.d_uv); cudaFree(s.d_depth); cudaFree(s.d_status); cudaFree(s.d_maps);
-        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split); cudaFree(s.d_labels); cudaFree(s.d_sem);
+        cudaFree(s.d_bits); cudaFree(s.d_coeffs); cudaFree(s.d_scratch); cudaFree(s.d_small); cudaFree(s.d_ovf); cudaFree(s.d_occ); cudaFree(s.d_split); cudaFree(s.d_labels); cudaFree(s.d_sem); cudaFree(s.d_flags);
         if (s.done) cudaEventDestroy(s.done);
         if (s.ev_k1) cudaEventDestroy(s.ev_k1);
         if (s.ev_k2) cudaEventDestroy(s.ev_k2);
@@ -1055,9 +1071,13 @@ int mld_semantic_ground_plane_device(mld_handle* h, const void* d_points, int64_
     unsigned int set8[8];
     ground_label_set(ground_labels, n_ground_labels, set8);
     int nl = 0;
+    unsigned char* fl = nullptr;
+    rc = sem_flags(h, s, n_points, nframes, &fl);
+    if (rc) return rc;
     CK(mld_launch_semantic_plane(T_cam_lidar, f, cu, cv, label_w, label_h, set8, inlier_threshold, reinterpret_cast<const float*>(d_points),
                                  stride_bytes / 4, n_points, frame_pitch_points, d_labels, (int)nframes, s.d_sem, d_coeffs_out,
-                                 d_inlier_bits_out, (n_points + 31) / 32, d_n_inliers_out, d_rc_out, reinterpret_cast<cudaStream_t>(stream), &nl));
+                                 d_inlier_bits_out, (n_points + 31) / 32, d_n_inliers_out, d_rc_out, reinterpret_cast<cudaStream_t>(stream), &nl, fl,
+                                 fl ? 1 : 0));
     h->launches += nl;
     return MLD_OK;
 }
@@ -1187,6 +1207,12 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
     return MLD_OK;
 }
 
+int mld_set_semantic_exact(mld_handle* h, int on) {
+    if (!h) return MLD_ERR_INVALID_ARG;
+    h->semantic_exact = on != 0;
+    return MLD_OK;
+}
+
 int mld_set_statistics(mld_handle* h, int on) {
     if (!h) return MLD_ERR_INVALID_ARG;
     h->stats_on = on != 0;
@@ -1274,10 +1300,13 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
             int nlp = 0;
             if (src && src->kind == PlaneSrc::SEMANTIC) {
                 CK(ensure(sk->d_sem, sk->sem_bytes, mld_semantic_state_bytes(ck)));
+                unsigned char* fl = nullptr;
+                int rcs = sem_flags(h, *sk, n_points, ck, &fl);
+                if (rcs) return rcs;
                 CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
                                              stride_f, n_points, frame_pitch_points, src->d_labels + f0k * (int64_t)src->label_w * src->label_h, ck,
                                              sk->d_sem, cdst, sk->d_bits, words, sk->d_small,
-                                             src->d_rc_out ? src->d_rc_out + f0k : sk->d_small + 2 * ck, sk->stream, &nlp));
+                                             src->d_rc_out ? src->d_rc_out + f0k : sk->d_small + 2 * ck, sk->stream, &nlp, fl, fl ? 1 : 0));
             } else {
                 CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, ck, seed, f0k, sk->d_scratch, cdst,
                                      sk->d_bits, words, sk->d_small, sk->d_small + ck, sk->d_small + 2 * ck, sk->stream, &nlp));
@@ -1391,10 +1420,13 @@ static int process_frames_device_pipeline(mld_handle* h, const float* pts, int64
             int nlp = 0;
             if (src && src->kind == PlaneSrc::SEMANTIC) {
                 CK(ensure(sp.d_sem, sp.sem_bytes, mld_semantic_state_bytes((int)c)));
+                unsigned char* fl = nullptr;
+                int rcs = sem_flags(h, sp, n_points, c, &fl);
+                if (rcs) return rcs;
                 CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
                                              stride_f, n_points, frame_pitch_points, src->d_labels + f0 * (int64_t)src->label_w * src->label_h, (int)c,
                                              sp.d_sem, cdst, sp.d_bits, words, sp.d_small, src->d_rc_out ? src->d_rc_out + f0 : sp.d_small + 2 * c,
-                                             sp.stream, &nlp));
+                                             sp.stream, &nlp, fl, fl ? 1 : 0));
             } else {
                 CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, (int)c, seed, f0, sp.d_scratch, cdst,
                                      sp.d_bits, words, sp.d_small, sp.d_small + c, sp.d_small + 2 * c, sp.stream, &nlp));

@@ -178,39 +178,71 @@ __device__ __forceinline__ int warp_min_i(int v) {
     return v;
 }
 
-// Jacobi eigen-decomposition of a symmetric 3x3 held in registers. a = (a00,a01,a02,a11,a12,a22).
-// Eigenvalues are returned unsorted in w with eigenvector columns v[c] (each a D3).
-#define MLD_JACOBI_ROT(app, aqq, apq, arp, arq, vp, vq)                                   \
-    if ((apq) != 0.0) {                                                                  \
-        double theta = ((aqq) - (app)) / (2.0 * (apq));                                   \
-        double tt = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0)); \
-        if (!isfinite(theta)) tt = 0.0;                                                   \
-        double cc = 1.0 / sqrt(tt * tt + 1.0), ss = tt * cc;                              \
-        double napp = (app) - tt * (apq), naqq = (aqq) + tt * (apq);                      \
-        double nrp = cc * (arp) - ss * (arq), nrq = ss * (arp) + cc * (arq);              \
-        (app) = napp; (aqq) = naqq; (apq) = 0.0; (arp) = nrp; (arq) = nrq;                \
-        D3 nvp = (vp) * cc - (vq) * ss, nvq = (vp) * ss + (vq) * cc;                      \
-        (vp) = nvp; (vq) = nvq;                                                           \
+// Cyclic Jacobi eigen-decomposition of a symmetric 3x3 in registers, operation for operation the algorithm the CPU oracle pins
+// against the reference for Eigen::SelfAdjointEigenSolver's contract (the test-side CPU restatement: full two-sided updates
+// A <- A J, A <- J^T A in the pair order (0,1), (0,2), (1,2), the same stopping test, a stable ascending sort): the float-cast
+// eigenvalue ratios of the PCA variant (PCA.cpp:27-37) and the RANSAC refit then agree with the oracle bit for bit.
+// Input a = (a00,a01,a02,a11,a12,a22); output: w ascending, v[c] = eigenvector of w[c].
+template <int p, int q>
+__device__ __forceinline__ void mld_jacobi_rotate(double (&a)[9], double (&v)[9]) {
+    const double apq = a[p * 3 + q];
+    if (apq == 0.0) return;
+    const double app = a[p * 3 + p], aqq = a[q * 3 + q];
+    const double theta = (aqq - app) / (2.0 * apq);
+    double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+    if (!isfinite(theta)) t = 0.0;
+    const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {  // A <- A * J
+        const double akp = a[k * 3 + p], akq = a[k * 3 + q];
+        a[k * 3 + p] = c * akp - s * akq;
+        a[k * 3 + q] = s * akp + c * akq;
     }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {  // A <- J^T * A
+        const double apk = a[p * 3 + k], aqk = a[q * 3 + k];
+        a[p * 3 + k] = c * apk - s * aqk;
+        a[q * 3 + k] = s * apk + c * aqk;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const double vkp = v[k * 3 + p], vkq = v[k * 3 + q];
+        v[k * 3 + p] = c * vkp - s * vkq;
+        v[k * 3 + q] = s * vkp + c * vkq;
+    }
+}
 
-static __device__ __noinline__ void eig3_sym_regs(double a00, double a01, double a02, double a11, double a12, double a22,
-                                              double w[3], D3 v[3]) {
-    // v[c] is eigenvector c (columns of the rotation product)
-    D3 v0 = D3{1, 0, 0}, v1 = D3{0, 1, 0}, v2 = D3{0, 0, 1};
-    // store eigenvector *columns* as (row0,row1,row2) triples: updating columns p,q of V
-    for (int sweep = 0; sweep < 16; sweep++) {
-        double off = a01 * a01 + a02 * a02 + a12 * a12;
-        double diag = a00 * a00 + a11 * a11 + a22 * a22;
+static __device__ __noinline__ void eig3_sym_regs(double a00, double a01, double a02, double a11, double a12, double a22, double w[3],
+                                                  D3 v[3]) {
+    double a[9] = {a00, a01, a02, a01, a11, a12, a02, a12, a22};
+    double r[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int sweep = 0; sweep < 60; sweep++) {
+        const double off = a[1] * a[1] + a[2] * a[2] + a[5] * a[5];
+        const double diag = a[0] * a[0] + a[4] * a[4] + a[8] * a[8];
         if (!(off > 1e-32 * diag) || !(off > 0)) break;
-        // (p,q) = (0,1): r = 2 -> a02 (arp), a12 (arq)
-        MLD_JACOBI_ROT(a00, a11, a01, a02, a12, v0, v1)
-        // (p,q) = (0,2): r = 1 -> a01 (arp), a12 (arq)
-        MLD_JACOBI_ROT(a00, a22, a02, a01, a12, v0, v2)
-        // (p,q) = (1,2): r = 0 -> a01 (arp), a02 (arq)
-        MLD_JACOBI_ROT(a11, a22, a12, a01, a02, v1, v2)
+        mld_jacobi_rotate<0, 1>(a, r);
+        mld_jacobi_rotate<0, 2>(a, r);
+        mld_jacobi_rotate<1, 2>(a, r);
     }
-    w[0] = a00; w[1] = a11; w[2] = a22;
-    v[0] = v0; v[1] = v1; v[2] = v2;
+    // stable ascending order of the diagonal (what std::sort does on three elements)
+    const double d0 = a[0], d1 = a[4], d2 = a[8];
+    int i0 = 0, i1 = 1, i2 = 2;
+    if (d1 < d0) { i0 = 1; i1 = 0; }
+    {
+        const double di1 = (i1 == 0) ? d0 : d1, di0 = (i0 == 0) ? d0 : d1;
+        if (d2 < di1) {
+            i2 = i1;
+            i1 = 2;
+            if (d2 < di0) {
+                i1 = i0;
+                i0 = 2;
+            }
+        }
+    }
+    auto diag_of = [&](int i) { return i == 0 ? d0 : (i == 1 ? d1 : d2); };
+    auto col_of = [&](int i) { return i == 0 ? D3{r[0], r[3], r[6]} : (i == 1 ? D3{r[1], r[4], r[7]} : D3{r[2], r[5], r[8]}); };
+    w[0] = diag_of(i0); w[1] = diag_of(i1); w[2] = diag_of(i2);
+    v[0] = col_of(i0); v[1] = col_of(i1); v[2] = col_of(i2);
 }
 
 // cofactor inverse of a row-major 3x3, the way Eigen evaluates Matrix3d::inverse()

@@ -251,33 +251,30 @@ __device__ void slab_z_range(int n, int lane, const WarpSlab& s, double& minZ, d
     maxZ = warp_max_d(hi);
 }
 
-// weighted centroid + scatter of slab[0..n); w_i = 1/|prior.n . p + prior.off| or 1
+// weighted centroid + scatter of slab[0..n); w_i = 1/|prior.n . p + prior.off| or 1. Every lane runs the SAME sequential sums in
+// the reference's order (PCA.cpp:42-50, PlaneEstimationMEstimator.cpp:24-45) -- lane-strided partial sums would differ from the
+// oracle and from the thread-per-feature kernels in the last bits, enough to flip a float-cast PCA ratio on a threshold; the
+// warp path only sees the rare windows that overflow a thread's slab, so the redundant work does not matter.
 __device__ void slab_weighted_scatter(int n, int lane, const WarpSlab& s, bool weighted, const Plane& prior, D3& center,
                                       double c[6]) {
-    double sw = 0, sx = 0, sy = 0, sz = 0;
-    for (int i = lane; i < n; i += 32) {
+    (void)lane;
+    D3 acc = D3{0, 0, 0};
+    double wsum = 0;
+    for (int i = 0; i < n; i++) {
         D3 p = slab_pt(s, i);
         double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
-        sw += w;
-        sx += w * p.x;
-        sy += w * p.y;
-        sz += w * p.z;
+        acc = acc + p * w;
+        wsum += w;
     }
-    sw = warp_sum_d(sw);
-    sx = warp_sum_d(sx);
-    sy = warp_sum_d(sy);
-    sz = warp_sum_d(sz);
-    center = D3{sx / sw, sy / sw, sz / sw};
-    double a00 = 0, a01 = 0, a02 = 0, a11 = 0, a12 = 0, a22 = 0;
-    for (int i = lane; i < n; i += 32) {
+    center = acc / wsum;
+    c[0] = c[1] = c[2] = c[3] = c[4] = c[5] = 0;
+    for (int i = 0; i < n; i++) {
         D3 p = slab_pt(s, i);
         double w = weighted ? 1 / fabs(dot3(prior.n, p) + prior.off) : 1.0;
         D3 d = p - center;
-        a00 += w * d.x * d.x; a01 += w * d.x * d.y; a02 += w * d.x * d.z;
-        a11 += w * d.y * d.y; a12 += w * d.y * d.z; a22 += w * d.z * d.z;
+        c[0] += w * d.x * d.x; c[1] += w * d.x * d.y; c[2] += w * d.x * d.z;
+        c[3] += w * d.y * d.y; c[4] += w * d.y * d.z; c[5] += w * d.z * d.z;
     }
-    c[0] = warp_sum_d(a00); c[1] = warp_sum_d(a01); c[2] = warp_sum_d(a02);
-    c[3] = warp_sum_d(a11); c[4] = warp_sum_d(a12); c[5] = warp_sum_d(a22);
 }
 
 // ---- A12: CalculateDepthSegmented ----------------------------------------------------------------

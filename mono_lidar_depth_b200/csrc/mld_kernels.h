@@ -104,7 +104,8 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
                                       long long n_points, long long pitch_pts, const unsigned char* d_labels, int nframes,
                                       void* d_state, float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame,
                                       int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches,
-                                      unsigned char* d_flags_out = nullptr /* debug: ground-labelled flag per point */);
+                                      unsigned char* d_flags_out = nullptr /* ground-labelled flag per point (debug view; input of the exact mode) */,
+                                      int exact = 0 /* PCL's sequential float accumulation order: bit-exact coefficients and inlier set */);
 // Fits one plane per frame. Outputs per frame: coeffs[4] (float), inlier bitmask over raw indices
 // (words_per_frame uint32), n_inliers, iterations, rc (0 ok, MLD_ERR_PCL_INVALID, MLD_ERR_NO_MODEL).
 cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int stride_f, long long n_points,

@@ -119,8 +119,9 @@ ransac_candidates_kernel(RansacConfig cfg, const float* __restrict__ pts, int st
         long long i = base + threadIdx.x;
         bool keep = false;
         if (i < n) {
-            float z = fp[i * stride_f + 2];
-            keep = isfinite(z) && !((double)z < cfg.min_z) && !((double)z > cfg.max_z);
+            // pcl::PassThrough::applyFilterIndices drops every point with a non-finite x, y or z before it tests the field
+            const float x = fp[i * stride_f], y = fp[i * stride_f + 1], z = fp[i * stride_f + 2];
+            keep = isfinite(x) && isfinite(y) && isfinite(z) && !((double)z < cfg.min_z) && !((double)z > cfg.max_z);
         }
         unsigned m = __ballot_sync(MLD_FULL_MASK, keep);
         if (lane == 0) warp_tot[warp] = __popc(m);

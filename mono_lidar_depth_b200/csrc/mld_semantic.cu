@@ -240,6 +240,135 @@ semantic_select_kernel(const float* __restrict__ pts, int stride_f, int n, long 
     }
 }
 
+// ---- exact mode: PCL's own accumulation order -----------------------------------------------------------------------------
+// SampleConsensusModelPlane::optimizeModelCoefficients = computeMeanAndCovarianceMatrix with nine sequential FLOAT accumulators
+// over the (finite) inliers in index order, a float covariance, the eigenvector of the smallest eigenvalue (RansacPlane.cpp:
+// 236-256 via PCL). Float addition is not associative, so bit-exact coefficients -- and with them a bit-exact inlier set in
+// the select pass -- need exactly that order: one block per frame streams the cloud in tiles, compacts the flagged points of a
+// tile in index order into shared memory, and lanes 0..8 each run ONE accumulator's dependent chain over the tile (the nine
+// chains are independent of each other). ~0.2 ms per 120 k-point sweep and pass instead of ~15 us: the mode exists for parity
+// with the reference's numbers, the double-precision moments of the default mode are the better fit.
+// FLAG_BITS: flags are a bitmask over raw indices (pass 2: the inlier mask) or one byte per point (pass 1: the labelled set).
+constexpr int SX_THREADS = 256, SX_PPT = 4, SX_TILE = SX_THREADS * SX_PPT;
+
+template <bool FLAG_BITS>
+__global__ void __launch_bounds__(SX_THREADS)
+semantic_exact_fit_kernel(const float* __restrict__ pts, int stride_f, int n, long long pitch_pts, const void* __restrict__ flags_all,
+                          long long flags_pitch, float* __restrict__ coeff_all, unsigned int* __restrict__ ctl_all,
+                          float* __restrict__ coeffs_out) {
+    __shared__ float sx[SX_TILE], sy[SX_TILE], sz[SX_TILE];
+    __shared__ int s_warp[SX_THREADS / 32];
+    __shared__ float s_acc[9];
+    const long long frame = blockIdx.x;
+    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
+    float* coeff = coeff_all + frame * 8;
+    unsigned int* ctl = ctl_all + frame * 8;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // accumulator k of lane k: acc += a * b with (a, b) = (x,x) (x,y) (x,z) (y,y) (y,z) (z,z) (x,1) (y,1) (z,1); x * 1 is exact
+    const int ia = (tid < 3) ? 0 : (tid < 5 ? 1 : (tid == 5 ? 2 : tid - 6));
+    const int ib = (tid < 3) ? tid : (tid < 5 ? tid - 2 : (tid == 5 ? 2 : 3));
+    float acc = 0.f;
+    long long total = 0, flagged = 0;
+    for (int base = 0; base < n; base += SX_TILE) {
+        float4 p[SX_PPT];
+        bool keep[SX_PPT];
+        int cnt = 0, nflag = 0;
+#pragma unroll
+        for (int j = 0; j < SX_PPT; j++) {  // thread t owns the consecutive points base + 4 t .. + 3: ranks follow index order
+            const int i = base + tid * SX_PPT + j;
+            keep[j] = false;
+            if (i < n) {
+                bool f;
+                if (FLAG_BITS)
+                    f = (reinterpret_cast<const unsigned int*>(flags_all)[frame * flags_pitch + (i >> 5)] >> (i & 31)) & 1u;
+                else
+                    f = reinterpret_cast<const unsigned char*>(flags_all)[frame * flags_pitch + i] != 0;
+                if (f) {
+                    nflag++;
+                    p[j] = __ldg(reinterpret_cast<const float4*>(fp + (long long)i * stride_f));
+                    keep[j] = isfinite(p[j].x) && isfinite(p[j].y) && isfinite(p[j].z);  // PCL skips non-finite points
+                    cnt += keep[j] ? 1 : 0;
+                }
+            }
+        }
+        int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(MLD_FULL_MASK, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        // flagged count of the tile (all points the model was asked to fit, finite or not: inliers.size())
+        int nf = nflag;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nf += __shfl_xor_sync(MLD_FULL_MASK, nf, o);
+        __syncthreads();
+        int pos = incl - cnt, tile_cnt = 0;
+#pragma unroll
+        for (int w = 0; w < SX_THREADS / 32; w++) {
+            if (w < warp) pos += s_warp[w];
+            tile_cnt += s_warp[w];
+        }
+#pragma unroll
+        for (int j = 0; j < SX_PPT; j++) {
+            if (!keep[j]) continue;
+            sx[pos] = p[j].x;
+            sy[pos] = p[j].y;
+            sz[pos] = p[j].z;
+            pos++;
+        }
+        __syncthreads();  // the tile is complete and every thread has read the scan counts
+        if (lane == 0) s_warp[warp] = nf;  // now: flagged points per warp
+        if (tid < 9) {
+            for (int q = 0; q < tile_cnt; q++) {
+                const float x = sx[q], y = sy[q], z = sz[q];
+                const float a = ia == 0 ? x : (ia == 1 ? y : z);
+                const float b = ib == 0 ? x : (ib == 1 ? y : (ib == 2 ? z : 1.f));
+                acc = __fadd_rn(acc, __fmul_rn(a, b));
+            }
+        }
+        total += tile_cnt;
+        __syncthreads();  // the tile is consumed, the flagged counts are in place
+        if (tid == 0)
+            for (int w = 0; w < SX_THREADS / 32; w++) flagged += s_warp[w];
+        __syncthreads();
+    }
+    if (tid < 9) s_acc[tid] = acc;
+    __syncthreads();
+    if (tid != 0) return;
+    const bool second = FLAG_BITS;
+    float in[4] = {0.f, 0.f, 1.f, 0.f};  // dummy_model_coeffs (RansacPlane.cpp:239-240)
+    if (second)
+        for (int q = 0; q < 4; q++) in[q] = coeff[q];
+    float out[4] = {in[0], in[1], in[2], in[3]};
+    if (flagged > 3 && total > 0) {  // inliers.size() <= 3: the input model is returned; no finite point: likewise
+        float a9[9];
+        const float cntf = (float)total;
+        for (int q = 0; q < 9; q++) a9[q] = __fdiv_rn(s_acc[q], cntf);
+        const float cx = a9[6], cy = a9[7], cz = a9[8];
+        double w[3];
+        D3 ev[3];
+        eig3_sym_regs((double)__fsub_rn(a9[0], __fmul_rn(cx, cx)), (double)__fsub_rn(a9[1], __fmul_rn(cx, cy)),
+                      (double)__fsub_rn(a9[2], __fmul_rn(cx, cz)), (double)__fsub_rn(a9[3], __fmul_rn(cy, cy)),
+                      (double)__fsub_rn(a9[4], __fmul_rn(cy, cz)), (double)__fsub_rn(a9[5], __fmul_rn(cz, cz)), w, ev);
+        out[0] = (float)ev[0].x;
+        out[1] = (float)ev[0].y;
+        out[2] = (float)ev[0].z;
+        out[3] = __fmul_rn(-1.f, __fadd_rn(__fadd_rn(__fmul_rn(out[0], cx), __fmul_rn(out[1], cy)), __fmul_rn(out[2], cz)));
+    }
+    if (!second) {
+        for (int q = 0; q < 4; q++) coeff[q] = out[q];
+        ctl[2] = (unsigned int)flagged;
+        ctl[4] = (flagged < 3) ? 1u : 0u;  // ExceptionPclInvalid (RansacPlane.cpp:224-227)
+    } else {
+        const bool invalid = ctl[4] != 0u;
+        for (int q = 0; q < 4; q++) {
+            coeff[4 + q] = out[q];
+            coeffs_out[frame * 4 + q] = invalid ? 0.f : out[q];
+        }
+    }
+}
+
 }  // namespace
 
 size_t mld_semantic_state_bytes(int nframes) { return (size_t)nframes * (2 * SP_NSUM * sizeof(double) + 8 * sizeof(float) + 8 * sizeof(unsigned int)); }
@@ -248,8 +377,10 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
                                       const unsigned int* ground_set8, double inlier_threshold, const float* d_pts, int stride_f,
                                       long long n_points, long long pitch_pts, const unsigned char* d_labels, int nframes,
                                       void* d_state, float* d_coeffs, unsigned int* d_inlier_bits, long long words_per_frame,
-                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches, unsigned char* d_flags_out) {
+                                      int* d_n_inliers, int* d_rc, cudaStream_t stream, int* launches, unsigned char* d_flags_out,
+                                      int exact) {
     if (nframes <= 0) return cudaSuccess;
+    if (exact && !d_flags_out) return cudaErrorInvalidValue;  // the exact mode fits from the labelled flags
     if (n_points > 0x7fffffffLL / 8) return cudaErrorInvalidValue;
     SemCam C;
     for (int i = 0; i < 12; i++) C.T[i] = T_cam_lidar[i];
@@ -272,8 +403,20 @@ cudaError_t mld_launch_semantic_plane(const double* T_cam_lidar, double f, doubl
         semantic_label_kernel<false><<<grid, SP_THREADS, 0, stream>>>(C, d_pts, stride_f, (int)n_points, pitch_pts, d_labels, acc, coeff, ctl, iters, nullptr);
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    if (exact) {  // first model from PCL's sequential float moments of the labelled points (replaces the double-precision fit)
+        semantic_exact_fit_kernel<false><<<(unsigned)nframes, SX_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, d_flags_out,
+                                                                                     n_points, coeff, ctl, d_coeffs);
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (launches) (*launches)++;
+    }
     semantic_select_kernel<<<grid, SP_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, inlier_threshold, acc, coeff, ctl,
                                                            d_inlier_bits, words_per_frame, d_coeffs, d_n_inliers, d_rc, iters);
     if (launches) *launches += 2;
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (exact) {  // refit from the inlier mask in the same order
+        semantic_exact_fit_kernel<true><<<(unsigned)nframes, SX_THREADS, 0, stream>>>(d_pts, stride_f, (int)n_points, pitch_pts, d_inlier_bits,
+                                                                                    words_per_frame, coeff, ctl, d_coeffs);
+        if (launches) (*launches)++;
+    }
     return cudaGetLastError();
 }

@@ -511,6 +511,11 @@ class DepthEstimator:
         """Frames per fused K1 + gather launch of device-resident non-road sequences, 0 when that pipeline is off."""
         return int(self._lib.mld_fused_chunk_frames(self._h))
 
+    def setSemanticExact(self, on: bool = True) -> None:
+        """SemanticPlane fits of this estimator in PCL's sequential float accumulation order (bit-identical to the reference's
+        coefficients and inlier set) instead of the default double-precision moments; see mld_set_semantic_exact."""
+        self._check(self._lib.mld_set_semantic_exact(self._h, int(on)))
+
     def hostPipelineStats(self) -> dict:
         """Counters of processFramesHost since creation (mld_host_pipeline_stats)."""
         out = (C.c_int64 * 4)()

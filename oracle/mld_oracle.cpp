@@ -893,7 +893,7 @@ int orc_image_point(int W, int H, double f, double cx, double cy, const double* 
 // ----------------------------------------------------------------------------------------------
 // R1  RansacPlane::CalculateInliersPlane, MF/src/RansacPlane.cpp:41-140.  PARITY UNPINNED except for the
 // reference's +-0.2 coefficient test. PCL (un-vendored, unpinned; 1.8 semantics assumed) restated:
-//   PassThrough("z", min_z, max_z)            -> keep finite z with min_z <= z <= max_z           (:58-64)
+//   PassThrough("z", min_z, max_z)            -> keep finite points with min_z <= z <= max_z      (:58-64)
 //   RandomSample(6000)                        -> order-preserving subsample; PCL's is time-seeded
 //                                                selection sampling, restated as stratified sampling
 //                                                driven by a counter-based hash                    (:66-74)
@@ -948,7 +948,10 @@ int orc_ransac_plane(const orc_params* P, const float* pts, int64_t n, int strid
     if (P->ransac_plane_min_z > -1001.) {
         for (int64_t i = 0; i < n; i++) {
             float z = pts[i * stride_floats + 2];
-            if (std::isfinite(z) && !((double)z < P->ransac_plane_min_z) && !((double)z > P->ransac_plane_max_z)) cand.push_back((int32_t)i);
+            // pcl::PassThrough::applyFilterIndices first drops every point with a non-finite x, y or z, then tests the field
+            const float x = pts[i * stride_floats], y = pts[i * stride_floats + 1];
+            if (std::isfinite(x) && std::isfinite(y) && std::isfinite(z) && !((double)z < P->ransac_plane_min_z) && !((double)z > P->ransac_plane_max_z))
+                cand.push_back((int32_t)i);
         }
     } else {
         for (int64_t i = 0; i < n; i++) cand.push_back((int32_t)i);

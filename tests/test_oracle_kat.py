@@ -153,3 +153,21 @@ def test_planar_wall_depth_matches_geometry():
     d, s = o.calculate_depth(uv)
     assert list(s) == [1, 1, 1]
     np.testing.assert_allclose(d, 7.0, rtol=1e-6)
+
+
+def test_passthrough_drops_points_with_non_finite_x_or_y():
+    """pcl::PassThrough::applyFilterIndices removes every point with a non-finite x, y or z before it tests the field
+    (RansacPlane.cpp:58-64): a point with NaN x and a z inside the limits never becomes a candidate or an inlier."""
+    p = O.yaml_params()
+    p.ransac_plane_min_z = -3.0
+    p.ransac_plane_max_z = 0.0
+    rng = np.random.RandomState(2)
+    cloud = np.zeros((400, 4), np.float32)
+    cloud[:, :2] = rng.uniform(-10, 10, (400, 2))
+    cloud[:, 2] = -1.7 + rng.normal(0, 0.01, 400)
+    cloud[::7, 0] = np.nan
+    cloud[3::11, 1] = np.inf
+    rc, coeffs, inl, _ = O.ransac_plane(p, cloud, 5)
+    assert rc == 0 and np.isfinite(coeffs).all()
+    bad = ~np.isfinite(cloud[:, :3]).all(axis=1)
+    assert not bad[inl].any() and len(inl) == (~bad).sum()

@@ -94,16 +94,15 @@ def test_parameter_variants(variant):
     cloud = PU.random_scene_cloud(rng, 10000, W, H, f, cx, cy, KT, dense_patches=45)
     uv = np.stack([rng.uniform(0, W, 2000), rng.uniform(0, H, 2000)], 1)
     if variant == "pca":
-        # eigenvalue ratios are compared in float against thresholds (PCA.cpp:27-37): the warp-parallel
-        # scatter sums differ from the oracle's sequential sums in the last ulp, which can flip a
-        # status only when a ratio sits on a threshold; allow a handful of such flips.
+        # eigenvalue ratios are compared in float against thresholds (PCA.cpp:27-37): mean, scatter and the Jacobi solver run in
+        # the oracle's operation order on the GPU (mld_common.cuh eig3_sym_regs), so every status is exact, not 99.9 % of them
         est.setInputCloud(cloud)
         orc.set_cloud(cloud)
         d_gpu, s_gpu = est.CalculateDepth(uv)
         d_ref, s_ref = orc.calculate_depth(uv)
-        same = s_gpu == s_ref
-        assert same.mean() > 0.999
-        PU.assert_depth_status_equal(d_gpu[same], s_gpu[same], d_ref[same], s_ref[same], "pca")
+        assert np.array_equal(s_gpu, s_ref)
+        assert len(set(s_ref.tolist()) & {12, 13, 14}) >= 2  # the PCA verdicts occur
+        PU.assert_depth_status_equal(d_gpu, s_gpu, d_ref, s_ref, "pca")
     else:
         PU.compare_frame(est, orc, cloud, uv, what=variant)
 

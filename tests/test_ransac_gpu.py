@@ -48,10 +48,10 @@ def test_reference_kat_within_0p2():
         assert _ulp_close(c, c_ref), (c, c_ref)
 
 
-@pytest.mark.parametrize("variant", ["yaml", "passthrough", "no_refine", "few_iterations"])
+@pytest.mark.parametrize("variant", ["yaml", "passthrough", "passthrough_nan_xy", "no_refine", "few_iterations"])
 def test_gpu_ransac_equals_oracle_on_synthetic_sweeps(variant):
     p = O.yaml_params()
-    if variant == "passthrough":
+    if variant.startswith("passthrough"):
         p.ransac_plane_min_z = -3.0
         p.ransac_plane_max_z = -0.5
     elif variant == "no_refine":
@@ -62,6 +62,13 @@ def test_gpu_ransac_equals_oracle_on_synthetic_sweeps(variant):
     cfg = synth.default_config()
     for frame in range(3):
         cloud = synth.points_host(cfg, 31, frame)
+        if variant == "passthrough_nan_xy":
+            # pcl::PassThrough drops a point whose x or y is not finite even when its z passes the limits: such points must not
+            # reach the 6000-point subsample (a NaN hypothesis / poisoned refit otherwise)
+            rng = np.random.RandomState(frame)
+            bad = rng.choice(len(cloud), 4000, replace=False)
+            cloud[bad[:2000], 0] = np.nan
+            cloud[bad[2000:], 1] = np.inf
         seed = 1000 + frame
         pl = est.estimateGroundPlane(cloud, seed)
         rc, c_ref, inl_ref, it_ref = O.ransac_plane(p, cloud, seed)
@@ -69,6 +76,8 @@ def test_gpu_ransac_equals_oracle_on_synthetic_sweeps(variant):
         assert pl.iterations == it_ref, (variant, frame)
         assert np.array_equal(pl.getInlinersIndex(), inl_ref), (variant, frame)
         assert _ulp_close(pl.getModelCoeffs(), c_ref), (pl.getModelCoeffs(), c_ref)
+        if variant == "passthrough_nan_xy":
+            assert np.isfinite(pl.getModelCoeffs()).all() and not np.isin(bad, pl.getInlinersIndex()).any()
         # the fitted plane is the synthetic ground (z = -1.73 in the lidar frame)
         c = pl.getModelCoeffs()
         fin = np.isfinite(cloud[:, 2])

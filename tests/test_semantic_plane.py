@@ -369,3 +369,66 @@ def test_feature_layout_is_explicit_for_2x2():
     with pytest.raises(ValueError):
         f(b)
     assert np.array_equal(f(b, "2xF"), b.T) and np.array_equal(f(b, "Fx2"), b)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_gpu_semantic_plane_exact_mode_is_bit_identical_to_the_reference(case):
+    """Exact mode (mld_set_semantic_exact): PCL's nine sequential float accumulators in index order, float covariance, the same Jacobi
+    solver -- coefficients and inlier set equal the outputs of the reference's own code (tests/golden/ref_golden.npz, made by
+    oracle/_ref) bit for bit, where the default double-precision moments only agree to 2e-3."""
+    cloud, labels, gl, thr = MK.semantic_case(case)
+    est = _estimator()
+    est.setSemanticExact(True)
+    plane = SemanticPlane(labels, SemanticPlane.Camera(F_, CU, CV, KT), gl, thr, est)
+    plane.CalculateInliersPlane(cloud)
+    assert np.array_equal(plane.getInlinersIndex(), G[f"sem{case}_inliers"])
+    assert np.array_equal(np.asarray(plane.getModelCoeffs(), np.float32).view(np.uint32), G[f"sem{case}_coeffs"].astype(np.float32).view(np.uint32)), (
+        plane.getModelCoeffs(), G[f"sem{case}_coeffs"])
+    # 32-byte records give the same
+    c8 = np.zeros((len(cloud), 8), np.float32)
+    c8[:, :3] = cloud[:, :3]
+    p8 = SemanticPlane(labels, SemanticPlane.Camera(F_, CU, CV, KT), gl, thr, est)
+    p8.CalculateInliersPlane(c8)
+    assert np.array_equal(p8.getInlinersIndex(), plane.getInlinersIndex()) and np.array_equal(p8.getModelCoeffs(), plane.getModelCoeffs())
+
+
+@pytest.mark.gpu
+def test_road_depths_under_the_default_fit_stay_within_tolerance_of_the_exact_fit():
+    """End to end: the default (double-precision) SemanticPlane fit differs from the reference's float fit by ~2e-3 in the
+    coefficients and by a few boundary points in the inlier set. What that does to the road depths: features whose status agrees
+    under both planes (all but a small fraction) get depths within the 1e-4 relative contract."""
+    import torch
+
+    p = DepthEstimatorParameters.reference_yaml(1)
+    cases = [MK.semantic_case(c) for c in (0, 1, 2)]
+    nf, n, F = len(cases), len(cases[0][0]), 2000
+    thr, gl = 0.1, [6, 7, 8, 9]
+    cam = SemanticPlane.Camera(F_, CU, CV, KT)
+    cfg = synth.default_config(road=True)
+    uv_h = np.stack([synth.features_host(cfg, 9, f, F) for f in range(nf)])
+    pts = torch.from_numpy(np.stack([c[0] for c in cases])).cuda()
+    labs = torch.from_numpy(np.stack([c[1] for c in cases])).cuda()
+    uv = torch.from_numpy(uv_h).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    res = []
+    for exact in (False, True):
+        est = DepthEstimator()
+        est.InitConfig(p)
+        est.Initialize(synth.kitti_camera(), KT)
+        est.setSemanticExact(exact)
+        dep = torch.empty((nf, F), dtype=torch.float64, device="cuda")
+        sta = torch.empty((nf, F), dtype=torch.int32, device="cuda")
+        est.processFramesDeviceSemantic(pts.data_ptr(), n, n, 16, labs.data_ptr(), 1241, 376, cam, gl, thr, uv.data_ptr(), F, dep.data_ptr(),
+                                        sta.data_ptr(), nf, 0, 0, st)
+        torch.cuda.synchronize()
+        res.append((dep.cpu().numpy(), sta.cpu().numpy()))
+    (d0, s0), (d1, s1) = res
+    assert (s1 == 16).sum() > 100  # the road path is exercised
+    same = s0 == s1
+    assert same.mean() > 0.995, same.mean()
+    road = same & (s1 == 16)
+    rel = np.abs(d0[road] - d1[road]) / np.abs(d1[road])
+    assert np.quantile(rel, 0.99) <= 1e-4, (np.quantile(rel, 0.99), rel.max())
+    assert rel.max() <= 1e-3, rel.max()
+    assert np.array_equal(d0[same & (s1 != 16)], d1[same & (s1 != 16)])  # everything off the road path is untouched by the plane
