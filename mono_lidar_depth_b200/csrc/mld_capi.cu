@@ -170,8 +170,7 @@ struct mld_handle {
     bool have_cloud = false;
     int kcap = 0;
     int chunk_frames = 128;
-    // 2: split gather/solve(/road) thread-per-feature kernels + warp-per-feature overflow pass (default)
-    // 1: fused thread-per-feature kernel + overflow pass; 0: warp per feature only
+    // 2: split gather/solve(/road) thread-per-feature kernels + warp-per-feature overflow pass (default); 0: warp per feature only
     int feature_mode = 2;
     int overflow_blocks = 296;
     bool use_tagged_maps = true;
@@ -387,18 +386,6 @@ int launch_features(mld_handle* h, Slot& s, const MapCode& mc, cudaStream_t st, 
                                     bits, words, frames, s.d_ovf + 1, s.d_ovf, overflow_grid(h, s), st));
         CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
         h->launches += nl + 1;
-    } else if (h->feature_mode == 1) {
-        if (ev_mid) {
-            CK(cudaEventRecord(ev_mid[0], st));
-            CK(cudaEventRecord(ev_mid[1], st));
-        }
-        CK(cudaMemsetAsync(s.d_ovf, 0, sizeof(int), st));
-        CK(mld_launch_feature_depth_thread(h->dp, mc, d_pts, stride_f, pitch_pts, s.d_maps, s.d_occ, d_uv, F, d_depth, d_status, coeffs, bits,
-                                           words, frames, s.d_ovf + 1, s.d_ovf, st));
-        CK(mld_launch_feature_depth(h->dp, mc, h->kcap, d_pts, stride_f, pitch_pts, s.d_maps, d_uv, F, d_depth, d_status, coeffs,
-                                    bits, words, frames, s.d_ovf + 1, s.d_ovf, overflow_grid(h, s), st));
-        CK(cudaMemcpyAsync(s.h_ovf_seen, s.d_ovf, sizeof(int), cudaMemcpyDeviceToHost, st));
-        h->launches += 2;
     } else {
         if (ev_mid) {
             CK(cudaEventRecord(ev_mid[0], st));
@@ -719,9 +706,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     h->device = device;
     const char* env = getenv("MLD_CHUNK_FRAMES");
     if (env && atoi(env) > 0) h->chunk_frames = atoi(env);
-    env = getenv("MLD_FEATURE_MODE");  // "warp" / "fused" / "split": K2 variants (A/B measurements)
+    env = getenv("MLD_FEATURE_MODE");  // "warp" / "split": K2 variants (A/B measurements)
     if (env && strcmp(env, "warp") == 0) h->feature_mode = 0;
-    if (env && strcmp(env, "fused") == 0) h->feature_mode = 1;
     if (env && strcmp(env, "split") == 0) h->feature_mode = 2;
     env = getenv("MLD_TAGGED_MAPS");   // "0": clear the pixel maps before every use instead of epoch tags
     if (env && strcmp(env, "0") == 0) h->use_tagged_maps = false;
@@ -904,7 +890,6 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     mld_setup_prefilter(d);
     DeviceGuard g(h->device);
     CK(mld_configure_feature_depth(h->kcap));
-    CK(mld_configure_feature_depth_thread());
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) {
         h->overflow_blocks = 2 * sms;

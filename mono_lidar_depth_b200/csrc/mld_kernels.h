@@ -37,17 +37,6 @@ cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int 
 cudaError_t mld_launch_neighbors_debug(const DevParams& P, const MapCode& mc, const unsigned int* d_map, double u, double v,
                                        double hx, double hy, int* d_out, int cap, int* d_k, cudaStream_t stream);
 
-// K2/K3, thread per feature (mld_feature_thread.cu): features whose window holds more than
-// mld_thread_feature_capacity() points are appended to d_overflow_list (global feature ids).
-int mld_thread_feature_capacity(int road);
-cudaError_t mld_configure_feature_depth_thread(void);
-cudaError_t mld_launch_feature_depth_thread(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,
-                                            long long pitch_pts, const unsigned int* d_maps, const unsigned int* d_occ,
-                                            const double* d_uv, int F,
-                                            double* d_depth, int* d_status, const float* d_plane_coeffs,
-                                            const unsigned int* d_inlier_bits, long long words_per_frame, int nframes,
-                                            int* d_overflow_list, int* d_overflow_count, cudaStream_t stream);
-
 // K2/K3 split into gather / solve / road kernels with a chunk-wide compaction (mld_feature_split.cu)
 size_t mld_split_scratch_bytes(long long features, int road);
 cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f,

@@ -147,9 +147,9 @@ def test_edge_cases_empty_nan_offimage():
     est, orc = kitti_pair(p)
     # empty cloud
     empty = np.zeros((0, 4), np.float32)
-    uv = np.array([[10.0, 10.0], [600.0, 200.0]])
+    uv = np.array([[10.0, 10.0], [600.0, 200.0]])  # two features as Fx2: a 2x2 array needs its layout spelled out
     est.setInputCloud(empty)
-    d, s = est.CalculateDepth(uv)
+    d, s = est.CalculateDepth(uv, layout="Fx2")
     assert list(s) == [2, 2] and list(d) == [-1, -1]
     # all-NaN cloud, off-image / NaN / huge features, zero features
     cloud = np.full((1000, 4), np.nan, np.float32)
@@ -294,12 +294,11 @@ def test_batched_device_and_host_paths_match_per_frame():
     assert est.kernelLaunchCount() > 0
 
 
-@pytest.mark.parametrize("mode", ["warp", "fused", "untagged"])
+@pytest.mark.parametrize("mode", ["warp", "untagged"])
 def test_alternative_kernel_modes(mode, monkeypatch):
-    """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp), the fused thread-per-feature kernel (=fused)
-    and cleared (un-tagged) pixel maps (MLD_TAGGED_MAPS=0) give the same results as the default path (split
-    gather/solve/road kernels + epoch tags)."""
-    if mode in ("warp", "fused"):
+    """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp) and cleared (un-tagged) pixel maps (MLD_TAGGED_MAPS=0) give the
+    same results as the default path (split gather/solve/road kernels + epoch tags)."""
+    if mode == "warp":
         monkeypatch.setenv("MLD_FEATURE_MODE", mode)
     else:
         monkeypatch.setenv("MLD_TAGGED_MAPS", "0")
@@ -566,9 +565,11 @@ def test_persistent_pipeline_matches_chunked_launches(monkeypatch, case):
 
 
 @pytest.mark.gpu
-def test_persistent_pipeline_against_oracle():
+def test_persistent_pipeline_against_oracle(monkeypatch):
     """Frames of a pipelined sequence checked against the oracle directly (status exact, depth 1e-4), including frames at
     both ends of the sequence and across a ring wrap."""
+    monkeypatch.setenv("MLD_PIPE", "1")
+    monkeypatch.setenv("MLD_PIPE_RING", "32")
     p = O.yaml_params()
     p.do_use_ransac_plane = 0
     est, orc = kitti_pair(p)
