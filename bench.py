@@ -512,6 +512,8 @@ def run_gpu(args, rank, local_rank, world):
     else:
         for i in range(warm):
             seq.step()
+        if gather is not None:  # warm-up of the collective too: NCCL sets its connections up on the first call
+            gather(0)
         barrier()
         clocks.start()
         time.sleep(0.3)
