@@ -23,6 +23,7 @@
 
 #include "mld_c_api.h"
 #include "mld_common.cuh"
+#include "mld_host_pack.h"
 #include "mld_kernels.h"
 
 namespace {
@@ -1614,7 +1615,8 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
     // the chunk's points to 12-byte xyz in a pinned staging buffer, one contiguous copy moves them, a kernel expands them to the
     // float4 layout the projection kernel streams. (A strided 2-D DMA copy that skips the padding runs at 11 GB/s and a kernel
     // reading mapped pinned memory transfers every byte of the 32-byte sectors anyway: measured, scripts/pcie_probe.cu.)
-    const bool pack = n_points > 0 && (h->host_pack == 1 || (h->host_pack != 0 && stride_bytes > 16));
+    // 16-byte float4 records are packed as well where the host squeezes whole cache lines (AVX-512): 12 instead of 16 bytes cross the link
+    const bool pack = n_points > 0 && (h->host_pack == 1 || (h->host_pack != 0 && (stride_bytes > 16 || (stride_bytes == 16 && mld_host_pack_level() == 512))));
     if (pack && !h->pool) {
         int t = h->host_pack_threads;
         if (t <= 0) t = std::max(1, std::min(14, (int)std::thread::hardware_concurrency() - 2));
@@ -1673,16 +1675,7 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
                 const long long lo = (long long)pc * per, hi = std::min<long long>(n_points, lo + per);
                 const unsigned char* p = src + ((size_t)(f0 + fr) * (size_t)frame_pitch_points + (size_t)lo) * (size_t)stride_bytes;
                 float* q = reinterpret_cast<float*>(stage + ((size_t)fr * (size_t)n_points + (size_t)lo) * 12);
-                // a core's streaming bandwidth is bounded by its outstanding cache misses: prefetch ~1 KB ahead and store past the
-                // cache (no read-for-ownership of the staging lines)
-                for (long long i = lo; i < hi; i++, p += stride_bytes, q += 3) {
-                    const int* f = reinterpret_cast<const int*>(p);
-                    _mm_prefetch(reinterpret_cast<const char*>(p) + 1024, _MM_HINT_NTA);
-                    _mm_stream_si32(reinterpret_cast<int*>(q), f[0]);
-                    _mm_stream_si32(reinterpret_cast<int*>(q) + 1, f[1]);
-                    _mm_stream_si32(reinterpret_cast<int*>(q) + 2, f[2]);
-                }
-                _mm_sfence();
+                mld_host_pack_xyz(p, stride_bytes, q, hi - lo, 0);  // AVX-512 line-at-a-time squeeze where the host has it (mld_host_pack.cpp)
             };
             const auto tp0 = std::chrono::steady_clock::now();
             h->pool->run(c * pieces, job);

@@ -294,6 +294,45 @@ def test_batched_device_and_host_paths_match_per_frame():
     assert est.kernelLaunchCount() > 0
 
 
+@pytest.mark.parametrize("floats_per_record", [4, 8])
+@pytest.mark.parametrize("force", ["1", "0"])
+def test_host_pipeline_packed_records(floats_per_record, force, monkeypatch):
+    """mld_process_frames_host with every chunk packed to 12-byte xyz on the host (MLD_HOST_PACK=1: the AVX-512 / scalar squeeze of
+    csrc/mld_host_pack.cpp, H2D of 12 bytes per point, device-side expansion) and with whole records copied (=0) gives the device
+    path's results bit for bit, for float4 and for 32-byte pcl::PointXYZI records; ragged point count and chunking."""
+    import torch
+
+    monkeypatch.setenv("MLD_HOST_PACK", force)
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    est, _ = kitti_pair(p)
+    cfg = synth.default_config()
+    n_full = synth.points_per_frame(cfg)
+    n = n_full - 13  # not a multiple of 16: pieces start off the 64-byte lines of the staging buffer
+    F, nframes = 700, 41
+    clouds = np.stack([synth.points_host(cfg, 77, i)[:n] for i in range(nframes)])
+    uv = np.stack([synth.features_host(cfg, 77, i, F) for i in range(nframes)])
+    rec = np.full((nframes, n, floats_per_record), 1e30, np.float32)  # padding / intensity must never be read as coordinates
+    rec[:, :, :3] = clouds[:, :, :3]
+    d_host = np.empty((nframes, F), np.float64)
+    s_host = np.empty((nframes, F), np.int32)
+    est.processFramesHost(rec, uv, d_host, s_host)
+    stats = est.hostPipelineStats()
+    pts = torch.from_numpy(clouds).cuda()
+    uvd = torch.from_numpy(uv).cuda()
+    depth = torch.empty((nframes, F), dtype=torch.float64, device="cuda")
+    status = torch.empty((nframes, F), dtype=torch.int32, device="cuda")
+    est.processFramesDevice(pts.data_ptr(), n, n, 16, uvd.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes,
+                            stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(status.cpu().numpy(), s_host) and np.array_equal(depth.cpu().numpy(), d_host)
+    assert (s_host == 1).sum() > 100
+    if force == "1":
+        assert stats["frames_packed"] == nframes, stats
+    else:
+        assert stats["frames_packed"] == 0, stats
+
+
 @pytest.mark.parametrize("mode", ["warp", "untagged"])
 def test_alternative_kernel_modes(mode, monkeypatch):
     """The warp-per-feature kernel alone (MLD_FEATURE_MODE=warp) and cleared (un-tagged) pixel maps (MLD_TAGGED_MAPS=0) give the
