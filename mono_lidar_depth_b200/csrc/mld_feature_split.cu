@@ -6,14 +6,16 @@
 // compaction, occupancy pinned at 16 warps/SM by the per-thread XYZ slabs that only the later phases
 // need, and 44 % of the features (empty windows) idle through those phases. Splitting fixes all three:
 //
-//   K2a gather  every feature: occupancy words -> pixel offsets -> map cells -> points -> FP64 camera
-//               frame. No XYZ slab (8 KB of shared memory per block), so it runs at register-limited
-//               occupancy where the load latency is hidden. Features with k >= radiusSearch_count_min are
-//               appended to a chunk-wide survivor list (one atomic per block) with their points in SoA
-//               form [entry][xyz][slot]; empty windows get status 2 right here.
-//   K2b solve   one thread per SURVIVOR (dense warps over the whole chunk): histogram segmentation,
-//               corner selection, in-block compaction, geometry tail. With a plane, unsolved features go
-//               to a second list.
+//   K2a gather  every feature: occupancy words -> pixel offsets -> map cells -> raw point indices. No XYZ
+//               slab (8 KB of shared memory per block), so it runs at register-limited occupancy where
+//               the load latency is hidden. Features with k >= radiusSearch_count_min are appended to a
+//               chunk-wide survivor list (one atomic per block) with the raw indices of their neighbours
+//               as [entry][slot]; empty windows get status 2 right here. (Round 1 handed the FP64
+//               camera-frame points over instead: 24 bytes per neighbour written by the DRAM-bound fused
+//               launch and read back by the solve -- 7.2x the solve's algorithmic bytes, ncu r1f.)
+//   K2b solve   one thread per SURVIVOR (dense warps over the whole chunk): raw indices -> points ->
+//               FP64 camera frame (bit-identical to K1), histogram segmentation, corner selection,
+//               in-block compaction, geometry tail. With a plane, unsolved features go to a second list.
 //   K2c road    one thread per road candidate: wide-window gather + plane gate + road estimator.
 //
 // Reference routines restated: see mld_feature.cu / mld_thread_helpers.cuh (DepthEstimator.cpp:491-600).
@@ -48,8 +50,12 @@ constexpr int SBT_B = MLD_SBT_B;  // threads per block, solve
 constexpr int RCAP = 24;    // neighbours per feature in the road window
 constexpr int SBT_C = 64;   // threads per block, road
 
-// survivor record: (k << 27) | global feature id
+// road-survivor record: (k << 27) | global feature id
 __device__ __forceinline__ unsigned int pack_rec(int k, long long o) { return ((unsigned int)k << 27) | (unsigned int)o; }
+// survivor class k (= neighbour count, 0..SCAP): records at surv_rec[k][slot], raw neighbour indices at
+// surv_idx[class_row(k) + entry][slot]; rows of all classes: class_row(SCAP + 1)
+__host__ __device__ constexpr int class_row(int k) { return k * (k - 1) / 2; }
+constexpr int CLASS_COUNT_AT = 16;  // class counters: ints 16 .. 16 + SCAP of the scratch header (0..2: road / road-survivor counters)
 
 // ---- K2a ------------------------------------------------------------------------------------------
 // one block of SBT_A features of `frame` (bx = block index inside the frame)
@@ -58,18 +64,17 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
                                              const unsigned int* __restrict__ occs, const double* __restrict__ uv, int F,
                                              double* __restrict__ depth, int* __restrict__ status, int* __restrict__ overflow_list,
                                              int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
-                                             double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap, int bx,
+                                             unsigned int* __restrict__ surv_idx, int* __restrict__ class_count, long long cap, int bx,
                                              long long frame) {
     __shared__ int s_aux[SCAP * SBT_A];
     __shared__ int s_hist[SCAP + 1], s_start[SCAP + 2], s_off[SCAP + 1];
-    __shared__ unsigned char s_order[SBT_A];
-    __shared__ int s_base;
+    __shared__ unsigned char s_order[SBT_A], s_kof[SBT_A];
+    __shared__ int s_cbase[SCAP + 1];
     static_assert(SBT_A <= 256, "s_order holds thread ids in a byte");
     const int tid = threadIdx.x;
     const int fi = bx * SBT_A + tid;
     const bool valid = fi < F;
     const long long o = frame * (long long)F + fi;
-    const float* fp = pts + frame * pitch_pts * (long long)stride_f;
     const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
     const unsigned int* occ = occs + frame * occ_words_per_frame(P.W, P.H);
     int* aux = s_aux + tid;
@@ -108,9 +113,10 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             depth[o] = -1;
         }
     }
-    // chunk-wide survivor slots, ordered by neighbour count inside the block (counting sort over k): the solve
-    // kernel's warps then hold features of (nearly) equal k, so its per-thread loops over the neighbours stop
-    // diverging; one global atomic per block reserves the block's slots.
+    // chunk-wide survivor lists, ONE PER NEIGHBOUR COUNT k (class): the solve kernel's blocks then hold survivors of equal k, so
+    // its per-thread loops over the neighbours do not diverge (ncu r2q with one list sorted by k inside each gather block only:
+    // 15 of 32 lanes active in the histogram, 10 in the triangle search -- a block's ~50 survivors spread over every k). The
+    // block's survivors are counting-sorted by k in shared memory; one global atomic per class reserves their slots.
     if (tid <= SCAP) s_hist[tid] = 0;
     __syncthreads();
     int r = 0;
@@ -130,23 +136,22 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             pairs += acc - s_start[i + 1];  // survivors with k > i own an entry i
         }
         s_off[SCAP] = pairs;
-        s_base = acc ? atomicAdd(surv_count, acc) : 0;
     }
+    if (tid <= SCAP && s_hist[tid] > 0) s_cbase[tid] = atomicAdd(class_count + tid, s_hist[tid]);  // first slot of the block in class tid
     __syncthreads();
     const int S = s_start[SCAP + 1];
     if (S == 0) return;  // uniform per block
     if (surv) {
         const int rank = s_start[k] + r;
         s_order[rank] = (unsigned char)tid;
-        surv_rec[(long long)s_base + rank] = pack_rec(k, o);
+        s_kof[rank] = (unsigned char)k;
+        surv_rec[(long long)k * cap + (s_cbase[k] + r)] = (unsigned int)o;
     }
     __syncthreads();
-    // phases 2 and 3 over the flattened (entry i, survivor rank) pairs, entry-major: every lane owns one neighbour
-    // (dense warps whatever the spread of k), lanes of equal i store to consecutive slots.
-    // map cell -> raw index -> point -> FP64 camera frame, stored [entry][xyz][slot]
+    // phase 2 over the flattened (entry i, survivor rank) pairs, entry-major: every lane owns one neighbour (dense warps
+    // whatever the spread of k), lanes of equal i store to consecutive slots. map cell -> raw index, stored [entry][slot]
     const int T = s_off[SCAP];
-    // GILP pairs per thread and pass: the map loads of all of them are issued before the first point load, the point
-    // loads before the first FP64 transform, so a thread keeps GILP independent load chains in flight
+    // GILP pairs per thread and pass: the map loads of all of them are issued before the first store
     for (int p0 = tid; p0 < T; p0 += GILP * SBT_A) {
         long long dsti[GILP];
         const unsigned int* cellp[GILP];
@@ -160,25 +165,16 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             for (int j = 1; j < SCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
             const int rank = ok[u] ? s_start[i + 1] + (p - s_off[i]) : 0;
             const int owner = s_order[rank];
+            const int kc = s_kof[rank];  // class k owns the index rows tri(k) .. tri(k) + k - 1 of [row][slot]
             cellp[u] = map + s_aux[i * SBT_A + owner];
-            dsti[u] = (long long)i * 3 * cap + ((long long)s_base + rank);
+            dsti[u] = (long long)(class_row(kc) + i) * cap + (s_cbase[kc] + (rank - s_start[kc]));
         }
         unsigned int raw[GILP];
 #pragma unroll
         for (int u = 0; u < GILP; u++) raw[u] = ok[u] ? map_cell_index(mc, __ldg(cellp[u])) : 0u;
-        float4 q[GILP];
 #pragma unroll
         for (int u = 0; u < GILP; u++)
-            q[u] = ok[u] ? __ldg(reinterpret_cast<const float4*>(fp + (long long)raw[u] * stride_f)) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < GILP; u++) {
-            if (!ok[u]) continue;
-            const D3 c = lidar_to_cam(P, q[u].x, q[u].y, q[u].z);
-            double* dst = surv_xyz + dsti[u];
-            dst[0] = c.x;
-            dst[cap] = c.y;
-            dst[2 * cap] = c.z;
-        }
+            if (ok[u]) surv_idx[dsti[u]] = raw[u];
     }
 }
 
@@ -187,9 +183,9 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
                       const unsigned int* __restrict__ maps, const unsigned int* __restrict__ occs,
                       const double* __restrict__ uv, int F, double* __restrict__ depth, int* __restrict__ status,
                       int* __restrict__ overflow_list, int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
-                      double* __restrict__ surv_xyz, int* __restrict__ surv_count, long long cap) {
-    gather_block(P, mc, pts, stride_f, pitch_pts, maps, occs, uv, F, depth, status, overflow_list, overflow_count, surv_rec, surv_xyz,
-                 surv_count, cap, (int)blockIdx.x, (long long)blockIdx.y);
+                      unsigned int* __restrict__ surv_idx, int* __restrict__ class_count, long long cap) {
+    gather_block(P, mc, pts, stride_f, pitch_pts, maps, occs, uv, F, depth, status, overflow_list, overflow_count, surv_rec, surv_idx,
+                 class_count, cap, (int)blockIdx.x, (long long)blockIdx.y);
 }
 
 // ---- K1 of one chunk and K2a of the previous chunk in ONE launch ------------------------------------------------
@@ -218,8 +214,8 @@ struct FusedGather {
     int* overflow_list;
     int* overflow_count;
     unsigned int* surv_rec;
-    double* surv_xyz;
-    int* surv_count;
+    unsigned int* surv_idx;
+    int* class_count;
     long long cap;
     int blocks_per_frame;
 };
@@ -232,7 +228,7 @@ fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g,
     if (b % period == period - 1 && gi < g_blocks) {  // uniform per block
         const int frame = gi / g.blocks_per_frame;
         gather_block(P, g.mc, g.pts, stride_f, g.pitch_pts, g.maps, g.occs, g.uv, g.F, g.depth, g.status, g.overflow_list, g.overflow_count,
-                     g.surv_rec, g.surv_xyz, g.surv_count, g.cap, gi - frame * g.blocks_per_frame, (long long)frame);
+                     g.surv_rec, g.surv_idx, g.class_count, g.cap, gi - frame * g.blocks_per_frame, (long long)frame);
         return;
     }
     const int ki = b - min(g_blocks, gi);  // gather blocks with a smaller block index: min(g_blocks, b / period)
@@ -242,84 +238,122 @@ fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g,
 }
 
 // ---- K2b ------------------------------------------------------------------------------------------
+// One block = SBT_B survivors of ONE class (equal neighbour count k); classes are laid out heaviest first. Phases:
+//   load     raw indices -> points -> FP64 camera frame into the thread's shared-memory slab
+//   P2a      histogram segmentation per thread -> n points kept (or a final status)
+//   sort     block-wide counting sort of the still-alive survivors by n, largest first: the triangle search is O(n^2) and ran
+//            with 10 of 32 lanes active while every warp held every n
+//   P2b+P3   corner selection and the geometry tail for the sorted survivors (dense lanes, equal n inside a warp)
 __global__ void __launch_bounds__(SBT_B, MLD_SOLVE_MINBLOCKS)
-feature_solve_kernel(DevParams P, const double* __restrict__ uv, double* __restrict__ depth, int* __restrict__ status,
-                     const unsigned int* __restrict__ surv_rec, const double* __restrict__ surv_xyz,
-                     const int* __restrict__ surv_count, long long cap, int road, int* __restrict__ road_list,
+feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long pitch_pts, int F,
+                     const double* __restrict__ uv, double* __restrict__ depth, int* __restrict__ status,
+                     const unsigned int* __restrict__ surv_rec, const unsigned int* __restrict__ surv_idx,
+                     const int* __restrict__ class_count, long long cap, int road, int* __restrict__ road_list,
                      int* __restrict__ road_count) {
     using TSlab = TSlabT<SCAP, SBT_B>;
     __shared__ double sx[SCAP * SBT_B], sy[SCAP * SBT_B], sz[SCAP * SBT_B];
     __shared__ int saux[SCAP * SBT_B];
     __shared__ double s_u[SBT_B], s_v[SBT_B];
     __shared__ int s_o[SBT_B];
-    __shared__ short s_list[SBT_B], s_cnt[SBT_B];
-    __shared__ signed char s_st[SBT_B], s_ci[SBT_B], s_cj[SBT_B], s_ck[SBT_B];
+    __shared__ short s_list[SBT_B];
+    __shared__ signed char s_st[SBT_B], s_cnt[SBT_B];
+    __shared__ int s_hist[SCAP + 1], s_start[SCAP + 1];
     __shared__ int s_wtot[SBT_B / 32];
-    __shared__ int s_base;
+    __shared__ int s_base, s_n2;
     const int tid = threadIdx.x;
-    const int count = *surv_count;
-    const long long slot = (long long)blockIdx.x * SBT_B + tid;
-    if ((long long)blockIdx.x * SBT_B >= count) return;  // uniform per block
+    // which class, and which SBT_B survivors of it (uniform per block)
+    int k = SCAP, b = (int)blockIdx.x, count = 0;
+    for (; k >= 0; k--) {
+        count = __ldg(class_count + k);
+        const int nb = (count + SBT_B - 1) / SBT_B;
+        if (b < nb) break;
+        b -= nb;
+    }
+    if (k < 0) return;
+    const long long slot = (long long)b * SBT_B + tid;
     const bool valid = slot < count;
     auto slab_of = [&](int owner) { return TSlab{sx + owner, sy + owner, sz + owner, saux + owner}; };
 
-    // P2: histogram segmentation + corner selection
-    bool surv = false;
+    // load + P2a
+    int n = 0;
+    bool alive = false;
     s_st[tid] = ST_Unspecified;
+    if (tid <= SCAP) s_hist[tid] = 0;
     if (valid) {
-        const unsigned int rec = surv_rec[slot];
-        const int k = (int)(rec >> 27);
-        const int o = (int)(rec & 0x7FFFFFFu);
+        const int o = (int)surv_rec[(long long)k * cap + slot];
         s_o[tid] = o;
         const double2 f2 = __ldg(reinterpret_cast<const double2*>(uv) + o);
         s_u[tid] = f2.x;
         s_v[tid] = f2.y;
         const TSlab s = slab_of(tid);
+        // raw indices (coalesced: [row][slot]) -> points -> FP64 camera frame, the same expression K1 evaluated
+        const float* fp = pts + (long long)(o / F) * pitch_pts * (long long)stride_f;
+        const unsigned int* idx = surv_idx + (long long)class_row(k) * cap + slot;
         for (int i = 0; i < k; i++) {
-            const double* src = surv_xyz + (long long)i * 3 * cap + slot;
-            s.set(i, D3{src[0], src[cap], src[2 * cap]});
+            const int raw = (int)__ldg(idx + (long long)i * cap);
+            s.A(i) = raw;
+            // the points are random 16-byte reads of a cloud that left L2 long ago, and the slabs cap this kernel at 24 warps per SM:
+            // ask L2 for all of a survivor's points at once (no registers held), the loads below then find them there
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(fp + (long long)raw * stride_f));
         }
-        int n = k;
+#pragma unroll 2
+        for (int i = 0; i < k; i++) {
+            const float4 q = __ldg(reinterpret_cast<const float4*>(fp + (long long)s.A(i) * stride_f));
+            s.set(i, lidar_to_cam(P, q.x, q.y, q.z));
+        }
+        n = k;
         int st = ST_Unspecified;
         if (P.use_hist) {
             n = t_histogram_segment(P, k, s);
             if (n < 0) st = ST_HistogramNoLocalMax;
         }
-        if (st != ST_HistogramNoLocalMax) {
-            int ci, cj, ck;
-            st = t_select_corners(P, n, s, ci, cj, ck);
-            if (st == 0) {
-                s_cnt[tid] = (short)n;
-                s_ci[tid] = (signed char)ci;
-                s_cj[tid] = (signed char)cj;
-                s_ck[tid] = (signed char)ck;
-                surv = true;
-            }
+        if (st == ST_Unspecified && n < 3)  // t_select_corners without the search (DepthEstimator.cpp:915-926)
+            st = (!P.use_pca && P.use_tri_max) ? ST_TriangleNotPlanarInsufficientPoints : ST_HistogramNoLocalMax;
+        if (st == ST_Unspecified) {
+            alive = true;
+            s_cnt[tid] = (signed char)n;
+        } else {
+            s_st[tid] = (signed char)st;
         }
-        if (!surv) s_st[tid] = (signed char)st;
     }
     __syncthreads();
-    const int n2 = block_compact<SBT_B>(surv, tid, s_list, s_wtot);
+    // counting sort of the alive survivors by n, largest n first
+    int r = 0;
+    if (alive) r = atomicAdd(&s_hist[n], 1);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int j = SCAP; j >= 0; j--) {
+            s_start[j] = acc;
+            acc += s_hist[j];
+        }
+        s_n2 = acc;
+    }
+    __syncthreads();
+    if (alive) s_list[s_start[n] + r] = (short)tid;
+    __syncthreads();
 
-    // P3: geometry tail on dense lanes
-    double dp_mine = -1;
-    if (tid < n2) {
+    // P2b + P3 on dense lanes
+    if (tid < s_n2) {
         const int owner = s_list[tid];
-        double dp;
-        const int st = t_depth_from_corners(P, s_u[owner], s_v[owner], (int)s_cnt[owner], slab_of(owner), (int)s_ci[owner],
-                                            (int)s_cj[owner], (int)s_ck[owner], dp);
+        const TSlab s = slab_of(owner);
+        const int no = (int)s_cnt[owner];
+        int ci, cj, ck;
+        int st = t_select_corners(P, no, s, ci, cj, ck);
+        if (st == 0) {
+            double dp;
+            st = t_depth_from_corners(P, s_u[owner], s_v[owner], no, s, ci, cj, ck, dp);
+            sx[owner] = dp;  // park the depth in the owner's slab (entry 0 is no longer needed once the tail is done)
+        }
         s_st[owner] = (signed char)st;
-        // park the depth in the owner's slab (entry 0 is no longer needed once the tail is done)
-        sx[owner] = dp;
     }
     __syncthreads();
     if (valid) {
         const int st = s_st[tid];
         const int o = s_o[tid];
-        if (st == ST_Success) dp_mine = sx[tid];
         // the road path overwrites status/depth of its candidates later; everything gets a normal-path result first
         status[o] = st;
-        depth[o] = (st == ST_Success) ? dp_mine : -1.0;
+        depth[o] = (st == ST_Success) ? sx[tid] : -1.0;
     }
     if (road) {
         const bool want = valid && s_st[tid] != ST_Success;
@@ -471,29 +505,35 @@ feature_road_solve_kernel(DevParams P, const double* __restrict__ uv, int F, dou
 }  // namespace
 
 size_t mld_split_scratch_bytes(long long features, int road) {
-    // counters (64 B) + survivor records + road list + survivor points [entries][3][features]; the road pass
-    // reuses the arrays for its own (rarer, up to RCAP-entry) survivors
-    const int entries = road ? (SCAP > RCAP ? SCAP : RCAP) : SCAP;
-    return 64 + (size_t)features * (sizeof(unsigned int) + sizeof(int)) + (size_t)features * entries * 3 * sizeof(double) + 256;
+    // header (128 B: counters) + survivor records [class][features] + road list + the survivors' raw neighbour indices
+    // [class rows][features]; with a plane the same area holds the road pass's (rarer, up to RCAP-entry) survivor points
+    // [RCAP][3][features] once K2b has finished. A class can hold every feature, so most of this is never touched.
+    const size_t idx_area = (size_t)features * class_row(SCAP + 1) * sizeof(unsigned int);
+    const size_t road_area = road ? (size_t)features * RCAP * 3 * sizeof(double) : 0;
+    return 128 + (size_t)features * ((SCAP + 1) * sizeof(unsigned int) + sizeof(int)) + (idx_area > road_area ? idx_area : road_area) + 256;
 }
 
 namespace {
 struct SplitLayout {
-    int *surv_count, *road_count, *rs_count, *road_list;
+    int *header, *class_count, *road_count, *rs_count, *road_list;
     unsigned int* surv_rec;
-    double* surv_xyz;
+    unsigned int* surv_idx;  // normal path: raw neighbour indices [SCAP][features]
+    double* surv_xyz;        // road pass: survivor points [RCAP][3][features] (same area)
 };
 SplitLayout split_layout(void* d_scratch, long long features) {
     unsigned char* base = reinterpret_cast<unsigned char*>(d_scratch);
     SplitLayout L;
-    L.surv_count = reinterpret_cast<int*>(base);
-    L.road_count = L.surv_count + 1;
-    L.rs_count = L.surv_count + 2;
-    L.surv_rec = reinterpret_cast<unsigned int*>(base + 64);
-    L.road_list = reinterpret_cast<int*>(L.surv_rec + features);
-    size_t off = 64 + (size_t)features * 8;
+    L.header = reinterpret_cast<int*>(base);
+    L.road_count = L.header + 1;
+    L.rs_count = L.header + 2;
+    L.class_count = L.header + CLASS_COUNT_AT;
+    static_assert(CLASS_COUNT_AT + SCAP + 1 <= 32, "counters live in the 128-byte header");
+    L.surv_rec = reinterpret_cast<unsigned int*>(base + 128);
+    L.road_list = reinterpret_cast<int*>(L.surv_rec + (size_t)features * (SCAP + 1));
+    size_t off = 128 + (size_t)features * ((SCAP + 1) * sizeof(unsigned int) + sizeof(int));
     off = (off + 255) & ~(size_t)255;
     L.surv_xyz = reinterpret_cast<double*>(base + off);
+    L.surv_idx = reinterpret_cast<unsigned int*>(base + off);
     return L;
 }
 }  // namespace
@@ -520,10 +560,10 @@ cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, co
     g.blocks_per_frame = (int)std::max<long long>(gbpf, 1);
     if (g_blocks > 0) {
         const SplitLayout L = split_layout(d_scratch_g, features);
-        cudaError_t e = cudaMemsetAsync(L.surv_count, 0, 3 * sizeof(int), stream);
+        cudaError_t e = cudaMemsetAsync(L.header, 0, 128, stream);
         if (e != cudaSuccess) return e;
         g = FusedGather{mc_g, d_pts_g, pitch_pts, d_maps_g, d_occ_g, d_uv_g, F, d_depth_g, d_status_g, d_overflow_list, d_overflow_count,
-                        L.surv_rec, L.surv_xyz, L.surv_count, features, (int)gbpf};
+                        L.surv_rec, L.surv_idx, L.class_count, features, (int)gbpf};
     }
     // one gather block after every (period - 1) K1 blocks; when there are fewer K1 blocks than that the gather blocks simply
     // come every second block and the K1 blocks run out first
@@ -552,9 +592,10 @@ cudaError_t mld_launch_feature_solve(const DevParams& P, const MapCode& mc, cons
     const SplitLayout L = split_layout(d_scratch, features);
     const bool road = d_plane_coeffs != nullptr && P.road_mode != ROAD_NONE;
     cudaError_t e;
-    const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B);
-    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_uv, d_depth, d_status, L.surv_rec, L.surv_xyz, L.surv_count, features, road ? 1 : 0,
-                                                  L.road_list, L.road_count);
+    // every class rounds its survivors up to whole blocks; blocks past the last class leave at once
+    const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B) + SCAP + 1;
+    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_pts, stride_f, pitch_pts, F, d_uv, d_depth, d_status, L.surv_rec, L.surv_idx, L.class_count,
+                                                  features, road ? 1 : 0, L.road_list, L.road_count);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (ev_after_solve && (e = cudaEventRecord(*ev_after_solve, stream)) != cudaSuccess) return e;  // profiling: end of the solve
     if (launches) (*launches)++;
@@ -584,11 +625,11 @@ cudaError_t mld_launch_feature_depth_split(const DevParams& P, const MapCode& mc
     const long long features = (long long)nframes * F;
     if (features >= (1ll << 27)) return cudaErrorInvalidValue;  // survivor records hold 27-bit feature ids
     const SplitLayout L = split_layout(d_scratch, features);
-    cudaError_t e = cudaMemsetAsync(L.surv_count, 0, 3 * sizeof(int), stream);
+    cudaError_t e = cudaMemsetAsync(L.header, 0, 128, stream);
     if (e != cudaSuccess) return e;
     dim3 ga((unsigned)((F + SBT_A - 1) / SBT_A), (unsigned)nframes);
     feature_gather_kernel<<<ga, SBT_A, 0, stream>>>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_occ, d_uv, F, d_depth, d_status,
-                                                   d_overflow_list, d_overflow_count, L.surv_rec, L.surv_xyz, L.surv_count, features);
+                                                   d_overflow_list, d_overflow_count, L.surv_rec, L.surv_idx, L.class_count, features);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (launches) (*launches)++;
     if (ev_mid && (e = cudaEventRecord(ev_mid[0], stream)) != cudaSuccess) return e;  // profiling: end of the gather
