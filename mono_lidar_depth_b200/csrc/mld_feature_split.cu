@@ -35,7 +35,7 @@ namespace {
 #define MLD_SCAP 9  // 3 rings x 3 returns fit (round 2 scene: HDL-64E ring layout); 8 sent 3.5 % of the features to the overflow pass
 #endif
 #ifndef MLD_SOLVE_MINBLOCKS
-#define MLD_SOLVE_MINBLOCKS 6  // 9-entry slabs: 35 KB of shared memory per block -> 6 blocks per SM; 80 registers, no spills
+#define MLD_SOLVE_MINBLOCKS 5  // 5 blocks per SM let the kernel keep its FP64 state in registers (6: capped at 80, 60 + 160 bytes of spills per thread): 1.41 -> 1.47 M frames/s; 4 and 3 measure the same
 #endif
 #ifndef MLD_SBT_B
 #define MLD_SBT_B 128
@@ -221,8 +221,16 @@ struct FusedGather {
 };
 static_assert(SBT_A == K1_THREADS, "the fused launch uses one block size for both roles");
 
-__global__ void __launch_bounds__(SBT_A, 8)
+#ifndef MLD_FUSED_MINBLOCKS
+#define MLD_FUSED_MINBLOCKS 8
+#endif
+__global__ void __launch_bounds__(SBT_A, MLD_FUSED_MINBLOCKS)
 fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g, int k1_blocks, int g_blocks, int period) {
+#ifdef MLD_FUSED_PAD_SMEM
+    __shared__ int s_pad[MLD_FUSED_PAD_SMEM / 4];  // experiment: fewer resident blocks per SM
+    if (period < 0) s_pad[threadIdx.x] = period;
+    if (period < -1) a.maps[0] = s_pad[(threadIdx.x + 1) % 32];
+#endif
     const int b = (int)blockIdx.x;
     const int gi = b / period;
     if (b % period == period - 1 && gi < g_blocks) {  // uniform per block
