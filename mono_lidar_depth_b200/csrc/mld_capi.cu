@@ -181,7 +181,7 @@ struct mld_handle {
     bool fuse_serial = false;       // MLD_FUSE_SERIAL=1: solve + overflow pass on the front stream too (no concurrency at all)
     int k1_persist_per_sm = 0;
     int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
-    int overlap_slots = 3;          // chunks of a device-resident sequence alternate over this many slots/streams
+    int overlap_slots = 5;          // chunks of a device-resident sequence alternate over this many slots/streams (MLD_OVERLAP). The solve and overflow pass of a chunk are starved by the fused launch that runs beside them and finish near its end; with 3 slots the launch after next waited for them (1.47 M frames/s), 4 / 5 / 6 slots: 1.50 / 1.52 / 1.49 M
     cudaEvent_t ev_fork = nullptr;
     // priority mode: every K1 of a sequence runs on a low-priority stream, every K2 on a high-priority one, so the
     // latency-bound K2 blocks are placed first and the streaming K1 fills what is left

@@ -155,6 +155,25 @@ cudaError_t mld_launch_feature_depth(const DevParams& P, const MapCode& mc, int 
                                      long long words_per_frame, int nframes, const int* d_list, const int* d_list_count,
                                      int list_blocks, cudaStream_t stream, double* d_corners) {
     if (F <= 0 || nframes <= 0) return cudaSuccess;
+    if (d_list != nullptr) {
+        // list mode (overflow pass beside the fused launches): 2-warp blocks. A 256-thread block of this 126-register kernel needs
+        // half of an SM's register file at once and was only ever placed in the tail of the co-running fused launch, so the
+        // slot's "done" event -- which the launch after next waits for -- came a whole launch late (7 % of the step).
+        const int blocks = list_blocks * 4;
+        switch (kcap) {
+            case 96:
+                return launch_feature<96, 2>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                             d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, blocks, stream, d_corners);
+            case 256:
+                return launch_feature<256, 2>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                              d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, blocks, stream, d_corners);
+            case 1024:
+                return launch_feature<1024, 2>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
+                                               d_inlier_bits, words_per_frame, nframes, d_list, d_list_count, blocks, stream, d_corners);
+            default:
+                return cudaErrorInvalidValue;
+        }
+    }
     switch (kcap) {
         case 96:
             return launch_feature<96, 8>(P, mc, d_pts, stride_f, pitch_pts, d_maps, d_uv, F, d_depth, d_status, d_plane_coeffs,
@@ -175,7 +194,10 @@ cudaError_t mld_configure_feature_depth(int kcap) {
     switch (kcap) {
         case 96: return configure_feature<96, 8>();
         case 256: return configure_feature<256, 8>();
-        case 1024: return configure_feature<1024, 4>();
+        case 1024: {
+            cudaError_t e = configure_feature<1024, 4>();
+            return e != cudaSuccess ? e : configure_feature<1024, 2>();  // 57 KB: the only 2-warp variant past the 48 KB default
+        }
         default: return cudaErrorInvalidValue;
     }
 }

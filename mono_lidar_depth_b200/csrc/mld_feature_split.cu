@@ -43,19 +43,29 @@ namespace {
 #ifndef MLD_GATHER_ILP
 #define MLD_GATHER_ILP 2
 #endif
+#ifndef MLD_GCAP
+#define MLD_GCAP 16
+#endif
 constexpr int GILP = MLD_GATHER_ILP;  // (entry, survivor) pairs a gather thread keeps in flight
-constexpr int SCAP = MLD_SCAP;  // neighbours per feature in the normal window (more -> warp-kernel overflow list)
+constexpr int SCAP = MLD_SCAP;  // neighbours per feature the main solve kernel's slabs hold
+// neighbours per feature the gather lists hold (more -> warp-kernel overflow list). Windows of SCAP + 1 .. GCAP points (one
+// feature in 2000 on the KITTI shape) are solved by a second, small instantiation of the solve kernel with bigger slabs: the
+// warp-per-feature overflow pass they took before cost 7 % of the step (126 blocks x 256 threads x 25 us per 512 frames beside
+// the fused launch; measured by leaving the pass out).
+constexpr int GCAP = MLD_GCAP > MLD_SCAP ? MLD_GCAP : MLD_SCAP;
 constexpr int SBT_A = 128;  // threads per block, gather
 constexpr int SBT_B = MLD_SBT_B;  // threads per block, solve
+constexpr int SBT_B2 = 64;  // threads per block, solve of the classes SCAP + 1 .. GCAP
 constexpr int RCAP = 24;    // neighbours per feature in the road window
 constexpr int SBT_C = 64;   // threads per block, road
 
 // road-survivor record: (k << 27) | global feature id
 __device__ __forceinline__ unsigned int pack_rec(int k, long long o) { return ((unsigned int)k << 27) | (unsigned int)o; }
-// survivor class k (= neighbour count, 0..SCAP): records at surv_rec[k][slot], raw neighbour indices at
-// surv_idx[class_row(k) + entry][slot]; rows of all classes: class_row(SCAP + 1)
+// survivor class k (= neighbour count, 0..GCAP): records at surv_rec[k][slot], raw neighbour indices at
+// surv_idx[class_row(k) + entry][slot]; rows of all classes: class_row(GCAP + 1)
 __host__ __device__ constexpr int class_row(int k) { return k * (k - 1) / 2; }
-constexpr int CLASS_COUNT_AT = 16;  // class counters: ints 16 .. 16 + SCAP of the scratch header (0..2: road / road-survivor counters)
+constexpr int CLASS_COUNT_AT = 8;  // class counters: ints 8 .. 8 + GCAP of the scratch header (0..2: road / road-survivor counters)
+static_assert(CLASS_COUNT_AT + GCAP + 1 <= 32, "counters live in the 128-byte header");
 
 // ---- K2a ------------------------------------------------------------------------------------------
 // one block of SBT_A features of `frame` (bx = block index inside the frame)
@@ -66,10 +76,10 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
                                              int* __restrict__ overflow_count, unsigned int* __restrict__ surv_rec,
                                              unsigned int* __restrict__ surv_idx, int* __restrict__ class_count, long long cap, int bx,
                                              long long frame) {
-    __shared__ int s_aux[SCAP * SBT_A];
-    __shared__ int s_hist[SCAP + 1], s_start[SCAP + 2], s_off[SCAP + 1];
+    __shared__ int s_aux[GCAP * SBT_A];
+    __shared__ int s_hist[GCAP + 1], s_start[GCAP + 2], s_off[GCAP + 1];
     __shared__ unsigned char s_order[SBT_A], s_kof[SBT_A];
-    __shared__ int s_cbase[SCAP + 1];
+    __shared__ int s_cbase[GCAP + 1];
     static_assert(SBT_A <= 256, "s_order holds thread ids in a byte");
     const int tid = threadIdx.x;
     const int fi = bx * SBT_A + tid;
@@ -97,13 +107,13 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             const int y0 = (int)fmax(v - P.hy1, 0.), y1 = (int)fmin(v + P.hy1, (double)(P.H - 1));
             if (x1 >= x0 && y1 >= y0) {
                 occ_scan_window(occ, P.W, x0, x1, y0, y1, [&](int off) {
-                    if (k < SCAP) aux[k * SBT_A] = off;
+                    if (k < GCAP) aux[k * SBT_A] = off;
                     k++;
                 });
             }
         }
     }
-    const bool overflow = valid && k > SCAP;
+    const bool overflow = valid && k > GCAP;
     const bool surv = valid && !overflow && (unsigned)k >= (unsigned)P.count_min;
     if (valid && !surv) {
         if (overflow) {
@@ -117,7 +127,7 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
     // its per-thread loops over the neighbours do not diverge (ncu r2q with one list sorted by k inside each gather block only:
     // 15 of 32 lanes active in the histogram, 10 in the triangle search -- a block's ~50 survivors spread over every k). The
     // block's survivors are counting-sorted by k in shared memory; one global atomic per class reserves their slots.
-    if (tid <= SCAP) s_hist[tid] = 0;
+    if (tid <= GCAP) s_hist[tid] = 0;
     __syncthreads();
     int r = 0;
     if (surv) r = atomicAdd(&s_hist[k], 1);  // rank among the block's survivors with the same k
@@ -125,21 +135,21 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
     if (tid == 0) {
         // s_start[j] = survivors with k < j; s_off[i] = (entry, survivor) pairs with entry < i
         int acc = 0;
-        for (int j = 0; j <= SCAP; j++) {
+        for (int j = 0; j <= GCAP; j++) {
             s_start[j] = acc;
             acc += s_hist[j];
         }
-        s_start[SCAP + 1] = acc;
+        s_start[GCAP + 1] = acc;
         int pairs = 0;
-        for (int i = 0; i < SCAP; i++) {
+        for (int i = 0; i < GCAP; i++) {
             s_off[i] = pairs;
             pairs += acc - s_start[i + 1];  // survivors with k > i own an entry i
         }
-        s_off[SCAP] = pairs;
+        s_off[GCAP] = pairs;
     }
-    if (tid <= SCAP && s_hist[tid] > 0) s_cbase[tid] = atomicAdd(class_count + tid, s_hist[tid]);  // first slot of the block in class tid
+    if (tid <= GCAP && s_hist[tid] > 0) s_cbase[tid] = atomicAdd(class_count + tid, s_hist[tid]);  // first slot of the block in class tid
     __syncthreads();
-    const int S = s_start[SCAP + 1];
+    const int S = s_start[GCAP + 1];
     if (S == 0) return;  // uniform per block
     if (surv) {
         const int rank = s_start[k] + r;
@@ -150,7 +160,7 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
     __syncthreads();
     // phase 2 over the flattened (entry i, survivor rank) pairs, entry-major: every lane owns one neighbour (dense warps
     // whatever the spread of k), lanes of equal i store to consecutive slots. map cell -> raw index, stored [entry][slot]
-    const int T = s_off[SCAP];
+    const int T = s_off[GCAP];
     // GILP pairs per thread and pass: the map loads of all of them are issued before the first store
     for (int p0 = tid; p0 < T; p0 += GILP * SBT_A) {
         long long dsti[GILP];
@@ -162,7 +172,7 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
             ok[u] = p < T;
             int i = 0;
 #pragma unroll
-            for (int j = 1; j < SCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
+            for (int j = 1; j < GCAP; j++) i += (p >= s_off[j]) ? 1 : 0;
             const int rank = ok[u] ? s_start[i + 1] + (p - s_off[i]) : 0;
             const int owner = s_order[rank];
             const int kc = s_kof[rank];  // class k owns the index rows tri(k) .. tri(k) + k - 1 of [row][slot]
@@ -246,39 +256,43 @@ fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g,
 }
 
 // ---- K2b ------------------------------------------------------------------------------------------
-// One block = SBT_B survivors of ONE class (equal neighbour count k); classes are laid out heaviest first. Phases:
+// One block = TBT survivors of ONE class (equal neighbour count k); classes are laid out heaviest first. Phases:
 //   load     raw indices -> points -> FP64 camera frame into the thread's shared-memory slab
 //   P2a      histogram segmentation per thread -> n points kept (or a final status)
 //   sort     block-wide counting sort of the still-alive survivors by n, largest first: the triangle search is O(n^2) and ran
 //            with 10 of 32 lanes active while every warp held every n
 //   P2b+P3   corner selection and the geometry tail for the sorted survivors (dense lanes, equal n inside a warp)
-__global__ void __launch_bounds__(SBT_B, MLD_SOLVE_MINBLOCKS)
+// CAP = slab entries = largest class of this instantiation, KLO = its smallest class, TBT = threads per block
+template <int CAP, int KLO, int TBT, int MINB>
+__global__ void __launch_bounds__(TBT, MINB)
 feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long pitch_pts, int F,
                      const double* __restrict__ uv, double* __restrict__ depth, int* __restrict__ status,
                      const unsigned int* __restrict__ surv_rec, const unsigned int* __restrict__ surv_idx,
                      const int* __restrict__ class_count, long long cap, int road, int* __restrict__ road_list,
-                     int* __restrict__ road_count) {
-    using TSlab = TSlabT<SCAP, SBT_B>;
-    __shared__ double sx[SCAP * SBT_B], sy[SCAP * SBT_B], sz[SCAP * SBT_B];
-    __shared__ int saux[SCAP * SBT_B];
-    __shared__ double s_u[SBT_B], s_v[SBT_B];
-    __shared__ int s_o[SBT_B];
-    __shared__ short s_list[SBT_B];
-    __shared__ signed char s_st[SBT_B], s_cnt[SBT_B];
-    __shared__ int s_hist[SCAP + 1], s_start[SCAP + 1];
-    __shared__ int s_wtot[SBT_B / 32];
+                     int* __restrict__ road_count, int strided) {
+    using TSlab = TSlabT<CAP, TBT>;
+    __shared__ double sx[CAP * TBT], sy[CAP * TBT], sz[CAP * TBT];
+    __shared__ int saux[CAP * TBT];
+    __shared__ double s_u[TBT], s_v[TBT];
+    __shared__ int s_o[TBT];
+    __shared__ short s_list[TBT];
+    __shared__ signed char s_st[TBT], s_cnt[TBT];
+    __shared__ int s_hist[CAP + 1], s_start[CAP + 1];
+    __shared__ int s_wtot[TBT / 32];
     __shared__ int s_base, s_n2;
     const int tid = threadIdx.x;
-    // which class, and which SBT_B survivors of it (uniform per block)
-    int k = SCAP, b = (int)blockIdx.x, count = 0;
-    for (; k >= 0; k--) {
+    // one work item (TBT survivors of one class) per block; a grid smaller than the item count strides over the items
+    for (int item = (int)blockIdx.x;; item += (int)gridDim.x) {
+    // which class, and which TBT survivors of it (uniform per block)
+    int k = CAP, b = item, count = 0;
+    for (; k >= KLO; k--) {
         count = __ldg(class_count + k);
-        const int nb = (count + SBT_B - 1) / SBT_B;
+        const int nb = (count + TBT - 1) / TBT;
         if (b < nb) break;
         b -= nb;
     }
-    if (k < 0) return;
-    const long long slot = (long long)b * SBT_B + tid;
+    if (k < KLO) return;
+    const long long slot = (long long)b * TBT + tid;
     const bool valid = slot < count;
     auto slab_of = [&](int owner) { return TSlab{sx + owner, sy + owner, sz + owner, saux + owner}; };
 
@@ -286,7 +300,7 @@ feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, l
     int n = 0;
     bool alive = false;
     s_st[tid] = ST_Unspecified;
-    if (tid <= SCAP) s_hist[tid] = 0;
+    if (tid <= CAP) s_hist[tid] = 0;
     if (valid) {
         const int o = (int)surv_rec[(long long)k * cap + slot];
         s_o[tid] = o;
@@ -331,7 +345,7 @@ feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, l
     __syncthreads();
     if (tid == 0) {
         int acc = 0;
-        for (int j = SCAP; j >= 0; j--) {
+        for (int j = CAP; j >= 0; j--) {
             s_start[j] = acc;
             acc += s_hist[j];
         }
@@ -371,7 +385,7 @@ feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, l
         __syncthreads();
         int base = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < SBT_B / 32; w++) {
+        for (int w = 0; w < TBT / 32; w++) {
             const int c = s_wtot[w];
             if (w < warp) base += c;
             total += c;
@@ -379,6 +393,9 @@ feature_solve_kernel(DevParams P, const float* __restrict__ pts, int stride_f, l
         if (tid == 0) s_base = total ? atomicAdd(road_count, total) : 0;
         __syncthreads();
         if (want) road_list[s_base + base + __popc(bm & ((1u << lane) - 1u))] = s_o[tid];
+    }
+    if (!strided) return;  // the grid covers every item: one per block
+    __syncthreads();  // the shared arrays are reused by the block's next item
     }
 }
 
@@ -516,16 +533,16 @@ size_t mld_split_scratch_bytes(long long features, int road) {
     // header (128 B: counters) + survivor records [class][features] + road list + the survivors' raw neighbour indices
     // [class rows][features]; with a plane the same area holds the road pass's (rarer, up to RCAP-entry) survivor points
     // [RCAP][3][features] once K2b has finished. A class can hold every feature, so most of this is never touched.
-    const size_t idx_area = (size_t)features * class_row(SCAP + 1) * sizeof(unsigned int);
+    const size_t idx_area = (size_t)features * class_row(GCAP + 1) * sizeof(unsigned int);
     const size_t road_area = road ? (size_t)features * RCAP * 3 * sizeof(double) : 0;
-    return 128 + (size_t)features * ((SCAP + 1) * sizeof(unsigned int) + sizeof(int)) + (idx_area > road_area ? idx_area : road_area) + 256;
+    return 128 + (size_t)features * ((GCAP + 1) * sizeof(unsigned int) + sizeof(int)) + (idx_area > road_area ? idx_area : road_area) + 256;
 }
 
 namespace {
 struct SplitLayout {
     int *header, *class_count, *road_count, *rs_count, *road_list;
     unsigned int* surv_rec;
-    unsigned int* surv_idx;  // normal path: raw neighbour indices [SCAP][features]
+    unsigned int* surv_idx;  // normal path: raw neighbour indices [class rows][features]
     double* surv_xyz;        // road pass: survivor points [RCAP][3][features] (same area)
 };
 SplitLayout split_layout(void* d_scratch, long long features) {
@@ -535,10 +552,9 @@ SplitLayout split_layout(void* d_scratch, long long features) {
     L.road_count = L.header + 1;
     L.rs_count = L.header + 2;
     L.class_count = L.header + CLASS_COUNT_AT;
-    static_assert(CLASS_COUNT_AT + SCAP + 1 <= 32, "counters live in the 128-byte header");
     L.surv_rec = reinterpret_cast<unsigned int*>(base + 128);
-    L.road_list = reinterpret_cast<int*>(L.surv_rec + (size_t)features * (SCAP + 1));
-    size_t off = 128 + (size_t)features * ((SCAP + 1) * sizeof(unsigned int) + sizeof(int));
+    L.road_list = reinterpret_cast<int*>(L.surv_rec + (size_t)features * (GCAP + 1));
+    size_t off = 128 + (size_t)features * ((GCAP + 1) * sizeof(unsigned int) + sizeof(int));
     off = (off + 255) & ~(size_t)255;
     L.surv_xyz = reinterpret_cast<double*>(base + off);
     L.surv_idx = reinterpret_cast<unsigned int*>(base + off);
@@ -602,8 +618,18 @@ cudaError_t mld_launch_feature_solve(const DevParams& P, const MapCode& mc, cons
     cudaError_t e;
     // every class rounds its survivors up to whole blocks; blocks past the last class leave at once
     const unsigned gb = (unsigned)((features + SBT_B - 1) / SBT_B) + SCAP + 1;
-    feature_solve_kernel<<<gb, SBT_B, 0, stream>>>(P, d_pts, stride_f, pitch_pts, F, d_uv, d_depth, d_status, L.surv_rec, L.surv_idx, L.class_count,
-                                                  features, road ? 1 : 0, L.road_list, L.road_count);
+    feature_solve_kernel<SCAP, 0, SBT_B, MLD_SOLVE_MINBLOCKS><<<gb, SBT_B, 0, stream>>>(
+        P, d_pts, stride_f, pitch_pts, F, d_uv, d_depth, d_status, L.surv_rec, L.surv_idx, L.class_count, features, road ? 1 : 0, L.road_list,
+        L.road_count, 0);
+    if ((e = cudaGetLastError()) != cudaSuccess) return e;
+    if (GCAP > SCAP) {
+        // the rare fuller windows: 64-thread blocks with GCAP-entry slabs; a small grid strides over however many there are
+        const unsigned gb2 = (unsigned)std::min<long long>((features + SBT_B2 - 1) / SBT_B2 + (GCAP - SCAP), 2 * 148);
+        feature_solve_kernel<GCAP, (GCAP > SCAP ? SCAP + 1 : 0), SBT_B2, 4><<<gb2, SBT_B2, 0, stream>>>(
+            P, d_pts, stride_f, pitch_pts, F, d_uv, d_depth, d_status, L.surv_rec, L.surv_idx, L.class_count, features, road ? 1 : 0,
+            L.road_list, L.road_count, 1);
+        if (launches) (*launches)++;
+    }
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
     if (ev_after_solve && (e = cudaEventRecord(*ev_after_solve, stream)) != cudaSuccess) return e;  // profiling: end of the solve
     if (launches) (*launches)++;
