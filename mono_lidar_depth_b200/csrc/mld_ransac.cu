@@ -151,7 +151,10 @@ __device__ __forceinline__ double block_sum_d(double v, double* scratch /* >= 8 
     return t;
 }
 
-__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(RS_THREADS)
+#ifndef MLD_RS_MINBLOCKS
+#define MLD_RS_MINBLOCKS 4
+#endif
+__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(RS_THREADS, MLD_RS_MINBLOCKS)
 ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
                       uint64_t seed, long long frame0, const int* __restrict__ cand_all, const int* __restrict__ cand_count,
                       float* __restrict__ out_coeffs, unsigned int* __restrict__ out_bits, long long words_per_frame,
@@ -169,8 +172,10 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
     __shared__ float s_best[4];
     __shared__ int s_state[4];                 // done, have_model, iterations, n_best
     __shared__ double s_k;
+    __shared__ double s_khyp[RS_HYP];         // iteration bound if hypothesis t becomes the best
     __shared__ double s_red[8];
     __shared__ double s_sums[10];              // this CTA's refinement partial sums
+    __shared__ double s_wsum[RS_THREADS / 32][10];
 
     FrameView fv;
     fv.pts = pts + frame * pitch_pts * (long long)stride_f;
@@ -267,11 +272,19 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
 #pragma unroll
             for (unsigned r = 0; r < RS_CLUSTER; r++) total += *cluster.map_shared_rank(&s_partial[tid], r);
             s_total[tid] = total;
+            // the iteration bound PCL would compute if this hypothesis became the best one (RandomSampleConsensus::computeModel):
+            // evaluated here by 64 threads at once -- pow and log in double on one thread, 15-20 times per frame, were the longest
+            // serial stretch of the kernel -- and only picked up by the sequential replay below
+            double w = (double)total * one_over_indices;
+            double p_no_outliers = 1.0 - pow(w, 3.0);
+            p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
+            p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
+            s_khyp[tid] = log_probability / log(p_no_outliers);
         }
         __syncthreads();
         // ---- PCL's sequential update over the round (RandomSampleConsensus::computeModel) ------
         if (tid == 0) {
-            int iterations = s_state[2], n_best = s_state[3], have = s_state[1], done = 0;
+            int iterations = s_state[2], n_best = s_state[3], have = s_state[1], done = 0, best_t = -1;
             double k = s_k;
             for (int t = 0; t < RS_HYP; t++) {
                 if (!((double)iterations < k) || !(0u < max_skip)) { done = 1; break; }
@@ -279,16 +292,15 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
                 int cnt = s_total[t];
                 if (cnt > n_best) {
                     n_best = cnt;
-                    s_best[0] = s_hyp[t][0]; s_best[1] = s_hyp[t][1]; s_best[2] = s_hyp[t][2]; s_best[3] = s_hyp[t][3];
+                    best_t = t;
                     have = 1;
-                    double w = (double)n_best * one_over_indices;
-                    double p_no_outliers = 1.0 - pow(w, 3.0);
-                    p_no_outliers = fmax(2.220446049250313e-16, p_no_outliers);
-                    p_no_outliers = fmin(1.0 - 2.220446049250313e-16, p_no_outliers);
-                    k = log_probability / log(p_no_outliers);
+                    k = s_khyp[t];
                 }
                 ++iterations;
                 if (iterations > cfg.max_iterations) { done = 1; break; }
+            }
+            if (best_t >= 0) {
+                s_best[0] = s_hyp[best_t][0]; s_best[1] = s_hyp[best_t][1]; s_best[2] = s_hyp[best_t][2]; s_best[3] = s_hyp[best_t][3];
             }
             s_state[0] = done; s_state[1] = have; s_state[2] = iterations; s_state[3] = n_best;
             s_k = k;
@@ -327,36 +339,51 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
                 }
             }
         }
-        for (int q = 0; q < 10; q++) {
-            double t = block_sum_d(v[q], s_red);
-            if (tid == 0) s_sums[q] = t;
-        }
-        cluster.sync();
-        double tot[10];
-        for (int q = 0; q < 10; q++) {
-            double t = 0;
-            for (unsigned r = 0; r < RS_CLUSTER; r++) t += *cluster.map_shared_rank(&s_sums[q], r);
-            tot[q] = t;
-        }
-        cluster.sync();
-        if (tot[0] >= 4.0) {
-            double m = tot[0];
-            double mx = tot[1] / m, my = tot[2] / m, mz = tot[3] / m;
-            double w[3];
-            D3 ev[3];
-            eig3_sym_regs(tot[4] / m - mx * mx, tot[5] / m - mx * my, tot[6] / m - mx * mz, tot[7] / m - my * my,
-                          tot[8] / m - my * mz, tot[9] / m - mz * mz, w, ev);
-            int bi = 0;
-            if (w[1] < w[bi]) bi = 1;
-            if (w[2] < w[bi]) bi = 2;
-            D3 e = (bi == 0) ? ev[0] : (bi == 1 ? ev[1] : ev[2]);
-            float ex = (float)e.x, ey = (float)e.y, ez = (float)e.z;
-            float cand4[4] = {ex, ey, ez, 0.f};
-            cand4[3] = -1 * __fadd_rn(__fadd_rn(__fmul_rn(ex, (float)mx), __fmul_rn(ey, (float)my)), __fmul_rn(ez, (float)mz));
-            if (model_valid(cand4, cos_eps)) {
-                outc[0] = cand4[0]; outc[1] = cand4[1]; outc[2] = cand4[2]; outc[3] = cand4[3];
+        // block sums of the ten moments: butterfly inside the warp, then the warps in order (the order block_sum_d uses), with
+        // two barriers for all ten instead of two each
+        {
+            const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+            for (int q = 0; q < 10; q++) {
+                const double t = warp_sum_d(v[q]);
+                if (lane == 0) s_wsum[warp][q] = t;
+            }
+            __syncthreads();
+            if (tid < 10) {
+                double t = 0;
+                for (int w = 0; w < RS_THREADS / 32; w++) t += s_wsum[w][tid];
+                s_sums[tid] = t;
             }
         }
+        cluster.sync();
+        // cluster totals and the eigen solve: only the thread that writes the coefficients needs them
+        if (rank == 0 && tid == 0) {
+            double tot[10];
+            for (int q = 0; q < 10; q++) {
+                double t = 0;
+                for (unsigned r = 0; r < RS_CLUSTER; r++) t += *cluster.map_shared_rank(&s_sums[q], r);
+                tot[q] = t;
+            }
+            if (tot[0] >= 4.0) {
+                double m = tot[0];
+                double mx = tot[1] / m, my = tot[2] / m, mz = tot[3] / m;
+                double w[3];
+                D3 ev[3];
+                eig3_sym_regs(tot[4] / m - mx * mx, tot[5] / m - mx * my, tot[6] / m - mx * mz, tot[7] / m - my * my,
+                              tot[8] / m - my * mz, tot[9] / m - mz * mz, w, ev);
+                int bi = 0;
+                if (w[1] < w[bi]) bi = 1;
+                if (w[2] < w[bi]) bi = 2;
+                D3 e = (bi == 0) ? ev[0] : (bi == 1 ? ev[1] : ev[2]);
+                float ex = (float)e.x, ey = (float)e.y, ez = (float)e.z;
+                float cand4[4] = {ex, ey, ez, 0.f};
+                cand4[3] = -1 * __fadd_rn(__fadd_rn(__fmul_rn(ex, (float)mx), __fmul_rn(ey, (float)my)), __fmul_rn(ez, (float)mz));
+                if (model_valid(cand4, cos_eps)) {
+                    outc[0] = cand4[0]; outc[1] = cand4[1]; outc[2] = cand4[2]; outc[3] = cand4[3];
+                }
+            }
+        }
+        cluster.sync();  // the other CTAs keep their partial sums alive until rank 0 has read them
     }
     // final inlier set: selectWithinDistance with the UN-refined coefficients (RansacPlane.cpp:121)
     const float final_lt = cfg.use_refinement ? cfg.refine_lt : thr_lt;
