@@ -14,7 +14,10 @@
 // hash of (seed, draw index, attempt) -- the same definition the CPU oracle restates -- which makes
 // the sequential semantics (first best hypothesis wins, adaptive stop) reproducible in parallel.
 //
-// Mapping. A cluster of 8 CTAs owns one frame. CTA r keeps sample points [750 r, 750 (r+1)) in shared
+// Mapping. Two instantiations of one body. Batches (>= RS_BATCH_FRAMES frames per launch): ONE CTA per frame with the whole
+// 6000-point subsample in its shared memory (96 KB, two frames per SM) -- no cluster barriers, every SM busy with its own
+// frames (252 -> ~100 us per 512 frames). Few frames (the per-call drop-in path): a cluster of 8 CTAs owns one frame, below.
+// A cluster of 8 CTAs owns one frame. CTA r keeps sample points [750 r, 750 (r+1)) in shared
 // memory. Per round, thread t of every CTA derives hypothesis (round*256 + t), scores it against the
 // CTA's slice with broadcast shared-memory reads, and the 8 partial counts are summed through
 // distributed shared memory. Every CTA then replays PCL's sequential update over the 256 totals
@@ -30,11 +33,14 @@ namespace {
 
 constexpr int RS_CLUSTER = 8;
 constexpr int RS_THREADS = 256;
-constexpr int RS_SLICE = (MLD_RANSAC_SAMPLE + RS_CLUSTER - 1) / RS_CLUSTER;  // 750
+constexpr int RS_BATCH_FRAMES = 64;  // launches of at least this many frames use one CTA per frame
 constexpr int RS_MAX_SAMPLE_CHECKS = 1000;  // pcl::SampleConsensusModel::max_sample_checks_
 // PCL's adaptive loop usually stops after 50-250 iterations, so a round scores only RS_HYP hypotheses;
 // the RS_THREADS / RS_HYP threads that share a hypothesis split the CTA's slice of the sample.
-constexpr int RS_HYP = 64;
+#ifndef MLD_RS_HYP
+#define MLD_RS_HYP 32
+#endif
+constexpr int RS_HYP = MLD_RS_HYP;
 constexpr int RS_PARTS = RS_THREADS / RS_HYP;
 
 struct F3 {
@@ -151,20 +157,24 @@ __device__ __forceinline__ double block_sum_d(double v, double* scratch /* >= 8 
     return t;
 }
 
-#ifndef MLD_RS_MINBLOCKS
-#define MLD_RS_MINBLOCKS 4
-#endif
-__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(RS_THREADS, MLD_RS_MINBLOCKS)
-ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
-                      uint64_t seed, long long frame0, const int* __restrict__ cand_all, const int* __restrict__ cand_count,
-                      float* __restrict__ out_coeffs, unsigned int* __restrict__ out_bits, long long words_per_frame,
-                      int* __restrict__ out_n_inliers, int* __restrict__ out_iterations, int* __restrict__ out_rc) {
+// NC = CTAs that share a frame (thread-block cluster of NC, or 1); s_pts = NC-th part of the subsample (dynamic shared memory)
+template <int NC>
+__device__ __forceinline__ void ransac_frame(const RansacConfig& cfg, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
+                                             uint64_t seed, long long frame0, const int* __restrict__ cand_all, const int* __restrict__ cand_count,
+                                             float* __restrict__ out_coeffs, unsigned int* __restrict__ out_bits, long long words_per_frame,
+                                             int* __restrict__ out_n_inliers, int* __restrict__ out_iterations, int* __restrict__ out_rc,
+                                             float4* s_pts, long long frame) {
+    constexpr int RS_SLICE = (MLD_RANSAC_SAMPLE + NC - 1) / NC;  // 750 of the 6000 sample points per CTA of a cluster of 8
     cg::cluster_group cluster = cg::this_cluster();
-    const unsigned rank = cluster.block_rank();
+    const unsigned rank = NC > 1 ? cluster.block_rank() : 0u;
     const int tid = threadIdx.x;
-    const long long frame = blockIdx.y;
-
-    __shared__ float4 s_pts[RS_SLICE];         // x, y, z, raw index bits
+    auto cluster_sync = [&]() {
+        if (NC > 1)
+            cluster.sync();
+        else
+            __syncthreads();
+    };
+    // s_pts: x, y, z, raw index bits
     __shared__ int s_partial[RS_HYP];          // this CTA's counts for the round's hypotheses
     __shared__ int s_total[RS_HYP];
     __shared__ float s_hyp[RS_HYP][4];
@@ -266,11 +276,15 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
             }
             if (count) atomicAdd(&s_partial[hyp], count);
         }
-        cluster.sync();
+        cluster_sync();
         if (tid < RS_HYP) {
             int total = 0;
+            if (NC > 1) {
 #pragma unroll
-            for (unsigned r = 0; r < RS_CLUSTER; r++) total += *cluster.map_shared_rank(&s_partial[tid], r);
+                for (unsigned r = 0; r < NC; r++) total += *cluster.map_shared_rank(&s_partial[tid], r);
+            } else {
+                total = s_partial[tid];
+            }
             s_total[tid] = total;
             // the iteration bound PCL would compute if this hypothesis became the best one (RandomSampleConsensus::computeModel):
             // evaluated here by 64 threads at once -- pow and log in double on one thread, 15-20 times per frame, were the longest
@@ -307,7 +321,7 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
         }
         __syncthreads();
         const int done = s_state[0];
-        cluster.sync();  // every CTA has consumed the partials before the next round overwrites them
+        cluster_sync();  // every CTA has consumed the partials before the next round overwrites them
         if (done) break;
     }
 
@@ -355,13 +369,17 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
                 s_sums[tid] = t;
             }
         }
-        cluster.sync();
+        cluster_sync();
         // cluster totals and the eigen solve: only the thread that writes the coefficients needs them
         if (rank == 0 && tid == 0) {
             double tot[10];
             for (int q = 0; q < 10; q++) {
                 double t = 0;
-                for (unsigned r = 0; r < RS_CLUSTER; r++) t += *cluster.map_shared_rank(&s_sums[q], r);
+                if (NC > 1) {
+                    for (unsigned r = 0; r < NC; r++) t += *cluster.map_shared_rank(&s_sums[q], r);
+                } else {
+                    t = s_sums[q];
+                }
                 tot[q] = t;
             }
             if (tot[0] >= 4.0) {
@@ -383,7 +401,7 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
                 }
             }
         }
-        cluster.sync();  // the other CTAs keep their partial sums alive until rank 0 has read them
+        cluster_sync();  // the other CTAs keep their partial sums alive until rank 0 has read them
     }
     // final inlier set: selectWithinDistance with the UN-refined coefficients (RansacPlane.cpp:121)
     const float final_lt = cfg.use_refinement ? cfg.refine_lt : thr_lt;
@@ -406,6 +424,29 @@ ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int strid
         out_iterations[frame] = s_state[2];
         for (int q = 0; q < 4; q++) out_coeffs[frame * 4 + q] = outc[q];
     }
+}
+
+#ifndef MLD_RS_MINBLOCKS
+#define MLD_RS_MINBLOCKS 4
+#endif
+__global__ void __cluster_dims__(RS_CLUSTER, 1, 1) __launch_bounds__(RS_THREADS, MLD_RS_MINBLOCKS)
+ransac_cluster_kernel(RansacConfig cfg, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
+                      uint64_t seed, long long frame0, const int* __restrict__ cand_all, const int* __restrict__ cand_count,
+                      float* __restrict__ out_coeffs, unsigned int* __restrict__ out_bits, long long words_per_frame,
+                      int* __restrict__ out_n_inliers, int* __restrict__ out_iterations, int* __restrict__ out_rc) {
+    extern __shared__ float4 rs_dyn_pts[];
+    ransac_frame<RS_CLUSTER>(cfg, pts, stride_f, n, pitch_pts, seed, frame0, cand_all, cand_count, out_coeffs, out_bits, words_per_frame,
+                             out_n_inliers, out_iterations, out_rc, rs_dyn_pts, (long long)blockIdx.y);
+}
+
+__global__ void __launch_bounds__(RS_THREADS, 2)
+ransac_frame_kernel(RansacConfig cfg, const float* __restrict__ pts, int stride_f, long long n, long long pitch_pts,
+                    uint64_t seed, long long frame0, const int* __restrict__ cand_all, const int* __restrict__ cand_count,
+                    float* __restrict__ out_coeffs, unsigned int* __restrict__ out_bits, long long words_per_frame,
+                    int* __restrict__ out_n_inliers, int* __restrict__ out_iterations, int* __restrict__ out_rc) {
+    extern __shared__ float4 rs_dyn_pts[];
+    ransac_frame<1>(cfg, pts, stride_f, n, pitch_pts, seed, frame0, cand_all, cand_count, out_coeffs, out_bits, words_per_frame,
+                    out_n_inliers, out_iterations, out_rc, rs_dyn_pts, (long long)blockIdx.x);
 }
 
 }  // namespace
@@ -434,10 +475,26 @@ cudaError_t mld_launch_ransac(const RansacConfig& cfg, const float* d_pts, int s
         if (e != cudaSuccess) return e;
         if (launches) (*launches)++;
     }
-    dim3 grid(RS_CLUSTER, (unsigned)nframes);
-    ransac_cluster_kernel<<<grid, RS_THREADS, 0, stream>>>(cfg, d_pts, stride_f, n_points, pitch_pts, seed, frame0, cand_all,
-                                                          cand_count, d_coeffs, d_inlier_bits, words_per_frame, d_n_inliers,
-                                                          d_iterations, d_rc);
+    if (nframes >= RS_BATCH_FRAMES) {
+        constexpr size_t smem1 = (size_t)MLD_RANSAC_SAMPLE * sizeof(float4);  // 96 KB: opt in once per device
+        static thread_local int configured_device = -1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (configured_device != dev) {
+            e = cudaFuncSetAttribute(ransac_frame_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem1);
+            if (e != cudaSuccess) return e;
+            configured_device = dev;
+        }
+        ransac_frame_kernel<<<(unsigned)nframes, RS_THREADS, smem1, stream>>>(cfg, d_pts, stride_f, n_points, pitch_pts, seed, frame0, cand_all,
+                                                                            cand_count, d_coeffs, d_inlier_bits, words_per_frame, d_n_inliers,
+                                                                            d_iterations, d_rc);
+    } else {
+        dim3 grid(RS_CLUSTER, (unsigned)nframes);
+        constexpr size_t smem8 = (size_t)((MLD_RANSAC_SAMPLE + RS_CLUSTER - 1) / RS_CLUSTER) * sizeof(float4);
+        ransac_cluster_kernel<<<grid, RS_THREADS, smem8, stream>>>(cfg, d_pts, stride_f, n_points, pitch_pts, seed, frame0, cand_all,
+                                                                  cand_count, d_coeffs, d_inlier_bits, words_per_frame, d_n_inliers,
+                                                                  d_iterations, d_rc);
+    }
     e = cudaGetLastError();
     if (launches) (*launches)++;
     return e;

@@ -123,14 +123,17 @@ def test_set_cloud_fits_plane_and_road_depths_match_oracle():
     assert np.array_equal(plane.getModelCoeffs(), c0)
 
 
-def test_batched_road_sequence_matches_oracle():
+@pytest.mark.parametrize("nframes,F", [(19, 1500), (330, 400)])
+def test_batched_road_sequence_matches_oracle(nframes, F):
+    """19 frames: launches of a few frames each, one 8-CTA cluster per frame (ransac_cluster_kernel); 330 frames: launches of 66
+    frames, one CTA per frame with the whole subsample in its shared memory (ransac_frame_kernel). Same body, same results."""
     import torch
 
     p = O.yaml_params()
     est, orc = PU.make_pair(p, synth.kitti_camera(), KT)
     cfg = synth.default_config()
     n = synth.points_per_frame(cfg)
-    F, nframes, seed = 1500, 19, 4242
+    seed = 4242
     pts = torch.empty((nframes, n, 4), dtype=torch.float32, device="cuda")
     uv = torch.empty((nframes, F, 2), dtype=torch.float64, device="cuda")
     depth = torch.empty((nframes, F), dtype=torch.float64, device="cuda")
@@ -143,7 +146,7 @@ def test_batched_road_sequence_matches_oracle():
     torch.cuda.synchronize()
     pts_h, uv_h = pts.cpu().numpy(), uv.cpu().numpy()
     hist = collections.Counter()
-    for i in (0, 7, 16, 18):
+    for i in (0, 7, 16, nframes - 1):
         rc, c_ref, inl_ref, _ = O.ransac_plane(p, pts_h[i], seed + i)
         assert rc == 0
         c_gpu = coeffs[i].cpu().numpy()
