@@ -212,17 +212,25 @@ __device__ __forceinline__ void ransac_frame(const RansacConfig& cfg, const floa
     const long long j0 = (long long)rank * RS_SLICE;
     long long cnt_ll = M - j0;
     const int slice_n = cnt_ll <= 0 ? 0 : (cnt_ll < RS_SLICE ? (int)cnt_ll : RS_SLICE);
-    for (int q = tid; q < slice_n; q += RS_THREADS) {
-        int raw = sub_raw(fv, j0 + q);
-        F3 p = load_pt(fv, raw);
-        s_pts[q] = make_float4(p.x, p.y, p.z, __int_as_float(raw));
+    // four points per pass: their index chains (hash, 64-bit divisions) and random 12-byte reads are independent, one after the other
+    // a CTA that stages the whole subsample (24 points per thread) spent more time here than scoring its hypotheses
+    for (int q0 = tid; q0 < slice_n; q0 += 4 * RS_THREADS) {
+        int raw[4];
+        F3 p[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) raw[u] = (q0 + u * RS_THREADS < slice_n) ? sub_raw(fv, j0 + q0 + u * RS_THREADS) : 0;
+#pragma unroll
+        for (int u = 0; u < 4; u++) p[u] = load_pt(fv, raw[u]);
+#pragma unroll
+        for (int u = 0; u < 4; u++)
+            if (q0 + u * RS_THREADS < slice_n) s_pts[q0 + u * RS_THREADS] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(raw[u]));
     }
     if (tid == 0) {
         s_state[0] = 0; s_state[1] = 0; s_state[2] = 0; s_state[3] = -2147483647;
         s_k = 1.0;
         s_best[0] = s_best[1] = s_best[2] = s_best[3] = 0.f;
     }
-    __syncthreads();
+    cluster_sync();  // every slice is staged: the hypotheses read their sample points from any CTA's slice
 
     const double cos_eps = cfg.cos_eps;  // cos(M_PI / 18.), evaluated on the host
     const double log_probability = cfg.log_probability;  // log(1 - probability), evaluated on the host
@@ -249,9 +257,15 @@ __device__ __forceinline__ void ransac_frame(const RansacConfig& cfg, const floa
                 long long lo = i0 < i1 ? i0 : i1, hi = i0 < i1 ? i1 : i0;
                 if (i2 >= lo) i2++;
                 if (i2 >= hi) i2++;
-                p0 = load_pt(fv, sub_raw(fv, i0));
-                p1 = load_pt(fv, sub_raw(fv, i1));
-                p2 = load_pt(fv, sub_raw(fv, i2));
+                // sample point i is entry i % RS_SLICE of CTA i / RS_SLICE's staged slice (own or distributed shared memory)
+                auto staged = [&](long long i) {
+                    const int r = (int)(i / RS_SLICE), q = (int)(i - (long long)r * RS_SLICE);
+                    const float4 v = NC > 1 ? *cluster.map_shared_rank(&s_pts[q], (unsigned)r) : s_pts[q];
+                    return F3{v.x, v.y, v.z};
+                };
+                p0 = staged(i0);
+                p1 = staged(i1);
+                p2 = staged(i2);
                 got = sample_good(p0, p1, p2);
             }
             float c[4] = {0.f, 0.f, 0.f, 0.f};
