@@ -525,8 +525,8 @@ def run_gpu(args, rank, local_rank, world):
         tw1 = time.perf_counter()
         ms_total = max_over_ranks(ms_rank)
     est.profileEnable(False)
-    pipelined = est.pipelineFrames()
-    fused = 0 if pipelined else est.fusedChunkFrames()
+    pipelined = False
+    fused = est.fusedChunkFrames()
     per_class, prof_frames = kernel_profile(est, pipelined, fused)
     launches = est.kernelLaunchCount() - launches0
     clocks.stop()
@@ -645,7 +645,10 @@ def run_gpu(args, rank, local_rank, world):
             try:
                 tr = json.loads(traffic_file.read_text())
                 if tr.get("source_hash") != source_hash():
-                    tr = {"stale": f"profiles/traffic.json was taken from sources {tr.get('source_hash')}, running {source_hash()}"}
+                    # a list taken from other sources still ranks the kernels better than overlapping brackets do; its byte counts are dropped
+                    tr = {"stale": f"profiles/traffic.json was taken from sources {tr.get('source_hash')}, running {source_hash()}: "
+                                   "kernel ranking taken from it, traffic not reported",
+                          "share_of_step_ncu": tr.get("share_of_step_ncu", {})}
             except Exception:
                 tr = {}
         shares = {k: v for k, v in tr.get("share_of_step_ncu", {}).items() if k in kernels}
@@ -666,10 +669,11 @@ def run_gpu(args, rank, local_rank, world):
                     "kernel": dom, "peak_source": peak_src, "algorithmic_bytes_per_launch": per_frame_bytes * frames_per_launch,
                     "avg_launch_ms": per_class[dom]["avg_launch_ms"], "frames_per_launch": frames_per_launch,
                     "share_of_step": shares.get(dom) if shares else (per_class[dom]["ms_total"] / sampled_ms if sampled_ms else None),
-                    "share_source": "ncu launch list (serialised), profiles/traffic.json" if shares else "event brackets (overlapping)",
+                    "share_source": ("ncu launch list (serialised), profiles/traffic.json" + (" (of an older build)" if tr.get("stale") else "")) if shares
+                                    else "event brackets (overlapping)",
                     "per_kernel": per_class,
                     "algorithmic_bytes_split": "per frame: project_scatter 16 N (point stream), feature_gather 16 F (feature reads), feature_solve "
-                                               "12 F (result writes); fused_project_gather = project_scatter of one chunk + feature_gather of the "
+                                               "12 F (result writes; its point re-reads are not algorithmic bytes); fused_project_gather = project_scatter of one chunk + feature_gather of the "
                                                "previous one in one launch = 16 N + 16 F. SURVEY.md 8(d)'s 4 W H map term is not charged to a kernel "
                                                "(the epoch-tagged map is never rewritten as a whole); `path` reports both accountings",
                     "path": {"algorithmic_bytes_per_frame": seq.algorithmic_bytes_per_frame(),

@@ -287,16 +287,6 @@ int mld_chunk_frames(const mld_handle* h);
 /* frames per fused K1 + gather launch of device-resident non-road sequences (env MLD_FUSE_CHUNK, default 512), or 0 when
  * the fused pipeline is off (MLD_FUSE=0 or another K2 mode): such sequences then use mld_chunk_frames() like the rest */
 int mld_fused_chunk_frames(const mld_handle* h);
-/* 1 when device-resident sequences run through the persistent pipeline (env MLD_PIPE=1: one launch per sequence, projection
- * and feature estimation as two roles of one grid) instead of the default chunked launches */
-int mld_pipeline_frames(const mld_handle* h);
-/* error flag of the last persistent-pipeline launch (valid once its stream is idle): non-zero when a dependency wait timed
- * out and the launch was abandoned -- the results of that call are then incomplete */
-int mld_pipeline_aborted(const mld_handle* h);
-/* profiling accumulators of the last pipeline launch (env MLD_PIPE_TIMING=1; valid once its stream is idle), SM clock
- * cycles summed over blocks: [0] K1 items, [1] looking for a runnable item (idle + claim latency), [2] unused, [3] window scan +
- * gather, [4] solve, [5] road path, [6] warp path, [7] features that took the warp path */
-int mld_pipeline_counters(const mld_handle* h, int64_t* out8);
 /* largest neighbour count per feature the kernels were built for */
 int mld_neighbor_capacity(void);
 

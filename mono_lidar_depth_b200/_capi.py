@@ -202,9 +202,6 @@ SYMBOLS = {
     "mld_kernel_launch_count": (C.c_int64, [_H]),
     "mld_neighbor_capacity": (C.c_int, []),
     "mld_host_pipeline_stats": (C.c_int, [_H, C.POINTER(C.c_int64)]),
-    "mld_pipeline_frames": (C.c_int, [_H]),
-    "mld_pipeline_aborted": (C.c_int, [_H]),
-    "mld_pipeline_counters": (C.c_int, [_H, C.POINTER(C.c_int64)]),
     "mld_profile_enable": (C.c_int, [_H, C.c_int]),
     "mld_profile_read": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "mld_fused_chunk_frames": (C.c_int, [_H]),

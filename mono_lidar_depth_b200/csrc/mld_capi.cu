@@ -178,14 +178,12 @@ struct mld_handle {
     bool fuse_k1_gather = true;     // K1 of chunk j and the gather of chunk j-1 in one heterogeneous launch (MLD_FUSE=0: off)
     int fuse_chunk = 512;           // frames per fused launch (MLD_FUSE_CHUNK)
     bool fuse_road = true;          // the road / SemanticPlane / external-plane sequences use the fused pipeline too (MLD_FUSE=2: no)
-    bool fuse_serial = false;       // MLD_FUSE_SERIAL=1: solve + overflow pass on the front stream too (no concurrency at all)
-    int k1_persist_per_sm = 0;
-    int k1_persistent_blocks = 0;   // > 0: K1 of a multi-frame chunk runs as a persistent grid of this many blocks (MLD_K1_PERSIST)
     int overlap_slots = 5;          // chunks of a device-resident sequence alternate over this many slots/streams (MLD_OVERLAP). The solve and overflow pass of a chunk are starved by the fused launch that runs beside them and finish near its end; with 3 slots the launch after next waited for them (1.47 M frames/s), 4 / 5 / 6 slots: 1.50 / 1.52 / 1.49 M
     cudaEvent_t ev_fork = nullptr;
     // priority mode: every K1 of a sequence runs on a low-priority stream, every K2 on a high-priority one, so the
     // latency-bound K2 blocks are placed first and the streaming K1 fills what is left
     int overlap_mode = 0;           // 0: whole chunks alternate over slot streams (faster, measured), 1: priority streams
+    int sm_count = 148;
     cudaStream_t st_lo = nullptr, st_hi = nullptr;
     cudaEvent_t ev_join = nullptr;
     long long cur_n = 0;
@@ -194,23 +192,6 @@ struct mld_handle {
     long long prev_n = 0;
     int prev_stride_f = 4;
     Slot slots[MLD_PIPE_SLOTS];
-    // persistent pipeline (mld_pipeline.cu): one launch per device-resident sequence; ring of map / occupancy slots
-    bool use_pipeline = false;      // MLD_PIPE=1: one persistent launch per sequence (mld_pipeline.cu) instead of the chunked launches
-                                    // (fused K1 + gather, solve, overflow pass); measured 2.3x slower on B200, kept as an option
-    int pipe_delay = 64;            // K1 may run this many frames ahead of the feature queue (MLD_PIPE_DELAY; <= ring slots)
-    int pipe_hint = 1;              // evict_first L2 policy on the point stream (MLD_PIPE_HINT)
-    int pipe_bps = 0;               // resident blocks per SM of the persistent grid (MLD_PIPE_BPS; 0 = what fits)
-    int pipe_ring = 0;              // ring slots (MLD_PIPE_RING; 0 = mld_pipeline_ring_slots())
-    int pipe_k1_group = 8;          // consecutive K1 tiles per work item, streamed through two staging buffers (MLD_PIPE_K1_GROUP)
-    int pipe_timing = 0;            // MLD_PIPE_TIMING=1: clock64() accumulators per role / phase (mld_pipeline_counters)
-    int pipe_road_chunk = 512;      // frames per launch when a ground plane is fitted per frame (plane buffers are per chunk)
-    int sm_count = 148;
-    unsigned int* d_ring_maps = nullptr; size_t ring_maps_bytes = 0;
-    unsigned int* d_ring_occ = nullptr;  size_t ring_occ_bytes = 0;
-    int* d_ring_sync = nullptr;          size_t ring_sync_bytes = 0;
-    unsigned ring_epoch = 0;        // epochs consumed by every slot of the ring since its last clear (0 = never cleared)
-    int* h_pipe_flags = nullptr;    // pinned: [0] error flag of the last pipeline launch (read back asynchronously)
-    int* h_pipe_counters = nullptr; // pinned: the 16 sync words of the last launch (ticket, error, profiling accumulators)
     bool semantic_exact = false;    // mld_set_semantic_exact / MLD_SEMANTIC_EXACT=1: PCL's sequential float accumulation order
     bool stats_on = false;          // mld_set_statistics: status histogram of every mld_calculate_depth call
     unsigned long long* d_hist = nullptr;  // 21 counters on the device
@@ -464,8 +445,7 @@ int enqueue_chunk(mld_handle* h, Slot& s, cudaStream_t st, const float* d_pts, l
     int rcm = begin_maps(h, s, frames, n_points, st, mc);
     if (rcm) return rcm;
     if (ev) CK(cudaEventRecord(ev[1], st));
-    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st,
-                                  h->k1_persistent_blocks));
+    CK(mld_launch_project_scatter(h->dp, mc, d_pts, stride_f, n_points, pitch_pts, s.d_maps, h->feature_mode >= 1 ? s.d_occ : nullptr, frames, st));
     if (n_points > 0) h->launches++;
     if (ev) CK(cudaEventRecord(ev[2], st));
     if (two) {
@@ -715,28 +695,8 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     env = getenv("MLD_FUSE");          // "0": separate K1 / gather launches for device-resident non-road sequences too
     if (env) h->fuse_k1_gather = atoi(env) != 0;
     if (env) h->fuse_road = atoi(env) == 1;
-    env = getenv("MLD_FUSE_SERIAL");
-    if (env) h->fuse_serial = atoi(env) != 0;
     env = getenv("MLD_FUSE_CHUNK");
     if (env && atoi(env) > 0) h->fuse_chunk = atoi(env);
-    env = getenv("MLD_PIPE");          // "0": chunked launches instead of the persistent pipeline
-    if (env) h->use_pipeline = atoi(env) != 0;
-    env = getenv("MLD_PIPE_DELAY");
-    if (env && atoi(env) > 0) h->pipe_delay = atoi(env);
-    env = getenv("MLD_PIPE_HINT");
-    if (env) h->pipe_hint = atoi(env) != 0;
-    env = getenv("MLD_PIPE_BPS");
-    if (env && atoi(env) > 0) h->pipe_bps = atoi(env);
-    env = getenv("MLD_PIPE_RING");
-    if (env && atoi(env) >= 4) h->pipe_ring = atoi(env);
-    env = getenv("MLD_PIPE_K1_GROUP");
-    if (env && atoi(env) > 0) h->pipe_k1_group = atoi(env);
-    env = getenv("MLD_PIPE_TIMING");
-    if (env) h->pipe_timing = atoi(env) != 0;
-    env = getenv("MLD_PIPE_ROAD_CHUNK");
-    if (env && atoi(env) > 0) h->pipe_road_chunk = atoi(env);
-    env = getenv("MLD_K1_PERSIST");    // blocks per SM of the persistent K1 grid (0 = one block per tile)
-    if (env && atoi(env) >= 0) h->k1_persist_per_sm = atoi(env);
     env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
     if (env && strcmp(env, "slots") == 0) h->overlap_mode = 0;
     if (env && strcmp(env, "prio") == 0) h->overlap_mode = 1;
@@ -759,13 +719,10 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
         }
     }
     e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaHostAlloc(reinterpret_cast<void**>(&h->h_pipe_flags), 36 * sizeof(int), cudaHostAllocDefault);
     if (e != cudaSuccess) {
         delete h;
         return fail_cuda(nullptr, e, "event creation");
     }
-    memset(h->h_pipe_flags, 0, 36 * sizeof(int));
-    h->h_pipe_counters = h->h_pipe_flags + 4;
     env = getenv("MLD_SEMANTIC_EXACT");
     if (env) h->semantic_exact = atoi(env) != 0;
     env = getenv("MLD_HOST_PACK");
@@ -774,12 +731,10 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env && atof(env) > 0) h->pcie_gbs = atof(env);
     env = getenv("MLD_PACK_THREADS");
     if (env && atoi(env) > 0) h->host_pack_threads = atoi(env);
-    env = getenv("MLD_SOLVE_PRIO");    // "1": slot streams (solve + overflow pass of the fused pipeline) at the highest priority
-    const bool slot_prio = env && atoi(env) != 0;
     for (int i = 0; i < MLD_PIPE_SLOTS; i++) {
         int lo = 0, hi = 0;
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
-        e = cudaStreamCreateWithPriority(&h->slots[i].stream, cudaStreamNonBlocking, slot_prio ? hi : lo);
+        e = cudaStreamCreateWithPriority(&h->slots[i].stream, cudaStreamNonBlocking, lo);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].done, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k1, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->slots[i].ev_k2, cudaEventDisableTiming);
@@ -815,8 +770,6 @@ int mld_destroy(mld_handle* h) {
     cudaFree(h->d_hist);
     if (h->h_hist) cudaFreeHost(h->h_hist);
     cudaFree(h->d_synth_tables);
-    cudaFree(h->d_ring_maps); cudaFree(h->d_ring_occ); cudaFree(h->d_ring_sync);
-    if (h->h_pipe_flags) cudaFreeHost(h->h_pipe_flags);
     for (cudaEvent_t e : h->prof_events) cudaEventDestroy(e);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -894,11 +847,9 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
     int sms = 148;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device) == cudaSuccess && sms > 0) {
         h->overflow_blocks = 2 * sms;
-        h->k1_persistent_blocks = h->k1_persist_per_sm * sms;
         h->sm_count = sms;
     }
     for (auto& sl : h->slots) sl.epoch = 0;  // image size may have changed
-    h->ring_epoch = 0;
     h->initialized = true;
     h->have_cloud = false;
     h->have_prev = false;
@@ -946,15 +897,6 @@ int mld_host_pipeline_stats(const mld_handle* h, int64_t* out4) {
     for (int i = 0; i < 4; i++) out4[i] = h->host_stats[i];
     return MLD_OK;
 }
-int mld_pipeline_frames(const mld_handle* h) { return (h && h->use_pipeline && h->feature_mode == 2 && h->use_tagged_maps) ? 1 : 0; }
-int mld_pipeline_counters(const mld_handle* h, int64_t* out8) {
-    if (!h || !out8 || !h->h_pipe_counters) return MLD_ERR_INVALID_ARG;
-    const unsigned long long* c = reinterpret_cast<const unsigned long long*>(h->h_pipe_counters + 8);
-    for (int i = 0; i < 7; i++) out8[i] = (int64_t)c[i];
-    out8[7] = (int64_t)h->h_pipe_counters[24];  // features that took the warp path
-    return MLD_OK;
-}
-int mld_pipeline_aborted(const mld_handle* h) { return (h && h->h_pipe_flags) ? *reinterpret_cast<volatile int*>(h->h_pipe_flags) : 0; }
 
 static int check_stride(mld_handle* h, int stride_bytes) {
     if (stride_bytes < 16 || stride_bytes % 16 != 0)
@@ -1309,8 +1251,8 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
                                            have_g ? sg->d_ovf : nullptr, have_g ? sg->d_split : nullptr, front, &nl));
         h->launches += nl;
         if (ev) CK(cudaEventRecord(ev[2], front));
-        cudaStream_t s2 = (have_g && !h->fuse_serial) ? sg->stream : front;
-        if (have_g && !h->fuse_serial) {
+        cudaStream_t s2 = have_g ? sg->stream : front;
+        if (have_g) {
             CK(cudaEventRecord(sg->ev_k1, front));
             CK(cudaStreamWaitEvent(sg->stream, sg->ev_k1, 0));
         }
@@ -1341,7 +1283,7 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
                                         sg->d_ovf, overflow_grid(h, *sg), s2));
             CK(cudaMemcpyAsync(sg->h_ovf_seen, sg->d_ovf, sizeof(int), cudaMemcpyDeviceToHost, s2));
             if (ev) CK(cudaEventRecord(ev[5], s2));
-            if (!h->fuse_serial) {  // the overflow pass was the slot's last reader: clear its occupancy bitmaps for the next chunk here
+            {  // the overflow pass was the slot's last reader: clear its occupancy bitmaps for the next chunk here
                 const size_t ob = (size_t)chunk * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int);
                 CK(cudaMemsetAsync(sg->d_occ, 0, std::min(ob, sg->occ_bytes), s2));
                 sg->occ_clean_bytes = std::min(ob, sg->occ_bytes);
@@ -1357,99 +1299,6 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
     for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(st, h->slots[i].done, 0));
     CK(cudaEventRecord(h->ev_join, front));
     CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-    h->have_cloud = false;
-    return MLD_OK;
-}
-
-// Device-resident sequence through the persistent pipeline (mld_pipeline.cu): ONE launch for the whole sequence when no plane
-// has to be fitted; with a per-frame ground plane (RANSAC / SemanticPlane) the sequence is cut into chunks whose planes are fitted
-// on a slot stream while the previous chunk's launch runs. Profiling brackets: [1,2] = the pipeline launch (class 1).
-static int process_frames_device_pipeline(mld_handle* h, const float* pts, int64_t n_points, int64_t frame_pitch_points, int stride_f,
-                                          const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, cudaStream_t st,
-                                          bool use_road, uint64_t seed, float* d_plane_coeffs_out, const PlaneSrc* src) {
-    const int R = h->pipe_ring > 0 ? h->pipe_ring : mld_pipeline_ring_slots();
-    const size_t WH = (size_t)h->dp.W * (size_t)h->dp.H;
-    const size_t OW = (size_t)occ_words_per_frame(h->dp.W, h->dp.H);
-    bool fresh = false;
-    CK(ensure(h->d_ring_maps, h->ring_maps_bytes, (size_t)R * WH * sizeof(unsigned int), &fresh));
-    CK(ensure(h->d_ring_occ, h->ring_occ_bytes, (size_t)R * OW * sizeof(unsigned int)));
-    CK(ensure(h->d_ring_sync, h->ring_sync_bytes, mld_pipeline_sync_bytes(R)));
-    if (fresh) h->ring_epoch = 0;
-    const int bps = h->pipe_bps > 0 ? h->pipe_bps : mld_pipeline_blocks_per_sm();
-    const int grid = bps * h->sm_count;
-    const long long words = (n_points + 31) / 32;
-    const bool fit_planes = use_road && !(src && src->kind == PlaneSrc::EXTERNAL);
-    const int64_t chunk = fit_planes ? std::min<int64_t>(h->pipe_road_chunk, nframes) : std::min<int64_t>(nframes, 1 << 20);
-    const int64_t nchunks = (nframes + chunk - 1) / chunk;
-    if (fit_planes) {
-        for (int i = 0; i < 2; i++) {
-            int rc = slot_reserve(h, h->slots[i], std::max<int64_t>(n_points, 1), stride_f * 4, F, (int)chunk, false, true);
-            if (rc) return rc;
-        }
-        CK(cudaEventRecord(h->ev_fork, st));
-        for (int i = 0; i < 2; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
-    }
-    for (int64_t j = 0; j < nchunks; j++) {
-        const int64_t f0 = j * chunk;
-        const int64_t c = std::min<int64_t>(chunk, nframes - f0);
-        const float* cp = pts + f0 * frame_pitch_points * stride_f;
-        const float* coeffs = nullptr;
-        const unsigned int* bits = nullptr;
-        if (use_road && !fit_planes) {
-            coeffs = src->d_coeffs + f0 * 4;
-            bits = src->d_bits + f0 * words;
-        } else if (fit_planes) {
-            Slot& sp = h->slots[j & 1];
-            // the slot's plane buffers are free once the launch of chunk j - 2 has finished reading them
-            if (j >= 2) CK(cudaStreamWaitEvent(sp.stream, sp.done, 0));
-            float* cdst = d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : sp.d_coeffs;
-            int nlp = 0;
-            if (src && src->kind == PlaneSrc::SEMANTIC) {
-                CK(ensure(sp.d_sem, sp.sem_bytes, mld_semantic_state_bytes((int)c)));
-                unsigned char* fl = nullptr;
-                int rcs = sem_flags(h, sp, n_points, c, &fl);
-                if (rcs) return rcs;
-                CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
-                                             stride_f, n_points, frame_pitch_points, src->d_labels + f0 * (int64_t)src->label_w * src->label_h, (int)c,
-                                             sp.d_sem, cdst, sp.d_bits, words, sp.d_small, src->d_rc_out ? src->d_rc_out + f0 : sp.d_small + 2 * c,
-                                             sp.stream, &nlp, fl, fl ? 1 : 0));
-            } else {
-                CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, (int)c, seed, f0, sp.d_scratch, cdst,
-                                     sp.d_bits, words, sp.d_small, sp.d_small + c, sp.d_small + 2 * c, sp.stream, &nlp));
-            }
-            h->launches += nlp;
-            CK(cudaEventRecord(sp.ev_k1, sp.stream));
-            CK(cudaStreamWaitEvent(st, sp.ev_k1, 0));
-            coeffs = cdst;
-            bits = sp.d_bits;
-        }
-        const unsigned uses = (unsigned)((c + R - 1) / R);
-        if (h->ring_epoch == 0 || h->ring_epoch + uses > MLD_TAG_MAX_EPOCH) {
-            CK(cudaMemsetAsync(h->d_ring_maps, 0xFF, h->ring_maps_bytes, st));
-            h->ring_epoch = 0;
-        }
-        cudaEvent_t* ev = nullptr;
-        int rcp = prof_acquire(h, (int)c, &ev);
-        if (rcp) return rcp;
-        if (ev) {
-            CK(cudaEventRecord(ev[0], st));
-            CK(cudaEventRecord(ev[1], st));
-        }
-        int nl = 0;
-        CK(mld_launch_depth_pipeline(h->dp, cp, stride_f, n_points, frame_pitch_points, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F,
-                                     d_status + f0 * (int64_t)F, c, h->d_ring_maps, h->d_ring_occ, R, h->ring_epoch, h->d_ring_sync, coeffs, bits,
-                                     words, h->kcap, h->pipe_delay, h->pipe_hint, h->pipe_timing, h->pipe_k1_group, grid, st, &nl));
-        h->ring_epoch += uses;
-        h->launches += nl;
-        if (ev) {
-            for (int q = 2; q < MLD_PROF_EVENTS; q++) CK(cudaEventRecord(ev[q], st));
-            h->prof_used++;
-        }
-        if (fit_planes) CK(cudaEventRecord(h->slots[j & 1].done, st));
-    }
-    // error flag of the (last) launch: read back asynchronously, reported by mld_pipeline_aborted() once the stream is idle
-    CK(cudaMemcpyAsync(h->h_pipe_flags, h->d_ring_sync + 1, sizeof(int), cudaMemcpyDeviceToHost, st));
-    if (h->pipe_timing) CK(cudaMemcpyAsync(h->h_pipe_counters, h->d_ring_sync, 32 * sizeof(int), cudaMemcpyDeviceToHost, st));
     h->have_cloud = false;
     return MLD_OK;
 }
@@ -1479,7 +1328,7 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
     // MLD_FUSE=2 restricts the fused pipeline to the non-road path
     const bool fused_ok = h->fuse_k1_gather && (!(use_road || src) || h->fuse_road) && h->feature_mode == 2 && h->overlap_slots >= 2 && F > 0 &&
-                          n_points > 0 && !(h->fuse_serial && use_road);
+                          n_points > 0;
     const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(fused_ok ? h->fuse_chunk : h->chunk_frames,
                                                                   std::max<int64_t>(8, (nframes + h->overlap_slots - 1) / h->overlap_slots)));
     const int64_t nchunks = (nframes + chunk - 1) / chunk;
@@ -1492,10 +1341,6 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
-    if (h->use_pipeline && h->feature_mode == 2 && F > 0 && n_points > 0 && nframes > 0 && n_points <= (long long)(MLD_TAG_IDX_MASK + 1u) &&
-        h->use_tagged_maps)
-        return process_frames_device_pipeline(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, st, use_road,
-                                              seed, d_plane_coeffs_out, src);
     if (fused_ok && nchunks >= 2 && nslots >= 2)
         return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st,
                                            use_road, seed, d_plane_coeffs_out, src);

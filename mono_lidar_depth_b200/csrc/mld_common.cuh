@@ -135,20 +135,6 @@ __device__ __forceinline__ float4 ld_stream_f4(const float* p) {
     return v;
 }
 
-// the same load with an L2 eviction-priority policy (createpolicy) attached
-__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
-    unsigned long long pol;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
-    return pol;
-}
-__device__ __forceinline__ float4 ld_stream_f4_hint(const float* p, unsigned long long policy) {
-    float4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                 : "l"(p), "l"(policy));
-    return v;
-}
-
 __device__ __forceinline__ double shfl_xor_d(double v, int m) { return __shfl_xor_sync(MLD_FULL_MASK, v, m); }
 
 __device__ __forceinline__ double warp_sum_d(double v) {

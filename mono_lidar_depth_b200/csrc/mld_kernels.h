@@ -14,7 +14,7 @@ void mld_setup_prefilter(DevParams& P);
 // d_occ: occupancy bitmaps (occ_words_per_row(W) * H words per frame, zeroed by the caller) or nullptr
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
-                                       cudaStream_t stream, int persistent_blocks = 0);
+                                       cudaStream_t stream);
 // visible-order compaction: _pointIndex, _points_cs_image_visible (2 x nvis), camera-frame depth
 size_t mld_visible_scratch_bytes(long long n);
 cudaError_t mld_launch_visible_compact(const DevParams& P, const float* d_pts, int stride_f, long long n, void* d_scratch, long long capacity,
@@ -59,16 +59,6 @@ cudaError_t mld_launch_feature_solve(const DevParams& P, const MapCode& mc, cons
                                      long long words_per_frame, int nframes, int* d_overflow_list, int* d_overflow_count, void* d_scratch,
                                      cudaStream_t stream, int* launches, cudaEvent_t* ev_after_solve = nullptr);
 
-// The whole batched path as one persistent kernel (mld_pipeline.cu): K1 tiles and feature blocks are work items of one grid,
-// a frame's features run `delay` frames behind its projection so that map, occupancy and points are still in L2.
-int mld_pipeline_ring_slots(void);
-size_t mld_pipeline_sync_bytes(int R);
-int mld_pipeline_blocks_per_sm(void);
-cudaError_t mld_launch_depth_pipeline(const DevParams& P, const float* d_pts, int stride_f, long long n_points, long long pitch_pts,
-                                      const double* d_uv, int F, double* d_depth, int* d_status, long long nframes,
-                                      unsigned int* d_map_ring, unsigned int* d_occ_ring, int R, unsigned int epoch0, int* d_sync,
-                                      const float* d_plane_coeffs, const unsigned int* d_inlier_bits, long long words_per_frame, int kcap,
-                                      int delay, int hint, int timing, int k1_group, int grid_blocks, cudaStream_t stream, int* launches);
 
 // K4 (mld_ransac.cu): per-frame ground-plane RANSAC.
 struct RansacConfig {

@@ -28,46 +28,6 @@ project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, i
     k1_tile(P, mc, pts, stride_f, n, pitch_pts, maps, occ, blockIdx.y, (int)blockIdx.x);
 }
 
-// Persistent variant: gridDim.x blocks loop over the (frame, tile) pairs of the chunk with the next tile's loads
-// already in flight. Launched with a grid of (SM count x blocks-per-SM) it holds only part of every SM for the
-// whole chunk, so the latency-bound K2 blocks of the previous chunk (other stream) stay co-resident with the
-// DRAM-bound stream instead of queueing behind a full-machine grid.
-__global__ void __launch_bounds__(K1_THREADS)
-project_scatter_persistent_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
-                                  unsigned int* __restrict__ maps, unsigned int* __restrict__ occ, int tiles_per_frame, int total_tiles) {
-    const int occ_pitch = occ_tiles_x(P.W);
-    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
-    const int step = K1_THREADS * stride_f;
-    auto load_tile = [&](int t, float4 (&q)[K1_PPT]) {
-        const int frame = t / tiles_per_frame, tile = t - frame * tiles_per_frame;
-        const int base = tile * (K1_THREADS * K1_PPT) + threadIdx.x;
-        const float* src = pts + ((size_t)frame * (size_t)pitch_pts + (size_t)base) * (size_t)stride_f;
-#pragma unroll
-        for (int j = 0; j < K1_PPT; j++) {
-            if (base + j * K1_THREADS < n)
-                q[j] = ld_stream_f4(src + j * step);
-            else
-                q[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-    };
-    int t = blockIdx.x;
-    if (t >= total_tiles) return;
-    float4 cur[K1_PPT], nxt[K1_PPT];
-    load_tile(t, cur);
-    while (true) {
-        const int tn = t + gridDim.x;
-        if (tn < total_tiles) load_tile(tn, nxt);
-        const int frame = t / tiles_per_frame, tile = t - frame * tiles_per_frame;
-        unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-        unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
-        scatter_points<false>(P, cur, tile * (K1_THREADS * K1_PPT) + threadIdx.x, n, hi, map, ob, occ_pitch);
-        if (tn >= total_tiles) break;
-#pragma unroll
-        for (int j = 0; j < K1_PPT; j++) cur[j] = nxt[j];
-        t = tn;
-    }
-}
-
 // debug view: Transform_Cloud_LidarToCamera's visibility cull (no z > 0 test, DepthEstimator.cpp:184-207)
 // and the camera-frame coordinates (_points_cs_camera). Not on the hot path.
 __global__ void visible_debug_kernel(DevParams P, const float* __restrict__ pts, int stride_f, long long n,
@@ -264,15 +224,9 @@ void mld_setup_prefilter(DevParams& P) {
 
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
-                                       cudaStream_t stream, int persistent_blocks) {
+                                       cudaStream_t stream) {
     if (n <= 0 || nframes <= 0) return cudaSuccess;
     if (n > 0x7fffffffLL / 8) return cudaErrorInvalidValue;  // 32-bit point indexing inside a frame
-    const long long tiles = (n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT);
-    if (persistent_blocks > 0 && tiles * nframes > persistent_blocks && tiles * nframes < 0x7fffffffLL) {
-        project_scatter_persistent_kernel<<<persistent_blocks, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps,
-                                                                                        d_occ, (int)tiles, (int)(tiles * nframes));
-        return cudaGetLastError();
-    }
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
     project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps, d_occ);
     return cudaGetLastError();

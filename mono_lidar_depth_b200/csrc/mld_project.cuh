@@ -137,12 +137,10 @@ __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 
 // one K1 tile: K1_THREADS x K1_PPT consecutive points of one frame, starting at point tile * K1_THREADS * K1_PPT of the cloud at
 // `cloud` (n points), scattered into `map` / `ob` (the frame's pixel map and occupancy bitmap). STRIDE_F = 4 (float4) or 8
 // (pcl::PointXYZI) makes the eight load offsets immediates; a tile that lies completely inside the frame (all but the last)
-// loads without per-point bounds predicates. HINT: the loads carry an L2 eviction-priority policy (evict_first: the stream is
-// read once, the pixel maps it is scattered into should stay resident -- the persistent pipeline, mld_pipeline.cu).
-template <int STRIDE_F, bool HINT>
+// loads without per-point bounds predicates.
+template <int STRIDE_F>
 __device__ __forceinline__ void k1_tile_at(const DevParams& P, unsigned int hi, const float* __restrict__ cloud, int stride_rt, int n,
-                                           unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int tile,
-                                           unsigned long long policy) {
+                                           unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int tile) {
     const int stride_f = STRIDE_F > 0 ? STRIDE_F : stride_rt;
     const int occ_pitch = occ_tiles_x(P.W);
     const int base = tile * (K1_THREADS * K1_PPT) + threadIdx.x;
@@ -152,13 +150,13 @@ __device__ __forceinline__ void k1_tile_at(const DevParams& P, unsigned int hi, 
     float4 p[K1_PPT];
     if ((tile + 1) * (K1_THREADS * K1_PPT) <= n) {  // uniform per block
 #pragma unroll
-        for (int j = 0; j < K1_PPT; j++) p[j] = HINT ? ld_stream_f4_hint(src + j * step, policy) : ld_stream_f4(src + j * step);
+        for (int j = 0; j < K1_PPT; j++) p[j] = ld_stream_f4(src + j * step);
         scatter_points<true>(P, p, base, n, hi, map, ob, occ_pitch);
     } else {
 #pragma unroll
         for (int j = 0; j < K1_PPT; j++) {
             if (base + j * K1_THREADS < n)
-                p[j] = HINT ? ld_stream_f4_hint(src + j * step, policy) : ld_stream_f4(src + j * step);
+                p[j] = ld_stream_f4(src + j * step);
             else
                 p[j] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -175,7 +173,7 @@ __device__ __forceinline__ void k1_tile_s(const DevParams& P, const MapCode& mc,
     unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
     const float* cloud = pts + (size_t)frame * (size_t)pitch_pts * (size_t)stride_f;
     const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
-    k1_tile_at<STRIDE_F, false>(P, hi, cloud, stride_rt, n, map, ob, tile, 0ull);
+    k1_tile_at<STRIDE_F>(P, hi, cloud, stride_rt, n, map, ob, tile);
 }
 
 __device__ __forceinline__ void k1_tile(const DevParams& P, const MapCode& mc, const float* __restrict__ pts, int stride_f, int n,

@@ -522,21 +522,6 @@ class DepthEstimator:
         self._check(self._lib.mld_host_pipeline_stats(self._h, out))
         return dict(zip(("h2d_bytes", "d2h_bytes", "frames_packed", "frames_direct"), [int(x) for x in out]))
 
-    def pipelineFrames(self) -> bool:
-        """True when device-resident sequences run through the persistent pipeline (one launch per sequence)."""
-        return bool(self._lib.mld_pipeline_frames(self._h))
-
-    def pipelineAborted(self) -> bool:
-        """Error flag of the last persistent-pipeline launch; call after synchronising its stream."""
-        return bool(self._lib.mld_pipeline_aborted(self._h))
-
-    def pipelineCounters(self):
-        """clock64() accumulators of the last pipeline launch (MLD_PIPE_TIMING=1), see mld_pipeline_counters."""
-        out = (C.c_int64 * 8)()
-        self._check(self._lib.mld_pipeline_counters(self._h, out))
-        names = ("k1", "idle_claim", "unused", "gather", "solve", "road", "warp_path", "warp_path_features")
-        return dict(zip(names, [int(x) for x in out]))
-
     def chunkFrames(self) -> int:
         return int(self._lib.mld_chunk_frames(self._h))
 

@@ -6,7 +6,7 @@ timeout 900 python -m pytest tests/test_parity_gpu.py tests/test_ref_golden.py -
 export MLD_BENCH_CPU_SECONDS=0 MLD_BENCH_E2E_FRAMES=16 MLD_BENCH_NO_OTHERS=1
 python bench.py --steps 5 --warmup 3 2>/dev/null | tail -1 > gpurun_out/bench_$TAG.json
 python -c "import json; d=json.load(open('gpurun_out/bench_$TAG.json')); print('$TAG fps', round(d['value']), 'ms', round(d['ms_per_step'],3), 'parity', d['parity']['status_exact'], {k:round(x['avg_launch_ms'],4) for k,x in d['roofline']['per_kernel'].items() if isinstance(x,dict) and x.get('avg_launch_ms')})"
-MLD_BENCH_FRAMES=2048 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 20 -c 45 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 > /dev/null 2>&1
+MLD_BENCH_FRAMES=2560 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 20 -c 45 --csv --log-file gpurun_out/launches_$TAG.csv python bench.py --steps 2 --warmup 3 > /dev/null 2>&1
 python scripts/launch_list_summary.py gpurun_out/launches_$TAG.csv gpurun_out/traffic_$TAG.json 512 "$TAG" > /dev/null
 python -c "
 import json; t=json.load(open('gpurun_out/traffic_$TAG.json'))

@@ -516,7 +516,6 @@ def test_fused_and_separate_launch_pipelines_agree(monkeypatch):
     st = torch.cuda.current_stream().cuda_stream
     for F, nframes, chunk in ((700, 50, 8), (2000, 29, 512), (9000, 31, 8)):
         outs = []
-        monkeypatch.setenv("MLD_PIPE", "0")  # the chunked pipelines (the persistent pipeline has its own tests below)
         for fuse in ("1", "0"):
             monkeypatch.setenv("MLD_FUSE", fuse)
             monkeypatch.setenv("MLD_FUSE_CHUNK", str(chunk))
@@ -560,43 +559,33 @@ def _run_sequence(est, cfg, seed, nframes, F, road=False, passes=1, stride=16, n
         est.processFramesDevice(src.data_ptr(), nn, n, stride, uv.data_ptr(), F, depth.data_ptr(), status.data_ptr(), nframes, road=road,
                                 seed=seed, d_plane_coeffs_out=coeffs.data_ptr() if road else 0, stream=st)
     torch.cuda.synchronize()
-    assert not est.pipelineAborted()
     return depth.cpu().numpy(), status.cpu().numpy(), coeffs.cpu().numpy(), pts, uv
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["short", "ring_reuse", "ragged_features", "xyzi32", "ragged_cloud", "road", "small_ring"])
-def test_persistent_pipeline_matches_chunked_launches(monkeypatch, case):
-    """The persistent pipeline (one launch per sequence, K1 tiles and feature blocks as work items of one grid; the default)
-    against the chunked launches of round 1 (MLD_PIPE=0), bit for bit: sequences shorter than the pipeline delay, longer than
-    the map ring (slot reuse inside one launch and across calls), feature counts that are not a multiple of the block size,
-    32-byte PointXYZI records, a cloud whose size is not a multiple of the tile, the road path with a RANSAC plane per frame,
-    and a 4-slot ring with delay 2 (every K1 tile waits for its slot)."""
+@pytest.mark.parametrize("case", ["short", "slot_reuse", "ragged_features", "xyzi32", "ragged_cloud", "road"])
+def test_fused_pipeline_matches_separate_launches(monkeypatch, case):
+    """The fused pipeline (K1 of chunk j + gather of chunk j-1 in one launch, per-class survivor lists, solve and overflow pass on
+    the slot streams, five slots) against separate launches per chunk (MLD_FUSE=0), bit for bit, with 16-frame chunks so that
+    short sequences still span many launches: a sequence shorter than one chunk, slot reuse inside one call and across calls,
+    feature counts that are not a multiple of the block size, 32-byte PointXYZI records, a cloud whose size is not a multiple
+    of the tile, and the road path with a RANSAC plane per frame."""
     p = O.yaml_params()
     road = case == "road"
     p.do_use_ransac_plane = 1 if road else 0
     cfg = synth.default_config(road=road)
-    nframes, F, passes, stride, nov = {"short": (5, 300, 1, 16, None), "ring_reuse": (150, 512, 2, 16, None),
+    nframes, F, passes, stride, nov = {"short": (5, 300, 1, 16, None), "slot_reuse": (150, 512, 2, 16, None),
                                        "ragged_features": (40, 2000 + 77, 1, 16, None), "xyzi32": (40, 700, 1, 32, None),
-                                       "ragged_cloud": (40, 700, 1, 16, 120000 - 517), "road": (70, 1500, 2, 16, None),
-                                       "small_ring": (60, 900, 2, 16, None)}[case]
-    if case == "small_ring":
-        monkeypatch.setenv("MLD_PIPE_RING", "4")
-        monkeypatch.setenv("MLD_PIPE_DELAY", "2")
+                                       "ragged_cloud": (40, 700, 1, 16, 120000 - 517), "road": (70, 1500, 2, 16, None)}[case]
+    monkeypatch.setenv("MLD_FUSE_CHUNK", "16")
+    monkeypatch.setenv("MLD_CHUNK_FRAMES", "16")
     outs = []
-    for pipe in ("1", "0"):
-        monkeypatch.setenv("MLD_PIPE", pipe)
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("MLD_FUSE", fuse)
         est, _ = kitti_pair(p)
-        assert est.pipelineFrames() == (pipe == "1")
         outs.append(_run_sequence(est, cfg, 91, nframes, F, road=road, passes=passes, stride=stride, n_override=nov))
     assert np.array_equal(outs[0][1], outs[1][1]), case
-    if road:
-        # a window of exactly 9 points fits a thread's slab here (sequential sums, like the oracle) but takes the warp-per-feature
-        # overflow pass in the chunked launches (lane-strided partial sums): the M-estimator's depth differs in the last bits
-        ok = np.abs(outs[0][0] - outs[1][0]) <= 1e-9 * np.abs(outs[1][0])
-        assert ok.all(), (case, int((~ok).sum()))
-    else:
-        assert np.array_equal(outs[0][0], outs[1][0]), case
+    assert np.array_equal(outs[0][0], outs[1][0]), case
     assert np.array_equal(outs[0][2], outs[1][2]), case
     assert outs[0][1].min() >= 1  # every feature got a status
     if road:
@@ -604,42 +593,45 @@ def test_persistent_pipeline_matches_chunked_launches(monkeypatch, case):
 
 
 @pytest.mark.gpu
-def test_persistent_pipeline_against_oracle(monkeypatch):
-    """Frames of a pipelined sequence checked against the oracle directly (status exact, depth 1e-4), including frames at
-    both ends of the sequence and across a ring wrap."""
-    monkeypatch.setenv("MLD_PIPE", "1")
-    monkeypatch.setenv("MLD_PIPE_RING", "32")
+def test_fused_pipeline_against_oracle(monkeypatch):
+    """Frames of a fused-pipeline sequence checked against the oracle directly (status exact, depth 1e-4), including frames at
+    both ends of the sequence and on both sides of chunk boundaries and of the first slot reuse."""
+    monkeypatch.setenv("MLD_FUSE_CHUNK", "8")
     p = O.yaml_params()
     p.do_use_ransac_plane = 0
     est, orc = kitti_pair(p)
-    assert est.pipelineFrames()
+    assert est.fusedChunkFrames() == 8
     cfg = synth.default_config()
     d, s, _, pts, uv = _run_sequence(est, cfg, 123, 70, 2000)
-    for i in (0, 1, 31, 32, 33, 68, 69):
+    for i in (0, 1, 7, 8, 39, 40, 41, 68, 69):
         orc.set_cloud(pts[i].cpu().numpy())
         d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy())
-        PU.assert_depth_status_equal(d[i], s[i], d_ref, s_ref, f"pipeline frame {i}")
+        PU.assert_depth_status_equal(d[i], s[i], d_ref, s_ref, f"fused pipeline frame {i}")
     assert (s == 1).mean() > 0.2  # the calibrated workload (~30 % Success): the geometry tail is exercised
 
 
 @pytest.mark.gpu
-def test_persistent_pipeline_warp_path_for_full_windows(monkeypatch):
-    """Windows with more points than a thread's slab (8) take the warp-per-feature path inside the feature block: a 20 x 20
-    pixel window over the dense 128-beam sweep overflows nearly every feature; compared with the chunked launches."""
+def test_full_windows_take_the_bigger_slabs_and_the_warp_path(monkeypatch):
+    """Windows with more points than the main solve kernel's slab (9) go to its 16-entry instantiation, fuller ones to the
+    warp-per-feature overflow pass: a 20 x 20 pixel window over the dense 128-beam sweep overflows nearly every feature. Fused
+    pipeline against separate launches, and sampled frames against the oracle."""
     p = O.yaml_params()
     p.do_use_ransac_plane = 0
     p.pixelarea_search_witdh = 20
     p.pixelarea_search_height = 20
     cfg = synth.default_config(dense=True)
     outs = []
-    for pipe in ("1", "0"):
-        monkeypatch.setenv("MLD_PIPE", pipe)
-        est = DepthEstimator()
-        est.InitConfig(PU.params_from_c(p))
-        est.Initialize(synth.dense_camera(), synth.KITTI_T_LIDAR_TO_CAM)
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("MLD_FUSE", fuse)
+        est, orc = PU.make_pair(p, synth.dense_camera(), synth.KITTI_T_LIDAR_TO_CAM)
         outs.append(_run_sequence(est, cfg, 5, 6, 3000))
     assert np.array_equal(outs[0][1], outs[1][1]) and np.array_equal(outs[0][0], outs[1][0])
     assert (outs[0][1] == 1).sum() > 100
+    d, s, _, pts, uv = outs[0]
+    for i in (0, 5):
+        orc.set_cloud(pts[i].cpu().numpy())
+        d_ref, s_ref = orc.calculate_depth(uv[i].cpu().numpy())
+        PU.assert_depth_status_equal(d[i], s[i], d_ref, s_ref, f"full windows frame {i}")
 
 
 @pytest.mark.gpu
