@@ -57,6 +57,10 @@ struct DevParams {
     // G*(|x|+|y|+|z|)+H each. A point is dropped without any FP64 work only when one of the exact
     // visibility tests is violated by more than that bound.
     float pf_g[5][3], pf_h[5], pf_G[5], pf_H[5];
+    // per-frame pitches of the map slots, precomputed (K1 used to derive them per thread: 4 % of its instructions, ncu r2o)
+    int map_cells;  // W * H
+    int occ_words;  // occ_words_per_frame(W, H)
+    int occ_tx;     // occ_tiles_x(W)
 };
 
 // pixel-map cell encoding. Tagged mode (clouds of <= 2^18 points): key = (tag << 18) | raw index

@@ -85,8 +85,8 @@ __device__ __forceinline__ void gather_block(const DevParams& P, const MapCode& 
     const int fi = bx * SBT_A + tid;
     const bool valid = fi < F;
     const long long o = frame * (long long)F + fi;
-    const unsigned int* map = maps + frame * (long long)P.W * (long long)P.H;
-    const unsigned int* occ = occs + frame * occ_words_per_frame(P.W, P.H);
+    const unsigned int* map = maps + frame * (long long)P.map_cells;
+    const unsigned int* occ = occs + frame * (long long)P.occ_words;
     int* aux = s_aux + tid;
 
     if (P.set_all_zero) {  // DepthEstimator.cpp:448-453
@@ -200,8 +200,8 @@ feature_gather_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, in
 
 // ---- K1 of one chunk and K2a of the previous chunk in ONE launch ------------------------------------------------
 // Both are latency bound and independent of each other (different map slots); on separate streams the hardware runs
-// them mostly back to back because K1's grid fills every SM. Here every `period`-th block is a gather block, so the two
-// kinds are co-resident in a fixed ratio for the whole launch and cover each other's memory stalls.
+// them mostly back to back because K1's grid fills every SM. Here a frame's gather blocks follow its K1 tiles in launch order,
+// so the two kinds are co-resident in a fixed ratio for the whole launch and cover each other's memory stalls.
 struct FusedK1 {
     MapCode mc;
     const float* pts;
@@ -234,25 +234,23 @@ static_assert(SBT_A == K1_THREADS, "the fused launch uses one block size for bot
 #ifndef MLD_FUSED_MINBLOCKS
 #define MLD_FUSED_MINBLOCKS 8
 #endif
+// grid = (K1 tiles per frame + gather blocks per frame, frames): block (x, y) is K1 tile x of frame y of the new chunk or gather
+// block x - tiles of frame y of the previous chunk, so a frame's 16 gather blocks follow its 118 K1 tiles in launch order (the two
+// roles stay co-resident in that ratio) and the role costs two compares. (Round 2 before this: a 1-D grid with every `period`-th
+// block a gather block; the three integer divisions that took a block to its role and frame were 8 % of the kernel's warp
+// instructions, ncu r2o.)
 __global__ void __launch_bounds__(SBT_A, MLD_FUSED_MINBLOCKS)
-fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g, int k1_blocks, int g_blocks, int period) {
-#ifdef MLD_FUSED_PAD_SMEM
-    __shared__ int s_pad[MLD_FUSED_PAD_SMEM / 4];  // experiment: fewer resident blocks per SM
-    if (period < 0) s_pad[threadIdx.x] = period;
-    if (period < -1) a.maps[0] = s_pad[(threadIdx.x + 1) % 32];
-#endif
-    const int b = (int)blockIdx.x;
-    const int gi = b / period;
-    if (b % period == period - 1 && gi < g_blocks) {  // uniform per block
-        const int frame = gi / g.blocks_per_frame;
-        gather_block(P, g.mc, g.pts, stride_f, g.pitch_pts, g.maps, g.occs, g.uv, g.F, g.depth, g.status, g.overflow_list, g.overflow_count,
-                     g.surv_rec, g.surv_idx, g.class_count, g.cap, gi - frame * g.blocks_per_frame, (long long)frame);
+fused_project_gather_kernel(DevParams P, int stride_f, FusedK1 a, FusedGather g, int frames_k1, int frames_g) {
+    const int x = (int)blockIdx.x, frame = (int)blockIdx.y;
+    if (x >= a.tiles_per_frame) {  // uniform per block
+        const int gb = x - a.tiles_per_frame;
+        if (frame < frames_g && gb < g.blocks_per_frame)
+            gather_block(P, g.mc, g.pts, stride_f, g.pitch_pts, g.maps, g.occs, g.uv, g.F, g.depth, g.status, g.overflow_list, g.overflow_count,
+                         g.surv_rec, g.surv_idx, g.class_count, g.cap, gb, (long long)frame);
         return;
     }
-    const int ki = b - min(g_blocks, gi);  // gather blocks with a smaller block index: min(g_blocks, b / period)
-    if (ki >= k1_blocks) return;
-    const int frame = ki / a.tiles_per_frame;
-    k1_tile(P, a.mc, a.pts, stride_f, a.n, a.pitch_pts, a.maps, a.occ, (unsigned int)frame, ki - frame * a.tiles_per_frame);
+    if (frame >= frames_k1) return;
+    k1_tile(P, a.mc, a.pts, stride_f, a.n, a.pitch_pts, a.maps, a.occ, (unsigned int)frame, x);
 }
 
 // ---- K2b ------------------------------------------------------------------------------------------
@@ -589,14 +587,12 @@ cudaError_t mld_launch_fused_project_gather(const DevParams& P, int stride_f, co
         g = FusedGather{mc_g, d_pts_g, pitch_pts, d_maps_g, d_occ_g, d_uv_g, F, d_depth_g, d_status_g, d_overflow_list, d_overflow_count,
                         L.surv_rec, L.surv_idx, L.class_count, features, (int)gbpf};
     }
-    // one gather block after every (period - 1) K1 blocks; when there are fewer K1 blocks than that the gather blocks simply
-    // come every second block and the K1 blocks run out first
-    int period = k1_blocks == 0 ? 1 : 2;
-    if (g_blocks > 0 && k1_blocks / g_blocks >= 1) period = (int)std::min<long long>(k1_blocks / g_blocks + 1, 1 << 20);
-    // every block index must map to a role: gather blocks sit at b = period*gi + period-1, so the grid must reach the last one
-    const long long need = std::max(k1_blocks + g_blocks, g_blocks > 0 ? (long long)period * g_blocks : 0);
-    if (need > 0x7fffffffLL) return cudaErrorInvalidValue;
-    fused_project_gather_kernel<<<(unsigned)need, SBT_A, 0, stream>>>(P, stride_f, a, g, (int)k1_blocks, (int)g_blocks, period);
+    const long long gx = (k1_blocks > 0 ? tiles : 0) + (g_blocks > 0 ? gbpf : 0);
+    const int gy = std::max(k1_blocks > 0 ? frames_k1 : 0, g_blocks > 0 ? frames_g : 0);
+    if (gx > 0x7fffffffLL || gy > 65535) return cudaErrorInvalidValue;
+    a.tiles_per_frame = k1_blocks > 0 ? (int)tiles : 0;
+    fused_project_gather_kernel<<<dim3((unsigned)gx, (unsigned)gy), SBT_A, 0, stream>>>(P, stride_f, a, g, k1_blocks > 0 ? frames_k1 : 0,
+                                                                                       g_blocks > 0 ? frames_g : 0);
     if (launches) (*launches)++;
     return cudaGetLastError();
 }

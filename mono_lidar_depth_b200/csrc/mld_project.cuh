@@ -74,9 +74,12 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
 // 4 of them constant loads: ncu r1c, 604 warp instructions per 8 points.)
 // Stage 2: ONE copy of the exact FP64 path, looped over the surviving points (a set bit per point): eight unrolled copies
 // cost 5.6 k instructions of I-cache and ~30 registers of hoisted FP64 constants (spills once the kernel carries a second role).
-template <bool FULL_TILE>
+// FROM_SMEM: the thread's points also sit in shared memory at sp[j * K1_THREADS] (the streamed K1 stages whole tiles there), so
+// stage 2 re-reads the point it needs instead of selecting it out of the register array.
+template <bool FULL_TILE, bool FROM_SMEM = false>
 __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 (&p)[K1_PPT], int base, int n, unsigned int hi,
-                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch) {
+                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch,
+                                               const float4* sp = nullptr) {
     unsigned int alive = 0u;
     {
         const float g0 = P.pf_g[0][0], g1 = P.pf_g[0][1], g2 = P.pf_g[0][2], h0 = P.pf_h[0], G0 = P.pf_G[0], H0 = P.pf_H[0];
@@ -115,12 +118,19 @@ __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 
         const int j = __ffs((int)alive) - 1;
         alive &= alive - 1u;
         float x = p[0].x, y = p[0].y, z = p[0].z;
+        if (FROM_SMEM) {
+            const float4 q4 = sp[j * K1_THREADS];
+            x = q4.x;
+            y = q4.y;
+            z = q4.z;
+        } else {
 #pragma unroll
-        for (int q = 1; q < K1_PPT; q++) {
-            if (j == q) {
-                x = p[q].x;
-                y = p[q].y;
-                z = p[q].z;
+            for (int q = 1; q < K1_PPT; q++) {
+                if (j == q) {
+                    x = p[q].x;
+                    y = p[q].y;
+                    z = p[q].z;
+                }
             }
         }
         int px, py;
@@ -142,7 +152,7 @@ template <int STRIDE_F>
 __device__ __forceinline__ void k1_tile_at(const DevParams& P, unsigned int hi, const float* __restrict__ cloud, int stride_rt, int n,
                                            unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int tile) {
     const int stride_f = STRIDE_F > 0 ? STRIDE_F : stride_rt;
-    const int occ_pitch = occ_tiles_x(P.W);
+    const int occ_pitch = P.occ_tx;
     const int base = tile * (K1_THREADS * K1_PPT) + threadIdx.x;
     const float* src = cloud + (size_t)base * (size_t)stride_f;
     const int step = K1_THREADS * stride_f;  // floats between this thread's consecutive points
@@ -169,8 +179,8 @@ __device__ __forceinline__ void k1_tile_s(const DevParams& P, const MapCode& mc,
                                           long long pitch_pts, unsigned int* __restrict__ maps, unsigned int* __restrict__ occ,
                                           unsigned int frame, int tile) {
     const int stride_f = STRIDE_F > 0 ? STRIDE_F : stride_rt;
-    unsigned int* map = maps + (size_t)frame * (size_t)(P.W * P.H);
-    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)occ_words_per_frame(P.W, P.H) : nullptr;
+    unsigned int* map = maps + (size_t)frame * (size_t)P.map_cells;
+    unsigned int* ob = occ ? occ + (size_t)frame * (size_t)P.occ_words : nullptr;
     const float* cloud = pts + (size_t)frame * (size_t)pitch_pts * (size_t)stride_f;
     const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
     k1_tile_at<STRIDE_F>(P, hi, cloud, stride_rt, n, map, ob, tile);
