@@ -177,8 +177,6 @@ struct mld_handle {
     bool use_tagged_maps = true;
     bool fuse_k1_gather = true;     // K1 of chunk j and the gather of chunk j-1 in one heterogeneous launch (MLD_FUSE=0: off)
     int fuse_chunk = 512;           // frames per fused launch (MLD_FUSE_CHUNK)
-    int k1_stream_bps = 0;          // > 0: streamed K1 (persistent bulk-copy fed grid of this many blocks per SM) on the front stream, the feature kernels of each chunk on its slot's stream (MLD_K1_STREAM); float4 clouds
-    int k1_stream_stages = 3;       // 16 KB tiles in flight per block of the streamed K1 (MLD_K1_STAGES: 2 / 3 / 4)
     bool fuse_road = true;          // the road / SemanticPlane / external-plane sequences use the fused pipeline too (MLD_FUSE=2: no)
     int overlap_slots = 5;          // chunks of a device-resident sequence alternate over this many slots/streams (MLD_OVERLAP). The solve and overflow pass of a chunk are starved by the fused launch that runs beside them and finish near its end; with 3 slots the launch after next waited for them (1.47 M frames/s), 4 / 5 / 6 slots: 1.50 / 1.52 / 1.49 M
     cudaEvent_t ev_fork = nullptr;
@@ -699,10 +697,6 @@ int mld_create(const mld_params* p, int device, mld_handle** out) {
     if (env) h->fuse_road = atoi(env) == 1;
     env = getenv("MLD_FUSE_CHUNK");
     if (env && atoi(env) > 0) h->fuse_chunk = atoi(env);
-    env = getenv("MLD_K1_STREAM");
-    if (env && atoi(env) >= 0 && atoi(env) <= 16) h->k1_stream_bps = atoi(env);
-    env = getenv("MLD_K1_STAGES");
-    if (env && atoi(env) >= 2 && atoi(env) <= 4) h->k1_stream_stages = atoi(env);
     env = getenv("MLD_OVERLAP_MODE");  // "slots": whole chunks alternate over slot streams; "prio": K1 / K2 priority streams
     if (env && strcmp(env, "slots") == 0) h->overlap_mode = 0;
     if (env && strcmp(env, "prio") == 0) h->overlap_mode = 1;
@@ -1309,96 +1303,6 @@ static int process_frames_device_fused(mld_handle* h, const float* pts, int64_t 
     return MLD_OK;
 }
 
-// Device-resident sequence with the streamed K1 (project_scatter_stream_kernel: a persistent grid with a small, fixed footprint per
-// SM) on the front stream, chunk after chunk, and everything else of a chunk -- ground plane, gather, solve, road kernels,
-// overflow pass -- on the chunk's slot stream once its K1 has finished: the latency-bound feature kernels of chunks j-1, j-2
-// fill the part of every SM that K1 of chunk j leaves free. Same slots / events / results as process_frames_device_fused.
-static int process_frames_device_streamed(mld_handle* h, const float* pts, int64_t n_points, int64_t frame_pitch_points, const double* d_uv,
-                                          int F, double* d_depth, int32_t* d_status, int64_t nframes, int chunk, cudaStream_t st, bool use_road,
-                                          uint64_t seed, float* d_plane_coeffs_out, const PlaneSrc* src) {
-    const int stride_f = 4;
-    const int nslots = h->overlap_slots < 2 ? 2 : h->overlap_slots;
-    const int64_t nchunks = (nframes + chunk - 1) / chunk;
-    cudaStream_t front = h->st_lo;
-    CK(cudaEventRecord(h->ev_fork, st));
-    CK(cudaStreamWaitEvent(front, h->ev_fork, 0));
-    for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(h->slots[i].stream, h->ev_fork, 0));
-    const long long words = (n_points + 31) / 32;
-    for (int64_t j = 0; j < nchunks; j++) {
-        Slot& s = h->slots[j % nslots];
-        const int64_t f0 = j * chunk;
-        const int c = (int)std::min<int64_t>(chunk, nframes - f0);
-        const float* cp = pts + f0 * frame_pitch_points * stride_f;
-        // profiling brackets: [0,1] clears, [1,2] K1, [3,4] ground plane, [4,6] gather, [6,7] solve (+ road), [7,5] overflow pass
-        cudaEvent_t* ev = nullptr;
-        if ((j & 3) == 1 && c == chunk) {
-            int rcp = prof_acquire(h, c, &ev);
-            if (rcp) return rcp;
-        }
-        if (j >= nslots) CK(cudaStreamWaitEvent(front, s.done, 0));  // chunk j - nslots has left the slot
-        if (ev) CK(cudaEventRecord(ev[0], front));
-        MapCode mc{0u, 0u};
-        int rcm = begin_maps(h, s, c, n_points, front, mc, true);
-        if (rcm) return rcm;
-        if (ev) CK(cudaEventRecord(ev[1], front));
-        CK(mld_launch_project_scatter_stream(h->dp, mc, cp, n_points, frame_pitch_points, s.d_maps, s.d_occ, c, h->k1_stream_bps,
-                                             h->k1_stream_stages, h->sm_count, front));
-        h->launches++;
-        if (ev) CK(cudaEventRecord(ev[2], front));
-        CK(cudaEventRecord(s.ev_k1, front));
-        cudaStream_t sb = s.stream;
-        if (ev) CK(cudaEventRecord(ev[3], sb));
-        const float* coeffs = nullptr;
-        const unsigned int* bits = nullptr;
-        if (use_road) {  // the plane only needs the points: it does not wait for K1
-            float* cdst = d_plane_coeffs_out ? d_plane_coeffs_out + f0 * 4 : s.d_coeffs;
-            int nlp = 0;
-            if (src && src->kind == PlaneSrc::EXTERNAL) {
-                coeffs = src->d_coeffs + f0 * 4;
-                bits = src->d_bits + f0 * words;
-            } else if (src && src->kind == PlaneSrc::SEMANTIC) {
-                CK(ensure(s.d_sem, s.sem_bytes, mld_semantic_state_bytes(c)));
-                unsigned char* fl = nullptr;
-                int rcs = sem_flags(h, s, n_points, c, &fl);
-                if (rcs) return rcs;
-                CK(mld_launch_semantic_plane(src->T, src->f, src->cu, src->cv, src->label_w, src->label_h, src->ground, src->inlier_threshold, cp,
-                                             stride_f, n_points, frame_pitch_points, src->d_labels + f0 * (int64_t)src->label_w * src->label_h, c,
-                                             s.d_sem, cdst, s.d_bits, words, s.d_small, src->d_rc_out ? src->d_rc_out + f0 : s.d_small + 2 * c, sb,
-                                             &nlp, fl, fl ? 1 : 0));
-                coeffs = cdst;
-                bits = s.d_bits;
-            } else {
-                CK(mld_launch_ransac(ransac_config(h->params), cp, stride_f, n_points, frame_pitch_points, c, seed, f0, s.d_scratch, cdst,
-                                     s.d_bits, words, s.d_small, s.d_small + c, s.d_small + 2 * c, sb, &nlp));
-                coeffs = cdst;
-                bits = s.d_bits;
-            }
-            h->launches += nlp;
-            if (ev) h->prof_ransac_launches[h->prof_used] = nlp;
-        }
-        CK(cudaStreamWaitEvent(sb, s.ev_k1, 0));
-        if (ev) CK(cudaEventRecord(ev[4], sb));
-        int rcf = launch_features(h, s, mc, sb, cp, stride_f, frame_pitch_points, d_uv + f0 * (int64_t)F * 2, F, d_depth + f0 * (int64_t)F,
-                                  d_status + f0 * (int64_t)F, coeffs, bits, words, c, ev ? ev + 6 : nullptr);
-        if (rcf) return rcf;
-        if (ev) {
-            CK(cudaEventRecord(ev[5], sb));
-            h->prof_used++;
-        }
-        {  // the overflow pass was the slot's last reader: clear its occupancy bitmaps for the next chunk here
-            const size_t ob = (size_t)chunk * (size_t)occ_words_per_frame(h->dp.W, h->dp.H) * sizeof(unsigned int);
-            CK(cudaMemsetAsync(s.d_occ, 0, std::min(ob, s.occ_bytes), sb));
-            s.occ_clean_bytes = std::min(ob, s.occ_bytes);
-        }
-        CK(cudaEventRecord(s.done, sb));
-    }
-    for (int i = 0; i < nslots; i++) CK(cudaStreamWaitEvent(st, h->slots[i].done, 0));
-    CK(cudaEventRecord(h->ev_join, front));
-    CK(cudaStreamWaitEvent(st, h->ev_join, 0));
-    h->have_cloud = false;
-    return MLD_OK;
-}
-
 static int process_frames_device_impl(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points, int stride_bytes,
                                       const double* d_uv, int F, double* d_depth, int32_t* d_status, int64_t nframes, int road,
                                       uint64_t seed, float* d_plane_coeffs_out, void* stream, const PlaneSrc* src) {
@@ -1437,9 +1341,6 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     }
     const int stride_f = stride_bytes / 4;
     const float* pts = reinterpret_cast<const float*>(d_points);
-    if (fused_ok && nchunks >= 2 && nslots >= 2 && h->k1_stream_bps > 0 && stride_f == 4)
-        return process_frames_device_streamed(h, pts, n_points, frame_pitch_points, d_uv, F, d_depth, d_status, nframes, chunk, st, use_road, seed,
-                                              d_plane_coeffs_out, src);
     if (fused_ok && nchunks >= 2 && nslots >= 2)
         return process_frames_device_fused(h, pts, n_points, frame_pitch_points, stride_f, d_uv, F, d_depth, d_status, nframes, chunk, st,
                                            use_road, seed, d_plane_coeffs_out, src);

@@ -15,11 +15,6 @@ void mld_setup_prefilter(DevParams& P);
 cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, const float* d_pts, int stride_f, long long n,
                                        long long pitch_pts, unsigned int* d_maps, unsigned int* d_occ, int nframes,
                                        cudaStream_t stream);
-// the same for float4 clouds as a persistent grid of blocks_per_sm x sm_count blocks fed by 1-D bulk async copies (`stages`
-// tiles of 16 KB in flight per block)
-cudaError_t mld_launch_project_scatter_stream(const DevParams& P, const MapCode& mc, const float* d_pts, long long n, long long pitch_pts,
-                                              unsigned int* d_maps, unsigned int* d_occ, int nframes, int blocks_per_sm, int stages,
-                                              int sm_count, cudaStream_t stream);
 // visible-order compaction: _pointIndex, _points_cs_image_visible (2 x nvis), camera-frame depth
 size_t mld_visible_scratch_bytes(long long n);
 cudaError_t mld_launch_visible_compact(const DevParams& P, const float* d_pts, int stride_f, long long n, void* d_scratch, long long capacity,

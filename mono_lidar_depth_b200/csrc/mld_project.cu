@@ -16,8 +16,6 @@
 // never reaches the image, so each point first goes through an FP32 pre-filter (5 linear forms with
 // rigorous error bounds, ~25 FP32 ops) and only the survivors pay the exact FP64 transform and the
 // two FP64 divisions whose truncated results index the map.
-#include <algorithm>
-
 #include "mld_common.cuh"
 #include "mld_kernels.h"
 #include "mld_project.cuh"
@@ -28,110 +26,6 @@ __global__ void __launch_bounds__(K1_THREADS, MLD_K1_MINBLOCKS)
 project_scatter_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int stride_f, int n, long long pitch_pts,
                        unsigned int* __restrict__ maps, unsigned int* __restrict__ occ) {
     k1_tile(P, mc, pts, stride_f, n, pitch_pts, maps, occ, blockIdx.y, (int)blockIdx.x);
-}
-
-// ---- K1 as a persistent, bulk-copy fed kernel ("streamed K1") ------------------------------------------------------
-// The tiled kernel above keeps its loads in flight in REGISTERS: 8 x 16 bytes per thread, 1024 resident threads per SM and the
-// whole register file to saturate HBM -- which is why nothing else (the solve kernel of the previous chunk) can share an SM with
-// it (ncu r2o: fused launch 242 us + solve 81 + 25 us serialised, 339 us measured: no overlap). Here a small fixed grid
-// (blocks_per_sm x SMs) stays resident for the whole chunk and one thread per block keeps STAGES tiles of 16 KB in flight
-// with 1-D bulk async copies (cp.async.bulk, completion on an mbarrier) into shared memory; the block's four warps run the
-// same pre-filter / exact projection / scatter on the tile that has landed. In-flight bytes no longer depend on resident
-// warps, so the rest of every SM (registers above all) is free for the latency-bound feature kernels of the previous chunk.
-// float4 clouds only (a tile must be one contiguous 16-byte aligned run).
-__device__ __forceinline__ unsigned int smem_u32(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned int bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned int bytes, unsigned long long* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)), "l"(src),
-                 "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned int parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "MLD_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
-        "@P1 bra MLD_DONE;\n"
-        "bra MLD_WAIT;\n"
-        "MLD_DONE:\n"
-        "}" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-
-constexpr int K1S_TILE = K1_THREADS * K1_PPT;  // points per tile (16 KB of float4)
-
-// The block's it-th tile is global tile blockIdx.x + it * gridDim.x of the chunk (frame-major: tile = frame * tiles_per_frame + t).
-// step_frames / step_tiles = gridDim.x / and % tiles_per_frame (host side), so walking the tiles needs no division.
-template <int STAGES>
-__global__ void __launch_bounds__(K1_THREADS)
-project_scatter_stream_kernel(DevParams P, MapCode mc, const float* __restrict__ pts, int n, long long pitch_pts,
-                              unsigned int* __restrict__ maps, unsigned int* __restrict__ occ, int tiles_per_frame, int nframes,
-                              int step_frames, int step_tiles) {
-    extern __shared__ __align__(128) float4 s_tiles[];  // STAGES x K1S_TILE
-    __shared__ __align__(8) unsigned long long s_bar[STAGES];
-    const int tid = threadIdx.x;
-    const unsigned int hi = mc.tagged ? (mc.tag << MLD_TAG_SHIFT) : 0u;
-    // (frame, tile in frame) of the tile being processed and of the tile being fetched (STAGES tiles ahead); uniform per block
-    int frame = (int)blockIdx.x / tiles_per_frame;
-    int t = (int)blockIdx.x - frame * tiles_per_frame;
-    int pf_frame = frame, pf_t = t;
-    auto advance = [&](int& f, int& tt) {
-        f += step_frames;
-        tt += step_tiles;
-        if (tt >= tiles_per_frame) {
-            tt -= tiles_per_frame;
-            f++;
-        }
-    };
-    auto fetch = [&](int stage) {  // thread 0: bulk copy of tile (pf_frame, pf_t) into `stage`
-        if (pf_frame < nframes) {
-            const int cnt = min(K1S_TILE, n - pf_t * K1S_TILE);
-            const float* src = pts + ((size_t)pf_frame * (size_t)pitch_pts + (size_t)pf_t * K1S_TILE) * 4;
-            mbar_expect_tx(&s_bar[stage], (unsigned int)cnt * 16u);
-            bulk_g2s(s_tiles + stage * K1S_TILE, src, (unsigned int)cnt * 16u, &s_bar[stage]);
-        }
-    };
-    if (tid == 0) {
-#pragma unroll
-        for (int s = 0; s < STAGES; s++) mbar_init(&s_bar[s], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-#pragma unroll
-    for (int s = 0; s < STAGES; s++) {
-        if (tid == 0) fetch(s);
-        advance(pf_frame, pf_t);
-    }
-    const int occ_pitch = P.occ_tx;
-    for (int it = 0; frame < nframes; it++) {
-        const int stage = it % STAGES;
-        mbar_wait(&s_bar[stage], (unsigned int)(it / STAGES) & 1u);
-        const float4* sp = s_tiles + stage * K1S_TILE + tid;
-        const int base = t * K1S_TILE + tid;
-        unsigned int* map = maps + (size_t)frame * (size_t)P.map_cells;
-        unsigned int* ob = occ ? occ + (size_t)frame * (size_t)P.occ_words : nullptr;
-        float4 p[K1_PPT];
-        if ((t + 1) * K1S_TILE <= n) {  // uniform per block
-#pragma unroll
-            for (int j = 0; j < K1_PPT; j++) p[j] = sp[j * K1_THREADS];
-            scatter_points<true, true>(P, p, base, n, hi, map, ob, occ_pitch, sp);
-        } else {
-#pragma unroll
-            for (int j = 0; j < K1_PPT; j++) p[j] = (base + j * K1_THREADS < n) ? sp[j * K1_THREADS] : make_float4(0.f, 0.f, 0.f, 0.f);
-            scatter_points<false, true>(P, p, base, n, hi, map, ob, occ_pitch, sp);
-        }
-        __syncthreads();  // every warp is done with the stage: refill it
-        if (tid == 0) fetch(stage);
-        advance(pf_frame, pf_t);
-        advance(frame, t);
-    }
 }
 
 // debug view: Transform_Cloud_LidarToCamera's visibility cull (no z > 0 test, DepthEstimator.cpp:184-207)
@@ -339,34 +233,6 @@ cudaError_t mld_launch_project_scatter(const DevParams& P, const MapCode& mc, co
     dim3 grid((unsigned)((n + K1_THREADS * K1_PPT - 1) / (K1_THREADS * K1_PPT)), (unsigned)nframes);
     project_scatter_kernel<<<grid, K1_THREADS, 0, stream>>>(P, mc, d_pts, stride_f, (int)n, pitch_pts, d_maps, d_occ);
     return cudaGetLastError();
-}
-
-// streamed K1 (see project_scatter_stream_kernel): float4 clouds, grid = blocks_per_sm x sm_count persistent blocks
-template <int STAGES>
-static cudaError_t launch_stream(const DevParams& P, const MapCode& mc, const float* d_pts, int n, long long pitch_pts, unsigned int* d_maps,
-                                 unsigned int* d_occ, int tiles, int nframes, int grid, cudaStream_t stream) {
-    const size_t smem = (size_t)STAGES * K1S_TILE * sizeof(float4);
-    cudaError_t e = cudaFuncSetAttribute(project_scatter_stream_kernel<STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    project_scatter_stream_kernel<STAGES><<<grid, K1_THREADS, smem, stream>>>(P, mc, d_pts, n, pitch_pts, d_maps, d_occ, tiles, nframes, grid / tiles,
-                                                                             grid % tiles);
-    return cudaGetLastError();
-}
-
-cudaError_t mld_launch_project_scatter_stream(const DevParams& P, const MapCode& mc, const float* d_pts, long long n, long long pitch_pts,
-                                              unsigned int* d_maps, unsigned int* d_occ, int nframes, int blocks_per_sm, int stages,
-                                              int sm_count, cudaStream_t stream) {
-    if (n <= 0 || nframes <= 0) return cudaSuccess;
-    if (n > 0x7fffffffLL / 8) return cudaErrorInvalidValue;
-    const long long tiles = (n + K1S_TILE - 1) / K1S_TILE;
-    const long long total = tiles * nframes;
-    if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
-    const int grid = (int)std::min<long long>(total, (long long)std::max(1, blocks_per_sm) * std::max(1, sm_count));
-    switch (stages) {
-        case 2: return launch_stream<2>(P, mc, d_pts, (int)n, pitch_pts, d_maps, d_occ, (int)tiles, nframes, grid, stream);
-        case 4: return launch_stream<4>(P, mc, d_pts, (int)n, pitch_pts, d_maps, d_occ, (int)tiles, nframes, grid, stream);
-        default: return launch_stream<3>(P, mc, d_pts, (int)n, pitch_pts, d_maps, d_occ, (int)tiles, nframes, grid, stream);
-    }
 }
 
 cudaError_t mld_launch_points_camera_indexed(const DevParams& P, const float* d_pts, int stride_f, long long n, const int* d_idx, long long n_idx,

@@ -74,12 +74,9 @@ __device__ __forceinline__ bool surely_outside(const DevParams& P, float x, floa
 // 4 of them constant loads: ncu r1c, 604 warp instructions per 8 points.)
 // Stage 2: ONE copy of the exact FP64 path, looped over the surviving points (a set bit per point): eight unrolled copies
 // cost 5.6 k instructions of I-cache and ~30 registers of hoisted FP64 constants (spills once the kernel carries a second role).
-// FROM_SMEM: the thread's points also sit in shared memory at sp[j * K1_THREADS] (the streamed K1 stages whole tiles there), so
-// stage 2 re-reads the point it needs instead of selecting it out of the register array.
-template <bool FULL_TILE, bool FROM_SMEM = false>
+template <bool FULL_TILE>
 __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 (&p)[K1_PPT], int base, int n, unsigned int hi,
-                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch,
-                                               const float4* sp = nullptr) {
+                                               unsigned int* __restrict__ map, unsigned int* __restrict__ ob, int occ_pitch) {
     unsigned int alive = 0u;
     {
         const float g0 = P.pf_g[0][0], g1 = P.pf_g[0][1], g2 = P.pf_g[0][2], h0 = P.pf_h[0], G0 = P.pf_G[0], H0 = P.pf_H[0];
@@ -118,19 +115,12 @@ __device__ __forceinline__ void scatter_points(const DevParams& P, const float4 
         const int j = __ffs((int)alive) - 1;
         alive &= alive - 1u;
         float x = p[0].x, y = p[0].y, z = p[0].z;
-        if (FROM_SMEM) {
-            const float4 q4 = sp[j * K1_THREADS];
-            x = q4.x;
-            y = q4.y;
-            z = q4.z;
-        } else {
 #pragma unroll
-            for (int q = 1; q < K1_PPT; q++) {
-                if (j == q) {
-                    x = p[q].x;
-                    y = p[q].y;
-                    z = p[q].z;
-                }
+        for (int q = 1; q < K1_PPT; q++) {
+            if (j == q) {
+                x = p[q].x;
+                y = p[q].y;
+                z = p[q].z;
             }
         }
         int px, py;
