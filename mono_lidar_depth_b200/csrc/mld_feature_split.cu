@@ -1,7 +1,7 @@
 // mld_feature_split.cu -- K2 as two (three with a ground plane) thread-per-feature kernels with a
 // chunk-wide compaction in between.
 //
-// ncu of the fused thread-per-feature kernel (profiles/r1_v4_*): 45 % of the stall samples wait on the
+// ncu of the fused thread-per-feature kernel (round-1 captures r1_v4, git history): 45 % of the stall samples wait on the
 // three dependent load rounds of the window gather, 23 % on the block barriers of the in-block
 // compaction, occupancy pinned at 16 warps/SM by the per-thread XYZ slabs that only the later phases
 // need, and 44 % of the features (empty windows) idle through those phases. Splitting fixes all three:

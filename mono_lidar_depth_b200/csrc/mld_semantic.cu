@@ -16,7 +16,7 @@
 // a warp's ballot IS word i/32 of the inlier bitmask: plain coalesced stores, no atomics, no clear. In pass 1 a float
 // quotient on the rounded camera-frame coordinates removes the ~85 % of a sweep that cannot hit the image before the two
 // FP64 divisions; in a batch every block streams 8 tiles so that the ten-moment reduction is paid once per 8192 points
-// (first version, one tile per block and no pre-filter: 224 + 129 us per 128 sweeps; profiles/r1b_*).
+// (first version, one tile per block and no pre-filter: 224 + 129 us per 128 sweeps; round-1 captures r1b, git history).
 //
 // Arithmetic: the transform is evaluated in double and rounded to float per coordinate (PCL 1.8 computes
 // transform(i,0)*x + ... in the transform's scalar and casts), the projection in double with true division and
