@@ -9,8 +9,12 @@ A step is one pass of the hot path over this rank's block of the synthetic frame
 (BASELINE.json configs[1]: 10k KITTI-shaped frames, 120 000 points, 1241x376, 2000 features, yaml
 parameters with the ground plane disabled), inputs resident in HBM. Frames are independent, so N
 ranks each own a contiguous block (weak scaling, no data-path collective); the per-frame results are
-gathered on rank 0 over NCCL once per step. `e2e` is the same metric through the C ABI's host-buffer entry
-point (mld_process_frames_host): pinned host memory in, H2D + kernels + D2H inside the timed region.
+gathered on rank 0 over NCCL once, at the end of the run, inside the timed region. `--workload seq100k` is
+BASELINE.json configs[4]: ONE 100k-frame sequence cut into contiguous blocks over the ranks (strong scaling).
+`e2e` is the same metric through the C ABI's host-buffer entry point (mld_process_frames_host): pinned host
+memory holding 32-byte pcl::PointXYZI records in, H2D + kernels + D2H inside the timed region. At N = 1 the
+line also carries short passes of the other BASELINE configs (`other_workloads`: road, dense, SemanticPlane),
+an in-run parity check against the oracle and the host-CPU baseline.
 """
 from __future__ import annotations
 
