@@ -67,6 +67,35 @@ def env_int(name, default):
         return default
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pins this process (and the library's pack threads, which inherit the mask) to the CPUs of the NUMA node the rank's GPU hangs
+    off, so that the pinned host buffers of the end-to-end pipeline are allocated next to the GPU's root complex. Best effort: a
+    flat or hidden topology leaves the mask alone. Returns what was done (reported in e2e.host)."""
+    info = {"cores_visible": len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else os.cpu_count()}
+    try:
+        import torch
+
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = "%04x:%02x:%02x.0" % (getattr(prop, "pci_domain_id", 0), prop.pci_bus_id, prop.pci_device_id)
+        node = int(Path(f"/sys/bus/pci/devices/{bus}/numa_node").read_text().strip())
+        info["gpu_pci"], info["numa_node"] = bus, node
+        nodes = [p for p in Path("/sys/devices/system/node").glob("node[0-9]*")]
+        info["numa_nodes"] = len(nodes)
+        if node < 0 or len(nodes) < 2 or os.environ.get("MLD_BENCH_NO_NUMA"):
+            return info
+        cpus = set()
+        for part in Path(f"/sys/devices/system/node/node{node}/cpulist").read_text().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            info["bound_cpus"] = len(cpus)
+    except Exception as e:  # no sysfs, no permission, older torch: run unbound
+        info["numa_note"] = f"{type(e).__name__}: {e}"[:120]
+    return info
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md)."""
 
@@ -436,11 +465,13 @@ def run_gpu(args, rank, local_rank, world):
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    host_info = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     cores = os.cpu_count() or 1
     # host threads that pack PointXYZI records in the end-to-end pipeline: the box's cores are shared by the ranks
     os.environ.setdefault("MLD_PACK_THREADS", str(max(1, min(14, cores // world - (1 if world > 1 else 2)))))
+    host_info["cores"], host_info["pack_threads"] = cores, int(os.environ["MLD_PACK_THREADS"])
 
     def barrier():
         if world > 1:
@@ -473,12 +504,15 @@ def run_gpu(args, rank, local_rank, world):
     gather = None
     if world > 1 and not seq100k:
         per = -(-frames_total // world)
+        # 9 bytes per feature on the wire: the depth stays f64, the DepthResultType (0..20) travels as one byte
         g_depth = torch.empty((world * per, F), dtype=torch.float64, device=dev) if rank == 0 else None
-        g_status = torch.empty((world * per, F), dtype=torch.int32, device=dev) if rank == 0 else None
+        g_status = torch.empty((world * per, F), dtype=torch.uint8, device=dev) if rank == 0 else None
+        s8 = torch.empty((per, F), dtype=torch.uint8, device=dev)
 
         def gather(b):
+            s8.copy_(seq.statuses[b])
             dist.gather(seq.depths[b], list(g_depth.split(per)) if rank == 0 else None, dst=0)
-            dist.gather(seq.statuses[b], list(g_status.split(per)) if rank == 0 else None, dst=0)
+            dist.gather(s8, list(g_status.split(per)) if rank == 0 else None, dst=0)
 
     steps, warm = max(1, args.steps), max(3, args.warmup)
     clocks = ClockSampler(local_rank)
@@ -588,6 +622,7 @@ def run_gpu(args, rank, local_rank, world):
            "d2h_bytes_per_step": int(hs["d2h_bytes"] / frames_moved * step_frames),
            "frames_timed_per_rank": ne * e2e_steps,
            "frames_packed_fraction": hs["frames_packed"] / frames_moved,
+           "host": host_info,
            "input": "pinned host memory, pcl::PointXYZI records (32 bytes per point, the drop-in caller's cloud layout)",
            "api": (f"mld_process_frames_host: 3-slot H2D / kernels / D2H pipeline; {os.environ['MLD_PACK_THREADS']} host threads strip the records to "
                    "12-byte xyz in pinned staging buffers while the copy engine has work queued, chunks go out as whole records when it would idle")}
@@ -712,7 +747,7 @@ def run_gpu(args, rank, local_rank, world):
                        "image": [seq.W, seq.H], "chunk_frames_per_launch": chunk,
                        "l2": f"inputs of one step ({nframes * n * 16 / 1e9:.1f} GB of points per GPU) are far larger than the 126 MB L2; no flush needed",
                        "parallelism": (f"frames sharded in contiguous blocks over {world} GPU(s), no collective on the data path; one gather of the per-frame "
-                                       "results on rank 0 at the end of the run (ncclSend/Recv under dist.gather), inside the timed region"
+                                       "results (f64 depth + one status byte per feature) on rank 0 at the end of the run (ncclSend/Recv under dist.gather), inside the timed region"
                                        if world > 1 and not seq100k else ("contiguous blocks, no collective" if world > 1 else "single GPU"))},
             "feature_depths_per_sec": value * F,
             "clocks": clk,

@@ -188,6 +188,7 @@ struct mld_handle {
     cudaEvent_t ev_join = nullptr;
     long long cur_n = 0;
     int cur_stride_f = 4;
+    bool cloud_in_flight = false;   // the last mld_set_cloud returned without waiting for slot 0's stream (packed upload)
     bool have_prev = false;         // slots[MLD_PREV_SLOT] holds the previous cloud of mld_calculate_depth_pair_resident
     long long prev_n = 0;
     int prev_stride_f = 4;
@@ -904,6 +905,71 @@ static int check_stride(mld_handle* h, int stride_bytes) {
     return MLD_OK;
 }
 
+static int ensure_pool(mld_handle* h) {
+    if (!h->pool) {
+        int t = h->host_pack_threads;
+        if (t <= 0) t = std::max(1, std::min(14, (int)std::thread::hardware_concurrency() - 2));
+        h->pool = new HostPool(t - 1);  // the calling thread is the t-th worker
+    }
+    return MLD_OK;
+}
+
+// One cloud of the per-call entry points (setInputCloud and friends) from host memory into the slot's point buffer. A cudaMemcpy
+// out of PAGEABLE memory -- what a pcl::PointCloud is -- is staged by the driver at ~12 GB/s: 0.16 ms for 120 000 float4 points,
+// 0.32 ms for 32-byte PointXYZI records, most of a frame's latency. Here the host workers strip such a cloud to 12-byte xyz
+// straight out of the caller's buffer into the slot's pinned staging buffer (the same squeeze the batched host pipeline uses),
+// one pinned copy moves 12 bytes per point and a kernel expands them to the float4 layout. Pinned (registered) sources and small
+// clouds are copied as they are. *stride_f_out = floats per point of the device copy.
+static int upload_cloud(mld_handle* h, Slot& s, const void* pts, int64_t n, int stride_bytes, int* stride_f_out, bool* consumed = nullptr) {
+    *stride_f_out = stride_bytes / 4;
+    if (consumed) *consumed = false;  // true: the caller's buffer has been read completely when this returns
+    if (n <= 0) return MLD_OK;
+    bool pack = h->host_pack != 0 && n >= 16384;
+    if (pack && h->host_pack != 1) {
+        cudaPointerAttributes at;
+        const cudaError_t e = cudaPointerGetAttributes(&at, pts);
+        if (e != cudaSuccess) (void)cudaGetLastError();
+        pack = e != cudaSuccess || at.type == cudaMemoryTypeUnregistered;
+    }
+    if (!pack) {
+        CK(cudaMemcpyAsync(s.d_pts, pts, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+        return MLD_OK;
+    }
+    int rc = ensure_pool(h);
+    if (rc) return rc;
+    const size_t need = (size_t)n * 12;
+    if (need > s.h_stage_bytes) {
+        CK(cudaStreamSynchronize(s.stream));
+        if (s.h_stage) CK(cudaFreeHost(s.h_stage));
+        s.h_stage = nullptr;
+        s.h_stage_bytes = 0;
+        CK(cudaHostAlloc(reinterpret_cast<void**>(&s.h_stage), need, cudaHostAllocDefault));
+        s.h_stage_bytes = need;
+        s.stage_busy = false;
+    }
+    CK(ensure(s.d_pack, s.d_pack_bytes, need));
+    CK(ensure(s.d_pts, s.pts_bytes, (size_t)n * 16));
+    if (!s.ev_stage) CK(cudaEventCreateWithFlags(&s.ev_stage, cudaEventDisableTiming));
+    if (s.stage_busy) CK(cudaEventSynchronize(s.ev_stage));  // the staging buffer's previous copy has left the host
+    const int pieces = 2 * (h->pool->workers() + 1);
+    const long long per = ((n + pieces - 1) / pieces + 15) & ~15LL;  // whole groups of 16 records: the squeeze works on cache lines
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(pts);
+    unsigned char* stage = s.h_stage;
+    const std::function<void(int)> job = [&](int pc) {
+        const long long lo = (long long)pc * per, hi = std::min<long long>(n, lo + per);
+        if (lo < hi) mld_host_pack_xyz(src + (size_t)lo * (size_t)stride_bytes, stride_bytes, reinterpret_cast<float*>(stage + (size_t)lo * 12), hi - lo, 0);
+    };
+    h->pool->run(pieces, job);
+    CK(cudaMemcpyAsync(s.d_pack, s.h_stage, need, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaEventRecord(s.ev_stage, s.stream));
+    s.stage_busy = true;
+    CK(mld_launch_unpack_xyz(s.d_pack, reinterpret_cast<float*>(s.d_pts), n, s.stream));
+    h->launches++;
+    *stride_f_out = 4;
+    if (consumed) *consumed = true;
+    return MLD_OK;
+}
+
 static void bits_to_plane(const std::vector<unsigned int>& bits, long long n, mld_plane* pl) {
     int64_t cnt = 0;
     for (long long i = 0; i < n; i++)
@@ -949,21 +1015,28 @@ int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_
     if (want_ransac && n < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, 0, 1, true, false);
     if (rc) return rc;
-    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    int sf = stride_bytes / 4;  // floats per point of the device copy (4 when the host workers packed the cloud)
+    bool consumed = false;
+    rc = upload_cloud(h, s, points_host, n, stride_bytes, &sf, &consumed);
+    if (rc) return rc;
     MapCode mc;
     rc = begin_maps(h, s, 1, n, s.stream, mc);
     if (rc) return rc;
-    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_bytes / 4, n, n, s.d_maps,
+    CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), sf, n, n, s.d_maps,
                                   h->feature_mode >= 1 ? s.d_occ : nullptr, 1, s.stream));
     if (n > 0) h->launches++;
     h->cur_n = n;
-    h->cur_stride_f = stride_bytes / 4;
+    h->cur_stride_f = sf;
     h->have_cloud = true;
     if (want_ransac) {
-        rc = run_ransac_single(h, s, n, stride_bytes / 4, ransac_seed, inout_plane, nullptr);
+        rc = run_ransac_single(h, s, n, sf, ransac_seed, inout_plane, nullptr);
         if (rc) return rc;
     }
-    CK(cudaStreamSynchronize(s.stream));
+    // A packed upload has read the caller's buffer completely: the copy out of the staging buffer, the expansion and the projection
+    // go on behind the caller's back and every later call on this handle is ordered behind them on the slot's stream (the
+    // reference's setInputCloud reports nothing either). Otherwise the source may still be in use by the copy engine: wait.
+    if (!consumed) CK(cudaStreamSynchronize(s.stream));
+    h->cloud_in_flight = consumed;
     return MLD_OK;
 }
 
@@ -977,8 +1050,10 @@ int mld_estimate_ground_plane(mld_handle* h, const void* points_host, int64_t n,
     DeviceGuard g(h->device);
     Slot& s = h->slots[1];  // does not disturb the current cloud of slot 0
     CK(ensure(s.d_pts, s.pts_bytes, (size_t)n * (size_t)stride_bytes));
-    CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
-    return run_ransac_single(h, s, n, stride_bytes / 4, seed, out_plane, iterations_out);
+    int sf = stride_bytes / 4;
+    rc = upload_cloud(h, s, points_host, n, stride_bytes, &sf);
+    if (rc) return rc;
+    return run_ransac_single(h, s, n, sf, seed, out_plane, iterations_out);
 }
 
 int mld_semantic_ground_plane_device(mld_handle* h, const void* d_points, int64_t n_points, int64_t frame_pitch_points,
@@ -1026,9 +1101,11 @@ int mld_semantic_ground_plane(mld_handle* h, const void* points_host, int64_t n,
     CK(ensure(s.d_bits, s.bits_bytes, (size_t)std::max<long long>(words, 1) * sizeof(unsigned int)));
     CK(ensure(s.d_coeffs, s.coeffs_bytes, 4 * sizeof(float)));
     CK(ensure(s.d_small, s.small_bytes, 3 * sizeof(int)));
-    if (n > 0) CK(cudaMemcpyAsync(s.d_pts, points_host, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+    int sf = stride_bytes / 4;
+    rc = upload_cloud(h, s, points_host, n, stride_bytes, &sf);
+    if (rc) return rc;
     CK(cudaMemcpyAsync(s.d_labels, labels_host, (size_t)label_w * (size_t)label_h, cudaMemcpyHostToDevice, s.stream));
-    rc = mld_semantic_ground_plane_device(h, s.d_pts, n, n, stride_bytes, s.d_labels, label_w, label_h, f, cu, cv, T_cam_lidar,
+    rc = mld_semantic_ground_plane_device(h, s.d_pts, n, n, sf * 4, s.d_labels, label_w, label_h, f, cu, cv, T_cam_lidar,
                                           ground_labels, n_ground_labels, inlier_threshold, 1, s.d_coeffs, s.d_bits, s.d_small,
                                           s.d_small + 2, s.stream);
     if (rc) return rc;
@@ -1128,6 +1205,7 @@ int mld_calculate_depth(mld_handle* h, const double* uv_host, int F, double* dep
         CK(cudaMemcpyAsync(h->h_hist, h->d_hist, 21 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s.stream));
     }
     CK(cudaStreamSynchronize(s.stream));
+    h->cloud_in_flight = false;
     if (h->stats_on) {
         for (int i = 0; i < 21; i++) h->last_hist[i] = (int64_t)h->h_hist[i];
         h->last_hist_valid = true;
@@ -1323,6 +1401,10 @@ static int process_frames_device_impl(mld_handle* h, const void* d_points, int64
     if (road && h->dp.road_mode == ROAD_NONE && src)
         return fail(h, MLD_ERR_NO_ROAD_ESTIMATOR, "a ground plane was given but do_use_ransac_plane is off: no road depth estimator (DepthEstimator.cpp:84-103)");
     DeviceGuard g(h->device);
+    if (h->cloud_in_flight) {  // the batch writes slot 0's maps from other streams: let the per-call projection finish first
+        CK(cudaStreamSynchronize(h->slots[0].stream));
+        h->cloud_in_flight = false;
+    }
     cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
     // short sequences are cut into at least `overlap_slots` chunks so that the streams still overlap
     const bool use_road = road && h->dp.road_mode != ROAD_NONE;
@@ -1445,6 +1527,7 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
         return fail(h, MLD_ERR_REGION_GROWING, "DepthEstimator: Region growing not supported!");
     if (road && n_points < 3) return fail(h, MLD_ERR_PCL_INVALID, "In GroundPlane: Input pointcloud is invalid");
     DeviceGuard g(h->device);
+    h->cloud_in_flight = false;  // slot 0's work is ordered on its own stream here
     // H2D copies, kernels and D2H copies of different chunks overlap: chunks are kept small (<= 32 frames, ~1 ms of
     // PCIe time each) and a sequence is cut into at least two chunks per slot
     const int chunk = (int)std::max<int64_t>(1, std::min<int64_t>(std::min(h->chunk_frames, 32), std::max<int64_t>(8, (nframes + 2 * MLD_HOST_SLOTS - 1) / (2 * MLD_HOST_SLOTS))));
@@ -1462,11 +1545,7 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
     // reading mapped pinned memory transfers every byte of the 32-byte sectors anyway: measured, scripts/pcie_probe.cu.)
     // 16-byte float4 records are packed as well where the host squeezes whole cache lines (AVX-512): 12 instead of 16 bytes cross the link
     const bool pack = n_points > 0 && (h->host_pack == 1 || (h->host_pack != 0 && (stride_bytes > 16 || (stride_bytes == 16 && mld_host_pack_level() == 512))));
-    if (pack && !h->pool) {
-        int t = h->host_pack_threads;
-        if (t <= 0) t = std::max(1, std::min(14, (int)std::thread::hardware_concurrency() - 2));
-        h->pool = new HostPool(t - 1);  // the calling thread is the t-th worker
-    }
+    if (pack) ensure_pool(h);
     if (pack) {
         for (int i = 0; i < MLD_HOST_SLOTS; i++) {
             Slot& s = h->slots[i];
@@ -1574,14 +1653,17 @@ int mld_process_frames_host(mld_handle* h, const void* points_host, int64_t n_po
 // resident: the slot already holds this cloud (points, pixel map, occupancy) from the call in which it was the current cloud; only
 // the features (and the plane) go to the device
 static int pair_side_begin(mld_handle* h, Slot& s, const void* pts, int64_t n, int stride_bytes, const double* uv, int F,
-                           const mld_plane* plane, bool want_ransac, uint64_t seed, std::vector<unsigned int>& hb, bool resident = false) {
+                           const mld_plane* plane, bool want_ransac, uint64_t seed, std::vector<unsigned int>& hb, bool resident = false,
+                           int* stride_f_out = nullptr) {
     int rc = MLD_OK;
-    const int stride_f = stride_bytes / 4;
+    int stride_f = stride_bytes / 4;  // resident: the stride the cloud was stored with; else set by the upload
     MapCode mc = s.mc;
     if (!resident) {
         rc = slot_reserve(h, s, std::max<int64_t>(n, 1), stride_bytes, std::max(F, 1), 1, true, want_ransac || plane != nullptr);
         if (rc) return rc;
-        if (n > 0) CK(cudaMemcpyAsync(s.d_pts, pts, (size_t)n * (size_t)stride_bytes, cudaMemcpyHostToDevice, s.stream));
+        rc = upload_cloud(h, s, pts, n, stride_bytes, &stride_f);
+        if (rc) return rc;
+        if (stride_f_out) *stride_f_out = stride_f;
         rc = begin_maps(h, s, 1, n, s.stream, mc);
         if (rc) return rc;
         CK(mld_launch_project_scatter(h->dp, mc, reinterpret_cast<const float*>(s.d_pts), stride_f, n, n, s.d_maps,
@@ -1679,8 +1761,9 @@ static int calculate_depth_pair_impl(mld_handle* h, const void* pts_prev, int64_
             if (status_prev) status_prev[i] = 0;
         }
     }
+    int cur_sf = stride_bytes / 4;
     rc = pair_side_begin(h, sc, pts_cur, n_cur, stride_bytes, uv_cur, F_cur, (road && plane_cur && !ransac_cur) ? plane_cur : nullptr, ransac_cur,
-                         ransac_seed + 1, hb_cur);
+                         ransac_seed + 1, hb_cur, false, &cur_sf);
     if (rc) return rc;
     auto finish = [&](Slot& s, int64_t n, int F, double* depth, int32_t* status, mld_plane* plane, bool ransac) -> int {
         if (F > 0) {
@@ -1710,7 +1793,7 @@ static int calculate_depth_pair_impl(mld_handle* h, const void* pts_prev, int64_
     rc = finish(sc, n_cur, F_cur, depth_cur, status_cur, plane_cur, ransac_cur);
     if (rc) return rc;
     h->cur_n = n_cur;
-    h->cur_stride_f = stride_bytes / 4;
+    h->cur_stride_f = cur_sf;
     h->have_cloud = true;
     return MLD_OK;
 }

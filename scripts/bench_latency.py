@@ -38,6 +38,10 @@ for road in (0, 1):
     est.Initialize(synth.kitti_camera(), synth.KITTI_T_LIDAR_TO_CAM)
     med, p95 = timed(lambda i: est.CalculateDepth(frames[i % 16], feats[i % 16], None), 300)
     out["gpu_road_ransac" if road else "gpu_non_road"] = {"median_ms": med, "p95_ms": p95}
+    if not road:  # the same frames as 32-byte pcl::PointXYZI records in pageable memory: what the drop-in caller hands over
+        frames32 = [synth.points_host_xyzi32(cfg, 5, f) for f in range(16)]
+        med, p95 = timed(lambda i: est.CalculateDepth(frames32[i % 16], feats[i % 16], None), 300)
+        out["gpu_non_road_pointxyzi"] = {"median_ms": med, "p95_ms": p95}
 lab = np.zeros((376, 1241), np.uint8)
 lab[200:] = 7
 cam = SemanticPlane.Camera(718.856, 607.1928, 185.2157, synth.KITTI_T_LIDAR_TO_CAM)

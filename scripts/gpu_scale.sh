@@ -1,9 +1,9 @@
 # multi-GPU bench lines on one box: weak scaling (10k frames per GPU) and the 100k-frame sequence (strong scaling)
-N=${1:-2}; TAG=${2:-r2}
+N=${1:-2}; TAG=${2:-r2}; STEPS=${3:-5}
 cd "${GRAFT_REPO_ROOT:-.}"
 mkdir -p gpurun_out
 export MLD_BENCH_CPU_SECONDS=2 MLD_BENCH_E2E_FRAMES=256
-python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/scale_${TAG}_n$N.json 2> gpurun_out/scale_${TAG}_n$N.err; tail -c 600 gpurun_out/scale_${TAG}_n$N.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps $STEPS --warmup 5 > gpurun_out/scale_${TAG}_n$N.json 2> gpurun_out/scale_${TAG}_n$N.err; tail -c 600 gpurun_out/scale_${TAG}_n$N.err
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29518 bench.py --gpus $N --steps 1 --warmup 3 --workload seq100k > gpurun_out/seq100k_${TAG}_n$N.json 2> gpurun_out/seq100k_${TAG}_n$N.err; tail -c 600 gpurun_out/seq100k_${TAG}_n$N.err
 python - <<PY
 import json
