@@ -673,3 +673,56 @@ def test_pair_adaptor_keeps_the_previous_cloud_on_the_device():
         est_b.processFramesHost(np.stack(clouds[:2]), np.stack(feats[:2]), np.empty((2, 800)), np.empty((2, 800), np.int32))
         dl_b, _, _, _ = est_b.CalculateDepthPair(None, feats[0][:10], None, clouds[0], feats[0], None, resident=True)
         assert np.all(dl_b == -1)
+
+
+@pytest.mark.parametrize("floats_per_record", [4, 8])
+def test_per_call_upload_paths_agree(floats_per_record, monkeypatch):
+    """setInputCloud uploads a cloud in pageable memory through the host-packed path (12-byte xyz in pinned staging, expanded
+    on the device; the call returns before the projection has finished), a pinned or small cloud as it is. Same results bit for
+    bit for pageable / pinned / MLD_HOST_PACK=0 sources, for back-to-back setInputCloud calls (staging reuse, the earlier cloud
+    is dropped), for a batched call issued right behind an un-waited setInputCloud, and against the oracle."""
+    import torch
+
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    cfg = synth.default_config()
+    n, F = synth.points_per_frame(cfg), 1500
+    make = synth.points_host if floats_per_record == 4 else synth.points_host_xyzi32
+    clouds = [make(cfg, 31, f) for f in range(3)]
+    feats = [synth.features_host(cfg, 31, f, F) for f in range(3)]
+    est, orc = kitti_pair(p)
+    ref = []
+    for c, uv in zip(clouds, feats):  # pageable numpy arrays: packed uploads
+        est.setInputCloud(c)
+        ref.append(est.CalculateDepth(uv))
+    orc.set_cloud(np.ascontiguousarray(clouds[1][:, [0, 1, 2, 4 if floats_per_record == 8 else 3]]))
+    d_ref, s_ref = orc.calculate_depth(feats[1])
+    PU.assert_depth_status_equal(ref[1][0], ref[1][1], d_ref, s_ref, "packed per-call upload")
+    # back to back: the second cloud replaces the first while the first upload may still be in flight
+    est.setInputCloud(clouds[0])
+    est.setInputCloud(clouds[2])
+    d, s = est.CalculateDepth(feats[2])
+    assert np.array_equal(s, ref[2][1]) and np.array_equal(d, ref[2][0])
+    # pinned source: copied as it is
+    pinned = torch.from_numpy(clouds[1]).pin_memory()
+    est.setInputCloud(pinned.numpy())
+    d, s = est.CalculateDepth(feats[1])
+    assert np.array_equal(s, ref[1][1]) and np.array_equal(d, ref[1][0])
+    # a batched call right behind an un-waited setInputCloud (both use slot 0's maps)
+    pts4 = torch.from_numpy(np.ascontiguousarray(np.stack([c[:, :4] if floats_per_record == 4 else c[:, [0, 1, 2, 4]] for c in clouds]))).cuda()
+    uvd = torch.from_numpy(np.stack(feats)).cuda()
+    depth = torch.empty((3, F), dtype=torch.float64, device="cuda")
+    status = torch.empty((3, F), dtype=torch.int32, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    torch.cuda.synchronize()
+    est.setInputCloud(clouds[0])
+    est.processFramesDevice(pts4.data_ptr(), n, n, 16, uvd.data_ptr(), F, depth.data_ptr(), status.data_ptr(), 3, stream=st)
+    torch.cuda.synchronize()
+    for i in range(3):
+        assert np.array_equal(status[i].cpu().numpy(), ref[i][1]) and np.array_equal(depth[i].cpu().numpy(), ref[i][0]), i
+    # the un-packed path
+    monkeypatch.setenv("MLD_HOST_PACK", "0")
+    est0, _ = kitti_pair(p)
+    est0.setInputCloud(clouds[1])
+    d, s = est0.CalculateDepth(feats[1])
+    assert np.array_equal(s, ref[1][1]) and np.array_equal(d, ref[1][0])
