@@ -1,7 +1,6 @@
-// mld_feature_warp.cuh -- the per-feature driver with one WARP per feature (device functions), shared by the warp-per-feature
-// kernel (mld_feature.cu: the general path for dense clouds / large windows and the overflow pass of the chunked pipelines) and
-// by the persistent pipeline (mld_pipeline.cu: windows that hold more points than a thread's slab). See mld_feature.cu for the
-// reference routines restated and the mapping.
+// mld_feature_warp.cuh -- the per-feature driver with one WARP per feature (device functions) of the warp-per-feature kernel
+// (mld_feature.cu: the general path for dense clouds / large windows and the overflow pass of the chunked pipelines). See
+// mld_feature.cu for the reference routines restated and the mapping.
 #pragma once
 #include "mld_common.cuh"
 #include "mld_geometry.cuh"
@@ -45,7 +44,7 @@ __device__ __forceinline__ int gather_window(const DevParams& P, const MapCode& 
         if (idx < area) {
             int ry = idx / wc;
             int rx = idx - ry * wc;
-            cell = __ldcg(&map[(long long)(y0 + ry) * P.W + (x0 + rx)]);  // L2: the persistent pipeline reuses map slots inside one launch
+            cell = __ldg(&map[(long long)(y0 + ry) * P.W + (x0 + rx)]);
         }
         const bool hit = (idx < area) && map_cell_valid(mc, cell);
         unsigned m = __ballot_sync(MLD_FULL_MASK, hit);

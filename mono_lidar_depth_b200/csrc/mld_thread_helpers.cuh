@@ -1,6 +1,5 @@
 // mld_thread_helpers.cuh -- per-thread (one feature per thread) restatements of the reference routines,
-// shared by the split gather / solve / road kernels (mld_feature_split.cu) and the feature role of the persistent pipeline
-// (mld_pipeline.cu). One thread per feature: the window of a lidar feature holds 2-9 points, so a warp per feature idles most
+// shared by the split gather / solve / road kernels (mld_feature_split.cu). One thread per feature: the window of a lidar feature holds 2-9 points, so a warp per feature idles most
 // lanes and runs the scalar FP64 tail 32x redundantly (measured in round 1: ~800 warp instructions per feature).
 #pragma once
 #include "mld_common.cuh"
@@ -49,12 +48,9 @@ __device__ __forceinline__ unsigned int row_mask(unsigned int w, int base_px, in
 // Occupied pixels of the window [x0, x1] x [y0, y1] in the reference's scan order (rows outer, columns inner,
 // NeighborFinderPixel.cpp:78-92): emit(pixel offset) per occupied pixel. The occupancy words of the first two tile
 // columns are fetched for all row pairs of a batch before any is used (independent loads); wider windows walk on.
-// COHERENT: read through L2 only (ld.cg) -- the persistent pipeline re-uses occupancy slots inside one launch, so a line cached in
-// L1 by an earlier frame of the same slot would be stale.
-template <bool COHERENT>
-__device__ __forceinline__ unsigned int occ_load(const unsigned int* p) { return COHERENT ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ unsigned int occ_load(const unsigned int* p) { return __ldg(p); }
 
-template <bool COHERENT = false, typename Emit>
+template <typename Emit>
 __device__ __forceinline__ void occ_scan_window(const unsigned int* __restrict__ occ, int W, int x0, int x1, int y0, int y1, Emit emit) {
     const int tiles_x = occ_tiles_x(W);
     const int tx0 = x0 >> 4, tx1 = x1 >> 4;
@@ -66,8 +62,8 @@ __device__ __forceinline__ void occ_scan_window(const unsigned int* __restrict__
             const int yp = ypb + r;  // rows 2 yp and 2 yp + 1: tile row yp >> 3, word yp & 7 of the tile
             const bool on = yp <= yp_last;
             const long long base = ((long long)(yp >> 3) * tiles_x + tx0) * 8 + (yp & 7);
-            w0[r] = on ? occ_load<COHERENT>(occ + base) : 0u;
-            w1[r] = (on && tx1 > tx0) ? occ_load<COHERENT>(occ + base + 8) : 0u;
+            w0[r] = on ? occ_load(occ + base) : 0u;
+            w1[r] = (on && tx1 > tx0) ? occ_load(occ + base + 8) : 0u;
         }
 #pragma unroll
         for (int r = 0; r < T_PAIRS; r++) {
@@ -89,7 +85,7 @@ __device__ __forceinline__ void occ_scan_window(const unsigned int* __restrict__
                     tx += 2;  // next 32-pixel span of a wide row
                     if ((tx << 4) > x1) break;
                     const long long base = ((long long)(yp >> 3) * tiles_x + tx) * 8 + (yp & 7);
-                    const unsigned int a = occ_load<COHERENT>(occ + base), c = (tx + 1 <= tx1) ? occ_load<COHERENT>(occ + base + 8) : 0u;
+                    const unsigned int a = occ_load(occ + base), c = (tx + 1 <= tx1) ? occ_load(occ + base + 8) : 0u;
                     m = row_mask(((a >> sh) & 0xFFFFu) | (((c >> sh) & 0xFFFFu) << 16), tx << 4, x0, x1);
                 }
             }
