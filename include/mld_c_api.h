@@ -149,7 +149,11 @@ int mld_initialize(mld_handle* h, int W, int H, double f, double cx, double cy, 
 /* ---- DepthEstimator::setInputCloud (DepthEstimator.cpp:220-312) ----
  * Host points in, one H2D copy, projection + pixel map on the device. When do_use_ransac_plane is
  * set and inout_plane is non-NULL with segmented == 0, the ground plane is fitted on the device
- * (RansacPlane::CalculateInliersPlane) with ransac_seed and written back to *inout_plane. */
+ * (RansacPlane::CalculateInliersPlane) with ransac_seed and written back to *inout_plane.
+ * points_host may be pageable (a pcl::PointCloud) or pinned and is free for reuse when the call returns. A large cloud in
+ * pageable memory is stripped to 12-byte xyz by host worker threads into a pinned staging buffer and the call returns while the
+ * copy and the projection are still running; every later call on the handle is ordered behind them (an error they raise is
+ * reported by that call). MLD_HOST_PACK=0 restores the plain copy + wait. */
 int mld_set_cloud(mld_handle* h, const void* points_host, int64_t n, int stride_bytes, mld_plane* inout_plane,
                   uint64_t ransac_seed);
 
