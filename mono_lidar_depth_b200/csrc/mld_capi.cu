@@ -203,7 +203,7 @@ struct mld_handle {
     int host_pack = -1;
     int host_pack_threads = 0;      // MLD_PACK_THREADS (0 = hardware concurrency - 2, at most 14)
     HostPool* pool = nullptr;
-    double pcie_gbs = 50.0;         // link rate the pack / copy choice is modelled with (MLD_PCIE_GBS)
+    double pcie_gbs = 42.0;         // link rate the pack / copy choice is modelled with (MLD_PCIE_GBS): below the ~55 GB/s of an idle link because the copy engine shares the host's memory system with the pack threads (25 / 30 / 35 / 40 / 45 / 50 / 60 / 75: 20.1 / 20.0 / 20.8 / 21.7 / 21.5 / 20.0 / 19.7 / 18.9 k frames/s on 32-byte records, 16-core host)
     int64_t host_stats[4] = {0, 0, 0, 0};  // since creation: H2D bytes, D2H bytes, frames packed, frames copied as they are
     int* d_dbg = nullptr;           // neighbour debug buffer
     float* d_synth_tables = nullptr;
