@@ -180,6 +180,7 @@ class DepthEstimator:
         rc = self._lib.mld_create(C.byref(parameters.c_struct), self._device, C.byref(self._h))
         if rc != _capi.MLD_OK:
             _capi.check(rc, None)
+        self._params_on_device = bytes(parameters.c_struct)  # re-checked in Initialize
         self._isInitializedConfig = True
         self._isInitialized = False
         self._isInitializedPointCloud = False
@@ -189,6 +190,10 @@ class DepthEstimator:
     def Initialize(self, camera: CameraPinhole, transform_lidar_to_cam) -> bool:
         if not self._isInitializedConfig:
             raise RuntimeError("Call 'InitConfig' before calling 'Initialize'.")
+        # the reference builds its modules from the live parameter block here (DepthEstimator.cpp:46-127): a block that was
+        # changed since InitConfig is handed to the device again
+        if bytes(self._parameters.c_struct) != self._params_on_device:
+            self.InitConfig(self._parameters, False)
         T = np.ascontiguousarray(np.asarray(transform_lidar_to_cam, np.float64)[:3, :4])
         if T.shape != (3, 4):
             raise ValueError("transform_lidar_to_cam must be 4x4 or 3x4")

@@ -99,6 +99,7 @@ private:
     std::shared_ptr<CameraPinhole> _camera;
     Eigen::Affine3d _transform_lidar_to_cam;
     mld_handle* _handle{nullptr};
+    mld_params _paramsOnDevice{};            // the parameter block the device handle was created from (re-checked in Initialize)
     bool _isInitializedConfig{false};
     bool _isInitialized{false};
     bool _isInitializedPointCloud{false};

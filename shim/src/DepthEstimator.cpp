@@ -162,6 +162,7 @@ bool DepthEstimator::InitConfig(std::shared_ptr<DepthEstimatorParameters> parame
     int rc = mld_create(_parameters.get(), -1, &_handle);
     if (rc != MLD_OK) throw std::runtime_error(std::string("mld: ") + mld_last_error(nullptr));
     mld_set_statistics(_handle, _parameters->do_depth_calc_statistics ? 1 : 0);
+    std::memcpy(&_paramsOnDevice, static_cast<const mld_params*>(_parameters.get()), sizeof(mld_params));
     _isInitializedConfig = true;
     _isInitialized = false;
     _isInitializedPointCloud = false;
@@ -170,6 +171,9 @@ bool DepthEstimator::InitConfig(std::shared_ptr<DepthEstimatorParameters> parame
 
 bool DepthEstimator::Initialize(const std::shared_ptr<CameraPinhole>& camera, const Eigen::Affine3d& transform_lidar_to_cam) {
     if (!_isInitializedConfig) throw "Call 'InitConfig' before calling 'Initialize'.";
+    // The reference builds its modules from the live parameter block HERE (DepthEstimator.cpp:46-127); the device handle holds the
+    // block as it was at InitConfig. A caller that changed it through the shared pointer in between gets the new values, like upstream.
+    if (std::memcmp(static_cast<const mld_params*>(_parameters.get()), &_paramsOnDevice, sizeof(mld_params)) != 0) InitConfig(_parameters, false);
     _camera = camera;
     _transform_lidar_to_cam = transform_lidar_to_cam;
     int W, H;

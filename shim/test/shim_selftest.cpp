@@ -46,13 +46,15 @@ int main(int argc, char** argv) {
         auto params = std::make_shared<DepthEstimatorParameters>();
         params->pixelarea_search_witdh = 6;
         params->pixelarea_search_height = 9;
-        params->radiusSearch_count_min = 1;
+        params->radiusSearch_count_min = 4;  // overwritten after InitConfig, see below
         params->histogram_segmentation_bin_witdh = 0.3;
         params->pca_treshold_2_1_rel_min = 1.5;
         params->ransac_plane_distance_treshold = 0.3;
-        params->viewray_plane_orthoganality_treshold = 0.03;
         params->do_use_ransac_plane = use_plane ? 1 : 0;
         est.InitConfig(params, false);
+        // changed through the shared pointer AFTER InitConfig: the reference reads the block when Initialize builds its modules
+        params->viewray_plane_orthoganality_treshold = 0.03;
+        params->radiusSearch_count_min = 1;
 
         Eigen::Affine3d T;
         const double Tm[12] = {7.533745e-03, -9.999714e-01, -6.166020e-04, -4.069766e-03, 1.480249e-02, 7.280733e-04,

@@ -726,3 +726,22 @@ def test_per_call_upload_paths_agree(floats_per_record, monkeypatch):
     est0.setInputCloud(clouds[1])
     d, s = est0.CalculateDepth(feats[1])
     assert np.array_equal(s, ref[1][1]) and np.array_equal(d, ref[1][0])
+
+
+def test_parameters_changed_between_initconfig_and_initialize_take_effect():
+    """The reference keeps the shared parameter block and builds its modules from it in Initialize (DepthEstimator.cpp:46-127): a
+    value changed after InitConfig but before Initialize counts. The mirror (and the C++ shim, shim_selftest) hand a changed
+    block to the device again in Initialize."""
+    p = O.yaml_params()
+    p.do_use_ransac_plane = 0
+    params = PU.params_from_c(p)
+    params.radiusSearch_count_min = 5  # not the value the oracle runs with
+    est = DepthEstimator()
+    est.InitConfig(params)
+    params.radiusSearch_count_min = p.radiusSearch_count_min
+    est.Initialize(synth.kitti_camera(), KT)
+    orc = O.Oracle(p)
+    cam = synth.kitti_camera()
+    orc.initialize(1241, 376, cam.focal_length_, cam.principal_point_x_, cam.principal_point_y_, KT)
+    cfg = synth.default_config()
+    PU.compare_frame(est, orc, synth.points_host(cfg, 41, 0), synth.features_host(cfg, 41, 0, 1200), what="late parameter change")
